@@ -6,6 +6,7 @@
 //   ref_driver --problem poisson|helmholtz|varcoef --solver fishpack|fivepoint
 //              --min-level a --max-level b --nx M --domain xl xu yl yu --threshold t
 //              [--homogeneous 0|1] [--cache 0|1] [--nsolves k] [--dump file] [--ops 0|1]
+//              [--refine-box x0 x1 y0 y1]   (refine inside a box instead of |f| > threshold)
 #include <EllipticForest.hpp>
 #include <Patches/FiniteVolume/FiniteVolume.hpp>
 #include <cstdio>
@@ -49,6 +50,7 @@ int main(int argc, char** argv) {
     std::string solver_name = "fishpack", dump;
     int min_level = 0, max_level = 2, nx = 8, nsolves = 1; bool homogeneous = false, cache = false, ops = true;
     double xl = -10, xu = 10, yl = -10, yu = 10, threshold = 1.2;
+    bool use_box = false; double rb[4] = {0, 0, 0, 0};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() { return std::string(argv[++i]); };
@@ -63,6 +65,7 @@ int main(int argc, char** argv) {
         else if (a == "--nsolves") nsolves = std::stoi(next());
         else if (a == "--ops") ops = std::stoi(next());
         else if (a == "--dump") dump = next();
+        else if (a == "--refine-box") { use_box = true; for (int k = 0; k < 4; k++) rb[k] = std::stod(next()); }
         else if (a == "--domain") { xl = std::stod(next()); xu = std::stod(next()); yl = std::stod(next()); yu = std::stod(next()); }
         else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
     }
@@ -76,7 +79,7 @@ int main(int argc, char** argv) {
     FiniteVolumeNodeFactory node_factory(MPI_COMM_WORLD);
     Mesh<FiniteVolumePatch> mesh{};
     auto t0 = std::chrono::steady_clock::now();
-    mesh.refineByFunction([&](double x, double y) { return fabs(-(sin(x) + sin(y))) > threshold; },
+    mesh.refineByFunction([&](double x, double y) { return use_box ? (x > rb[0] && x < rb[1] && y > rb[2] && y < rb[3]) : fabs(-(sin(x) + sin(y))) > threshold; },
                           threshold, min_level, max_level, root_patch, node_factory);
     double t_mesh = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
