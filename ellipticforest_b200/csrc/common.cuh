@@ -1,0 +1,60 @@
+// Shared declarations for the efgpu CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace efgpu {
+
+// ---- status codes (mirrored in include/efgpu.h) ---------------------------------------------
+enum : int { EF_OK = 0, EF_ERR_CUDA = 1, EF_ERR_BAD_ARG = 2, EF_ERR_BAD_SHAPE = 3, EF_ERR_OOM = 4,
+             EF_ERR_SINGULAR = 5, EF_ERR_STATE = 6, EF_ERR_UNSUPPORTED = 7 };
+
+struct Error { int code; std::string msg; };
+#define EF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw ::efgpu::Error{e__ == cudaErrorMemoryAllocation ? ::efgpu::EF_ERR_OOM : ::efgpu::EF_ERR_CUDA, \
+                                 std::string(#call) + ": " + cudaGetErrorString(e__)};             \
+    } while (0)
+
+// ---- descriptor-driven batched DGEMM (gemm.cu) ----------------------------------------------
+// One launch computes, for every batch entry z and every block descriptor d:
+//     C_d = [C0_d] + sum_t  sign_t * A_{d,t} (rows x K_t) * B_{d,t} (K_t x cols)
+// Operands are addressed as ptab[z * nops + op] + offset, row-major with their own leading
+// dimension, so a descriptor can point straight into the children's DtN matrices (the block
+// gathers, negations and the WESN block permutation of the reference's merge are folded into
+// operand/result addressing and never materialised).
+constexpr int GEMM_MAX_TERMS = 2;
+struct GemmTerm {
+    int a_op, b_op;
+    int lda, ldb;
+    long long a_off, b_off;   // element offsets of the (0,0) entry of the block
+    int K;
+    unsigned neg;             // 0 or 0x80000000: flips the sign of A on the fly
+};
+struct GemmBlock {
+    int c_op, c0_op;          // c0_op < 0: no additive term
+    int ldc, ldc0;
+    long long c_off, c0_off;
+    int rows, cols;
+    int nterms;
+    int pad_;
+    GemmTerm t[GEMM_MAX_TERMS];
+};
+// Launches the kernel on `stream`.  rows/cols/K of every block must be multiples of the chosen
+// tile; the tile configuration is picked from the block shape and the amount of parallelism.
+void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
+                  int nblocks, int batch, cudaStream_t stream, int force_tile = 0);
+
+// In-place inverse of `batch` small dense N x N matrices (N <= 128) held at
+// ptab[z*nops+op] + off with leading dimension ld; Gauss-Jordan in shared memory, no pivoting
+// (the merge matrices are SPD / diagonally dominant).  min |pivot| is folded
+// into *min_pivot (device scalar) for singularity reporting.
+void launch_invert_small(double* const* ptab, int nops, int op, long long off, int ld, int N, int batch,
+                         double* min_pivot, cudaStream_t stream);
+
+}  // namespace efgpu

@@ -1,0 +1,266 @@
+// Descriptor-driven batched FP64 GEMM on the sm_100a FP64 tensor path (DMMA, mma.sync m8n8k4)
+// and the small in-shared-memory Gauss-Jordan inverse used as the base case of the blocked
+// inversion of the merge matrix X.
+//
+// Replaces, for the 4-to-1 merge of the reference (src/HPSAlgorithm.hpp:497-518):
+//   createMatrixBlocks_ :799-859  (36 block gathers + 8 negations)  -> operand addressing + sign flip
+//   mergeS_ :906-929   dgesv  (Matrix.hpp:944)                      -> GEMMs with X^-1
+//   mergeT_ :940-968   dgemm  (Matrix.hpp:852) + T_LHS add          -> GEMM with additive C0
+//   reorderOperators_ :979-993 (blockPermute)                       -> result addressing
+//
+// FP64 has no tcgen05 kind on Blackwell; the FP64 tensor throughput of sm_100a (37 TFLOP/s
+// measured with a register-only DMMA loop on B200, cuBLAS DGEMM 35.4) is reached through
+// mma.sync.m8n8k4.f64 fed from shared memory that is filled by an asynchronous multi-stage
+// copy pipeline (cp.async 16-byte, LDGSTS).
+#include "common.cuh"
+
+namespace efgpu {
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double flip_sign(double x, unsigned neg) {
+    return __hiloint2double(__double2hiint(x) ^ (int)neg, __double2loint(x));
+}
+
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
+struct GemmCfg {
+    static constexpr int NT = WARPS_M * WARPS_N * 32;
+    static constexpr int LDA_S = BK + 4;   // == 4 (mod 8): conflict-free 8x4 fragment reads
+    static constexpr int LDB_S = BN + 4;   // == 4 (mod 16): conflict-free 4x8 fragment reads
+    static constexpr int A_STAGE = BM * LDA_S;
+    static constexpr int B_STAGE = BK * LDB_S;
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+    static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    static constexpr int FM = WM / 8, FN = WN / 8;
+};
+
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
+bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __restrict__ blocks,
+             int nblocks, int tiles_per_block)
+{
+    using C = GemmCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * C::A_STAGE;
+
+    // work decode: tile fastest, then block descriptor, then batch entry
+    const long long bid = blockIdx.x;
+    const int tile = (int)(bid % tiles_per_block);
+    const int blk = (int)((bid / tiles_per_block) % nblocks);
+    const long long z = bid / ((long long)tiles_per_block * nblocks);
+    const GemmBlock& bd = blocks[blk];
+    const int tiles_n = bd.cols / BN;
+    const int tm = tile / tiles_n, tn = tile % tiles_n;
+    if (tm >= bd.rows / BM) return;
+    double* const* ops = ptab + z * nops;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp / WARPS_N) * C::WM, wn0 = (warp % WARPS_N) * C::WN;
+
+    // flattened (term, k-tile) sequence
+    const int nterms = bd.nterms;
+    int nk_total = 0;
+    for (int t = 0; t < nterms; t++) nk_total += bd.t[t].K / BK;
+
+    auto load_stage = [&](int s, int buf) {
+        int t = 0, kt = s;
+        while (kt >= bd.t[t].K / BK) { kt -= bd.t[t].K / BK; t++; }
+        const GemmTerm& tr = bd.t[t];
+        const double* Ag = ops[tr.a_op] + tr.a_off + (long long)(tm * BM) * tr.lda + kt * BK;
+        const double* Bg = ops[tr.b_op] + tr.b_off + (long long)(kt * BK) * tr.ldb + tn * BN;
+        double* as = As + buf * C::A_STAGE;
+        double* bs = Bs + buf * C::B_STAGE;
+        constexpr int A_CHUNKS = BM * BK / 2, ACPR = BK / 2;
+#pragma unroll
+        for (int c = tid; c < A_CHUNKS; c += C::NT) {
+            int r = c / ACPR, cc = (c % ACPR) * 2;
+            cp_async16(as + r * C::LDA_S + cc, Ag + (long long)r * tr.lda + cc);
+        }
+        constexpr int B_CHUNKS = BK * BN / 2, BCPR = BN / 2;
+#pragma unroll
+        for (int c = tid; c < B_CHUNKS; c += C::NT) {
+            int r = c / BCPR, cc = (c % BCPR) * 2;
+            cp_async16(bs + r * C::LDB_S + cc, Bg + (long long)r * tr.ldb + cc);
+        }
+    };
+
+    double acc[C::FM][C::FN][2];
+#pragma unroll
+    for (int i = 0; i < C::FM; i++)
+#pragma unroll
+        for (int j = 0; j < C::FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk_total) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    int term_of_stage = 0, k_left = bd.t[0].K / BK;   // tracks the sign of the stage being computed
+    unsigned neg = bd.t[0].neg;
+    for (int kt = 0; kt < nk_total; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = kt + STAGES - 1;
+            if (nxt < nk_total) load_stage(nxt, nxt % STAGES);
+            cp_async_commit();
+        }
+        if (k_left == 0) { term_of_stage++; k_left = bd.t[term_of_stage].K / BK; neg = bd.t[term_of_stage].neg; }
+        k_left--;
+        const double* as = As + (kt % STAGES) * C::A_STAGE + (wm0 + (lane >> 2)) * C::LDA_S + (lane & 3);
+        const double* bs = Bs + (kt % STAGES) * C::B_STAGE + (lane & 3) * C::LDB_S + wn0 + (lane >> 2);
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double a[C::FM], b[C::FN];
+#pragma unroll
+            for (int i = 0; i < C::FM; i++) a[i] = flip_sign(as[i * 8 * C::LDA_S + kk * 4], neg);
+#pragma unroll
+            for (int j = 0; j < C::FN; j++) b[j] = bs[kk * 4 * C::LDB_S + j * 8];
+#pragma unroll
+            for (int i = 0; i < C::FM; i++)
+#pragma unroll
+                for (int j = 0; j < C::FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C = acc (+ C0); each thread owns rows (lane/4), column pairs (lane%4)*2
+    double* Cg = ops[bd.c_op] + bd.c_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc + tn * BN + wn0 + (lane & 3) * 2;
+    const double* C0g = nullptr;
+    if (bd.c0_op >= 0)
+        C0g = ops[bd.c0_op] + bd.c0_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc0 + tn * BN + wn0 + (lane & 3) * 2;
+#pragma unroll
+    for (int i = 0; i < C::FM; i++)
+#pragma unroll
+        for (int j = 0; j < C::FN; j++) {
+            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (C0g) {
+                double2 c0 = *reinterpret_cast<const double2*>(C0g + (long long)(i * 8) * bd.ldc0 + j * 8);
+                v.x += c0.x; v.y += c0.y;
+            }
+            *reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + j * 8) = v;
+        }
+}
+
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
+static void launch_cfg(double* const* ptab, int nops, const GemmBlock* d_blocks, int nblocks, int batch,
+                       int max_tiles, cudaStream_t stream)
+{
+    using C = GemmCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
+    auto kern = bgemm_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    long long grid = (long long)max_tiles * nblocks * batch;
+    if (grid <= 0) return;
+    if (grid > 2147483647LL) throw Error{EF_ERR_BAD_SHAPE, "bgemm grid too large"};
+    kern<<<(unsigned)grid, C::NT, C::SMEM_BYTES, stream>>>(ptab, nops, d_blocks, nblocks, max_tiles);
+    EF_CUDA(cudaGetLastError());
+}
+
+void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
+                  int nblocks, int batch, cudaStream_t stream, int force_tile)
+{
+    if (nblocks == 0 || batch == 0) return;
+    // largest power-of-two tile dividing every block dimension
+    int g = 128;
+    bool k16 = true;
+    for (int b = 0; b < nblocks; b++) {
+        const GemmBlock& bd = h_blocks[b];
+        while (g > 1 && (bd.rows % g || bd.cols % g)) g >>= 1;
+        for (int t = 0; t < bd.nterms; t++) {
+            if (bd.t[t].K % 16) k16 = false;
+            if (bd.t[t].K % 8) throw Error{EF_ERR_BAD_SHAPE, "bgemm: K must be a multiple of 8"};
+        }
+    }
+    if (g < 8) throw Error{EF_ERR_BAD_SHAPE, "bgemm: block dimensions must be multiples of 8"};
+    if (!k16 && g > 8) g = 8;
+    auto tiles_for = [&](int t) { int m = 0; for (int b = 0; b < nblocks; b++) { int v = (h_blocks[b].rows / t) * (h_blocks[b].cols / t); if (v > m) m = v; } return m; };
+    int tile = g;
+    if (force_tile) tile = force_tile < g ? force_tile : g;
+    else {
+        // prefer the largest tile that still fills the 148 SMs; never go below 32 for that reason
+        while (tile > 32 && (long long)tiles_for(tile) * nblocks * batch < 148) tile >>= 1;
+    }
+    int mt = tiles_for(tile);
+    switch (tile) {
+        case 128: launch_cfg<128, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        case 64: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        case 32: launch_cfg<32, 32, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        case 16: launch_cfg<16, 16, 16, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        case 8: launch_cfg<8, 8, 8, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        default: throw Error{EF_ERR_BAD_SHAPE, "bgemm: unsupported tile"};
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small in-place inverse (base case of the blocked inversion of X): one CTA per matrix,
+// Gauss-Jordan in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, int ld, int N,
+                    double* __restrict__ min_pivot)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int LDS = N + 1;
+    double* A = sm;                 // N x (N+1)
+    double* colk = sm + N * LDS;    // N  (column k before the update)
+    double* G = ptab[(long long)blockIdx.x * nops + op] + off;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (int e = tid; e < N * N; e += NT) { int r = e / N, c = e % N; A[r * LDS + c] = G[(long long)r * ld + c]; }
+    __syncthreads();
+    double minp = 1e300;
+    for (int k = 0; k < N; k++) {
+        const double piv = A[k * LDS + k];
+        const double p = 1.0 / piv;
+        minp = fmin(minp, fabs(piv));
+        for (int r = tid; r < N; r += NT) colk[r] = A[r * LDS + k];
+        __syncthreads();
+        // scale pivot row
+        for (int c = tid; c < N; c += NT) A[k * LDS + c] = (c == k) ? p : A[k * LDS + c] * p;
+        __syncthreads();
+        // eliminate column k from all other rows
+        for (int e = tid; e < N * N; e += NT) {
+            int r = e / N, c = e % N;
+            if (r == k) continue;
+            double f = colk[r];
+            A[r * LDS + c] = (c == k) ? -f * p : A[r * LDS + c] - f * A[k * LDS + c];
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < N * N; e += NT) { int r = e / N, c = e % N; G[(long long)r * ld + c] = A[r * LDS + c]; }
+    if (tid == 0 && min_pivot) {
+        // positive doubles order like their bit patterns
+        atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
+    }
+}
+
+void launch_invert_small(double* const* ptab, int nops, int op, long long off, int ld, int N, int batch,
+                         double* min_pivot, cudaStream_t stream)
+{
+    if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "invert_small: N > 128"};
+    int smem = (N * (N + 1) + N) * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        EF_CUDA(cudaFuncSetAttribute(invert_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 128) * 8));
+        attr_set = true;
+    }
+    invert_small_kernel<<<batch, 256, smem, stream>>>(ptab, nops, op, off, ld, N, min_pivot);
+    EF_CUDA(cudaGetLastError());
+}
+
+}  // namespace efgpu

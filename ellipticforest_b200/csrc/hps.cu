@@ -1,0 +1,752 @@
+// Host-side engine behind the C-ABI (include/efgpu.h): level-synchronous plan of the quadtree,
+// device memory layout, and the three stages of the HPS method (build / upwards / solve).
+//
+// Mirrors src/HPSAlgorithm.hpp of the reference: buildStage :120-161 (post-order leaf DtN +
+// merge4to1 :497-518), upwardsStage :225-272 (+ upwards4to1 :529-551), solveStage :291-445
+// (+ split1to4 :562-577, leafSolve :584-596).  The reference walks the tree node by node in p4est
+// DFS order; here every tree level becomes a handful of batched kernel launches (parents grouped
+// by child side n), which produces the same per-node operators because nodes of one level are
+// independent.  Node numbering, leaf order and all index conventions are the reference's.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "../../include/efgpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+
+namespace efgpu {
+
+// ---- merge topology (host copies of the tables in vec.cu) ------------------------------------
+static const int h_iface[4][4] = {{3, -1, 1, -1}, {-1, 3, 0, -1}, {2, -1, -1, 1}, {-1, 2, -1, 0}};
+static const int h_sgn[4][4] = {{-1, 0, -1, 0}, {0, -1, 1, 0}, {1, 0, 0, -1}, {0, 1, 0, 1}};
+static const int h_tau_side[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
+static const int h_kk[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
+static const int h_pos[8] = {0, 4, 2, 5, 1, 6, 3, 7};  // inverse of pi = {0,4,2,6,1,3,5,7}
+
+enum { OP_TC0 = 0, OP_XINV = 4, OP_S = 5, OP_T = 6, OP_W1 = 7, OP_W2 = 8, NOPS = 10 };
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void alloc(size_t b) {
+        if (b <= bytes && p) return;
+        release();
+        if (b == 0) return;
+        EF_CUDA(cudaMalloc(&p, b)); bytes = b;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    template <class T> void upload(const std::vector<T>& v, cudaStream_t s) {
+        alloc(v.size() * sizeof(T));
+        if (!v.empty()) EF_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+struct NodeH {
+    int level = 0, parent = -1, child[4] = {-1, -1, -1, -1};
+    bool leaf = true;
+    double box[4] = {0, 0, 0, 0};
+    int size = 0;       // cells per side of this node's own patch (leaf: M, parent: 2 n)
+    int ncoarsen = 0;   // times it is coarsened when merged into its parent (HPSAlgorithm.hpp:676-741)
+    int leaf_idx = -1, batch = -1, slot = -1;
+    std::vector<double*> Tbuf;        // [0] own DtN, [t] after t coarsening steps
+    std::vector<size_t> hbuf, gbuf;   // offsets into the vector arena, same indexing
+    size_t w_off = 0, hd_off = 0;
+};
+
+struct Step { int kind; int first, count; long long off; int N; };  // kind 0: small inverse, 1: gemm
+
+struct BatchH {
+    int level = 0, n = 0, count = 0;
+    std::vector<int> parents;
+    std::vector<GemmBlock> blocks;    // all descriptors of this batch (host copy)
+    std::vector<Step> steps;          // inversion, then S, then T
+    DevBuf d_blocks, d_entries, d_ptab;
+    DevBuf Xinv, S, Hc, T, Xcopy, Tcoarse;
+    std::vector<std::vector<CoarsenOp>> cT, cH, cG;  // per step
+    std::vector<std::unique_ptr<DevBuf>> d_cT, d_cH, d_cG;
+    std::vector<int> cT_max, cH_max, cG_max;
+    size_t ws_per_entry = 0;
+};
+
+}  // namespace efgpu
+
+using namespace efgpu;
+
+struct efgpu_handle {
+    int device = 0, M = 0, n_nodes = 0, n_leaves = 0, max_level = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<NodeH> nodes;
+    std::vector<int> leaf_nodes;                 // node id of each leaf, pre-order (= Morton order)
+    std::vector<std::vector<int>> level_batches; // batch ids per tree level
+    std::vector<BatchH> batches;
+    // leaf model
+    int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
+    // device state
+    DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
+    size_t vec_doubles = 0;
+    bool allocated = false, built = false, upwards_done = false;
+    const double* f_cur = nullptr; double fscale_cur = 1.0;   // load of the last upwards call (re-used by the leaf solves)
+    unsigned build_flags = 0;
+    std::string last_error;
+    efgpu_stats_t stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace efgpu {
+
+static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int depth, std::vector<long long>& w1_off, long long w2_off)
+{
+    const bool can_split = N > 64 && (N / 2) % 8 == 0;
+    if (!can_split) {
+        if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
+        b.steps.push_back({0, 0, 0, off, N});
+        return;
+    }
+    const int h = N / 2;
+    const long long A = off, B = off + h, C = off + (long long)h * ld, D = off + (long long)h * ld + h;
+    const long long W1 = w1_off[depth];
+    auto gemm = [&](int c_op, long long c_off, int ldc, int c0_op, long long c0_off, int ldc0,
+                    int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb, bool neg) {
+        GemmBlock g{};
+        g.c_op = c_op; g.c_off = c_off; g.ldc = ldc; g.c0_op = c0_op; g.c0_off = c0_off; g.ldc0 = ldc0;
+        g.rows = h; g.cols = h; g.nterms = 1;
+        g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, h, neg ? 0x80000000u : 0u};
+        b.steps.push_back({1, (int)b.blocks.size(), 1, 0, 0});
+        b.blocks.push_back(g);
+    };
+    build_inverse_steps(b, A, h, ld, depth + 1, w1_off, w2_off);                                 // A <- A^-1
+    gemm(OP_W1, W1, h, -1, 0, 0, OP_XINV, C, ld, OP_XINV, A, ld, false);                          // W1 = C A^-1
+    gemm(OP_XINV, D, ld, OP_XINV, D, ld, OP_W1, W1, h, OP_XINV, B, ld, true);                     // D <- D - W1 B   (Schur complement)
+    build_inverse_steps(b, D, h, ld, depth + 1, w1_off, w2_off);                                 // D <- S^-1
+    gemm(OP_W2, w2_off, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);                      // W2 = A^-1 B
+    gemm(OP_XINV, B, ld, -1, 0, 0, OP_W2, w2_off, h, OP_XINV, D, ld, true);                       // B <- -W2 S^-1
+    gemm(OP_XINV, C, ld, -1, 0, 0, OP_XINV, D, ld, OP_W1, W1, h, true);                           // C <- -S^-1 W1
+    gemm(OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W1, W1, h, true);                     // A <- A^-1 - B W1
+}
+
+static void plan_batch_gemms(BatchH& b)
+{
+    const int n = b.n, N = 4 * n;
+    // workspace layout per entry: W1 blocks per recursion depth (op 7), W2 (op 8)
+    std::vector<long long> w1_off; long long acc = 0;
+    for (int h = N / 2; h >= 8; h /= 2) { w1_off.push_back(acc); acc += (long long)h * h; }
+    w1_off.push_back(acc);
+    const long long w1_total = acc, w2_total = (long long)(N / 2) * (N / 2);
+    b.ws_per_entry = (size_t)(w1_total + w2_total);
+    build_inverse_steps(b, 0, N, N, 0, w1_off, 0);
+    // S = X^-1 S_RHS, written with WESN-permuted columns (mergeS_ + reorderOperators_)
+    int first = (int)b.blocks.size();
+    for (int k = 0; k < 4; k++)
+        for (int q = 0; q < 8; q++) {
+            const int c = q >> 1, side = h_tau_side[c][q & 1];
+            GemmBlock g{};
+            g.c_op = OP_S; g.c_off = (long long)(k * n) * (8 * n) + h_pos[q] * n; g.ldc = 8 * n; g.c0_op = -1;
+            g.rows = n; g.cols = n; g.nterms = 2;
+            for (int t = 0; t < 2; t++) {
+                const int k2 = h_kk[c][t];
+                g.t[t] = GemmTerm{OP_XINV, OP_TC0 + c, N, N, (long long)(k * n) * N + k2 * n,
+                                  (long long)(h_iface[c][k2] * n) * N + side * n, n, h_sgn[c][k2] < 0 ? 0x80000000u : 0u};
+            }
+            b.blocks.push_back(g);
+        }
+    b.steps.push_back({1, first, 32, 0, 0});
+    // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_)
+    first = (int)b.blocks.size();
+    for (int qr = 0; qr < 8; qr++)
+        for (int qc = 0; qc < 8; qc++) {
+            const int c = qr >> 1, side_r = h_tau_side[c][qr & 1];
+            const int c2 = qc >> 1, side_c = h_tau_side[c2][qc & 1];
+            GemmBlock g{};
+            g.c_op = OP_T; g.c_off = (long long)(h_pos[qr] * n) * (8 * n) + h_pos[qc] * n; g.ldc = 8 * n;
+            if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n) * N + side_c * n; g.ldc0 = N; }
+            else g.c0_op = -1;
+            g.rows = n; g.cols = n; g.nterms = 2;
+            for (int t = 0; t < 2; t++) {
+                const int k = h_kk[c][t];
+                g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n) * N + h_iface[c][k] * n,
+                                  (long long)(k * n) * (8 * n) + h_pos[qc] * n, n, 0u};
+            }
+            b.blocks.push_back(g);
+        }
+    b.steps.push_back({1, first, 64, 0, 0});
+}
+
+static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d)
+{
+    const int nn = d->n_nodes, M = d->nx;
+    if (nn <= 0 || !d->level || !d->child || !d->box) throw Error{EF_ERR_BAD_ARG, "empty tree description"};
+    if (M < 8 || M % 8) throw Error{EF_ERR_BAD_SHAPE, "nx must be a multiple of 8 (8, 16, 24, 32)"};
+    H->M = M; H->n_nodes = nn;
+    H->nodes.resize(nn);
+    for (int i = 0; i < nn; i++) {
+        NodeH& nd = H->nodes[i];
+        nd.level = d->level[i];
+        for (int c = 0; c < 4; c++) nd.child[c] = d->child[4 * i + c];
+        nd.leaf = nd.child[0] < 0;
+        for (int c = 0; c < 4; c++) {
+            if ((nd.child[c] < 0) != nd.leaf) throw Error{EF_ERR_BAD_ARG, "node with a partial set of children"};
+            if (!nd.leaf) {
+                if (nd.child[c] <= i || nd.child[c] >= nn) throw Error{EF_ERR_BAD_ARG, "children must follow their parent (pre-order table)"};
+                H->nodes[nd.child[c]].parent = i;
+            }
+        }
+        std::memcpy(nd.box, d->box + 4 * i, 4 * sizeof(double));
+        H->max_level = std::max(H->max_level, nd.level);
+        if (nd.leaf) { nd.leaf_idx = (int)H->leaf_nodes.size(); H->leaf_nodes.push_back(i); }
+    }
+    H->n_leaves = (int)H->leaf_nodes.size();
+    // sizes bottom-up (children have larger ids): parent = 2 * min child size (mergePatch_ :1004-1009)
+    for (int i = nn - 1; i >= 0; i--) {
+        NodeH& nd = H->nodes[i];
+        if (nd.leaf) { nd.size = M; continue; }
+        int mn = 1 << 30;
+        for (int c = 0; c < 4; c++) {
+            if (H->nodes[nd.child[c]].level != nd.level + 1) throw Error{EF_ERR_BAD_ARG, "child level must be parent level + 1"};
+            mn = std::min(mn, H->nodes[nd.child[c]].size);
+        }
+        for (int c = 0; c < 4; c++) {
+            NodeH& ch = H->nodes[nd.child[c]];
+            int t = 0; while ((mn << t) < ch.size) t++;   // tag = log2(size) - log2(min)  (:676-696)
+            ch.ncoarsen = t;
+        }
+        nd.size = 2 * mn;
+    }
+    // batches: parents grouped by (level, child side n)
+    H->level_batches.assign(H->max_level + 1, {});
+    std::map<std::pair<int, int>, int> key2batch;
+    for (int i = 0; i < nn; i++) {
+        NodeH& nd = H->nodes[i];
+        if (nd.leaf) continue;
+        const int n = nd.size / 2;
+        auto key = std::make_pair(nd.level, n);
+        auto it = key2batch.find(key);
+        if (it == key2batch.end()) {
+            it = key2batch.emplace(key, (int)H->batches.size()).first;
+            H->batches.emplace_back();
+            H->batches.back().level = nd.level; H->batches.back().n = n;
+            H->level_batches[nd.level].push_back(it->second);
+        }
+        BatchH& b = H->batches[it->second];
+        nd.batch = it->second; nd.slot = (int)b.parents.size();
+        b.parents.push_back(i);
+    }
+    for (auto& b : H->batches) { b.count = (int)b.parents.size(); plan_batch_gemms(b); }
+    // vector arena offsets
+    size_t off = 0;
+    auto take = [&](size_t nd_) { size_t o = off; off += (nd_ + 1) & ~size_t(1); return o; };
+    for (auto& nd : H->nodes) {
+        for (int t = 0; t <= nd.ncoarsen; t++) { nd.hbuf.push_back(take(4 * (size_t)(nd.size >> t))); nd.gbuf.push_back(take(4 * (size_t)(nd.size >> t))); }
+        if (!nd.leaf) { nd.w_off = take(2 * (size_t)nd.size); nd.hd_off = take(2 * (size_t)nd.size); }
+    }
+    H->vec_doubles = off;
+    // flop model: canonical dgesv+dgemm count and the count actually issued
+    double canon = 0, issued = 0, up_bytes = 0, so_bytes = 0;
+    for (auto& b : H->batches) {
+        const double n3 = (double)b.n * b.n * b.n;
+        canon += b.count * 810.0 * n3 + b.count * (2.0 / 3.0) * n3;
+        issued += b.count * (128.0 + 128.0 + 256.0) * n3;
+        up_bytes += b.count * 8.0 * (16.0 + 16.0) * b.n * b.n;
+        so_bytes += b.count * 8.0 * 32.0 * b.n * b.n;
+    }
+    H->stats.merge_flops_canonical = canon;
+    H->stats.merge_flops_issued = issued;
+    H->stats.upwards_bytes = up_bytes + 8.0 * H->n_leaves * M * M;
+    H->stats.solve_bytes = so_bytes + 16.0 * H->n_leaves * M * M;
+    H->stats.n_leaves = H->n_leaves;
+    H->stats.n_nodes = nn;
+    H->stats.dofs = (double)H->n_leaves * M * M;
+}
+
+static void allocate_device(efgpu_handle* H, unsigned flags)
+{
+    cudaStream_t s = H->stream;
+    const int M = H->M;
+    // leaf tables
+    std::vector<double> Q((size_t)M * M);
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int i = 0; i < M; i++)
+        for (int k = 0; k < M; k++)
+            Q[(size_t)i * M + k] = std::sqrt((k + 1 == M ? 1.0 : 2.0) / M) * std::sin((i + 0.5) * (k + 1) * pi / M);
+    H->d_Q.upload(Q, s);
+    std::vector<double> boxes((size_t)4 * H->n_nodes);
+    for (int i = 0; i < H->n_nodes; i++) std::memcpy(&boxes[4 * (size_t)i], H->nodes[i].box, 4 * sizeof(double));
+    H->d_boxes.upload(boxes, s);
+    H->d_leaf_nodes.upload(H->leaf_nodes, s);
+    H->d_leafT.alloc((size_t)H->n_leaves * 16 * M * M * sizeof(double));
+    H->d_vec.alloc(H->vec_doubles * sizeof(double));
+    EF_CUDA(cudaMemsetAsync(H->d_vec.p, 0, H->vec_doubles * sizeof(double), s));
+    H->d_f.alloc((size_t)H->n_leaves * M * M * sizeof(double));
+    H->d_u.alloc((size_t)H->n_leaves * M * M * sizeof(double));
+    H->d_minpiv.alloc(sizeof(double));
+    double* vec = H->d_vec.as<double>();
+    for (int l = 0; l < H->n_leaves; l++) H->nodes[H->leaf_nodes[l]].Tbuf.assign(1, H->d_leafT.as<double>() + (size_t)l * 16 * M * M);
+    std::vector<double*> lh(H->n_leaves), lg(H->n_leaves);
+    for (int l = 0; l < H->n_leaves; l++) { NodeH& nd = H->nodes[H->leaf_nodes[l]]; lh[l] = vec + nd.hbuf[0]; lg[l] = vec + nd.gbuf[0]; }
+    H->d_leaf_h.upload(lh, s); H->d_leaf_g.upload(lg, s);
+
+    // per-batch operator storage (deepest level first so children's buffers exist before the parents' tables)
+    size_t ws_max = 0;
+    for (int lev = H->max_level; lev >= 0; lev--)
+        for (int bi : H->level_batches[lev]) {
+            BatchH& b = H->batches[bi];
+            const size_t n = b.n, cnt = b.count;
+            b.Xinv.alloc(cnt * 16 * n * n * sizeof(double));
+            b.S.alloc(cnt * 32 * n * n * sizeof(double));
+            b.Hc.alloc(cnt * 16 * n * n * sizeof(double));
+            b.T.alloc(cnt * 64 * n * n * sizeof(double));
+            if (flags & EFGPU_KEEP_X) b.Xcopy.alloc(cnt * 16 * n * n * sizeof(double));
+            ws_max = std::max(ws_max, cnt * b.ws_per_entry);
+            for (size_t sl = 0; sl < cnt; sl++) H->nodes[b.parents[sl]].Tbuf.assign(1, b.T.as<double>() + sl * 64 * n * n);
+        }
+    H->d_ws.alloc(ws_max * sizeof(double));
+    // coarsened copies + tables
+    for (auto& b : H->batches) {
+        const size_t n = b.n, cnt = b.count;
+        size_t coarse_doubles = 0;
+        for (int p : b.parents)
+            for (int c = 0; c < 4; c++) {
+                NodeH& ch = H->nodes[H->nodes[p].child[c]];
+                for (int t = 1; t <= ch.ncoarsen; t++) { size_t sz = 4 * (size_t)(ch.size >> t); coarse_doubles += sz * sz; }
+            }
+        b.Tcoarse.alloc(coarse_doubles * sizeof(double));
+        size_t coff = 0;
+        b.cT.clear(); b.cH.clear(); b.cG.clear();
+        std::vector<MergeEntry> ent(cnt);
+        std::vector<double*> ptab(cnt * NOPS, nullptr);
+        for (size_t sl = 0; sl < cnt; sl++) {
+            NodeH& P = H->nodes[b.parents[sl]];
+            MergeEntry& e = ent[sl];
+            for (int c = 0; c < 4; c++) {
+                NodeH& ch = H->nodes[P.child[c]];
+                for (int t = 1; t <= ch.ncoarsen; t++) {
+                    size_t sz = 4 * (size_t)(ch.size >> t);
+                    ch.Tbuf.resize(t + 1);
+                    ch.Tbuf[t] = b.Tcoarse.as<double>() + coff; coff += sz * sz;
+                    if ((int)b.cT.size() < t) { b.cT.resize(t); b.cH.resize(t); }
+                    b.cT[t - 1].push_back(CoarsenOp{ch.Tbuf[t - 1], ch.Tbuf[t], ch.size >> (t - 1), 0});
+                    b.cH[t - 1].push_back(CoarsenOp{vec + ch.hbuf[t - 1], vec + ch.hbuf[t], ch.size >> (t - 1), 0});
+                }
+                if ((ch.size >> ch.ncoarsen) != (int)n) throw Error{EF_ERR_STATE, "internal: child size mismatch after coarsening"};
+                e.Tc[c] = ch.Tbuf[ch.ncoarsen];
+                e.hc[c] = vec + ch.hbuf[ch.ncoarsen];
+                e.gc[c] = vec + ch.gbuf[ch.ncoarsen];
+                ptab[sl * NOPS + OP_TC0 + c] = ch.Tbuf[ch.ncoarsen];
+            }
+            e.Xinv = b.Xinv.as<double>() + sl * 16 * n * n;
+            e.S = b.S.as<double>() + sl * 32 * n * n;
+            e.Hc = b.Hc.as<double>() + sl * 16 * n * n;
+            e.T = b.T.as<double>() + sl * 64 * n * n;
+            e.Xcopy = (flags & EFGPU_KEEP_X) ? b.Xcopy.as<double>() + sl * 16 * n * n : nullptr;
+            e.hd = vec + P.hd_off; e.h = vec + P.hbuf[0]; e.w = vec + P.w_off; e.g = vec + P.gbuf[0];
+            ptab[sl * NOPS + OP_XINV] = e.Xinv; ptab[sl * NOPS + OP_S] = e.S; ptab[sl * NOPS + OP_T] = e.T;
+            ptab[sl * NOPS + OP_W1] = H->d_ws.as<double>() + sl * b.ws_per_entry;
+            ptab[sl * NOPS + OP_W2] = H->d_ws.as<double>() + sl * b.ws_per_entry + (b.ws_per_entry - (size_t)(2 * n) * (2 * n));
+            // this parent's own Dirichlet data arrives coarsened when it was tagged: uncoarsen before the split
+            for (int t = P.ncoarsen; t >= 1; t--) {
+                const int step = P.ncoarsen - t;
+                if ((int)b.cG.size() <= step) b.cG.resize(step + 1);
+                b.cG[step].push_back(CoarsenOp{vec + P.gbuf[t], vec + P.gbuf[t - 1], P.size >> (t - 1), 0});
+            }
+        }
+        b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s);
+        auto up = [&](std::vector<std::vector<CoarsenOp>>& v, std::vector<std::unique_ptr<DevBuf>>& dv, std::vector<int>& mx) {
+            dv.clear(); mx.clear();
+            for (auto& ops : v) {
+                dv.emplace_back(new DevBuf()); dv.back()->upload(ops, s);
+                int m = 0; for (auto& o : ops) m = std::max(m, o.nfine);
+                mx.push_back(m);
+            }
+        };
+        up(b.cT, b.d_cT, b.cT_max); up(b.cH, b.d_cH, b.cH_max); up(b.cG, b.d_cG, b.cG_max);
+    }
+    EF_CUDA(cudaStreamSynchronize(s));
+    H->allocated = true; H->build_flags = flags;
+    size_t tot = 0;
+    for (auto& b : H->batches) tot += b.Xinv.bytes + b.S.bytes + b.Hc.bytes + b.T.bytes + b.Xcopy.bytes + b.Tcoarse.bytes;
+    H->stats.device_bytes = (double)(tot + H->d_leafT.bytes + H->d_vec.bytes + H->d_ws.bytes + H->d_f.bytes + H->d_u.bytes);
+}
+
+static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
+{
+    if (H->leaf_kind != EFGPU_LEAF_CONSTANT) throw Error{EF_ERR_UNSUPPORTED, "variable-coefficient leaves are not built yet"};
+    launch_leaf_dtn_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                          H->d_leafT.as<double>(), H->n_leaves, (flags & EFGPU_CACHE_OPERATORS) != 0, H->stream);
+}
+
+static void do_build(efgpu_handle* H, unsigned flags)
+{
+    if (!H->allocated || ((flags ^ H->build_flags) & EFGPU_KEEP_X)) allocate_device(H, flags);
+    cudaStream_t s = H->stream;
+    const double big = 1e300;
+    EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
+    EF_CUDA(cudaEventRecord(H->ev0, s));
+    run_leaf_dtn(H, flags);
+    for (int lev = H->max_level; lev >= 0; lev--)
+        for (int bi : H->level_batches[lev]) {
+            BatchH& b = H->batches[bi];
+            for (size_t t = 0; t < b.cT.size(); t++)
+                launch_coarsen_T(b.d_cT[t]->as<CoarsenOp>(), (int)b.cT[t].size(), b.cT_max[t], s);
+            const MergeEntry* ent = b.d_entries.as<MergeEntry>();
+            launch_assemble_X(ent, b.n, b.count, s);
+            launch_assemble_Hc(ent, b.n, b.count, s);
+            double* const* ptab = b.d_ptab.as<double*>();
+            for (const Step& st : b.steps) {
+                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
+                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
+            }
+        }
+    EF_CUDA(cudaEventRecord(H->ev1, s));
+    double minpiv = 0;
+    EF_CUDA(cudaMemcpyAsync(&minpiv, H->d_minpiv.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    EF_CUDA(cudaStreamSynchronize(s));
+    float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1));
+    H->stats.build_ms = ms; H->stats.min_pivot = minpiv;
+    H->built = true; H->upwards_done = false;
+    if (!(minpiv > 0.0) || !std::isfinite(minpiv)) throw Error{EF_ERR_SINGULAR, "non-positive or non-finite pivot in the merge factorisation"};
+}
+
+static void do_upwards(efgpu_handle* H, const double* f_dev, double fscale, unsigned flags)
+{
+    if (!H->built) throw Error{EF_ERR_STATE, "upwards before build"};
+    cudaStream_t s = H->stream;
+    EF_CUDA(cudaEventRecord(H->ev0, s));
+    launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                            f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
+    if (!(flags & EFGPU_HOMOGENEOUS_RHS))   // upwards4to1 is skipped entirely (HPSAlgorithm.hpp:532)
+        for (int lev = H->max_level; lev >= 0; lev--)
+            for (int bi : H->level_batches[lev]) {
+                BatchH& b = H->batches[bi];
+                for (size_t t = 0; t < b.cH.size(); t++)
+                    launch_coarsen_h(b.d_cH[t]->as<CoarsenOp>(), (int)b.cH[t].size(), b.cH_max[t], s);
+                launch_upwards(b.d_entries.as<MergeEntry>(), b.n, b.count, s);
+            }
+    EF_CUDA(cudaEventRecord(H->ev1, s));
+    H->upwards_done = true;
+}
+
+static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsigned flags)
+{
+    // root Dirichlet data must already be in the root's g buffer
+    cudaStream_t s = H->stream;
+    const bool homogeneous = (flags & EFGPU_HOMOGENEOUS_RHS) != 0;
+    for (int lev = 0; lev <= H->max_level; lev++)
+        for (int bi : H->level_batches[lev]) {
+            BatchH& b = H->batches[bi];
+            for (size_t t = 0; t < b.cG.size(); t++)
+                launch_uncoarsen_g(b.d_cG[t]->as<CoarsenOp>(), (int)b.cG[t].size(), b.cG_max[t], s);
+            launch_solve_split(b.d_entries.as<MergeEntry>(), b.n, b.count, !homogeneous, s);
+        }
+    launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                            homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
+}
+
+}  // namespace efgpu
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+#define EF_TRY(H) try {
+#define EF_CATCH(H)                                                                     \
+    } catch (const efgpu::Error& e) { if (H) (H)->last_error = e.msg; return e.code; }  \
+      catch (const std::bad_alloc&) { if (H) (H)->last_error = "host out of memory"; return EF_ERR_OOM; } \
+      catch (const std::exception& e) { if (H) (H)->last_error = e.what(); return EF_ERR_STATE; }          \
+    return EF_OK;
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int efgpu_create(const efgpu_tree_desc* desc, int device, efgpu_handle** out)
+{
+    if (!desc || !out) return EF_ERR_BAD_ARG;
+    efgpu_handle* H = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) throw Error{EF_ERR_CUDA, "no CUDA device available: the efgpu path has no CPU fallback"};
+        if (device < 0 || device >= ndev) throw Error{EF_ERR_BAD_ARG, "bad device ordinal"};
+        EF_CUDA(cudaSetDevice(device));
+        H = new efgpu_handle();
+        H->device = device;
+        make_plan(H, desc);
+        EF_CUDA(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
+        EF_CUDA(cudaEventCreate(&H->ev0)); EF_CUDA(cudaEventCreate(&H->ev1));
+        *out = H;
+        return EF_OK;
+    } catch (const efgpu::Error& e) { g_create_error = e.msg; delete H; return e.code; }
+      catch (const std::exception& e) { g_create_error = e.what(); delete H; return EF_ERR_STATE; }
+}
+
+void efgpu_destroy(efgpu_handle* H)
+{
+    if (!H) return;
+    cudaSetDevice(H->device);
+    if (H->stream) cudaStreamSynchronize(H->stream);
+    if (H->ev0) cudaEventDestroy(H->ev0);
+    if (H->ev1) cudaEventDestroy(H->ev1);
+    cudaStream_t s = H->stream;
+    delete H;
+    if (s) cudaStreamDestroy(s);
+}
+
+const char* efgpu_last_error(const efgpu_handle* H) { return H ? H->last_error.c_str() : g_create_error.c_str(); }
+
+int efgpu_set_leaf_constant(efgpu_handle* H, double lambda)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    H->leaf_kind = EFGPU_LEAF_CONSTANT; H->lambda = lambda; H->built = false;
+    return EF_OK;
+}
+
+int efgpu_set_leaf_variable(efgpu_handle* H, const double*, const double*, const double*, const double*, const double*, const double*)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    H->last_error = "variable-coefficient leaves are not built yet";
+    return EF_ERR_UNSUPPORTED;
+}
+
+int efgpu_build(efgpu_handle* H, unsigned flags)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    do_build(H, flags);
+    EF_CATCH(H)
+}
+
+int efgpu_upwards(efgpu_handle* H, const double* f_leaves, double fscale, unsigned flags)
+{
+    if (!H || !f_leaves) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->built) throw Error{EF_ERR_STATE, "upwards before build"};
+    EF_CUDA(cudaMemcpyAsync(H->d_f.p, f_leaves, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    H->f_cur = H->d_f.as<double>(); H->fscale_cur = fscale;
+    do_upwards(H, H->f_cur, fscale, flags);
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.upwards_ms = ms;
+    EF_CATCH(H)
+}
+
+int efgpu_upwards_device(efgpu_handle* H, const double* f_leaves_dev, double fscale, unsigned flags, int sync)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!f_leaves_dev) throw Error{EF_ERR_BAD_ARG, "null load vector"};
+    H->f_cur = f_leaves_dev; H->fscale_cur = fscale;   // borrowed until the next upwards call
+    do_upwards(H, H->f_cur, fscale, flags);
+    if (sync) {
+        EF_CUDA(cudaStreamSynchronize(H->stream));
+        float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.upwards_ms = ms;
+    }
+    EF_CATCH(H)
+}
+
+static void set_root_g(efgpu_handle* H, const double* g_root, cudaMemcpyKind kind)
+{
+    NodeH& root = H->nodes[0];
+    EF_CUDA(cudaMemcpyAsync(H->d_vec.as<double>() + root.gbuf[0], g_root, 4 * (size_t)root.size * sizeof(double), kind, H->stream));
+}
+
+int efgpu_solve_dirichlet(efgpu_handle* H, const double* g_root, unsigned flags, double* u_leaves)
+{
+    if (!H || !g_root) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->built) throw Error{EF_ERR_STATE, "solve before build"};
+    if (!(flags & EFGPU_HOMOGENEOUS_RHS) && !H->upwards_done) throw Error{EF_ERR_STATE, "solve before upwards (non-homogeneous right-hand side)"};
+    EF_CUDA(cudaEventRecord(H->ev0, H->stream));
+    set_root_g(H, g_root, cudaMemcpyHostToDevice);
+    do_solve(H, H->f_cur, H->fscale_cur, flags);
+    EF_CUDA(cudaEventRecord(H->ev1, H->stream));
+    if (u_leaves) EF_CUDA(cudaMemcpyAsync(u_leaves, H->d_u.p, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
+    EF_CATCH(H)
+}
+
+int efgpu_solve_dirichlet_device(efgpu_handle* H, const double* g_root_dev, unsigned flags, double* u_leaves_dev, int sync)
+{
+    if (!H || !g_root_dev) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->built) throw Error{EF_ERR_STATE, "solve before build"};
+    if (!(flags & EFGPU_HOMOGENEOUS_RHS) && !H->upwards_done) throw Error{EF_ERR_STATE, "solve before upwards (non-homogeneous right-hand side)"};
+    EF_CUDA(cudaEventRecord(H->ev0, H->stream));
+    set_root_g(H, g_root_dev, cudaMemcpyDeviceToDevice);
+    do_solve(H, H->f_cur, H->fscale_cur, flags);
+    if (u_leaves_dev) EF_CUDA(cudaMemcpyAsync(u_leaves_dev, H->d_u.p, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyDeviceToDevice, H->stream));
+    EF_CUDA(cudaEventRecord(H->ev1, H->stream));
+    if (sync) {
+        EF_CUDA(cudaStreamSynchronize(H->stream));
+        float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
+    }
+    EF_CATCH(H)
+}
+
+int efgpu_solve_robin(efgpu_handle* H, const double* a, const double* b, const double* r, unsigned flags, double* u_leaves)
+{
+    if (!H || !a || !b || !r) return EF_ERR_BAD_ARG;
+    const int len = 4 * H->nodes[0].size;
+    for (int i = 0; i < len; i++)
+        if (b[i] != 0.0) { H->last_error = "Robin/Neumann root data (b != 0) needs the dense root solve, not built yet"; return EF_ERR_UNSUPPORTED; }
+    std::vector<double> g(len);
+    for (int i = 0; i < len; i++) g[i] = r[i] / a[i];   // g = (diag a)^-1 r   (HPSAlgorithm.hpp:402-419 with b = 0)
+    return efgpu_solve_dirichlet(H, g.data(), flags, u_leaves);
+}
+
+int efgpu_sync(efgpu_handle* H)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CATCH(H)
+}
+
+void* efgpu_stream(efgpu_handle* H) { return H ? (void*)H->stream : nullptr; }
+
+int efgpu_node_info(const efgpu_handle* H, int node, int* size, int* n_coarsens, int* is_leaf, int* leaf_index)
+{
+    if (!H || node < 0 || node >= H->n_nodes) return EF_ERR_BAD_ARG;
+    const NodeH& nd = H->nodes[node];
+    if (size) *size = nd.size;
+    if (n_coarsens) *n_coarsens = nd.ncoarsen;
+    if (is_leaf) *is_leaf = nd.leaf ? 1 : 0;
+    if (leaf_index) *leaf_index = nd.leaf_idx;
+    return EF_OK;
+}
+
+int efgpu_operator_shape(const efgpu_handle* H, int node, int which, int* rows, int* cols)
+{
+    if (!H || node < 0 || node >= H->n_nodes || !rows || !cols) return EF_ERR_BAD_ARG;
+    const NodeH& nd = H->nodes[node];
+    const int n = nd.size / 2;
+    switch (which) {
+        case EFGPU_OP_T: *rows = *cols = 4 * (nd.size >> nd.ncoarsen); return EF_OK;   // coarsened in place by the parent's merge (quirk q3)
+        case EFGPU_OP_T_UNCOARSENED: *rows = *cols = 4 * nd.size; return EF_OK;
+        case EFGPU_OP_S: if (nd.leaf) return EF_ERR_BAD_ARG; *rows = 4 * n; *cols = 8 * n; return EF_OK;
+        case EFGPU_OP_X: case EFGPU_OP_XINV: if (nd.leaf) return EF_ERR_BAD_ARG; *rows = *cols = 4 * n; return EF_OK;
+        case EFGPU_OP_H: if (nd.leaf) return EF_ERR_BAD_ARG; *rows = 8 * n; *cols = 4 * n; return EF_OK;
+        default: return EF_ERR_BAD_ARG;
+    }
+}
+
+int efgpu_get_operator(efgpu_handle* H, int node, int which, double* out, size_t capacity)
+{
+    if (!H || !out) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    int rows = 0, cols = 0;
+    if (efgpu_operator_shape(H, node, which, &rows, &cols) != EF_OK) throw Error{EF_ERR_BAD_ARG, "bad node / operator"};
+    if (!H->built) throw Error{EF_ERR_STATE, "operators requested before build"};
+    if (capacity < (size_t)rows * cols) throw Error{EF_ERR_BAD_SHAPE, "output buffer too small"};
+    EF_CUDA(cudaSetDevice(H->device));
+    const NodeH& nd = H->nodes[node];
+    const size_t n = nd.size / 2, bytes = (size_t)rows * cols * sizeof(double);
+    const double* src = nullptr;
+    DevBuf tmp;
+    switch (which) {
+        case EFGPU_OP_T: src = nd.Tbuf[nd.ncoarsen]; break;
+        case EFGPU_OP_T_UNCOARSENED: src = nd.Tbuf[0]; break;
+        case EFGPU_OP_S: src = H->batches[nd.batch].S.as<double>() + nd.slot * 32 * n * n; break;
+        case EFGPU_OP_XINV: src = H->batches[nd.batch].Xinv.as<double>() + nd.slot * 16 * n * n; break;
+        case EFGPU_OP_X:
+            if (!H->batches[nd.batch].Xcopy.p) throw Error{EF_ERR_STATE, "X is only retained when built with EFGPU_KEEP_X"};
+            src = H->batches[nd.batch].Xcopy.as<double>() + nd.slot * 16 * n * n; break;
+        case EFGPU_OP_H:
+            tmp.alloc(bytes);
+            launch_expand_H(H->batches[nd.batch].Hc.as<double>() + nd.slot * 16 * n * n, (int)n, tmp.as<double>(), H->stream);
+            src = tmp.as<double>(); break;
+    }
+    EF_CUDA(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CATCH(H)
+}
+
+int efgpu_vector_length(const efgpu_handle* H, int node, int which, int* len)
+{
+    if (!H || node < 0 || node >= H->n_nodes || !len) return EF_ERR_BAD_ARG;
+    const NodeH& nd = H->nodes[node];
+    switch (which) {
+        case EFGPU_VEC_H: *len = 4 * (nd.size >> nd.ncoarsen); return EF_OK;   // coarsened in place by coarsenUpwards_
+        case EFGPU_VEC_G: *len = 4 * nd.size; return EF_OK;                     // uncoarsened in place by uncoarsen_
+        case EFGPU_VEC_W: if (nd.leaf) return EF_ERR_BAD_ARG; *len = 2 * nd.size; return EF_OK;
+        case EFGPU_VEC_U: case EFGPU_VEC_F: if (!nd.leaf) return EF_ERR_BAD_ARG; *len = nd.size * nd.size; return EF_OK;
+        default: return EF_ERR_BAD_ARG;
+    }
+}
+
+int efgpu_get_vector(efgpu_handle* H, int node, int which, double* out, size_t capacity)
+{
+    if (!H || !out) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    int len = 0;
+    if (efgpu_vector_length(H, node, which, &len) != EF_OK) throw Error{EF_ERR_BAD_ARG, "bad node / vector"};
+    if (capacity < (size_t)len) throw Error{EF_ERR_BAD_SHAPE, "output buffer too small"};
+    if (!H->allocated) throw Error{EF_ERR_STATE, "vectors requested before build"};
+    EF_CUDA(cudaSetDevice(H->device));
+    const NodeH& nd = H->nodes[node];
+    const double* vec = H->d_vec.as<double>();
+    const double* src = nullptr;
+    switch (which) {
+        case EFGPU_VEC_H: src = vec + nd.hbuf[nd.ncoarsen]; break;
+        case EFGPU_VEC_G: src = vec + nd.gbuf[0]; break;
+        case EFGPU_VEC_W: src = vec + nd.w_off; break;
+        case EFGPU_VEC_U: src = H->d_u.as<double>() + (size_t)nd.leaf_idx * len; break;
+        case EFGPU_VEC_F: src = H->d_f.as<double>() + (size_t)nd.leaf_idx * len; break;
+    }
+    EF_CUDA(cudaMemcpyAsync(out, src, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CATCH(H)
+}
+
+int efgpu_get_stats(const efgpu_handle* H, efgpu_stats_t* out)
+{
+    if (!H || !out) return EF_ERR_BAD_ARG;
+    *out = H->stats;
+    return EF_OK;
+}
+
+// Stand-alone entry to the descriptor GEMM for unit tests / roofline runs:
+// C[b] = A[b] (m x k) * B[b] (k x n), all row-major and densely packed, device pointers.
+int efgpu_dgemm_batched(const double* A, const double* B, double* C, int m, int n, int k, int batch, int tile, int iters, float* ms_out)
+{
+    try {
+        std::vector<double*> ptab((size_t)batch * 3);
+        for (int b = 0; b < batch; b++) {
+            ptab[3 * (size_t)b + 0] = const_cast<double*>(A) + (size_t)b * m * k;
+            ptab[3 * (size_t)b + 1] = const_cast<double*>(B) + (size_t)b * k * n;
+            ptab[3 * (size_t)b + 2] = C + (size_t)b * m * n;
+        }
+        GemmBlock g{};
+        g.c_op = 2; g.c_off = 0; g.ldc = n; g.c0_op = -1; g.rows = m; g.cols = n; g.nterms = 1;
+        g.t[0] = GemmTerm{0, 1, k, n, 0, 0, k, 0u};
+        DevBuf dp, db;
+        cudaStream_t s = nullptr;
+        dp.upload(ptab, s);
+        std::vector<GemmBlock> gb(1, g);
+        db.upload(gb, s);
+        cudaEvent_t e0, e1; EF_CUDA(cudaEventCreate(&e0)); EF_CUDA(cudaEventCreate(&e1));
+        launch_bgemm(dp.as<double*>(), 3, db.as<GemmBlock>(), gb.data(), 1, batch, s, tile);
+        EF_CUDA(cudaEventRecord(e0, s));
+        for (int it = 0; it < iters; it++) launch_bgemm(dp.as<double*>(), 3, db.as<GemmBlock>(), gb.data(), 1, batch, s, tile);
+        EF_CUDA(cudaEventRecord(e1, s));
+        EF_CUDA(cudaStreamSynchronize(s));
+        float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return EF_OK;
+    } catch (const efgpu::Error& e) { g_create_error = e.msg; return e.code; }
+}
+
+}  // extern "C"

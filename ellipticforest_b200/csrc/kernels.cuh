@@ -1,0 +1,44 @@
+// Launch wrappers of the non-GEMM kernels (leaf.cu, vec.cu).
+#pragma once
+#include "common.cuh"
+
+namespace efgpu {
+
+// ---- merge topology tables (src/HPSAlgorithm.hpp:752-990) -----------
+// children c: 0 alpha, 1 beta, 2 gamma, 3 omega; sides: 0 W, 1 E, 2 S, 3 N;
+// interior interfaces k: 0 alpha|gamma, 1 beta|omega, 2 alpha|beta, 3 gamma|omega.
+struct MergeEntry {
+    const double* Tc[4];  // children's DtN (coarsened where tagged), 4n x 4n, ld 4n
+    double* Xinv;         // 4n x 4n
+    double* S;            // 4n x 8n, columns in WESN order
+    double* Hc;           // 8n x 2n compact H (rows in WESN order, the two non-zero n x n blocks per row block)
+    double* T;            // 8n x 8n, WESN order (may be null when the DtN of this node is never used)
+    double* Xcopy;        // optional copy of X before inversion (parity/debug) or null
+    const double* hc[4];  // children's particular Neumann data (coarsened), 4n
+    double* hd;           // scratch: jump of the children's h across the interfaces, 4n
+    double* h;            // 8n
+    double* w;            // 4n
+    const double* g;      // 8n Dirichlet data of this node (uncoarsened)
+    double* gc[4];        // children's Dirichlet data, 4n each
+};
+
+struct CoarsenOp { const double* src; double* dst; int nfine; int pad_; };
+
+// leaf.cu
+void launch_leaf_dtn_const(int M, const double* Q, const double* boxes, const int* leaf_nodes, double lambda,
+                           double* T_all, int n_leaves, bool cache_operators, cudaStream_t s);
+void launch_leaf_solve_const(int M, const double* Q, const double* boxes, const int* leaf_nodes, double lambda,
+                             const double* f, double fscale, double* const* g_ptrs, double* u_out, double* const* h_ptrs,
+                             int mode, int n_leaves, cudaStream_t s);
+
+// vec.cu
+void launch_assemble_X(const MergeEntry* e, int n, int count, cudaStream_t s);
+void launch_assemble_Hc(const MergeEntry* e, int n, int count, cudaStream_t s);
+void launch_coarsen_T(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s);
+void launch_coarsen_h(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s);
+void launch_uncoarsen_g(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s);
+void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s);            // hd, w, h
+void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s);
+void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s);      // parity/debug: 8n x 4n, reference order
+
+}  // namespace efgpu

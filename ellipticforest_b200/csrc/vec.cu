@@ -1,0 +1,311 @@
+// Bandwidth-bound kernels of the merge / upwards / solve stages: block assembly of X and the
+// compact H, adaptive coarsening stencils, and the batched matrix-vector products.
+//
+// Reference call sites replaced (src/HPSAlgorithm.hpp):
+//   mergeX_ :870-895 + createMatrixBlocks_ :799-859          -> assemble_X_kernel
+//   mergeT_ :947-961 (H)                                      -> assemble_Hc_kernel (compact: the zero blocks are not stored)
+//   coarsen_ :707-741 (two dense dgemm with L21/L12)          -> coarsen_T_kernel (2-tap / 3-tap stencils)
+//   coarsenUpwards_ :1024-1048, uncoarsen_ :1165-1183         -> coarsen_h_kernel / uncoarsen_g_kernel
+//   mergeW_ :1059-1087 (fresh dgesv), mergeH_ :1098-1117,
+//   reorderOperatorsUpwards_ :1128-1150                       -> upwards kernels (cached X^-1, one GEMV each)
+//   applyS_ :1194-1230                                        -> solve_split_kernel (GEMV + add w + scatter)
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace efgpu {
+
+// side of child c that faces interior interface k (-1: not adjacent)
+__constant__ int c_iface[4][4] = {{3, -1, 1, -1}, {-1, 3, 0, -1}, {2, -1, -1, 1}, {-1, 2, -1, 0}};
+// sign with which child c enters the jump across interface k (first child -, second +)
+__constant__ double c_sgn[4][4] = {{-1, 0, -1, 0}, {0, -1, 1, 0}, {1, 0, 0, -1}, {0, 1, 0, 1}};
+// exterior sides of child c, in the order of its tau index set
+__constant__ int c_tau_side[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
+// the two interfaces adjacent to child c (ascending k)
+__constant__ int c_kk[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
+// the two children adjacent to interface k
+__constant__ int c_kids[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+// WESN block permutation (HPSAlgorithm.hpp:984): permuted position p holds pre-permutation block c_pi[p]
+__constant__ int c_pi[8] = {0, 4, 2, 6, 1, 3, 5, 7};
+
+// X[k][k'] = - sum_c sgn_c(k) T^c[iface_c(k), iface_c(k')]   (16 n x n blocks, 4 of them zero)
+__global__ void assemble_X_kernel(const MergeEntry* __restrict__ ent, int n)
+{
+    const MergeEntry& e = ent[blockIdx.y];
+    const int N = 4 * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * N; idx += gridDim.x * blockDim.x) {
+        const int row = idx / N, col = idx % N;
+        const int k = row / n, r = row % n, k2 = col / n, c = col % n;
+        double v = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            const int sa = c_iface[ch][k], sb = c_iface[ch][k2];
+            if (sa >= 0 && sb >= 0) v -= c_sgn[ch][k] * e.Tc[ch][(size_t)(sa * n + r) * N + sb * n + c];
+        }
+        e.Xinv[idx] = v;
+        if (e.Xcopy) e.Xcopy[idx] = v;
+    }
+}
+
+// Hc row block p (WESN position) of child c = [ T^c[side, iface_c(k0)] | T^c[side, iface_c(k1)] ]
+__global__ void assemble_Hc_kernel(const MergeEntry* __restrict__ ent, int n)
+{
+    const MergeEntry& e = ent[blockIdx.y];
+    const int N = 4 * n, W = 2 * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 8 * n * W; idx += gridDim.x * blockDim.x) {
+        const int row = idx / W, col = idx % W;
+        const int p = row / n, r = row % n, t = col / n, c = col % n;
+        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+        const int sb = c_iface[ch][c_kk[ch][t]];
+        e.Hc[idx] = e.Tc[ch][(size_t)(side * n + r) * N + sb * n + c];
+    }
+}
+
+// dense H in the reference's (pre-permutation) layout, for parity checks only
+__global__ void expand_H_kernel(const double* __restrict__ Hc, int n, double* __restrict__ H)
+{
+    const int W = 4 * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 8 * n * W; idx += gridDim.x * blockDim.x) {
+        const int row = idx / W, col = idx % W;
+        const int q = row / n, r = row % n, k = col / n, c = col % n;
+        const int ch = q >> 1;
+        int p = 0;
+        for (int pp = 0; pp < 8; pp++) if (c_pi[pp] == q) p = pp;
+        double v = 0.0;
+        for (int t = 0; t < 2; t++) if (c_kk[ch][t] == k) v = Hc[(size_t)(p * n + r) * (2 * n) + t * n + c];
+        H[idx] = v;
+    }
+}
+
+// ---- interpolation stencils (src/SpecialMatrices.hpp:93-173) -----------------------------------
+// column jc of L12(nfine x nc): up to 6 non-zero rows
+__device__ __forceinline__ int l12_col(int jc, int nc, int* rows, double* coef)
+{
+    const int nf = 2 * nc;
+    int m = 0;
+    if (jc <= 2) { rows[m] = 0; coef[m++] = jc == 0 ? 1.40625 : (jc == 1 ? -0.5625 : 0.15625); }
+    if (jc >= 1) { rows[m] = 2 * jc - 1; coef[m++] = 0.25; rows[m] = 2 * jc; coef[m++] = 0.75; }
+    if (jc <= nc - 2) { rows[m] = 2 * jc + 1; coef[m++] = 0.75; rows[m] = 2 * jc + 2; coef[m++] = 0.25; }
+    if (jc >= nc - 3) { rows[m] = nf - 1; coef[m++] = jc == nc - 1 ? 1.40625 : (jc == nc - 2 ? -0.5625 : 0.15625); }
+    // rows 2jc (jc >= 1) and 2jc+1 (jc <= nc-2) never coincide with row 0 / nf-1 except through the
+    // explicit edge rules above: row nf-1 = 2(nc-1)+1 is excluded by jc <= nc-2, row 0 by jc >= 1.
+    return m;
+}
+// row i of L12: up to 3 non-zero columns
+__device__ __forceinline__ int l12_row(int i, int nc, int* cols, double* coef)
+{
+    const int nf = 2 * nc;
+    if (i == 0) { cols[0] = 0; cols[1] = 1; cols[2] = 2; coef[0] = 1.40625; coef[1] = -0.5625; coef[2] = 0.15625; return 3; }
+    if (i == nf - 1) { cols[0] = nc - 3; cols[1] = nc - 2; cols[2] = nc - 1; coef[0] = 0.15625; coef[1] = -0.5625; coef[2] = 1.40625; return 3; }
+    const int j = (i - 1) >> 1;
+    cols[0] = j; cols[1] = j + 1;
+    if (i & 1) { coef[0] = 0.75; coef[1] = 0.25; } else { coef[0] = 0.25; coef[1] = 0.75; }
+    return 2;
+}
+
+// T_c = blkdiag4(L21) * T * blkdiag4(L12)  for one coarsening step (nfine -> nfine/2 per side)
+__global__ void coarsen_T_kernel(const CoarsenOp* __restrict__ ops)
+{
+    const CoarsenOp op = ops[blockIdx.y];
+    const int nf = op.nfine, nc = nf / 2, NF = 4 * nf, NC = 4 * nc;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NC * NC; idx += gridDim.x * blockDim.x) {
+        const int R = idx / NC, Cc = idx % NC;
+        const int a = R / nc, rc = R % nc, b = Cc / nc, jc = Cc % nc;
+        int rows[6]; double coef[6];
+        const int m = l12_col(jc, nc, rows, coef);
+        const double* r0 = op.src + (size_t)(a * nf + 2 * rc) * NF + b * nf;
+        const double* r1 = r0 + NF;
+        double v = 0.0;
+        for (int t = 0; t < m; t++) v += coef[t] * (0.5 * r0[rows[t]] + 0.5 * r1[rows[t]]);
+        op.dst[idx] = v;
+    }
+}
+__global__ void coarsen_h_kernel(const CoarsenOp* __restrict__ ops)
+{
+    const CoarsenOp op = ops[blockIdx.y];
+    const int nc = op.nfine / 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * nc; idx += gridDim.x * blockDim.x)
+        op.dst[idx] = 0.5 * op.src[2 * idx] + 0.5 * op.src[2 * idx + 1];   // side blocks are contiguous
+}
+__global__ void uncoarsen_g_kernel(const CoarsenOp* __restrict__ ops)
+{
+    const CoarsenOp op = ops[blockIdx.y];
+    const int nf = op.nfine, nc = nf / 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * nf; idx += gridDim.x * blockDim.x) {
+        const int a = idx / nf, i = idx % nf;
+        int cols[3]; double coef[3];
+        const int m = l12_row(i, nc, cols, coef);
+        double v = 0.0;
+        for (int t = 0; t < m; t++) v += coef[t] * op.src[a * nc + cols[t]];
+        op.dst[idx] = v;
+    }
+}
+
+// ---- upwards -----------------------------------------------------------------------------------
+// hd[k] = sum_c sgn_c(k) h^c[iface_c(k)]   (HPSAlgorithm.hpp:1062-1081)
+__global__ void hdiff_kernel(const MergeEntry* __restrict__ ent, int n)
+{
+    const MergeEntry& e = ent[blockIdx.y];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * n; idx += gridDim.x * blockDim.x) {
+        const int k = idx / n, r = idx % n;
+        const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+        e.hd[idx] = e.hc[c2][c_iface[c2][k] * n + r] - e.hc[c1][c_iface[c1][k] * n + r];
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// row-per-warp dot product, 16-byte loads, streaming (no L1 allocation) on the matrix
+__device__ __forceinline__ double row_dot(const double* __restrict__ a, const double* __restrict__ x, int len, int lane)
+{
+    double s0 = 0.0, s1 = 0.0;
+    const double2* a2 = reinterpret_cast<const double2*>(a);
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    const int len2 = len >> 1;
+#pragma unroll 4
+    for (int c = lane; c < len2; c += 32) {
+        double2 av = __ldcs(a2 + c);
+        double2 xv = __ldg(x2 + c);
+        s0 = fma(av.x, xv.x, s0);
+        s1 = fma(av.y, xv.y, s1);
+    }
+    return warp_sum(s0 + s1);
+}
+
+// w = X^-1 hd
+__global__ void __launch_bounds__(256) upwards_w_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
+{
+    const MergeEntry& e = ent[blockIdx.x];
+    const int N = 4 * n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    for (int r = r0 + warp; r < r1; r += 8) {
+        double s = row_dot(e.Xinv + (size_t)r * N, e.hd, N, lane);
+        if (lane == 0) e.w[r] = s;
+    }
+}
+
+// h = pi( H w + h_ext )   with the compact H: row block p of child c multiplies w[k0], w[k1]
+__global__ void __launch_bounds__(256) upwards_h_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
+{
+    const MergeEntry& e = ent[blockIdx.x];
+    const int R = 8 * n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+    for (int row = r0 + warp; row < r1; row += 8) {
+        const int p = row / n, r = row % n;
+        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+        const double* a = e.Hc + (size_t)row * (2 * n);
+        double s = row_dot(a, e.w + c_kk[ch][0] * n, n, lane) + row_dot(a + n, e.w + c_kk[ch][1] * n, n, lane);
+        if (lane == 0) e.h[row] = s + e.hc[ch][side * n + r];
+    }
+}
+
+// ---- solve -------------------------------------------------------------------------------------
+// u_int = S g (+ w); children's Dirichlet data assembled in WESN order (HPSAlgorithm.hpp:1206-1227)
+__global__ void __launch_bounds__(256) solve_split_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta, int add_w)
+{
+    const MergeEntry& e = ent[blockIdx.x];
+    const int N = 4 * n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    for (int row = r0 + warp; row < r1; row += 8) {
+        double s = row_dot(e.S + (size_t)row * (8 * n), e.g, 8 * n, lane);
+        if (lane == 0) {
+            if (add_w) s += e.w[row];
+            const int k = row / n, r = row % n;
+            const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+            e.gc[c1][c_iface[c1][k] * n + r] = s;
+            e.gc[c2][c_iface[c2][k] * n + r] = s;
+        }
+    }
+    // exterior segments are copied through: this CTA's share of the 8n entries
+    const int nct = gridDim.y, per = (8 * n + nct - 1) / nct;
+    const int x0 = blockIdx.y * per, x1 = min(8 * n, x0 + per);
+    for (int idx = x0 + threadIdx.x; idx < x1; idx += blockDim.x) {
+        const int p = idx / n, r = idx % n;
+        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+        e.gc[ch][side * n + r] = e.g[idx];
+    }
+}
+
+// ---- launch wrappers ---------------------------------------------------------------------------
+static inline int ew_blocks(long long elems) { long long b = (elems + 255) / 256; return (int)(b < 1 ? 1 : (b > 1024 ? 1024 : b)); }
+static inline void check_count(int count) { if (count > 65535) throw Error{EF_ERR_BAD_SHAPE, "batch too large for grid.y (chunk it)"}; }
+
+void launch_assemble_X(const MergeEntry* e, int n, int count, cudaStream_t s)
+{
+    for (int off = 0; off < count; off += 65535) {
+        int c = count - off < 65535 ? count - off : 65535;
+        assemble_X_kernel<<<dim3(ew_blocks(16LL * n * n), c), 256, 0, s>>>(e + off, n);
+    }
+    EF_CUDA(cudaGetLastError());
+}
+void launch_assemble_Hc(const MergeEntry* e, int n, int count, cudaStream_t s)
+{
+    for (int off = 0; off < count; off += 65535) {
+        int c = count - off < 65535 ? count - off : 65535;
+        assemble_Hc_kernel<<<dim3(ew_blocks(16LL * n * n), c), 256, 0, s>>>(e + off, n);
+    }
+    EF_CUDA(cudaGetLastError());
+}
+void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s)
+{
+    expand_H_kernel<<<ew_blocks(32LL * n * n), 256, 0, s>>>(Hc, n, H_dense);
+    EF_CUDA(cudaGetLastError());
+}
+void launch_coarsen_T(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s)
+{
+    if (!nops) return;
+    check_count(nops);
+    coarsen_T_kernel<<<dim3(ew_blocks(4LL * max_nfine * max_nfine), nops), 256, 0, s>>>(ops);
+    EF_CUDA(cudaGetLastError());
+}
+void launch_coarsen_h(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s)
+{
+    if (!nops) return;
+    check_count(nops);
+    coarsen_h_kernel<<<dim3(ew_blocks(2LL * max_nfine), nops), 256, 0, s>>>(ops);
+    EF_CUDA(cudaGetLastError());
+}
+void launch_uncoarsen_g(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s)
+{
+    if (!nops) return;
+    check_count(nops);
+    uncoarsen_g_kernel<<<dim3(ew_blocks(4LL * max_nfine), nops), 256, 0, s>>>(ops);
+    EF_CUDA(cudaGetLastError());
+}
+
+// rows per CTA: one row per warp at least; aim for >= 4 waves of CTAs over the whole batch
+static inline int pick_rows(int rows, int count)
+{
+    int rpc = rows;
+    while (rpc > 8 && (long long)count * ((rows + rpc - 1) / rpc) < 148LL * 16) rpc = (rpc + 1) / 2;
+    if (rpc < 8) rpc = 8;
+    return rpc;
+}
+
+void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
+{
+    if (!count) return;
+    for (int off = 0; off < count; off += 65535) {
+        int c = count - off < 65535 ? count - off : 65535;
+        hdiff_kernel<<<dim3(ew_blocks(4LL * n), c), 256, 0, s>>>(e + off, n);
+    }
+    int rpc = pick_rows(4 * n, count);
+    upwards_w_kernel<<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    rpc = pick_rows(8 * n, count);
+    upwards_h_kernel<<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    EF_CUDA(cudaGetLastError());
+}
+
+void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s)
+{
+    if (!count) return;
+    int rpc = pick_rows(4 * n, count);
+    solve_split_kernel<<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
+    EF_CUDA(cudaGetLastError());
+}
+
+}  // namespace efgpu

@@ -1,0 +1,141 @@
+/* efgpu.h - C-ABI of the B200-native Hierarchical Poincare-Steklov hot path.
+ *
+ * This is the drop-in boundary for EllipticForest's HPS path.  The
+ * reference has no FFI today: the path lives behind the C++ template
+ *   HPSAlgorithm<FiniteVolumeGrid, FiniteVolumeSolver, FiniteVolumePatch, double>
+ * (reference src/HPSAlgorithm.hpp:26-82).  Each entry point below names the reference
+ * interface it replaces; INTEGRATION.md shows the subclass a maintainer adds on the reference
+ * side (stage overrides that marshal to these calls).
+ *
+ * Conventions (identical to the reference):
+ *   - node table in p4est depth-first pre-order, root = node 0, children in Morton order
+ *     0 = lower-left, 1 = lower-right, 2 = upper-left, 3 = upper-right
+ *     (src/Quadtree.hpp:118-196, src/P4est.cpp:35-44, FiniteVolumeNodeFactory.cpp:38-57);
+ *   - leaves are numbered in that order (= the order of traversePreOrder over leaves, quirk q9);
+ *   - cell index inside a patch: j + i*ny, i = x index (FiniteVolumeSolver.cpp:17-19);
+ *   - boundary vectors / operator rows in WESN order, each side low -> high (PatchSolver.hpp:36);
+ *   - Neumann data are coordinate derivatives, not outward normals (FiniteVolumeSolver.cpp:332-343);
+ *   - all matrices row-major double.
+ *
+ * Every function returns an int status (0 = ok).  All calls are synchronous on the calling
+ * thread unless the name ends in _device and `sync` is 0.  Host arrays are borrowed for the
+ * duration of the call only.  There is NO CPU fallback: efgpu_create fails with EFGPU_ERR_CUDA
+ * when no device is present.
+ */
+#ifndef EFGPU_H_
+#define EFGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+enum {
+    EFGPU_OK = 0,
+    EFGPU_ERR_CUDA = 1,        /* CUDA runtime error (or no device) */
+    EFGPU_ERR_BAD_ARG = 2,     /* -> std::invalid_argument in the C++ shim */
+    EFGPU_ERR_BAD_SHAPE = 3,   /* -> std::invalid_argument (reference: HPSAlgorithm.hpp:761, Matrix.hpp:322) */
+    EFGPU_ERR_OOM = 4,
+    EFGPU_ERR_SINGULAR = 5,    /* zero / non-finite pivot (reference: LAPACK INFO > 0 warning, Matrix.hpp:898,947) */
+    EFGPU_ERR_STATE = 6,       /* stage called out of order */
+    EFGPU_ERR_UNSUPPORTED = 7
+};
+
+/* build / stage flags */
+enum {
+    EFGPU_CACHE_OPERATORS = 1u, /* option "cache-operators" (HPSAlgorithm.hpp:134-139): one T_leaf for every leaf */
+    EFGPU_HOMOGENEOUS_RHS = 2u, /* option "homogeneous-rhs" (HPSAlgorithm.hpp:532,587,1202) */
+    EFGPU_KEEP_X = 4u           /* parity/debug: retain a copy of X (the product only needs X^-1) */
+};
+
+enum { EFGPU_LEAF_CONSTANT = 0, EFGPU_LEAF_VARIABLE = 1 };
+
+/* operator / vector selectors for the parity accessors */
+enum { EFGPU_OP_T = 0, EFGPU_OP_S = 1, EFGPU_OP_X = 2, EFGPU_OP_H = 3, EFGPU_OP_XINV = 4, EFGPU_OP_T_UNCOARSENED = 5 };
+enum { EFGPU_VEC_H = 0, EFGPU_VEC_W = 1, EFGPU_VEC_G = 2, EFGPU_VEC_U = 3, EFGPU_VEC_F = 4 };
+
+typedef struct efgpu_handle efgpu_handle;
+
+/* Flat tree table = what Quadtree<FiniteVolumePatch>::traversePreOrder visits
+ * (src/Quadtree.hpp:236-260): one row per node. */
+typedef struct {
+    int32_t n_nodes;
+    int32_t nx;             /* cells per side of a leaf patch (nx == ny; 8, 16, 24 or 32) */
+    const int32_t* level;   /* [n_nodes] */
+    const int32_t* child;   /* [n_nodes*4] node ids of the children, -1 for a leaf */
+    const double* box;      /* [n_nodes*4] x_lower, x_upper, y_lower, y_upper of the node's grid (FiniteVolumeGrid) */
+} efgpu_tree_desc;
+
+typedef struct {
+    double dofs;                   /* n_leaves * nx * ny  (examples/elliptic-multiple/main.cpp:374) */
+    double n_leaves, n_nodes;
+    double build_ms, upwards_ms, solve_ms;   /* CUDA-event time of the last call of each stage (device work only) */
+    double merge_flops_canonical;  /* sum 810.67 n^3: the dgesv + dgemm work of the reference */
+    double merge_flops_issued;     /* sum 512 n^3: flops this implementation sends to the FP64 tensor pipe */
+    double upwards_bytes, solve_bytes;       /* algorithmic HBM bytes per upwards / solve call */
+    double device_bytes;           /* device memory held by the handle */
+    double min_pivot;              /* smallest |pivot| met while inverting the merge matrices */
+} efgpu_stats_t;
+
+/* ---- lifetime: replaces HPSAlgorithm ctor (HPSAlgorithm.hpp:78-82) + the Quadtree walk ---------- */
+int efgpu_create(const efgpu_tree_desc* desc, int device, efgpu_handle** out);
+void efgpu_destroy(efgpu_handle* h);
+const char* efgpu_last_error(const efgpu_handle* h);   /* h may be NULL after a failed create */
+
+/* ---- leaf model: replaces FiniteVolumeSolver's public fields (FiniteVolumeSolver.hpp:64-88) ---- */
+/* solver_type = FISHPACK90: constant coefficients, lambda = lambda_function(0,0) (FiniteVolumeSolver.cpp:254) */
+int efgpu_set_leaf_constant(efgpu_handle* h, double lambda);
+/* solver_type = FivePointStencil: coefficients sampled by the caller exactly where
+ * FiniteVolumeSolver.cpp:63-79 samples them; arrays are leaf-major, n_leaves * nx * ny, cell index j + i*ny.
+ * alpha, lambda at cell centres; beta at the W, E, S, N face midpoints of each cell. */
+int efgpu_set_leaf_variable(efgpu_handle* h, const double* alpha, const double* beta_w, const double* beta_e,
+                            const double* beta_s, const double* beta_n, const double* lambda);
+
+/* ---- stages ------------------------------------------------------------------------------------ */
+/* buildStage (HPSAlgorithm.hpp:120-161): leaf buildD2N + every merge4to1. */
+int efgpu_build(efgpu_handle* h, unsigned flags);
+/* upwardsStage (HPSAlgorithm.hpp:178-272): f_leaves = vectorF of every leaf (n_leaves*nx*ny), scaled by fscale. */
+int efgpu_upwards(efgpu_handle* h, const double* f_leaves, double fscale, unsigned flags);
+int efgpu_upwards_device(efgpu_handle* h, const double* f_leaves_dev, double fscale, unsigned flags, int sync);
+/* solveStage(fn(Patch&)) (HPSAlgorithm.hpp:291-324): g_root = root vectorG (4 * root size), u_leaves = vectorU of every leaf. */
+int efgpu_solve_dirichlet(efgpu_handle* h, const double* g_root, unsigned flags, double* u_leaves);
+int efgpu_solve_dirichlet_device(efgpu_handle* h, const double* g_root_dev, unsigned flags, double* u_leaves_dev, int sync);
+/* solveStage(fn(side,x,y,*a,*b)) (HPSAlgorithm.hpp:343-445): a u + b du/dn = r sampled at the root grid. */
+int efgpu_solve_robin(efgpu_handle* h, const double* a, const double* b, const double* r, unsigned flags, double* u_leaves);
+int efgpu_sync(efgpu_handle* h);
+void* efgpu_stream(efgpu_handle* h);   /* the cudaStream_t all work of this handle is issued on */
+
+/* ---- parity accessors: replace reading patch.matrixT()/S()/X()/H(), vectorH()/W()/G()/U() (Patch.hpp:103-171) */
+int efgpu_node_info(const efgpu_handle* h, int node, int* size, int* n_coarsens, int* is_leaf, int* leaf_index);
+int efgpu_operator_shape(const efgpu_handle* h, int node, int which, int* rows, int* cols);
+int efgpu_get_operator(efgpu_handle* h, int node, int which, double* out, size_t capacity);
+int efgpu_vector_length(const efgpu_handle* h, int node, int which, int* len);
+int efgpu_get_vector(efgpu_handle* h, int node, int which, double* out, size_t capacity);
+int efgpu_get_stats(const efgpu_handle* h, efgpu_stats_t* out);
+
+/* ---- host-side mesh: replaces Mesh::refineByFunction + Quadtree ctor + FiniteVolumeNodeFactory
+ * (src/Mesh.hpp:111-180, src/Quadtree.hpp:118-196, FiniteVolumeNodeFactory.cpp:15-67).  p4est itself
+ * stays on the host in the reference; this builder reproduces its result for the single-tree square
+ * connectivity (uniform min_level start, recursive refine by callback, 2:1 corner balance, Morton order)
+ * so that the library is usable stand-alone.  A reference-side caller passes its own p4est-derived table. */
+typedef int (*efgpu_refine_fn)(double x, double y, void* user);   /* non-zero: refine the patch containing (x,y) */
+typedef struct efgpu_mesh efgpu_mesh;
+int efgpu_mesh_create(double x_lower, double x_upper, double y_lower, double y_upper, int nx, int min_level,
+                      int max_level, efgpu_refine_fn fn, void* user, efgpu_mesh** out);
+int efgpu_mesh_desc(const efgpu_mesh* m, efgpu_tree_desc* out);   /* pointers stay owned by the mesh */
+int efgpu_mesh_n_leaves(const efgpu_mesh* m);
+const int32_t* efgpu_mesh_leaf_nodes(const efgpu_mesh* m);       /* node id of each leaf, pre-order */
+int efgpu_mesh_path(const efgpu_mesh* m, int node, char* buf, size_t capacity);   /* "0" + child ids (P4est.cpp:35-44) */
+void efgpu_mesh_destroy(efgpu_mesh* m);
+
+/* ---- stand-alone access to the GEMM kernel for unit tests and roofline measurements ------------ */
+int efgpu_dgemm_batched(const double* A_dev, const double* B_dev, double* C_dev, int m, int n, int k, int batch,
+                        int tile, int iters, float* ms_per_iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFGPU_H_ */

@@ -1,0 +1,156 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the reference's golden dumps and
+against the oracle on the same inputs.  Tolerance: FP64 relative max-norm 1e-10 (north_star) for
+operators and vectors; traversal order / leaf indexing bit-exact (checked in test_host.py too).
+The merge matrices X are inverted without pivoting (they are SPD / diagonally dominant);
+the reference uses LAPACK partial pivoting, hence a tolerance rather than bit equality."""
+import numpy as np
+import pytest
+
+import ellipticforest_b200 as ef
+import hps_oracle as O
+from conftest import GOLDEN_CASES, golden_case_args, load_golden
+from test_host import _mesh_for
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def run_gpu(kw, keep_x=True, options=None, scale=1.0):
+    P = O.problem(kw["problem_name"])
+    m = _mesh_for(kw)
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FISHPACK90" if kw["solver_kind"] == "fishpack" else "FivePointStencil"
+    s.alpha_function, s.beta_function, s.lambda_function = P["alpha"], P["beta"], P["lam"]
+    hps = ef.HPSAlgorithm(m, s, options=options)
+    hps.keep_x = keep_x
+    hps.setupStage()
+    hps.buildStage()
+    hps.upwardsStage(P["f"], scale)
+    hps.solveStage(lambda side, x, y: (scale * P["u"](x, y), 1.0, 0.0))
+    return hps
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN_CASES if "varcoef" not in c])
+def test_against_reference_dump(case):
+    gold = load_golden(case)
+    kw = golden_case_args(gold)
+    hps = run_gpu(kw)
+    m = hps.mesh
+    worst = {}
+    for i in range(m.n_nodes):
+        path = m.path(i)
+        info = hps.node_info(i)
+        assert info["n_coarsens"] == int(gold["build/%s/meta" % path][0])
+        names = ["T"] if info["leaf"] else ["T", "S", "X", "H"]
+        for nm in names:
+            ref = gold["build/%s/%s" % (path, nm)]
+            mine = hps.operator(i, nm)
+            assert mine.shape == ref.shape, (path, nm)
+            worst[nm] = max(worst.get(nm, 0.0), relerr(mine, ref))
+        vecs = ["h", "g", "u", "f"] if info["leaf"] else ["h", "g", "w"]
+        for nm in vecs:
+            key = ("up" if nm in "hwf" else "solve") + "/%s/%s" % (path, nm)
+            ref = gold[key]
+            mine = hps.vector(i, nm)
+            assert mine.shape == ref.shape, (path, nm)
+            worst[nm] = max(worst.get(nm, 0.0), relerr(mine, ref))
+    print(case, {k: "%.1e" % v for k, v in worst.items()}, "min pivot %.3e" % hps.stats()["min_pivot"])
+    for nm, v in worst.items():
+        assert v < TOL, (nm, v)
+
+
+@pytest.mark.parametrize("nx,level,problem", [(16, 3, "poisson"), (32, 2, "helmholtz"), (24, 2, "poisson")])
+def test_uniform_against_oracle(nx, level, problem):
+    kw = dict(problem_name=problem, solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=nx,
+              min_level=level, max_level=level, threshold=1.2, refine_box=None)
+    hps = run_gpu(kw)
+    ora = O.run(**kw)
+    worst = {}
+    for i, nd in enumerate(ora.nodes):
+        assert hps.mesh.path(i) == nd.path
+        for nm in (["T"] if nd.leaf else ["T", "S", "X", "H"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.operator(i, nm), getattr(nd, nm)))
+        for nm in (["h", "g", "u"] if nd.leaf else ["h", "g", "w"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.vector(i, nm), getattr(nd, nm)))
+    print(nx, level, problem, {k: "%.1e" % v for k, v in worst.items()})
+    for nm, v in worst.items():
+        assert v < TOL, (nm, v)
+    # and the solution converges to the manufactured one (2nd order, h = pi / (nx 2^level))
+    X, Y = hps.mesh.leaf_cell_centres()
+    err = np.max(np.abs(hps.u_leaves - (np.sin(X) + np.sin(Y))))
+    assert err < 3.0 * (np.pi / (nx * 2 ** level)) ** 2
+
+
+def test_adaptive_m16_against_oracle():
+    kw = dict(problem_name="poisson", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=16,
+              min_level=0, max_level=4, threshold=1.2, refine_box=None)
+    hps = run_gpu(kw)
+    ora = O.run(**kw)
+    assert max(nd.n_coarsens for nd in ora.nodes) >= 1
+    u_ref = np.stack([u.reshape(16, 16) for u in ora.leaf_solution()])
+    assert relerr(hps.u_leaves, u_ref) < TOL
+    root = ora.nodes[0]
+    assert relerr(hps.operator(0, "T"), root.T) < TOL
+    assert relerr(hps.operator(0, "S"), root.S) < TOL
+
+
+def test_options_cache_operators_and_homogeneous_rhs():
+    kw = dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=8,
+              min_level=2, max_level=2, threshold=1.2, refine_box=None)
+    P = O.problem("poisson")
+    # cache-operators: every leaf gets the first leaf's T (HPSAlgorithm.hpp:134-139)
+    hps = run_gpu(kw, options={"cache-operators": True})
+    T0 = hps.operator(int(hps.mesh.leaf_nodes[0]), "T")
+    for ln in hps.mesh.leaf_nodes[1:]:
+        assert np.array_equal(hps.operator(int(ln), "T"), T0)
+    ora = O.run(cache_operators=True, **kw)
+    assert relerr(hps.u_leaves, np.stack([u.reshape(8, 8) for u in ora.leaf_solution()])) < TOL
+    # homogeneous-rhs: upwards4to1 skipped, leaf solve with f = 0 (HPSAlgorithm.hpp:532,587-590)
+    hps = run_gpu(kw, options={"homogeneous-rhs": True})
+    nodes = O.build_tree(O.refine_indicator(1.2), kw["box"], 8, 2, 2)
+    oh = O.HPS(nodes, O.Solver(kind="fishpack"), homogeneous_rhs=True)
+    oh.build_stage()
+    oh.upwards_stage(P["f"])
+    side, x, y = hps.root_boundary_points()
+    oh.solve_stage_dirichlet(P["u"](x, y))
+    assert relerr(hps.u_leaves, np.stack([u.reshape(8, 8) for u in oh.leaf_solution()])) < TOL
+
+
+def test_linearity_and_repeat_solves():
+    """Size-independent properties: the solve is linear in (f, g) and repeatable on cached operators."""
+    kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16,
+              min_level=4, max_level=4, threshold=1.2, refine_box=None)
+    hps = run_gpu(kw, keep_x=False)
+    P = O.problem("helmholtz")
+    u1 = hps.u_leaves.copy()
+    bc = lambda side, x, y: (1.37 * P["u"](x, y), 1.0, 0.0)
+    hps.upwardsStage(P["f"], 1.37)
+    u2 = hps.solveStage(bc).copy()
+    assert relerr(u2, 1.37 * u1) < 1e-12
+    hps.upwardsStage(P["f"], 1.0)
+    u3 = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0))
+    assert np.array_equal(u3, u1)  # bit-reproducible
+    X, Y = hps.mesh.leaf_cell_centres()
+    assert np.max(np.abs(u1 - P["u"](X, Y))) < 3.0 * (np.pi / 256) ** 2
+
+
+def test_dgemm_kernel_against_numpy():
+    import ctypes as C
+    import torch
+    lib = ef.load()
+    rng = np.random.default_rng(0)
+    for (m, n, k, batch, tile) in [(128, 128, 128, 3, 128), (256, 256, 64, 2, 64), (64, 64, 64, 5, 32), (32, 32, 16, 7, 16),
+                                   (8, 8, 8, 9, 8), (256, 256, 256, 1, 0), (48, 48, 48, 4, 0)]:
+        A = rng.standard_normal((batch, m, k)); B = rng.standard_normal((batch, k, n))
+        dA, dB = torch.tensor(A, device="cuda"), torch.tensor(B, device="cuda")
+        dC = torch.zeros(batch, m, n, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        ms = C.c_float()
+        rc = lib.efgpu_dgemm_batched(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), m, n, k, batch, tile, 1, C.byref(ms))
+        assert rc == 0
+        ref = A @ B
+        assert relerr(dC.cpu().numpy(), ref) < 1e-13, (m, n, k, batch, tile)

@@ -1,0 +1,79 @@
+"""CPU tests of the host logic above the C-ABI: the library loads, exports every declared symbol,
+fails loudly without a GPU, and the stand-alone mesh builder reproduces p4est's result."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ellipticforest_b200 as ef
+from ellipticforest_b200 import _lib
+from conftest import GOLDEN_CASES, ROOT, golden_case_args, load_golden
+import hps_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "efgpu.h")).read()
+    declared = set(re.findall(r"\b(efgpu_[a-z_]+)\s*\(", header)) - {"efgpu_refine_fn"}
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def _mesh_for(kw):
+    ind = O.refine_box_indicator(kw["refine_box"]) if kw["refine_box"] is not None else O.refine_indicator(kw["threshold"])
+    g = ef.FiniteVolumeGrid(kw["nx"], kw["box"][0], kw["box"][1], kw["nx"], kw["box"][2], kw["box"][3])
+    return ef.Mesh().refineByFunction(lambda x, y: bool(ind(x, y)), kw["threshold"], kw["min_level"], kw["max_level"], g)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_mesh_builder_matches_p4est(case):
+    """Leaf/level indexing and traversal order bit-exact against the reference's real p4est run."""
+    gold = load_golden(case)
+    m = _mesh_for(golden_case_args(gold))
+    leaf = set(int(i) for i in m.leaf_nodes)
+    pre = "".join(m.path(i) + ";" for i in range(m.n_nodes))
+    post = "".join(m.path(i) + ("L" if i in leaf else "P") + ";" for i in m.post_order())
+    assert pre == gold["order/pre"]
+    assert post == gold["order/post"]
+    for i in range(m.n_nodes):
+        box = gold["grid0/" + m.path(i)]
+        assert int(box[5]) == m.level[i]
+        if i in leaf:  # child boxes by midpoint splitting: bit-exact
+            assert tuple(m.box[i]) == tuple(box[:4])
+
+
+def test_uniform_mesh_counts():
+    g = ef.FiniteVolumeGrid(16, 0.0, np.pi, 16, 0.0, np.pi)
+    m = ef.Mesh().refineByFunction(None, 0.0, 5, 5, g)
+    assert m.n_leaves == 4 ** 5 and m.n_nodes == (4 ** 6 - 1) // 3
+    X, Y = m.leaf_cell_centres()
+    assert X.shape == (1024, 16, 16)
+    # first leaf is the lower-left corner patch, second is its right neighbour (Morton order)
+    assert X[0, 0, 0] < X[1, 0, 0] and Y[0, 0, 0] == Y[1, 0, 0]
+
+
+def test_create_fails_loudly_without_gpu():
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    g = ef.FiniteVolumeGrid(8, 0.0, 1.0, 8, 0.0, 1.0)
+    m = ef.Mesh().refineByFunction(None, 0.0, 1, 1, g)
+    with pytest.raises(ef.EfgpuError) as e:
+        ef.HPSAlgorithm(m, ef.FiniteVolumeSolver())
+    assert e.value.code == 1 and "no CPU fallback" in str(e.value)
+
+
+def test_bad_arguments_are_rejected():
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    assert lib.efgpu_mesh_create(0.0, 1.0, 0.0, 1.0, 8, 3, 2, _lib.REFINE_FN(), None, ctypes.byref(out)) == 2
+    assert lib.efgpu_mesh_create(1.0, 0.0, 0.0, 1.0, 8, 0, 1, _lib.REFINE_FN(), None, ctypes.byref(out)) == 2
+    assert lib.efgpu_build(None, 0) == 2
