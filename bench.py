@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the HPS hot path (BASELINE.json metric: HPS build & solve DOFs/s, FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--level L] [--nx M] [--problem poisson|helmholtz] [--no-cpu-baseline]
+
+A "step" is one full pass of the hot path over the workload's quadtree: buildStage (leaf DtN +
+every 4-to-1 merge), upwardsStage and solveStage for one right-hand side.  DOFs = leaves * nx * ny
+(reference: examples/elliptic-multiple/main.cpp:374).  The default workload is BASELINE.json
+configs[1]: uniform level-8 quadtree of 16x16 finite-volume patches, constant-coefficient Poisson
+on [0, pi]^2, f = -(sin x + sin y), Dirichlet data from u = sin x + sin y.
+
+Legs of the JSON line:
+  value        DOFs/s with f and the root Dirichlet data already resident in HBM, device events.
+  e2e          the same step through the C-ABI with HOST buffers (efgpu_build, efgpu_upwards,
+               efgpu_solve_dirichlet): f and g copied H2D from pinned memory, u copied D2H, every step.
+  roofline     the dominant kernel (the FP64 tensor-core batched GEMM of the merges) timed with
+               CUDA events on the library's stream around every launch; numerator = flops issued.
+  cpu_baseline the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from /root/reference by
+               oracle/Makefile) on this box's host cores, on a bounded sample of the same workload.
+`--impl reference` times only that reference build (bounded sample per step) and prints the same line.
+
+Multi-GPU (torchrun, one rank per GPU): the quadtree is sharded by level-2 subtree;
+timing is barrier + synchronize on both sides and the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+PI = 3.141592653589793
+
+
+# ---------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--level", type=int, default=8)
+    ap.add_argument("--nx", type=int, default=16)
+    ap.add_argument("--problem", default="poisson", choices=["poisson", "helmholtz"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="for ncu: exactly --warmup/--steps device steps, nothing else, no JSON")
+    ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6 own arm, 5 reference arm)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "uniform level-%d quadtree, %dx%d FV patches, constant-coefficient %s on [0,pi]^2 (BASELINE configs[1] shape)" % (
+        a.level, a.nx, a.nx, "Poisson" if a.problem == "poisson" else "Helmholtz lambda=-1")
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_sample(level, nx, problem, threads):
+    """One run of the unmodified reference on a uniform level-`level` tree; returns its REF_RESULT dict."""
+    if not os.path.exists(REF_DRIVER):
+        raise RuntimeError("oracle/_ref/ref_driver is missing (built by __graft_entry__.build() where /root/reference exists)")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS=str(threads), OMP_NUM_THREADS=str(threads))
+    cmd = [REF_DRIVER, "--problem", problem, "--solver", "fishpack", "--min-level", str(level), "--max-level", str(level),
+           "--nx", str(nx), "--domain", "0", repr(PI), "0", repr(PI), "--ops", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("REF_RESULT")][-1]
+    return json.loads(line[len("REF_RESULT "):])
+
+
+def host_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def reference_arm(a):
+    """`--impl reference`: the reference's own CPU implementation (compiled, unmodified) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    level = a.cpu_level if a.cpu_level is not None else min(a.level, 5)
+    threads = host_threads()
+    for _ in range(a.warmup):
+        run_reference_sample(level, a.nx, a.problem, threads)
+    ts, res = [], None
+    for _ in range(a.steps):
+        res = run_reference_sample(level, a.nx, a.problem, threads)
+        ts.append(res["build_s"] + res["upwards_s"] + res["solve_s"])
+    t = sum(ts) / len(ts)
+    v = res["dofs"] / t
+    sample = "uniform level-%d, %dx%d patches (%d DOFs): build %.3f s, upwards %.3f s, solve %.3f s per step" % (
+        level, a.nx, a.nx, res["dofs"], res["build_s"], res["upwards_s"], res["solve_s"])
+    print(json.dumps({
+        "impl": "reference", "metric": "HPS build+upwards+solve DOFs/s (FP64)", "value": v, "unit": "DOFs/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "DOFs/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "DOFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def own_arm(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ellipticforest_b200 as ef
+    from ellipticforest_b200 import dist as efdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the HPS path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- workload (untimed set-up: mesh, plan, host sampling of f and the boundary data) ----
+    grid = ef.FiniteVolumeGrid(a.nx, 0.0, PI, a.nx, 0.0, PI)
+    mesh = ef.Mesh().refineByFunction(None, 0.0, a.level, a.level, grid)
+    solver = ef.FiniteVolumeSolver()
+    solver.solver_type = "FISHPACK90"
+    lam = 0.0 if a.problem == "poisson" else -1.0
+    solver.lambda_function = lambda x, y: lam + 0.0 * x
+    u_exact = lambda x, y: np.sin(x) + np.sin(y)
+    f_fn = lambda x, y: (lam - 1.0) * u_exact(x, y)
+
+    hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world)
+    hps.setupStage()
+    f_host, g_host = hps.sample_inputs(f_fn, u_exact)          # numpy, this rank's share
+    f_pin = torch.from_numpy(f_host).pin_memory()
+    g_pin = torch.from_numpy(g_host).pin_memory()
+    u_pin = torch.empty(f_host.size, dtype=torch.float64).pin_memory()
+    f_dev = f_pin.cuda()
+    g_dev = g_pin.cuda()
+    u_dev = torch.empty_like(f_dev)
+    torch.cuda.synchronize()
+    dofs = float(mesh.n_leaves * a.nx * a.nx)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        hps.buildStage()
+        hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=False)
+        hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True)
+
+    def step_host():
+        hps.buildStage()
+        hps.upwardsStageHost(f_pin.numpy())
+        hps.solveStageHost(g_pin.numpy(), u_pin.numpy())
+
+    def timed(fn, steps):
+        """barrier + synchronize on both sides; returns seconds (max over ranks) for `steps` steps."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = torch.cuda.ExternalStream(hps.stream())
+        t0 = time.perf_counter()
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev = e0.elapsed_time(e1) * 1e-3
+        t = torch.tensor([dev, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    if a.profile_run:   # launched under ncu: numbers printed by such a run are never bench values
+        for _ in range(a.warmup + a.steps):
+            step_device()
+        print("profile run done: %d steps" % (a.warmup + a.steps))
+        return
+
+    # ---- warm-up, then the device-resident leg under the clock sampler ----
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    hps.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_s, wall_s = timed(step_device, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = hps.profile()
+    stats = hps.stats()
+    hps.set_profiling(False)
+
+    # correctness of the timed computation: discretisation error against the manufactured solution
+    err = hps.max_error(u_dev, u_exact)
+
+    # ---- e2e leg: host buffers through the C-ABI, copies inside the timed region ----
+    step_host()
+    e2e_dev_s, e2e_wall_s = timed(step_host, a.steps)
+    err_e2e = float(np.max(np.abs(u_pin.numpy() - u_dev.cpu().numpy())))
+
+    # ---- stage split (one extra profiled pass, not part of the headline) ----
+    barrier()
+    hps.buildStage(); build_ms = hps.stats()["build_ms"]
+    hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True); up_ms = hps.stats()["upwards_ms"]
+    hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True); so_ms = hps.stats()["solve_ms"]
+
+    # ---- measured FP64 GEMM ceiling on this box (cuBLAS DGEMM 8192^3), the tensor roofline denominator ----
+    dgemm_tf = None
+    if rank == 0:
+        n = 8192
+        A = torch.randn(n, n, dtype=torch.float64, device="cuda"); B = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            A @ B
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); A @ B; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        dgemm_tf = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        del A, B
+
+    # ---- CPU baseline: the unmodified reference on a bounded sample, rank 0, N = 1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            lvl = a.cpu_level if a.cpu_level is not None else min(a.level, 6)
+            threads = host_threads()
+            r = run_reference_sample(lvl, a.nx, a.problem, threads)
+            t = r["build_s"] + r["upwards_s"] + r["solve_s"]
+            cpu = {"value": r["dofs"] / t, "unit": "DOFs/s", "cores": threads, "kind": "reference",
+                   "sample": "oracle/_ref/ref_driver (unmodified reference, OpenBLAS x%d threads), uniform level-%d %dx%d patches, %d DOFs: "
+                             "build %.2f s, upwards %.2f s, solve %.2f s" % (threads, lvl, a.nx, a.nx, r["dofs"], r["build_s"], r["upwards_s"], r["solve_s"]),
+                   "build_dofs_per_s": r["dofs"] / r["build_s"], "solve_dofs_per_s": r["dofs"] / (r["upwards_s"] + r["solve_s"])}
+        except Exception as e:  # the baseline is reported, never required for the GPU numbers
+            cpu = {"value": None, "unit": "DOFs/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    gemm_ms = sum(prof[k][0] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
+    gemm_launches = sum(prof[k][1] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
+    total_prof_ms = sum(v[0] for v in prof.values())
+    launches = sum(v[1] for v in prof.values())
+    flops_issued = hps.total_issued_flops() * a.steps
+    gemm_tf = flops_issued / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    ms_per_step = 1e3 * dev_s / a.steps
+    out = {
+        "metric": "HPS build+upwards+solve DOFs/s (FP64)", "value": dofs * a.steps / dev_s, "unit": "DOFs/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (stats["device_bytes"] / 1e9),
+                   "sharding": hps.sharding()},
+        "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,
+                   "build_dofs_per_s": dofs / (build_ms * 1e-3), "solve_dofs_per_s": dofs / ((up_ms + so_ms) * 1e-3),
+                   "upwards_gbs": stats["upwards_bytes"] / (up_ms * 1e-3) / 1e9, "solve_gbs": stats["solve_bytes"] / (so_ms * 1e-3) / 1e9,
+                   "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                   "merge_tflops_canonical": stats["merge_flops_canonical"] / (build_ms * 1e-3) / 1e12},
+        "linf_error_vs_exact": err, "e2e_vs_device_max_abs_diff": err_e2e,
+        "e2e": {"value": dofs * a.steps / e2e_wall_s, "unit": "DOFs/s", "h2d_bytes_per_step": int(f_host.nbytes + g_host.nbytes),
+                "d2h_bytes_per_step": int(f_host.nbytes), "ms_per_step": 1e3 * e2e_wall_s / a.steps, "timer": "host wall clock between device synchronisations"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)",
+                     "achieved": gemm_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": (gemm_tf / dgemm_tf) if (gemm_tf and dgemm_tf) else None,
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure; NVIDIA nominal FP64 tensor 37-40 TFLOP/s)",
+                     "flops": "issued to the tensor pipe (512 n^3 per merge; the reference's dgesv+dgemm count is 810.67 n^3)",
+                     "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
+                     "traffic": None},
+        "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        own_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,7 @@ struct NodeH {
     size_t w_off = 0, hd_off = 0;
 };
 
-struct Step { int kind; int first, count; long long off; int N; };  // kind 0: small inverse, 1: gemm
+struct Step { int kind; int first, count; long long off; int N; int cls; };  // kind 0: small inverse, 1: gemm; cls: profiling class
 
 struct BatchH {
     int level = 0, n = 0, count = 0;
@@ -99,16 +99,51 @@ struct efgpu_handle {
     std::string last_error;
     efgpu_stats_t stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-kernel-class timing (efgpu_set_profiling): event pairs around every launch group
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[EFGPU_PROF_NCLASSES] = {0};
+    double prof_launches[EFGPU_PROF_NCLASSES] = {0};
 };
 
 namespace efgpu {
+
+static cudaEvent_t take_event(efgpu_handle* H)
+{
+    if (!H->ev_pool.empty()) { cudaEvent_t e = H->ev_pool.back(); H->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; EF_CUDA(cudaEventCreate(&e)); return e;
+}
+// Runs `f` (which launches `nlaunch` kernels of class `cls` on the handle's stream); in profiling
+// mode the group is bracketed by an event pair that collect_profile() turns into milliseconds.
+template <class F>
+static inline void timed(efgpu_handle* H, int cls, int nlaunch, F&& f)
+{
+    H->prof_launches[cls] += nlaunch;
+    if (!H->profiling) { f(); return; }
+    cudaEvent_t a = take_event(H), b = take_event(H);
+    EF_CUDA(cudaEventRecord(a, H->stream));
+    f();
+    EF_CUDA(cudaEventRecord(b, H->stream));
+    H->prof_recs.push_back({cls, a, b});
+}
+static void collect_profile(efgpu_handle* H)   // stream must be synchronised
+{
+    for (auto& r : H->prof_recs) {
+        float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        H->prof_ms[r.cls] += ms;
+        H->ev_pool.push_back(r.a); H->ev_pool.push_back(r.b);
+    }
+    H->prof_recs.clear();
+}
 
 static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int depth, std::vector<long long>& w1_off, long long w2_off)
 {
     const bool can_split = N > 64 && (N / 2) % 8 == 0;
     if (!can_split) {
         if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
-        b.steps.push_back({0, 0, 0, off, N});
+        b.steps.push_back({0, 0, 0, off, N, EFGPU_PROF_INVERT_SMALL});
         return;
     }
     const int h = N / 2;
@@ -120,7 +155,7 @@ static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int dep
         g.c_op = c_op; g.c_off = c_off; g.ldc = ldc; g.c0_op = c0_op; g.c0_off = c0_off; g.ldc0 = ldc0;
         g.rows = h; g.cols = h; g.nterms = 1;
         g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, h, neg ? 0x80000000u : 0u};
-        b.steps.push_back({1, (int)b.blocks.size(), 1, 0, 0});
+        b.steps.push_back({1, (int)b.blocks.size(), 1, 0, 0, EFGPU_PROF_GEMM_XINV});
         b.blocks.push_back(g);
     };
     build_inverse_steps(b, A, h, ld, depth + 1, w1_off, w2_off);                                 // A <- A^-1
@@ -158,7 +193,7 @@ static void plan_batch_gemms(BatchH& b)
             }
             b.blocks.push_back(g);
         }
-    b.steps.push_back({1, first, 32, 0, 0});
+    b.steps.push_back({1, first, 32, 0, 0, EFGPU_PROF_GEMM_S});
     // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_)
     first = (int)b.blocks.size();
     for (int qr = 0; qr < 8; qr++)
@@ -177,7 +212,7 @@ static void plan_batch_gemms(BatchH& b)
             }
             b.blocks.push_back(g);
         }
-    b.steps.push_back({1, first, 64, 0, 0});
+    b.steps.push_back({1, first, 64, 0, 0, EFGPU_PROF_GEMM_T});
 }
 
 static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d)
@@ -389,25 +424,30 @@ static void do_build(efgpu_handle* H, unsigned flags)
     const double big = 1e300;
     EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
     EF_CUDA(cudaEventRecord(H->ev0, s));
-    run_leaf_dtn(H, flags);
+    timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, flags); });
     for (int lev = H->max_level; lev >= 0; lev--)
         for (int bi : H->level_batches[lev]) {
             BatchH& b = H->batches[bi];
             for (size_t t = 0; t < b.cT.size(); t++)
-                launch_coarsen_T(b.d_cT[t]->as<CoarsenOp>(), (int)b.cT[t].size(), b.cT_max[t], s);
+                timed(H, EFGPU_PROF_COARSEN_T, 1, [&] { launch_coarsen_T(b.d_cT[t]->as<CoarsenOp>(), (int)b.cT[t].size(), b.cT_max[t], s); });
             const MergeEntry* ent = b.d_entries.as<MergeEntry>();
-            launch_assemble_X(ent, b.n, b.count, s);
-            launch_assemble_Hc(ent, b.n, b.count, s);
+            timed(H, EFGPU_PROF_ASSEMBLE, 2, [&] {
+                launch_assemble_X(ent, b.n, b.count, s);
+                launch_assemble_Hc(ent, b.n, b.count, s);
+            });
             double* const* ptab = b.d_ptab.as<double*>();
             for (const Step& st : b.steps) {
-                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
-                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
+                timed(H, st.cls, 1, [&] {
+                    if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
+                    else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
+                });
             }
         }
     EF_CUDA(cudaEventRecord(H->ev1, s));
     double minpiv = 0;
     EF_CUDA(cudaMemcpyAsync(&minpiv, H->d_minpiv.p, sizeof(double), cudaMemcpyDeviceToHost, s));
     EF_CUDA(cudaStreamSynchronize(s));
+    collect_profile(H);
     float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1));
     H->stats.build_ms = ms; H->stats.min_pivot = minpiv;
     H->built = true; H->upwards_done = false;
@@ -419,15 +459,17 @@ static void do_upwards(efgpu_handle* H, const double* f_dev, double fscale, unsi
     if (!H->built) throw Error{EF_ERR_STATE, "upwards before build"};
     cudaStream_t s = H->stream;
     EF_CUDA(cudaEventRecord(H->ev0, s));
-    launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
-                            f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
+    timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
+        launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                                f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
+    });
     if (!(flags & EFGPU_HOMOGENEOUS_RHS))   // upwards4to1 is skipped entirely (HPSAlgorithm.hpp:532)
         for (int lev = H->max_level; lev >= 0; lev--)
             for (int bi : H->level_batches[lev]) {
                 BatchH& b = H->batches[bi];
                 for (size_t t = 0; t < b.cH.size(); t++)
-                    launch_coarsen_h(b.d_cH[t]->as<CoarsenOp>(), (int)b.cH[t].size(), b.cH_max[t], s);
-                launch_upwards(b.d_entries.as<MergeEntry>(), b.n, b.count, s);
+                    timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_coarsen_h(b.d_cH[t]->as<CoarsenOp>(), (int)b.cH[t].size(), b.cH_max[t], s); });
+                timed(H, EFGPU_PROF_UPWARDS_MATVEC, 3, [&] { launch_upwards(b.d_entries.as<MergeEntry>(), b.n, b.count, s); });
             }
     EF_CUDA(cudaEventRecord(H->ev1, s));
     H->upwards_done = true;
@@ -442,11 +484,13 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
         for (int bi : H->level_batches[lev]) {
             BatchH& b = H->batches[bi];
             for (size_t t = 0; t < b.cG.size(); t++)
-                launch_uncoarsen_g(b.d_cG[t]->as<CoarsenOp>(), (int)b.cG[t].size(), b.cG_max[t], s);
-            launch_solve_split(b.d_entries.as<MergeEntry>(), b.n, b.count, !homogeneous, s);
+                timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(b.d_cG[t]->as<CoarsenOp>(), (int)b.cG[t].size(), b.cG_max[t], s); });
+            timed(H, EFGPU_PROF_SOLVE_MATVEC, 1, [&] { launch_solve_split(b.d_entries.as<MergeEntry>(), b.n, b.count, !homogeneous, s); });
         }
-    launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
-                            homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
+    timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
+        launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                                homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
+    });
 }
 
 }  // namespace efgpu
@@ -493,6 +537,8 @@ void efgpu_destroy(efgpu_handle* H)
     if (H->stream) cudaStreamSynchronize(H->stream);
     if (H->ev0) cudaEventDestroy(H->ev0);
     if (H->ev1) cudaEventDestroy(H->ev1);
+    for (auto& r : H->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : H->ev_pool) cudaEventDestroy(e);
     cudaStream_t s = H->stream;
     delete H;
     if (s) cudaStreamDestroy(s);
@@ -532,7 +578,7 @@ int efgpu_upwards(efgpu_handle* H, const double* f_leaves, double fscale, unsign
     EF_CUDA(cudaMemcpyAsync(H->d_f.p, f_leaves, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyHostToDevice, H->stream));
     H->f_cur = H->d_f.as<double>(); H->fscale_cur = fscale;
     do_upwards(H, H->f_cur, fscale, flags);
-    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
     float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.upwards_ms = ms;
     EF_CATCH(H)
 }
@@ -546,7 +592,7 @@ int efgpu_upwards_device(efgpu_handle* H, const double* f_leaves_dev, double fsc
     H->f_cur = f_leaves_dev; H->fscale_cur = fscale;   // borrowed until the next upwards call
     do_upwards(H, H->f_cur, fscale, flags);
     if (sync) {
-        EF_CUDA(cudaStreamSynchronize(H->stream));
+        EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
         float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.upwards_ms = ms;
     }
     EF_CATCH(H)
@@ -570,7 +616,7 @@ int efgpu_solve_dirichlet(efgpu_handle* H, const double* g_root, unsigned flags,
     do_solve(H, H->f_cur, H->fscale_cur, flags);
     EF_CUDA(cudaEventRecord(H->ev1, H->stream));
     if (u_leaves) EF_CUDA(cudaMemcpyAsync(u_leaves, H->d_u.p, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
-    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
     float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
     EF_CATCH(H)
 }
@@ -588,7 +634,7 @@ int efgpu_solve_dirichlet_device(efgpu_handle* H, const double* g_root_dev, unsi
     if (u_leaves_dev) EF_CUDA(cudaMemcpyAsync(u_leaves_dev, H->d_u.p, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyDeviceToDevice, H->stream));
     EF_CUDA(cudaEventRecord(H->ev1, H->stream));
     if (sync) {
-        EF_CUDA(cudaStreamSynchronize(H->stream));
+        EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
         float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
     }
     EF_CATCH(H)
@@ -610,7 +656,7 @@ int efgpu_sync(efgpu_handle* H)
     if (!H) return EF_ERR_BAD_ARG;
     EF_TRY(H)
     EF_CUDA(cudaSetDevice(H->device));
-    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
     EF_CATCH(H)
 }
 
@@ -669,7 +715,7 @@ int efgpu_get_operator(efgpu_handle* H, int node, int which, double* out, size_t
             src = tmp.as<double>(); break;
     }
     EF_CUDA(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, H->stream));
-    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
     EF_CATCH(H)
 }
 
@@ -706,8 +752,31 @@ int efgpu_get_vector(efgpu_handle* H, int node, int which, double* out, size_t c
         case EFGPU_VEC_F: src = H->d_f.as<double>() + (size_t)nd.leaf_idx * len; break;
     }
     EF_CUDA(cudaMemcpyAsync(out, src, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
-    EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
     EF_CATCH(H)
+}
+
+int efgpu_set_profiling(efgpu_handle* H, int on)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    H->profiling = on != 0;
+    for (int c = 0; c < EFGPU_PROF_NCLASSES; c++) H->prof_ms[c] = H->prof_launches[c] = 0.0;
+    return EF_OK;
+}
+
+int efgpu_get_profile(const efgpu_handle* H, int cls, double* ms, double* launches)
+{
+    if (!H || cls < 0 || cls >= EFGPU_PROF_NCLASSES) return EF_ERR_BAD_ARG;
+    if (ms) *ms = H->prof_ms[cls];
+    if (launches) *launches = H->prof_launches[cls];
+    return EF_OK;
+}
+
+const char* efgpu_profile_class_name(int cls)
+{
+    static const char* names[EFGPU_PROF_NCLASSES] = {"leaf_dtn", "coarsen_T", "assemble_X_H", "invert_small", "gemm_Xinv", "gemm_S",
+                                                      "gemm_T", "leaf_solve", "upwards_matvec", "solve_matvec", "coarsen_vec", "leaf_lu"};
+    return (cls >= 0 && cls < EFGPU_PROF_NCLASSES) ? names[cls] : "";
 }
 
 int efgpu_get_stats(const efgpu_handle* H, efgpu_stats_t* out)

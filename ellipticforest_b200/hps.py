@@ -262,6 +262,35 @@ class HPSAlgorithm:
         check(self._lib.efgpu_get_vector(self._h, int(node), VEC[which], out.ctypes.data, out.size), self._h)
         return out
 
+    # -- device-resident variants (inputs already in HBM; used by the benchmark's `value` leg) ---
+    def upwardsStageDevice(self, f_dev_ptr: int, scale: float = 1.0, sync: bool = True):
+        check(self._lib.efgpu_upwards_device(self._h, C.c_void_p(f_dev_ptr), float(scale), self._flags(), int(sync)), self._h)
+
+    def solveStageDevice(self, g_dev_ptr: int, u_dev_ptr: int = 0, sync: bool = True):
+        check(self._lib.efgpu_solve_dirichlet_device(self._h, C.c_void_p(g_dev_ptr), self._flags(),
+                                                     C.c_void_p(u_dev_ptr) if u_dev_ptr else None, int(sync)), self._h)
+
+    def sync(self):
+        check(self._lib.efgpu_sync(self._h), self._h)
+
+    def stream(self) -> int:
+        return int(self._lib.efgpu_stream(self._h) or 0)
+
+    def set_profiling(self, on: bool = True):
+        check(self._lib.efgpu_set_profiling(self._h, int(on)), self._h)
+
+    def profile(self):
+        """{class name: (device ms, launches)} accumulated since set_profiling()."""
+        out = {}
+        for cls in range(64):
+            name = self._lib.efgpu_profile_class_name(cls)
+            if not name:
+                break
+            ms, n = C.c_double(), C.c_double()
+            check(self._lib.efgpu_get_profile(self._h, cls, C.byref(ms), C.byref(n)), self._h)
+            out[name.decode()] = (ms.value, n.value)
+        return out
+
     def stats(self):
         s = Stats()
         check(self._lib.efgpu_get_stats(self._h, C.byref(s)), self._h)

@@ -57,6 +57,14 @@ enum { EFGPU_LEAF_CONSTANT = 0, EFGPU_LEAF_VARIABLE = 1 };
 enum { EFGPU_OP_T = 0, EFGPU_OP_S = 1, EFGPU_OP_X = 2, EFGPU_OP_H = 3, EFGPU_OP_XINV = 4, EFGPU_OP_T_UNCOARSENED = 5 };
 enum { EFGPU_VEC_H = 0, EFGPU_VEC_W = 1, EFGPU_VEC_G = 2, EFGPU_VEC_U = 3, EFGPU_VEC_F = 4 };
 
+/* kernel classes of the optional per-launch profiling (efgpu_set_profiling / efgpu_get_profile) */
+enum {
+    EFGPU_PROF_LEAF_DTN = 0, EFGPU_PROF_COARSEN_T = 1, EFGPU_PROF_ASSEMBLE = 2, EFGPU_PROF_INVERT_SMALL = 3,
+    EFGPU_PROF_GEMM_XINV = 4, EFGPU_PROF_GEMM_S = 5, EFGPU_PROF_GEMM_T = 6, EFGPU_PROF_LEAF_SOLVE = 7,
+    EFGPU_PROF_UPWARDS_MATVEC = 8, EFGPU_PROF_SOLVE_MATVEC = 9, EFGPU_PROF_COARSEN_VEC = 10, EFGPU_PROF_LEAF_LU = 11,
+    EFGPU_PROF_NCLASSES = 12
+};
+
 typedef struct efgpu_handle efgpu_handle;
 
 /* Flat tree table = what Quadtree<FiniteVolumePatch>::traversePreOrder visits
@@ -115,6 +123,12 @@ int efgpu_get_operator(efgpu_handle* h, int node, int which, double* out, size_t
 int efgpu_vector_length(const efgpu_handle* h, int node, int which, int* len);
 int efgpu_get_vector(efgpu_handle* h, int node, int which, double* out, size_t capacity);
 int efgpu_get_stats(const efgpu_handle* h, efgpu_stats_t* out);
+/* Per-kernel-class device time (CUDA events on the handle's stream around every launch group) and launch
+ * counts, accumulated since profiling was switched on; replaces app.timers (EllipticForestApp.hpp:39-137),
+ * which only has whole-stage wall clocks.  Launch counts are kept even when profiling is off. */
+int efgpu_set_profiling(efgpu_handle* h, int on);
+int efgpu_get_profile(const efgpu_handle* h, int cls, double* ms, double* launches);
+const char* efgpu_profile_class_name(int cls);
 
 /* ---- host-side mesh: replaces Mesh::refineByFunction + Quadtree ctor + FiniteVolumeNodeFactory
  * (src/Mesh.hpp:111-180, src/Quadtree.hpp:118-196, FiniteVolumeNodeFactory.cpp:15-67).  p4est itself
