@@ -261,11 +261,17 @@ def own_arm(a):
     e2e_dev_s, e2e_wall_s = timed(step_host, a.steps)
     err_e2e = float(np.max(np.abs(u_pin.numpy() - u_dev.cpu().numpy())))
 
-    # ---- stage split (one extra profiled pass, not part of the headline) ----
-    barrier()
-    hps.buildStage(); build_ms = hps.stats()["build_ms"]
-    hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True); up_ms = hps.stats()["upwards_ms"]
-    hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True); so_ms = hps.stats()["solve_ms"]
+    # ---- stage split (extra passes, not part of the headline): each stage between barriers, max over ranks ----
+    build_s, _ = timed(lambda: hps.buildStage(), 1)
+    up_s, _ = timed(lambda: hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True), 1)
+    so_s, _ = timed(lambda: hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True), 1)
+    build_ms, up_ms, so_ms = 1e3 * build_s, 1e3 * up_s, 1e3 * so_s
+    # whole-job totals of the per-rank work models (flops issued, algorithmic bytes, device memory)
+    agg = torch.tensor([stats[k] for k in ("merge_flops_issued", "merge_flops_canonical", "upwards_bytes", "solve_bytes", "device_bytes")],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg)
+    tot = dict(zip(("issued", "canonical", "upwards_bytes", "solve_bytes", "device_bytes"), [float(v) for v in agg]))
 
     # ---- measured FP64 GEMM ceiling on this box (cuBLAS DGEMM 8192^3), the tensor roofline denominator ----
     dgemm_tf = None
@@ -297,9 +303,24 @@ def own_arm(a):
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             cpu = {"value": None, "unit": "DOFs/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
 
-    if rank != 0:
+    def cleanup():
+        # torch frees pinned buffers by recording events on the streams they were used on: release every tensor
+        # while the library's stream still exists, then the handles, then the process group
+        nonlocal f_pin, g_pin, u_pin, f_dev, g_dev, u_dev, hps
+        import gc
+        torch.cuda.synchronize()
+        hps._f_dev = hps._g_dev = hps._u_dev = None
+        f_pin = g_pin = u_pin = f_dev = g_dev = u_dev = None
+        gc.collect()
+        torch.cuda.synchronize()
+        hps = None
+        gc.collect()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        cleanup()
         return
 
     peaks = {}
@@ -314,25 +335,26 @@ def own_arm(a):
     gemm_launches = sum(prof[k][1] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
     total_prof_ms = sum(v[0] for v in prof.values())
     launches = sum(v[1] for v in prof.values())
-    flops_issued = hps.total_issued_flops() * a.steps
+    flops_issued = stats["merge_flops_issued"] * a.steps      # rank 0's own merges (its subtrees + the upper tree when sharded)
     gemm_tf = flops_issued / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     ms_per_step = 1e3 * dev_s / a.steps
     out = {
         "metric": "HPS build+upwards+solve DOFs/s (FP64)", "value": dofs * a.steps / dev_s, "unit": "DOFs/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (stats["device_bytes"] / 1e9),
+        "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
                    "sharding": hps.sharding()},
         "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,
                    "build_dofs_per_s": dofs / (build_ms * 1e-3), "solve_dofs_per_s": dofs / ((up_ms + so_ms) * 1e-3),
-                   "upwards_gbs": stats["upwards_bytes"] / (up_ms * 1e-3) / 1e9, "solve_gbs": stats["solve_bytes"] / (so_ms * 1e-3) / 1e9,
+                   "upwards_gbs": tot["upwards_bytes"] / (up_ms * 1e-3) / 1e9, "solve_gbs": tot["solve_bytes"] / (so_ms * 1e-3) / 1e9,
                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
-                   "merge_tflops_canonical": stats["merge_flops_canonical"] / (build_ms * 1e-3) / 1e12},
+                   "merge_tflops_issued": tot["issued"] / (build_ms * 1e-3) / 1e12,
+                   "merge_tflops_canonical": tot["canonical"] / (build_ms * 1e-3) / 1e12},
         "linf_error_vs_exact": err, "e2e_vs_device_max_abs_diff": err_e2e,
         "e2e": {"value": dofs * a.steps / e2e_wall_s, "unit": "DOFs/s", "h2d_bytes_per_step": int(f_host.nbytes + g_host.nbytes),
                 "d2h_bytes_per_step": int(f_host.nbytes), "ms_per_step": 1e3 * e2e_wall_s / a.steps, "timer": "host wall clock between device synchronisations"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)",
+        "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)%s" % (" on rank 0" if world > 1 else ""),
                      "achieved": gemm_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": (gemm_tf / dgemm_tf) if (gemm_tf and dgemm_tf) else None,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure; NVIDIA nominal FP64 tensor 37-40 TFLOP/s)",
                      "flops": "issued to the tensor pipe (512 n^3 per merge; the reference's dgesv+dgemm count is 810.67 n^3)",
@@ -343,8 +365,8 @@ def own_arm(a):
         "clocks": clocks,
     }
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stdout.flush()
+    cleanup()
 
 
 def main():

@@ -31,6 +31,7 @@ _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int)
 SIGNATURES = {
     "efgpu_create": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(_P)]),
+    "efgpu_create_ex": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(C.c_int32), C.POINTER(_P)]),
     "efgpu_destroy": (None, [_P]),
     "efgpu_last_error": (C.c_char_p, [_P]),
     "efgpu_set_leaf_constant": (C.c_int, [_P, C.c_double]),
@@ -40,9 +41,13 @@ SIGNATURES = {
     "efgpu_upwards_device": (C.c_int, [_P, _P, C.c_double, C.c_uint, C.c_int]),
     "efgpu_solve_dirichlet": (C.c_int, [_P, _P, C.c_uint, _P]),
     "efgpu_solve_dirichlet_device": (C.c_int, [_P, _P, C.c_uint, _P, C.c_int]),
+    "efgpu_solve_from_roots_device": (C.c_int, [_P, C.c_uint, _P, C.c_int]),
+    "efgpu_operator_device": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I, _I]),
+    "efgpu_vector_device": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I]),
     "efgpu_solve_robin": (C.c_int, [_P, _P, _P, _P, C.c_uint, _P]),
     "efgpu_sync": (C.c_int, [_P]),
     "efgpu_stream": (_P, [_P]),
+    "efgpu_set_stream": (C.c_int, [_P, _P]),
     "efgpu_node_info": (C.c_int, [_P, C.c_int, _I, _I, _I, _I]),
     "efgpu_operator_shape": (C.c_int, [_P, C.c_int, C.c_int, _I, _I]),
     "efgpu_get_operator": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),

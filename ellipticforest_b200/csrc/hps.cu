@@ -84,8 +84,17 @@ using namespace efgpu;
 struct efgpu_handle {
     int device = 0, M = 0, n_nodes = 0, n_leaves = 0, max_level = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     std::vector<NodeH> nodes;
     std::vector<int> leaf_nodes;                 // node id of each leaf, pre-order (= Morton order)
+    std::vector<int> roots;                      // nodes without a parent (one for a tree; several for a forest of subtrees)
+    bool external_leaves = false;                // leaf T / h are supplied by the caller (upper tree of a sharded run)
+    std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
+    // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
+    // (in an unsharded run this is the first thing the leaf's own split1to4 would do, HPSAlgorithm.hpp:1165-1183)
+    std::vector<std::vector<efgpu::CoarsenOp>> extG;
+    std::vector<std::unique_ptr<efgpu::DevBuf>> d_extG;
+    std::vector<int> extG_max;
     std::vector<std::vector<int>> level_batches; // batch ids per tree level
     std::vector<BatchH> batches;
     // leaf model
@@ -215,11 +224,12 @@ static void plan_batch_gemms(BatchH& b)
     b.steps.push_back({1, first, 64, 0, 0, EFGPU_PROF_GEMM_T});
 }
 
-static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d)
+static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* ext_leaf_size)
 {
     const int nn = d->n_nodes, M = d->nx;
     if (nn <= 0 || !d->level || !d->child || !d->box) throw Error{EF_ERR_BAD_ARG, "empty tree description"};
     if (M < 8 || M % 8) throw Error{EF_ERR_BAD_SHAPE, "nx must be a multiple of 8 (8, 16, 24, 32)"};
+    H->external_leaves = ext_leaf_size != nullptr;
     H->M = M; H->n_nodes = nn;
     H->nodes.resize(nn);
     for (int i = 0; i < nn; i++) {
@@ -239,10 +249,15 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d)
         if (nd.leaf) { nd.leaf_idx = (int)H->leaf_nodes.size(); H->leaf_nodes.push_back(i); }
     }
     H->n_leaves = (int)H->leaf_nodes.size();
+    for (int i = 0; i < nn; i++) if (H->nodes[i].parent < 0) H->roots.push_back(i);
     // sizes bottom-up (children have larger ids): parent = 2 * min child size (mergePatch_ :1004-1009)
     for (int i = nn - 1; i >= 0; i--) {
         NodeH& nd = H->nodes[i];
-        if (nd.leaf) { nd.size = M; continue; }
+        if (nd.leaf) {
+            nd.size = ext_leaf_size ? ext_leaf_size[nd.leaf_idx] : M;
+            if (nd.size < 8 || nd.size % 8) throw Error{EF_ERR_BAD_SHAPE, "external leaf sizes must be multiples of 8"};
+            continue;
+        }
         int mn = 1 << 30;
         for (int c = 0; c < 4; c++) {
             if (H->nodes[nd.child[c]].level != nd.level + 1) throw Error{EF_ERR_BAD_ARG, "child level must be parent level + 1"};
@@ -294,11 +309,12 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d)
     }
     H->stats.merge_flops_canonical = canon;
     H->stats.merge_flops_issued = issued;
-    H->stats.upwards_bytes = up_bytes + 8.0 * H->n_leaves * M * M;
-    H->stats.solve_bytes = so_bytes + 16.0 * H->n_leaves * M * M;
+    const double leaf_cells = H->external_leaves ? 0.0 : (double)H->n_leaves * M * M;
+    H->stats.upwards_bytes = up_bytes + 8.0 * leaf_cells;
+    H->stats.solve_bytes = so_bytes + 16.0 * leaf_cells;
     H->stats.n_leaves = H->n_leaves;
     H->stats.n_nodes = nn;
-    H->stats.dofs = (double)H->n_leaves * M * M;
+    H->stats.dofs = leaf_cells;
 }
 
 static void allocate_device(efgpu_handle* H, unsigned flags)
@@ -316,14 +332,18 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
     for (int i = 0; i < H->n_nodes; i++) std::memcpy(&boxes[4 * (size_t)i], H->nodes[i].box, 4 * sizeof(double));
     H->d_boxes.upload(boxes, s);
     H->d_leaf_nodes.upload(H->leaf_nodes, s);
-    H->d_leafT.alloc((size_t)H->n_leaves * 16 * M * M * sizeof(double));
+    H->leafT_off.assign(H->n_leaves + 1, 0);
+    for (int l = 0; l < H->n_leaves; l++) { const size_t sz = 4 * (size_t)H->nodes[H->leaf_nodes[l]].size; H->leafT_off[l + 1] = H->leafT_off[l] + sz * sz; }
+    H->d_leafT.alloc(H->leafT_off[H->n_leaves] * sizeof(double));
     H->d_vec.alloc(H->vec_doubles * sizeof(double));
     EF_CUDA(cudaMemsetAsync(H->d_vec.p, 0, H->vec_doubles * sizeof(double), s));
-    H->d_f.alloc((size_t)H->n_leaves * M * M * sizeof(double));
-    H->d_u.alloc((size_t)H->n_leaves * M * M * sizeof(double));
+    if (!H->external_leaves) {
+        H->d_f.alloc((size_t)H->n_leaves * M * M * sizeof(double));
+        H->d_u.alloc((size_t)H->n_leaves * M * M * sizeof(double));
+    }
     H->d_minpiv.alloc(sizeof(double));
     double* vec = H->d_vec.as<double>();
-    for (int l = 0; l < H->n_leaves; l++) H->nodes[H->leaf_nodes[l]].Tbuf.assign(1, H->d_leafT.as<double>() + (size_t)l * 16 * M * M);
+    for (int l = 0; l < H->n_leaves; l++) H->nodes[H->leaf_nodes[l]].Tbuf.assign(1, H->d_leafT.as<double>() + H->leafT_off[l]);
     std::vector<double*> lh(H->n_leaves), lg(H->n_leaves);
     for (int l = 0; l < H->n_leaves; l++) { NodeH& nd = H->nodes[H->leaf_nodes[l]]; lh[l] = vec + nd.hbuf[0]; lg[l] = vec + nd.gbuf[0]; }
     H->d_leaf_h.upload(lh, s); H->d_leaf_g.upload(lg, s);
@@ -403,6 +423,21 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
         };
         up(b.cT, b.d_cT, b.cT_max); up(b.cH, b.d_cH, b.cH_max); up(b.cG, b.d_cG, b.cG_max);
     }
+    H->extG.clear(); H->d_extG.clear(); H->extG_max.clear();
+    if (H->external_leaves)
+        for (int l = 0; l < H->n_leaves; l++) {
+            NodeH& P = H->nodes[H->leaf_nodes[l]];
+            for (int t = P.ncoarsen; t >= 1; t--) {
+                const size_t step = (size_t)(P.ncoarsen - t);
+                if (H->extG.size() <= step) H->extG.resize(step + 1);
+                H->extG[step].push_back(CoarsenOp{vec + P.gbuf[t], vec + P.gbuf[t - 1], P.size >> (t - 1), 0});
+            }
+        }
+    for (auto& ops : H->extG) {
+        H->d_extG.emplace_back(new DevBuf()); H->d_extG.back()->upload(ops, s);
+        int m = 0; for (auto& o : ops) m = std::max(m, o.nfine);
+        H->extG_max.push_back(m);
+    }
     EF_CUDA(cudaStreamSynchronize(s));
     H->allocated = true; H->build_flags = flags;
     size_t tot = 0;
@@ -412,6 +447,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
 
 static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
 {
+    if (H->external_leaves) return;   // leaf DtN maps were written by the caller (efgpu_operator_device)
     if (H->leaf_kind != EFGPU_LEAF_CONSTANT) throw Error{EF_ERR_UNSUPPORTED, "variable-coefficient leaves are not built yet"};
     launch_leaf_dtn_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
                           H->d_leafT.as<double>(), H->n_leaves, (flags & EFGPU_CACHE_OPERATORS) != 0, H->stream);
@@ -459,7 +495,7 @@ static void do_upwards(efgpu_handle* H, const double* f_dev, double fscale, unsi
     if (!H->built) throw Error{EF_ERR_STATE, "upwards before build"};
     cudaStream_t s = H->stream;
     EF_CUDA(cudaEventRecord(H->ev0, s));
-    timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
+    if (!H->external_leaves) timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
         launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
                                 f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
     });
@@ -487,7 +523,9 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
                 timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(b.d_cG[t]->as<CoarsenOp>(), (int)b.cG[t].size(), b.cG_max[t], s); });
             timed(H, EFGPU_PROF_SOLVE_MATVEC, 1, [&] { launch_solve_split(b.d_entries.as<MergeEntry>(), b.n, b.count, !homogeneous, s); });
         }
-    timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
+    for (size_t t = 0; t < H->extG.size(); t++)
+        timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(H->d_extG[t]->as<CoarsenOp>(), (int)H->extG[t].size(), H->extG_max[t], s); });
+    if (!H->external_leaves) timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
         launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
                                 homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
     });
@@ -509,7 +547,9 @@ static thread_local std::string g_create_error;
 
 extern "C" {
 
-int efgpu_create(const efgpu_tree_desc* desc, int device, efgpu_handle** out)
+int efgpu_create(const efgpu_tree_desc* desc, int device, efgpu_handle** out) { return efgpu_create_ex(desc, device, nullptr, out); }
+
+int efgpu_create_ex(const efgpu_tree_desc* desc, int device, const int32_t* external_leaf_size, efgpu_handle** out)
 {
     if (!desc || !out) return EF_ERR_BAD_ARG;
     efgpu_handle* H = nullptr;
@@ -521,7 +561,7 @@ int efgpu_create(const efgpu_tree_desc* desc, int device, efgpu_handle** out)
         EF_CUDA(cudaSetDevice(device));
         H = new efgpu_handle();
         H->device = device;
-        make_plan(H, desc);
+        make_plan(H, desc, external_leaf_size);
         EF_CUDA(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
         EF_CUDA(cudaEventCreate(&H->ev0)); EF_CUDA(cudaEventCreate(&H->ev1));
         *out = H;
@@ -539,7 +579,7 @@ void efgpu_destroy(efgpu_handle* H)
     if (H->ev1) cudaEventDestroy(H->ev1);
     for (auto& r : H->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : H->ev_pool) cudaEventDestroy(e);
-    cudaStream_t s = H->stream;
+    cudaStream_t s = H->own_stream ? H->stream : nullptr;
     delete H;
     if (s) cudaStreamDestroy(s);
 }
@@ -588,7 +628,7 @@ int efgpu_upwards_device(efgpu_handle* H, const double* f_leaves_dev, double fsc
     if (!H) return EF_ERR_BAD_ARG;
     EF_TRY(H)
     EF_CUDA(cudaSetDevice(H->device));
-    if (!f_leaves_dev) throw Error{EF_ERR_BAD_ARG, "null load vector"};
+    if (!f_leaves_dev && !H->external_leaves) throw Error{EF_ERR_BAD_ARG, "null load vector"};
     H->f_cur = f_leaves_dev; H->fscale_cur = fscale;   // borrowed until the next upwards call
     do_upwards(H, H->f_cur, fscale, flags);
     if (sync) {
@@ -600,6 +640,7 @@ int efgpu_upwards_device(efgpu_handle* H, const double* f_leaves_dev, double fsc
 
 static void set_root_g(efgpu_handle* H, const double* g_root, cudaMemcpyKind kind)
 {
+    if (H->roots.size() != 1) throw Error{EF_ERR_STATE, "this handle holds a forest: set each root's g through efgpu_vector_device and call efgpu_solve_from_roots_device"};
     NodeH& root = H->nodes[0];
     EF_CUDA(cudaMemcpyAsync(H->d_vec.as<double>() + root.gbuf[0], g_root, 4 * (size_t)root.size * sizeof(double), kind, H->stream));
 }
@@ -640,9 +681,72 @@ int efgpu_solve_dirichlet_device(efgpu_handle* H, const double* g_root_dev, unsi
     EF_CATCH(H)
 }
 
+int efgpu_solve_from_roots_device(efgpu_handle* H, unsigned flags, double* u_leaves_dev, int sync)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->built) throw Error{EF_ERR_STATE, "solve before build"};
+    if (!(flags & EFGPU_HOMOGENEOUS_RHS) && !H->upwards_done) throw Error{EF_ERR_STATE, "solve before upwards (non-homogeneous right-hand side)"};
+    EF_CUDA(cudaEventRecord(H->ev0, H->stream));
+    do_solve(H, H->f_cur, H->fscale_cur, flags);
+    if (u_leaves_dev && !H->external_leaves)
+        EF_CUDA(cudaMemcpyAsync(u_leaves_dev, H->d_u.p, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyDeviceToDevice, H->stream));
+    EF_CUDA(cudaEventRecord(H->ev1, H->stream));
+    if (sync) {
+        EF_CUDA(cudaStreamSynchronize(H->stream)); collect_profile(H);
+        float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
+    }
+    EF_CATCH(H)
+}
+
+int efgpu_operator_device(efgpu_handle* H, int node, int which, double** ptr, int* rows, int* cols)
+{
+    if (!H || !ptr) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    int r = 0, c = 0;
+    if (efgpu_operator_shape(H, node, which, &r, &c) != EF_OK) throw Error{EF_ERR_BAD_ARG, "bad node / operator"};
+    if (!H->allocated) { EF_CUDA(cudaSetDevice(H->device)); allocate_device(H, H->build_flags); }
+    const NodeH& nd = H->nodes[node];
+    const size_t n = nd.size / 2;
+    switch (which) {
+        case EFGPU_OP_T: *ptr = nd.Tbuf[nd.ncoarsen]; break;
+        case EFGPU_OP_T_UNCOARSENED: *ptr = nd.Tbuf[0]; break;
+        case EFGPU_OP_S: *ptr = H->batches[nd.batch].S.as<double>() + nd.slot * 32 * n * n; break;
+        case EFGPU_OP_XINV: *ptr = H->batches[nd.batch].Xinv.as<double>() + nd.slot * 16 * n * n; break;
+        default: throw Error{EF_ERR_UNSUPPORTED, "no device view of this operator (X and H are not stored densely)"};
+    }
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    EF_CATCH(H)
+}
+
+int efgpu_vector_device(efgpu_handle* H, int node, int which, double** ptr, int* len)
+{
+    if (!H || !ptr) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    int l = 0;
+    if (efgpu_vector_length(H, node, which, &l) != EF_OK) throw Error{EF_ERR_BAD_ARG, "bad node / vector"};
+    if (!H->allocated) { EF_CUDA(cudaSetDevice(H->device)); allocate_device(H, H->build_flags); }
+    const NodeH& nd = H->nodes[node];
+    double* vec = H->d_vec.as<double>();
+    switch (which) {
+        case EFGPU_VEC_H: *ptr = vec + nd.hbuf[nd.ncoarsen]; break;
+        case EFGPU_VEC_H_UNCOARSENED: *ptr = vec + nd.hbuf[0]; l = 4 * nd.size; break;
+        case EFGPU_VEC_G: *ptr = vec + nd.gbuf[0]; break;
+        case EFGPU_VEC_W: *ptr = vec + nd.w_off; break;
+        case EFGPU_VEC_U: if (H->external_leaves) throw Error{EF_ERR_BAD_ARG, "external leaves have no u"}; *ptr = H->d_u.as<double>() + (size_t)nd.leaf_idx * l; break;
+        case EFGPU_VEC_F: if (H->external_leaves) throw Error{EF_ERR_BAD_ARG, "external leaves have no f"}; *ptr = H->d_f.as<double>() + (size_t)nd.leaf_idx * l; break;
+        default: throw Error{EF_ERR_BAD_ARG, "bad vector selector"};
+    }
+    if (len) *len = l;
+    EF_CATCH(H)
+}
+
 int efgpu_solve_robin(efgpu_handle* H, const double* a, const double* b, const double* r, unsigned flags, double* u_leaves)
 {
     if (!H || !a || !b || !r) return EF_ERR_BAD_ARG;
+    if (H->roots.size() != 1) { H->last_error = "root boundary solve on a forest handle"; return EF_ERR_STATE; }
     const int len = 4 * H->nodes[0].size;
     for (int i = 0; i < len; i++)
         if (b[i] != 0.0) { H->last_error = "Robin/Neumann root data (b != 0) needs the dense root solve, not built yet"; return EF_ERR_UNSUPPORTED; }
@@ -661,6 +765,17 @@ int efgpu_sync(efgpu_handle* H)
 }
 
 void* efgpu_stream(efgpu_handle* H) { return H ? (void*)H->stream : nullptr; }
+
+int efgpu_set_stream(efgpu_handle* H, void* stream)
+{
+    if (!H || !stream) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    if (H->own_stream) EF_CUDA(cudaStreamDestroy(H->stream));
+    H->stream = (cudaStream_t)stream; H->own_stream = false;
+    EF_CATCH(H)
+}
 
 int efgpu_node_info(const efgpu_handle* H, int node, int* size, int* n_coarsens, int* is_leaf, int* leaf_index)
 {
@@ -725,6 +840,7 @@ int efgpu_vector_length(const efgpu_handle* H, int node, int which, int* len)
     const NodeH& nd = H->nodes[node];
     switch (which) {
         case EFGPU_VEC_H: *len = 4 * (nd.size >> nd.ncoarsen); return EF_OK;   // coarsened in place by coarsenUpwards_
+        case EFGPU_VEC_H_UNCOARSENED: *len = 4 * nd.size; return EF_OK;
         case EFGPU_VEC_G: *len = 4 * nd.size; return EF_OK;                     // uncoarsened in place by uncoarsen_
         case EFGPU_VEC_W: if (nd.leaf) return EF_ERR_BAD_ARG; *len = 2 * nd.size; return EF_OK;
         case EFGPU_VEC_U: case EFGPU_VEC_F: if (!nd.leaf) return EF_ERR_BAD_ARG; *len = nd.size * nd.size; return EF_OK;
@@ -746,6 +862,7 @@ int efgpu_get_vector(efgpu_handle* H, int node, int which, double* out, size_t c
     const double* src = nullptr;
     switch (which) {
         case EFGPU_VEC_H: src = vec + nd.hbuf[nd.ncoarsen]; break;
+        case EFGPU_VEC_H_UNCOARSENED: src = vec + nd.hbuf[0]; break;
         case EFGPU_VEC_G: src = vec + nd.gbuf[0]; break;
         case EFGPU_VEC_W: src = vec + nd.w_off; break;
         case EFGPU_VEC_U: src = H->d_u.as<double>() + (size_t)nd.leaf_idx * len; break;

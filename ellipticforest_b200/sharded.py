@@ -1,0 +1,432 @@
+"""Quadtree sharded by subtree over the GPUs of one NVSwitch domain.
+
+Reference mechanism being replaced: p4est_partition gives every MPI rank a contiguous Morton range
+of leaves (src/Mesh.hpp:169-170); nodes above are replicated on every rank that shares them and
+their children arrive by MPI::broadcast of the WHOLE child patch (src/Quadtree.hpp:464-507,
+src/QuadNode.hpp:191-199, FiniteVolumePatch.cpp:118-134), after which every sharing rank repeats
+the same merge.  Here ownership is static: the tree is cut at `cut` (level 2: 16 subtrees, Morton
+order); rank r owns subtrees [16 r / P, 16 (r+1) / P) - exactly p4est's partition of a uniform
+tree - builds them as one batched forest on its GPU, and only what a parent needs crosses NVLink:
+the subtree roots' DtN maps (build), particular Neumann data h (upwards) and Dirichlet data g
+(solve).  The upper tree (levels < cut) is merged once, on rank 0, never redundantly.
+
+ShardPlan is pure host logic (numpy) and is what the world_size-2 gloo tests exercise; the engines
+(forest / upper-tree handles of libefgpu.so on the GPU; the numpy oracle in the CPU tests) plug in
+underneath through the same small interface.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import TreeDesc, check
+from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, OP, VEC, FiniteVolumeGrid
+
+
+class ShardPlan:
+    """Static ownership of the subtrees below `cut` and the node tables of every piece."""
+
+    def __init__(self, level, child, box, nx, world, cut=2):
+        self.level = np.asarray(level, dtype=np.int32)
+        self.child = np.asarray(child, dtype=np.int32).reshape(-1, 4)
+        self.box = np.asarray(box, dtype=np.float64).reshape(-1, 4)
+        self.nx, self.world, self.cut = int(nx), int(world), int(cut)
+        nn = len(self.level)
+        leaf = self.child[:, 0] < 0
+        if np.any(leaf & (self.level < cut)):
+            raise ValueError("tree too shallow to shard: a leaf lies above the cut level %d" % cut)
+        self.cut_nodes = np.nonzero(self.level == cut)[0]            # pre-order = Morton order
+        ncut = len(self.cut_nodes)
+        if ncut != 4 ** cut or ncut % world:
+            raise ValueError("%d subtrees cannot be dealt to %d ranks" % (ncut, world))
+        self.owner = (np.arange(ncut) * world) // ncut                # contiguous Morton blocks, as p4est_partition
+        # subtree extents: the table is in pre-order, so a subtree is a contiguous id range
+        self.sub_end = np.empty(ncut, dtype=np.int64)
+        for k, r in enumerate(self.cut_nodes):
+            e = r + 1
+            while e < nn and self.level[e] > cut:
+                e += 1
+            self.sub_end[k] = e
+        # node sizes bottom-up: leaf = nx, parent = 2 * min(child sizes) (mergePatch_, HPSAlgorithm.hpp:1004-1009)
+        self.size = np.zeros(nn, dtype=np.int64)
+        for i in range(nn - 1, -1, -1):
+            self.size[i] = self.nx if leaf[i] else 2 * min(self.size[c] for c in self.child[i])
+        self.leaf = leaf
+        self.leaf_index = np.cumsum(leaf) - 1                        # global leaf numbering (pre-order)
+
+    # -- pieces ------------------------------------------------------------------------------
+    def subtrees_of(self, rank) -> List[int]:
+        return [k for k in range(len(self.cut_nodes)) if self.owner[k] == rank]
+
+    def local_table(self, rank):
+        """Forest of the subtrees rank owns: (global ids, level, child (local ids), box, local id of each subtree root)."""
+        ids = np.concatenate([np.arange(self.cut_nodes[k], self.sub_end[k]) for k in self.subtrees_of(rank)])
+        remap = -np.ones(len(self.level), dtype=np.int64)
+        remap[ids] = np.arange(len(ids))
+        child = self.child[ids].copy()
+        m = child >= 0
+        child[m] = remap[child[m]]
+        roots = remap[[self.cut_nodes[k] for k in self.subtrees_of(rank)]]
+        return ids, self.level[ids].copy(), child.astype(np.int32), self.box[ids].copy(), roots.astype(np.int64)
+
+    def local_leaf_range(self, rank):
+        """Global leaf indices [lo, hi) owned by rank (contiguous: Morton order)."""
+        ks = self.subtrees_of(rank)
+        lo_node, hi_node = self.cut_nodes[ks[0]], self.sub_end[ks[-1]]
+        lo = int(np.sum(self.leaf[:lo_node]))
+        return lo, lo + int(np.sum(self.leaf[lo_node:hi_node]))
+
+    def top_table(self):
+        """Upper tree (levels <= cut) whose leaves are the subtree roots: (global ids, level, child (local), box, ext sizes)."""
+        ids = np.nonzero(self.level <= self.cut)[0]
+        remap = -np.ones(len(self.level), dtype=np.int64)
+        remap[ids] = np.arange(len(ids))
+        child = self.child[ids].copy()
+        child[self.level[ids] == self.cut] = -1
+        m = child >= 0
+        child[m] = remap[child[m]]
+        ext = self.size[self.cut_nodes].astype(np.int32)             # one per top-tree leaf, pre-order
+        return ids, self.level[ids].copy(), child.astype(np.int32), self.box[ids].copy(), ext
+
+    def root_size(self):
+        return int(self.size[0])
+
+
+# ---------------------------------------------------------------------------------------------
+def _dev_tensor(ptr: int, n: int):
+    """torch view of `n` doubles of device memory owned by libefgpu.so (no copy)."""
+    import torch
+
+    class _View:
+        pass
+
+    v = _View()
+    v.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(v, device="cuda")
+
+
+class GpuEngine:
+    """One libefgpu handle: a forest of owned subtrees (leaves = FV patches) or the upper tree (external leaves)."""
+
+    def __init__(self, level, child, box, nx, device, ext_sizes=None, stream=None):
+        self._lib = _lib.load()
+        self.level = np.ascontiguousarray(level, dtype=np.int32)
+        self.child = np.ascontiguousarray(child, dtype=np.int32)
+        self.box = np.ascontiguousarray(box, dtype=np.float64)
+        d = TreeDesc()
+        d.n_nodes, d.nx = len(self.level), int(nx)
+        d.level = self.level.ctypes.data_as(C.POINTER(C.c_int32))
+        d.child = self.child.ctypes.data_as(C.POINTER(C.c_int32))
+        d.box = self.box.ctypes.data_as(C.POINTER(C.c_double))
+        self._h = C.c_void_p()
+        ext = None
+        if ext_sizes is not None:
+            self._ext = np.ascontiguousarray(ext_sizes, dtype=np.int32)
+            ext = self._ext.ctypes.data_as(C.POINTER(C.c_int32))
+        check(self._lib.efgpu_create_ex(C.byref(d), device, ext, C.byref(self._h)))
+        if stream:
+            check(self._lib.efgpu_set_stream(self._h, C.c_void_p(stream)), self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.efgpu_destroy(self._h)
+            self._h = None
+
+    def stream(self):
+        return int(self._lib.efgpu_stream(self._h) or 0)
+
+    def set_leaf_constant(self, lam):
+        check(self._lib.efgpu_set_leaf_constant(self._h, float(lam)), self._h)
+
+    def operator_view(self, node, which):
+        p, r, c = C.c_void_p(), C.c_int(), C.c_int()
+        check(self._lib.efgpu_operator_device(self._h, int(node), OP[which], C.byref(p), C.byref(r), C.byref(c)), self._h)
+        return _dev_tensor(p.value, r.value * c.value)
+
+    def vector_view(self, node, which):
+        p, n = C.c_void_p(), C.c_int()
+        code = {"h0": 5}.get(which, VEC.get(which))
+        check(self._lib.efgpu_vector_device(self._h, int(node), code, C.byref(p), C.byref(n)), self._h)
+        return _dev_tensor(p.value, n.value)
+
+    def build(self, flags):
+        check(self._lib.efgpu_build(self._h, flags), self._h)
+
+    def upwards(self, f_dev_ptr, scale, flags, sync=False):
+        check(self._lib.efgpu_upwards_device(self._h, C.c_void_p(f_dev_ptr) if f_dev_ptr else None, float(scale), flags, int(sync)), self._h)
+
+    def solve_from_roots(self, u_dev_ptr, flags, sync=False):
+        check(self._lib.efgpu_solve_from_roots_device(self._h, flags, C.c_void_p(u_dev_ptr) if u_dev_ptr else None, int(sync)), self._h)
+
+    def sync(self):
+        check(self._lib.efgpu_sync(self._h), self._h)
+
+    def set_profiling(self, on):
+        check(self._lib.efgpu_set_profiling(self._h, int(on)), self._h)
+
+    def profile(self):
+        out = {}
+        for cls in range(64):
+            name = self._lib.efgpu_profile_class_name(cls)
+            if not name:
+                break
+            ms, n = C.c_double(), C.c_double()
+            check(self._lib.efgpu_get_profile(self._h, cls, C.byref(ms), C.byref(n)), self._h)
+            out[name.decode()] = (ms.value, n.value)
+        return out
+
+    def stats(self):
+        s = _lib.Stats()
+        check(self._lib.efgpu_get_stats(self._h, C.byref(s)), self._h)
+        return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+
+class ShardedExchange:
+    """The three exchanges of a sharded run, written against torch.distributed point-to-point calls so
+    that the same code runs over NCCL (GPU) and gloo (CPU tests).  `local` / `top` expose
+    root_T(k) / root_h(k) / root_g(k) for the k-th owned subtree and leaf_T(j) / leaf_h(j) / leaf_g(j)
+    for the j-th leaf of the upper tree (tensors that alias the engines' storage)."""
+
+    def __init__(self, plan: ShardPlan, rank: int, dist, root_rank=0):
+        self.plan, self.rank, self.dist, self.root = plan, rank, dist, root_rank
+
+    def _gather(self, send_of, recv_of):
+        """subtree k: owner -> root (root's own subtrees are copied)."""
+        ops, copies = [], []
+        for k in range(len(self.plan.cut_nodes)):
+            o = int(self.plan.owner[k])
+            if self.rank == self.root:
+                if o == self.root:
+                    copies.append((recv_of(k), send_of(k)))
+                else:
+                    ops.append(self.dist.P2POp(self.dist.irecv, recv_of(k), o))
+            elif o == self.rank:
+                ops.append(self.dist.P2POp(self.dist.isend, send_of(k), self.root))
+        for dst, src in copies:
+            dst.copy_(src)
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _scatter(self, send_of, recv_of):
+        """subtree k: root -> owner."""
+        ops, copies = [], []
+        for k in range(len(self.plan.cut_nodes)):
+            o = int(self.plan.owner[k])
+            if self.rank == self.root:
+                if o == self.root:
+                    copies.append((recv_of(k), send_of(k)))
+                else:
+                    ops.append(self.dist.P2POp(self.dist.isend, send_of(k), o))
+            elif o == self.rank:
+                ops.append(self.dist.P2POp(self.dist.irecv, recv_of(k), self.root))
+        for dst, src in copies:
+            dst.copy_(src)
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def gather_T(self, local, top):
+        self._gather(lambda k: local.root_T(k), lambda k: top.leaf_T(k) if top is not None else None)
+
+    def gather_h(self, local, top):
+        self._gather(lambda k: local.root_h(k), lambda k: top.leaf_h(k) if top is not None else None)
+
+    def scatter_g(self, top, local):
+        self._scatter(lambda k: top.leaf_g(k) if top is not None else None, lambda k: local.root_g(k))
+
+
+class _LocalGpu:
+    def __init__(self, eng: GpuEngine, roots, my_subtrees):
+        self.eng = eng
+        self.idx = {k: int(r) for k, r in zip(my_subtrees, roots)}
+
+    def root_T(self, k):
+        return self.eng.operator_view(self.idx[k], "T_uncoarsened")
+
+    def root_h(self, k):
+        return self.eng.vector_view(self.idx[k], "h0")
+
+    def root_g(self, k):
+        return self.eng.vector_view(self.idx[k], "g")
+
+
+class _TopGpu:
+    def __init__(self, eng: GpuEngine, leaf_nodes):
+        self.eng, self.leaf_nodes = eng, leaf_nodes
+
+    def leaf_T(self, j):
+        return self.eng.operator_view(self.leaf_nodes[j], "T_uncoarsened")
+
+    def leaf_h(self, j):
+        return self.eng.vector_view(self.leaf_nodes[j], "h0")
+
+    def leaf_g(self, j):
+        return self.eng.vector_view(self.leaf_nodes[j], "g")
+
+
+class ShardedHPS:
+    """Benchmark/driver-facing sharded HPS (same stage names as HPSAlgorithm; inputs/outputs are this rank's share)."""
+
+    def __init__(self, mesh, solver, device=0, rank=0, world=1, options=None, cut=2):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.mesh, self.patch_solver, self.rank, self.world, self._device = mesh, solver, rank, world, device
+        self.options = {"cache-operators": False, "homogeneous-rhs": False}
+        if options:
+            self.options.update(options)
+        if solver.solver_type != "FISHPACK90":
+            raise NotImplementedError("sharded runs: constant-coefficient leaves only for now")
+        self.plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, cut)
+        ids, lev, ch, box, roots = self.plan.local_table(rank)
+        self.local = GpuEngine(lev, ch, box, mesh.nx, device)
+        self._stream = torch.cuda.ExternalStream(self.local.stream())
+        self.local_if = _LocalGpu(self.local, roots, self.plan.subtrees_of(rank))
+        self.top = self.top_if = None
+        if rank == 0:
+            tids, tlev, tch, tbox, ext = self.plan.top_table()
+            self.top = GpuEngine(tlev, tch, tbox, mesh.nx, device, ext_sizes=ext, stream=self.local.stream())
+            self.top_if = _TopGpu(self.top, [int(i) for i in np.nonzero(tch[:, 0] < 0)[0]])
+        self.xchg = ShardedExchange(self.plan, rank, dist)
+        self.leaf_lo, self.leaf_hi = self.plan.local_leaf_range(rank)
+        lam = float(solver.lambda_function(np.float64(0.0), np.float64(0.0)))
+        self.local.set_leaf_constant(lam)
+
+    def __del__(self):
+        self.top_if = self.top = None      # the upper-tree handle borrows the forest handle's stream: release it first
+        self.local_if = self.local = None
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _flags(self):
+        return (CACHE_OPERATORS if self.options["cache-operators"] else 0) | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0)
+
+    def sharding(self):
+        return "level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); subtree-root T/h gathered to rank 0 over NCCL, g scattered back" % (
+            self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world)
+
+    def stream(self):
+        return self.local.stream()
+
+    def setupStage(self):
+        return None
+
+    def sample_inputs(self, f_fn, u_fn):
+        """This rank's share of f (its leaves, global pre-order) and the root Dirichlet data (rank 0 uses it)."""
+        m = self.mesh
+        b = m.box[m.leaf_nodes[self.leaf_lo:self.leaf_hi]]
+        M = m.nx
+        dx = (b[:, 1] - b[:, 0]) / M
+        dy = (b[:, 3] - b[:, 2]) / M
+        k = np.arange(M)
+        xs = (b[:, 0] + dx / 2)[:, None] + k[None, :] * dx[:, None]
+        ys = (b[:, 2] + dy / 2)[:, None] + k[None, :] * dy[:, None]
+        X = np.broadcast_to(xs[:, :, None], (len(b), M, M))
+        Y = np.broadcast_to(ys[:, None, :], (len(b), M, M))
+        self._XY = (X, Y)
+        f = np.ascontiguousarray(f_fn(X, Y), dtype=np.float64).reshape(-1)
+        size = self.plan.root_size()
+        xl, xu, yl, yu = m.box[0]
+        g = FiniteVolumeGrid(size, xl, xu, size, yl, yu)
+        kk = np.arange(size)
+        xs, ys = g.point(0, kk), g.point(1, kk)
+        x = np.concatenate([np.full(size, xl), np.full(size, xu), xs, xs])
+        y = np.concatenate([ys, ys, np.full(size, yl), np.full(size, yu)])
+        gr = np.ascontiguousarray(u_fn(x, y), dtype=np.float64).reshape(-1)
+        return f, gr
+
+    # -- stages --------------------------------------------------------------------------------
+    def buildStage(self):
+        fl = self._flags()
+        self.local.build(fl)
+        with self.torch.cuda.stream(self._stream):
+            self.xchg.gather_T(self.local_if, self.top_if)
+        if self.top is not None:
+            self.top.build(fl)
+
+    def upwardsStageDevice(self, f_dev_ptr, scale=1.0, sync=True):
+        fl = self._flags()
+        self.local.upwards(f_dev_ptr, scale, fl)
+        if not (fl & HOMOGENEOUS_RHS):
+            with self.torch.cuda.stream(self._stream):
+                self.xchg.gather_h(self.local_if, self.top_if)
+            if self.top is not None:
+                self.top.upwards(0, 1.0, fl)
+        if sync:
+            self.local.sync()
+
+    def solveStageDevice(self, g_dev_ptr, u_dev_ptr=0, sync=True):
+        fl = self._flags()
+        if self.top is not None:
+            groot = self.top.vector_view(0, "g")
+            with self.torch.cuda.stream(self._stream):
+                groot.copy_(_dev_tensor(g_dev_ptr, groot.numel()))
+            self.top.solve_from_roots(0, fl)
+        with self.torch.cuda.stream(self._stream):
+            self.xchg.scatter_g(self.top_if, self.local_if)
+        self.local.solve_from_roots(u_dev_ptr, fl, sync=sync)
+
+    def upwardsStageHost(self, f_host):
+        t = self.torch
+        if getattr(self, "_f_dev", None) is None:
+            self._f_dev = t.empty(f_host.size, dtype=t.float64, device="cuda")
+        with t.cuda.stream(self._stream):
+            self._f_dev.copy_(t.from_numpy(f_host), non_blocking=True)
+        self.upwardsStageDevice(self._f_dev.data_ptr(), 1.0, sync=True)
+
+    def solveStageHost(self, g_host, u_host):
+        t = self.torch
+        if getattr(self, "_u_dev", None) is None:
+            self._u_dev = t.empty(u_host.size, dtype=t.float64, device="cuda")
+            self._g_dev = t.empty(g_host.size, dtype=t.float64, device="cuda")
+        with t.cuda.stream(self._stream):
+            self._g_dev.copy_(t.from_numpy(g_host), non_blocking=True)
+        self.solveStageDevice(self._g_dev.data_ptr(), self._u_dev.data_ptr(), sync=False)
+        with t.cuda.stream(self._stream):
+            t.from_numpy(u_host).copy_(self._u_dev, non_blocking=True)
+        self.local.sync()
+
+    def sync(self):
+        self.local.sync()
+
+    # -- reporting -----------------------------------------------------------------------------
+    def set_profiling(self, on=True):
+        self.local.set_profiling(on)
+        if self.top is not None:
+            self.top.set_profiling(on)
+
+    def profile(self):
+        """Per-class (ms, launches) of this rank: its forest plus, on rank 0, the upper tree."""
+        p = self.local.profile()
+        if self.top is not None:
+            for k, (ms, n) in self.top.profile().items():
+                p[k] = (p[k][0] + ms, p[k][1] + n)
+        return p
+
+    def stats(self):
+        s = self.local.stats()
+        if self.top is not None:
+            ts = self.top.stats()
+            for k in ("merge_flops_canonical", "merge_flops_issued", "upwards_bytes", "solve_bytes", "device_bytes"):
+                s[k] += ts[k]
+            for k in ("build_ms", "upwards_ms", "solve_ms"):
+                s[k] += ts[k]
+        return s
+
+    def total_issued_flops(self):
+        """Whole-tree issued flops (sum over ranks)."""
+        t = self.torch.tensor([self.stats()["merge_flops_issued"]], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return float(t[0])
+
+    def max_error(self, u_dev, u_fn):
+        X, Y = self._XY
+        u = u_dev.cpu().numpy().reshape(X.shape)
+        e = self.torch.tensor([float(np.max(np.abs(u - u_fn(X, Y))))], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(e, op=self.dist.ReduceOp.MAX)
+        return float(e[0])

@@ -55,7 +55,7 @@ enum { EFGPU_LEAF_CONSTANT = 0, EFGPU_LEAF_VARIABLE = 1 };
 
 /* operator / vector selectors for the parity accessors */
 enum { EFGPU_OP_T = 0, EFGPU_OP_S = 1, EFGPU_OP_X = 2, EFGPU_OP_H = 3, EFGPU_OP_XINV = 4, EFGPU_OP_T_UNCOARSENED = 5 };
-enum { EFGPU_VEC_H = 0, EFGPU_VEC_W = 1, EFGPU_VEC_G = 2, EFGPU_VEC_U = 3, EFGPU_VEC_F = 4 };
+enum { EFGPU_VEC_H = 0, EFGPU_VEC_W = 1, EFGPU_VEC_G = 2, EFGPU_VEC_U = 3, EFGPU_VEC_F = 4, EFGPU_VEC_H_UNCOARSENED = 5 };
 
 /* kernel classes of the optional per-launch profiling (efgpu_set_profiling / efgpu_get_profile) */
 enum {
@@ -90,6 +90,13 @@ typedef struct {
 
 /* ---- lifetime: replaces HPSAlgorithm ctor (HPSAlgorithm.hpp:78-82) + the Quadtree walk ---------- */
 int efgpu_create(const efgpu_tree_desc* desc, int device, efgpu_handle** out);
+/* Sharded runs (replaces the reference's rank-shared upper tree, Quadtree.hpp:146-151,464-507, where child
+ * patches arrive by MPI::broadcast(Node), QuadNode.hpp:191-199).  The node table may be a FOREST (several nodes
+ * without a parent: the subtrees one GPU owns), and with external_leaf_size != NULL (one entry per leaf, cells per
+ * side) the leaves are not finite-volume patches but already-merged subtrees whose DtN map / particular Neumann
+ * data the caller writes into the device views below (e.g. as the target of an NCCL receive) before
+ * efgpu_build / efgpu_upwards_device, and whose Dirichlet data it reads back after efgpu_solve_*_device. */
+int efgpu_create_ex(const efgpu_tree_desc* desc, int device, const int32_t* external_leaf_size, efgpu_handle** out);
 void efgpu_destroy(efgpu_handle* h);
 const char* efgpu_last_error(const efgpu_handle* h);   /* h may be NULL after a failed create */
 
@@ -112,9 +119,16 @@ int efgpu_upwards_device(efgpu_handle* h, const double* f_leaves_dev, double fsc
 int efgpu_solve_dirichlet(efgpu_handle* h, const double* g_root, unsigned flags, double* u_leaves);
 int efgpu_solve_dirichlet_device(efgpu_handle* h, const double* g_root_dev, unsigned flags, double* u_leaves_dev, int sync);
 /* solveStage(fn(side,x,y,*a,*b)) (HPSAlgorithm.hpp:343-445): a u + b du/dn = r sampled at the root grid. */
+/* solve with the Dirichlet data of every root already written into its EFGPU_VEC_G device view (forest handles) */
+int efgpu_solve_from_roots_device(efgpu_handle* h, unsigned flags, double* u_leaves_dev, int sync);
+/* device views of a node's operators / vectors (valid until efgpu_destroy; allocate the handle's memory on first use).
+ * which: T, T_UNCOARSENED, S, XINV / any EFGPU_VEC_*.  Work of the handle is ordered on efgpu_stream(h). */
+int efgpu_operator_device(efgpu_handle* h, int node, int which, double** ptr, int* rows, int* cols);
+int efgpu_vector_device(efgpu_handle* h, int node, int which, double** ptr, int* len);
 int efgpu_solve_robin(efgpu_handle* h, const double* a, const double* b, const double* r, unsigned flags, double* u_leaves);
 int efgpu_sync(efgpu_handle* h);
 void* efgpu_stream(efgpu_handle* h);   /* the cudaStream_t all work of this handle is issued on */
+int efgpu_set_stream(efgpu_handle* h, void* stream);   /* adopt a caller-owned cudaStream_t (e.g. share one stream between two handles) */
 
 /* ---- parity accessors: replace reading patch.matrixT()/S()/X()/H(), vectorH()/W()/G()/U() (Patch.hpp:103-171) */
 int efgpu_node_info(const efgpu_handle* h, int node, int* size, int* n_coarsens, int* is_leaf, int* leaf_index);

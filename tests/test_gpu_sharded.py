@@ -1,0 +1,104 @@
+"""GPU tests of the sharded path: forest handles (several subtree roots in one batched plan), the
+upper-tree handle with external leaves, and the NCCL exchanges.  With world = 1 one GPU owns all 16
+subtrees, which exercises every code path except the wire; the 2-rank NCCL test runs when the box has
+two GPUs.  Results must equal the unsharded handle's (same kernels, same per-node arithmetic)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import ellipticforest_b200 as ef
+import hps_oracle as O
+from ellipticforest_b200.sharded import ShardedHPS
+from test_host import _mesh_for
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "uniform_l3_m16": dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16, min_level=3, max_level=3,
+                           threshold=1.2, refine_box=None),
+    "adaptive_l2_4_m8": dict(problem_name="poisson", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=2, max_level=4,
+                             threshold=1.2, refine_box=(-10.0, 0.5, -10.0, 0.5)),
+}
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _solver(P):
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FISHPACK90"
+    s.alpha_function, s.beta_function, s.lambda_function = P["alpha"], P["beta"], P["lam"]
+    return s
+
+
+def _run_sharded(kw, rank, world, device):
+    import torch
+    P = O.problem(kw["problem_name"])
+    m = _mesh_for(kw)
+    hps = ShardedHPS(m, _solver(P), device=device, rank=rank, world=world)
+    f, g = hps.sample_inputs(P["f"], P["u"])
+    f_dev = torch.from_numpy(f).cuda(device)
+    g_dev = torch.from_numpy(g).cuda(device)
+    u_dev = torch.empty_like(f_dev)
+    hps.buildStage()
+    hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True)
+    hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True)
+    rootT = hps.top.operator_view(0, "T").cpu().numpy() if hps.top is not None else None
+    return hps, u_dev.cpu().numpy(), rootT
+
+
+def _run_single(kw):
+    P = O.problem(kw["problem_name"])
+    m = _mesh_for(kw)
+    hps = ef.HPSAlgorithm(m, _solver(P))
+    hps.buildStage()
+    hps.upwardsStage(P["f"])
+    hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0))
+    return hps
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_forest_and_upper_tree_on_one_gpu(case):
+    kw = CASES[case]
+    single = _run_single(kw)
+    hps, u, rootT = _run_sharded(kw, 0, 1, 0)
+    assert relerr(u, single.u_leaves.reshape(-1)) < 1e-12
+    assert relerr(rootT, single.operator(0, "T").reshape(-1)) < 1e-12
+    # and against the oracle, like every other parity test
+    ora = O.run(**kw)
+    assert relerr(u, np.concatenate(ora.leaf_solution())) < 1e-10
+
+
+def _worker(rank, world, port, case, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        hps, u, rootT = _run_sharded(CASES[case], rank, world, rank)
+        np.save(os.path.join(out_dir, "u_%d.npy" % rank), u)
+        np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array([hps.leaf_lo, hps.leaf_hi]))
+        if rootT is not None:
+            np.save(os.path.join(out_dir, "T_root.npy"), rootT)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_two_gpus_over_nccl(case, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+    single = _run_single(CASES[case])
+    u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
+    for r in range(2):
+        lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
+        assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-12
+    assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12

@@ -1,0 +1,239 @@
+"""World-size-2 gloo tests (CPU) of the sharded path's host logic: the ShardPlan node tables, the
+Morton-block ownership and the three exchanges (gather T, gather h, scatter g) of
+ellipticforest_b200.sharded.ShardedExchange.  The arithmetic underneath is the numpy oracle (test
+infrastructure); on the GPU box the same plan/exchange code drives libefgpu handles over NCCL
+(tests/test_gpu_sharded.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import hps_oracle as O
+from ellipticforest_b200.sharded import ShardPlan, ShardedExchange
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _tables(nodes):
+    level = np.array([n.level for n in nodes], dtype=np.int32)
+    child = np.array([n.children if n.children else [-1] * 4 for n in nodes], dtype=np.int32)
+    box = np.array([[n.grid.xl, n.grid.xu, n.grid.yl, n.grid.yu] for n in nodes])
+    return level, child, box
+
+
+class OracleEngine:
+    """Forest (FV leaves) or upper tree (external leaves) driven by the numpy oracle's per-node functions."""
+
+    def __init__(self, level, child, box, nx, solver, ext_sizes=None):
+        self.nodes, self.ext = [], ext_sizes is not None
+        li = 0
+        for i in range(len(level)):
+            leaf = child[i][0] < 0
+            n = int(ext_sizes[li]) if (leaf and self.ext) else nx
+            li += int(leaf)
+            self.nodes.append(O.Node(path=str(i), level=int(level[i]), grid=O.Grid(n, *box[i]), leaf=bool(leaf),
+                                     children=[] if leaf else [int(c) for c in child[i]]))
+        for i, nd in enumerate(self.nodes):
+            for c in nd.children:
+                self.nodes[c].parent = i
+        self.roots = [i for i, nd in enumerate(self.nodes) if nd.parent < 0]
+        self.hps = O.HPS(self.nodes, solver)
+        self.buf = {}
+
+    def _post(self):
+        return [i for r in self.roots for i in O.post_order(self.nodes, r)]
+
+    def tensor(self, node, name, n):
+        """storage that outlives the exchange (the engines' 'device views')"""
+        key = (node, name)
+        if key not in self.buf:
+            self.buf[key] = torch.zeros(n, dtype=torch.float64)
+        return self.buf[key]
+
+    def build(self):
+        for i in self._post():
+            nd = self.nodes[i]
+            if nd.leaf:
+                if self.ext:
+                    nd.T = self.buf[(i, "T")].numpy().reshape(4 * nd.grid.nx, 4 * nd.grid.nx).copy()
+                else:
+                    nd.T = self.hps.solver.buildD2N(nd.grid)
+            else:
+                self.hps.merge4to1(nd, *[self.nodes[c] for c in nd.children])
+
+    def upwards(self, f_fn):
+        for i in self._post():
+            nd = self.nodes[i]
+            if nd.leaf:
+                if self.ext:
+                    nd.h = self.buf[(i, "h")].numpy().copy()
+                else:
+                    g = nd.grid
+                    X, Y = np.meshgrid(g.x(np.arange(g.nx)), g.y(np.arange(g.nx)), indexing="ij")
+                    nd.f = np.asarray(f_fn(X, Y), dtype=np.float64).reshape(-1)
+                    nd.h = self.hps.solver.particularNeumannData(g, nd.f)
+            else:
+                self.hps.upwards4to1(nd, *[self.nodes[c] for c in nd.children])
+
+    def solve(self):
+        order = []
+        def pre(i):
+            order.append(i)
+            for c in self.nodes[i].children:
+                pre(c)
+        for r in self.roots:
+            pre(r)
+        for i in order:
+            nd = self.nodes[i]
+            if nd.leaf:
+                if not self.ext:
+                    nd.u = self.hps.solver.solve(nd.grid, nd.g, nd.f)
+                else:  # a subtree root tagged by its parent receives coarsened data: uncoarsen_ (HPSAlgorithm.hpp:1165-1183)
+                    for n in range(nd.n_coarsens):
+                        nfine = nd.grid.nx // (2 ** (nd.n_coarsens - (n + 1)))
+                        nd.g = O._blkdiag4(O.L12(nfine)) @ nd.g
+            else:
+                self.hps.split1to4(nd, *[self.nodes[c] for c in nd.children])
+
+
+class LocalIf:
+    def __init__(self, eng, roots, subtrees):
+        self.eng, self.idx = eng, {k: int(r) for k, r in zip(subtrees, roots)}
+
+    def root_T(self, k):
+        nd = self.eng.nodes[self.idx[k]]
+        return torch.from_numpy(np.ascontiguousarray(nd.T)).reshape(-1)
+
+    def root_h(self, k):
+        return torch.from_numpy(np.ascontiguousarray(self.eng.nodes[self.idx[k]].h))
+
+    def root_g(self, k):
+        nd = self.eng.nodes[self.idx[k]]
+        return self.eng.tensor(self.idx[k], "g", 4 * nd.grid.nx)
+
+
+class TopIf:
+    def __init__(self, eng):
+        self.eng = eng
+        self.leaves = [i for i, nd in enumerate(eng.nodes) if nd.leaf]
+
+    def leaf_T(self, j):
+        i = self.leaves[j]
+        return self.eng.tensor(i, "T", (4 * self.eng.nodes[i].grid.nx) ** 2)
+
+    def leaf_h(self, j):
+        i = self.leaves[j]
+        return self.eng.tensor(i, "h", 4 * self.eng.nodes[i].grid.nx)
+
+    def leaf_g(self, j):
+        return torch.from_numpy(np.ascontiguousarray(self.eng.nodes[self.leaves[j]].g))
+
+
+CASES = {
+    "uniform": dict(problem_name="helmholtz", box=(0.0, np.pi, 0.0, np.pi), nx=8, min_level=3, max_level=3, refine_box=None),
+    # adaptive below the cut, including a subtree root that is coarsened by its parent's merge
+    "adaptive": dict(problem_name="poisson", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=2, max_level=4, refine_box=(-10.0, 0.5, -10.0, 0.5)),
+}
+
+
+def _worker(rank, world, port, case, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kw = CASES[case]
+        P = O.problem(kw["problem_name"])
+        ind = O.refine_box_indicator(kw["refine_box"]) if kw["refine_box"] else O.refine_indicator(1.2)
+        nodes = O.build_tree(ind, kw["box"], kw["nx"], kw["min_level"], kw["max_level"])
+        solver = O.Solver(kind="fishpack", alpha=P["alpha"], beta=P["beta"], lam=P["lam"])
+        plan = ShardPlan(*_tables(nodes), kw["nx"], world)
+        ids, lev, ch, box, roots = plan.local_table(rank)
+        local = OracleEngine(lev, ch, box, kw["nx"], solver)
+        lif = LocalIf(local, roots, plan.subtrees_of(rank))
+        top = tif = None
+        if rank == 0:
+            tids, tlev, tch, tbox, ext = plan.top_table()
+            top = OracleEngine(tlev, tch, tbox, kw["nx"], solver, ext_sizes=ext)
+            tif = TopIf(top)
+        x = ShardedExchange(plan, rank, dist)
+        # build
+        local.build()
+        x.gather_T(lif, tif)
+        if top:
+            top.build()
+        # upwards
+        local.upwards(P["f"])
+        x.gather_h(lif, tif)
+        if top:
+            top.upwards(None)
+        # solve
+        if top:
+            r, a, b = O.HPS(nodes, solver).root_boundary.__func__(type("R", (), {"nodes": [top.nodes[0]]})(), lambda s, xx, yy: (float(P["u"](xx, yy)), 1.0, 0.0))
+            top.nodes[0].g = r / a
+            top.solve()
+        x.scatter_g(tif, lif)
+        for k in plan.subtrees_of(rank):
+            local.nodes[lif.idx[k]].g = lif.root_g(k).numpy().copy()
+        local.solve()
+        u = np.concatenate([nd.u for nd in local.nodes if nd.leaf])
+        np.save(os.path.join(out_dir, "u_%d.npy" % rank), u)
+        np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array(plan.local_leaf_range(rank)))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "T_root.npy"), top.nodes[0].T)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_two_rank_sharded_run_matches_single_process_oracle(case, tmp_path):
+    kw = CASES[case]
+    mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    ref = O.run(solver_kind="fishpack", **kw)
+    u_ref = ref.leaf_solution()
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    lo_seen = 0
+    for r in range(2):
+        lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
+        assert lo == lo_seen
+        lo_seen = hi
+        u = np.load(tmp_path / ("u_%d.npy" % r))
+        assert rel(u, np.concatenate(u_ref[lo:hi])) < 1e-11
+    assert lo_seen == len(u_ref)
+    assert rel(np.load(tmp_path / "T_root.npy"), ref.nodes[0].T) < 1e-11
+
+
+def test_shard_plan_tables():
+    nodes = O.build_tree(O.refine_indicator(1.2), (0.0, 1.0, 0.0, 1.0), 8, 3, 3)
+    level, child, box = _tables(nodes)
+    for world in (1, 2, 4, 8, 16):
+        plan = ShardPlan(level, child, box, 8, world)
+        assert len(plan.cut_nodes) == 16
+        seen, leaves = [], 0
+        for r in range(world):
+            ids, lev, ch, bx, roots = plan.local_table(r)
+            assert len(roots) == 16 // world and np.all(lev[roots] == 2)
+            assert np.all(ch[ch >= 0] < len(ids)) and np.all(ch[ch >= 0] > 0)
+            seen.extend(ids.tolist())
+            lo, hi = plan.local_leaf_range(r)
+            assert lo == leaves
+            leaves = hi
+        assert leaves == 64 and sorted(seen) == [i for i in range(len(nodes)) if level[i] >= 2]
+        tids, tlev, tch, tbox, ext = plan.top_table()
+        assert len(tids) == 21 and list(ext) == [16] * 16 and plan.root_size() == 64
+    with pytest.raises(ValueError):
+        ShardPlan(level, child, box, 8, 3)
+    shallow = O.build_tree(O.refine_indicator(1.2), (0.0, 1.0, 0.0, 1.0), 8, 1, 1)
+    with pytest.raises(ValueError):
+        ShardPlan(*_tables(shallow), 8, 2)
