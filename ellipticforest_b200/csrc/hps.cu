@@ -101,6 +101,7 @@ struct efgpu_handle {
     int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
     // device state
     DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
+    DevBuf d_coef_in[6], d_coef, d_P;            // variable-coefficient leaves: sampled alpha/beta/lambda, stencil coefficients, block-LU inverses
     size_t vec_doubles = 0;
     bool allocated = false, built = false, upwards_done = false;
     const double* f_cur = nullptr; double fscale_cur = 1.0;   // load of the last upwards call (re-used by the leaf solves)
@@ -448,7 +449,23 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
 static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
 {
     if (H->external_leaves) return;   // leaf DtN maps were written by the caller (efgpu_operator_device)
-    if (H->leaf_kind != EFGPU_LEAF_CONSTANT) throw Error{EF_ERR_UNSUPPORTED, "variable-coefficient leaves are not built yet"};
+    if (H->leaf_kind == EFGPU_LEAF_VARIABLE) {
+        const int M = H->M;
+        if (!H->d_coef_in[0].p) throw Error{EF_ERR_STATE, "variable-coefficient leaves: efgpu_set_leaf_variable was not called"};
+        H->d_coef.alloc((size_t)H->n_leaves * 4 * M * M * sizeof(double));
+        H->d_P.alloc((size_t)H->n_leaves * M * M * M * sizeof(double));
+        const double* cin[6];
+        for (int k = 0; k < 6; k++) cin[k] = H->d_coef_in[k].as<double>();
+        timed(H, EFGPU_PROF_LEAF_LU, 1, [&] {
+            launch_leaf_var_factor(M, cin, H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->d_coef.as<double>(), H->d_P.as<double>(),
+                                   H->d_minpiv.as<double>(), H->n_leaves, H->stream);
+        });
+        const bool cache = (flags & EFGPU_CACHE_OPERATORS) != 0;   // quirk q1: the first leaf's T for every leaf
+        launch_leaf_var_solve(M, H->d_coef.as<double>(), H->d_P.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), nullptr, 1.0,
+                              nullptr, nullptr, nullptr, H->d_leafT.as<double>(), 2, cache ? 1 : H->n_leaves, H->stream);
+        if (cache) launch_broadcast_leaf_T(H->d_leafT.as<double>(), M, H->n_leaves, H->stream);
+        return;
+    }
     launch_leaf_dtn_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
                           H->d_leafT.as<double>(), H->n_leaves, (flags & EFGPU_CACHE_OPERATORS) != 0, H->stream);
 }
@@ -496,8 +513,12 @@ static void do_upwards(efgpu_handle* H, const double* f_dev, double fscale, unsi
     cudaStream_t s = H->stream;
     EF_CUDA(cudaEventRecord(H->ev0, s));
     if (!H->external_leaves) timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
-        launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
-                                f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
+        if (H->leaf_kind == EFGPU_LEAF_VARIABLE)
+            launch_leaf_var_solve(H->M, H->d_coef.as<double>(), H->d_P.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), f_dev, fscale,
+                                  nullptr, nullptr, H->d_leaf_h.as<double*>(), nullptr, 1, H->n_leaves, s);
+        else
+            launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                                    f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
     });
     if (!(flags & EFGPU_HOMOGENEOUS_RHS))   // upwards4to1 is skipped entirely (HPSAlgorithm.hpp:532)
         for (int lev = H->max_level; lev >= 0; lev--)
@@ -526,8 +547,12 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
     for (size_t t = 0; t < H->extG.size(); t++)
         timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(H->d_extG[t]->as<CoarsenOp>(), (int)H->extG[t].size(), H->extG_max[t], s); });
     if (!H->external_leaves) timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
-        launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
-                                homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
+        if (H->leaf_kind == EFGPU_LEAF_VARIABLE)
+            launch_leaf_var_solve(H->M, H->d_coef.as<double>(), H->d_P.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(),
+                                  homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, nullptr, 0, H->n_leaves, s);
+        else
+            launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
+                                    homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
     });
 }
 
@@ -593,11 +618,22 @@ int efgpu_set_leaf_constant(efgpu_handle* H, double lambda)
     return EF_OK;
 }
 
-int efgpu_set_leaf_variable(efgpu_handle* H, const double*, const double*, const double*, const double*, const double*, const double*)
+int efgpu_set_leaf_variable(efgpu_handle* H, const double* alpha, const double* beta_w, const double* beta_e, const double* beta_s,
+                            const double* beta_n, const double* lambda)
 {
-    if (!H) return EF_ERR_BAD_ARG;
-    H->last_error = "variable-coefficient leaves are not built yet";
-    return EF_ERR_UNSUPPORTED;
+    if (!H || !alpha || !beta_w || !beta_e || !beta_s || !beta_n || !lambda) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    if (H->external_leaves) throw Error{EF_ERR_STATE, "external leaves have no coefficients"};
+    EF_CUDA(cudaSetDevice(H->device));
+    const double* src[6] = {alpha, beta_w, beta_e, beta_s, beta_n, lambda};
+    const size_t bytes = (size_t)H->n_leaves * H->M * H->M * sizeof(double);
+    for (int k = 0; k < 6; k++) {
+        H->d_coef_in[k].alloc(bytes);
+        EF_CUDA(cudaMemcpyAsync(H->d_coef_in[k].p, src[k], bytes, cudaMemcpyHostToDevice, H->stream));
+    }
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    H->leaf_kind = EFGPU_LEAF_VARIABLE; H->built = false;
+    EF_CATCH(H)
 }
 
 int efgpu_build(efgpu_handle* H, unsigned flags)

@@ -31,6 +31,15 @@ void launch_leaf_solve_const(int M, const double* Q, const double* boxes, const 
                              const double* f, double fscale, double* const* g_ptrs, double* u_out, double* const* h_ptrs,
                              int mode, int n_leaves, cudaStream_t s);
 
+// variable-coefficient leaves: coef_in = {alpha, beta_w, beta_e, beta_s, beta_n, lambda} (device, leaf-major);
+// coef = n_leaves x 4 x M^2 (cW, cE, cS, cN), P = n_leaves x M x M^2 (inverse diagonal blocks of the block LU)
+void launch_leaf_var_factor(int M, const double* const* coef_in, const double* boxes, const int* leaf_nodes, double* coef, double* P,
+                            double* min_pivot, int n_leaves, cudaStream_t s);
+// mode 0: u = solve(g, f); mode 1: h = mapD2N(0, f); mode 2: T = buildD2N
+void launch_leaf_var_solve(int M, const double* coef, const double* P, const double* boxes, const int* leaf_nodes, const double* f, double fscale,
+                           double* const* g_ptrs, double* u_out, double* const* h_ptrs, double* T_all, int mode, int n_leaves, cudaStream_t s);
+void launch_broadcast_leaf_T(double* T_all, int M, int n_leaves, cudaStream_t s);
+
 // vec.cu
 void launch_assemble_X(const MergeEntry* e, int n, int count, cudaStream_t s);
 void launch_assemble_Hc(const MergeEntry* e, int n, int count, cudaStream_t s);

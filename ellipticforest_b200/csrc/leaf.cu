@@ -152,6 +152,263 @@ leaf_solve_const_kernel(const double* __restrict__ Q, const double* __restrict__
     }
 }
 
+
+// =================================================================================================
+// Variable-coefficient leaves (reference: FivePointStencil branch, FiniteVolumeSolver.cpp:27-223).
+// The reference assembles the dense M^2 x M^2 five-point matrix and LU-factorises it (PETSc ->
+// LAPACK dgetrf, partial pivoting) once per solve() call, i.e. 4M+ times per leaf.  With cells
+// ordered j + i*M the matrix is block tridiagonal: M diagonal blocks D_i (tridiagonal in j, M x M),
+// off-diagonal blocks W_i = diag(cW[i][.]), E_i = diag(cE[i][.]).  Here each leaf is factorised ONCE
+// by block elimination along i (no pivoting: the matrix is row diagonally dominant for lambda <= 0):
+//     Delta_0 = D_0,  Delta_i = D_i - W_i Delta_{i-1}^{-1} E_{i-1},   P_i = Delta_i^{-1}  (dense M x M, stored)
+// and every later solve is two sweeps of M x M mat-vecs:
+//     forward   y_i = r_i - W_i z_{i-1},  z_i = P_i y_i
+//     backward  u_{M-1} = z_{M-1},        u_i = z_i - P_i (E_i u_{i+1}).
+// =================================================================================================
+
+// One CTA per leaf, thread (r, c) owns element (r, c) of the current block in a register; the
+// Gauss-Jordan inverse broadcasts pivot row / column through double-buffered shared memory
+// (one barrier per pivot).
+template <int M>
+__global__ void __launch_bounds__(M * M)
+leaf_var_factor_kernel(const double* __restrict__ alpha, const double* __restrict__ bw, const double* __restrict__ be,
+                       const double* __restrict__ bs, const double* __restrict__ bn, const double* __restrict__ lam,
+                       const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
+                       double* __restrict__ coef, double* __restrict__ P_all, double* __restrict__ min_pivot)
+{
+    __shared__ double sRow[2][M];
+    __shared__ double sCol[2][M];
+    __shared__ double sCE[M];   // cE of the previous block column
+    const int leaf = blockIdx.x;
+    const int r = threadIdx.x / M, c = threadIdx.x % M;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    const size_t cell0 = (size_t)leaf * M * M;
+    double* cf = coef + (size_t)leaf * 4 * M * M;
+    // coefficients (FiniteVolumeSolver.cpp:74-85); thread (r, c) handles cell i = r, j = c
+    {
+        const size_t k = cell0 + threadIdx.x;   // j + i*M with i = r, j = c
+        const double a = alpha[k];
+        cf[0 * M * M + threadIdx.x] = a * bw[k] / (dx * dx);
+        cf[1 * M * M + threadIdx.x] = a * be[k] / (dx * dx);
+        cf[2 * M * M + threadIdx.x] = a * bs[k] / (dy * dy);
+        cf[3 * M * M + threadIdx.x] = a * bn[k] / (dy * dy);
+    }
+    __syncthreads();
+    double prev = 0.0;   // P_{i-1}[r][c]
+    double minp = 1e300;
+    for (int i = 0; i < M; i++) {
+        // block row i, element (r, c): r, c are j indices
+        double a = 0.0;
+        {
+            const size_t kr = cell0 + (size_t)i * M + r;
+            const double al = alpha[kr];
+            const double cW = al * bw[kr] / (dx * dx), cE = al * be[kr] / (dx * dx), cS = al * bs[kr] / (dy * dy), cN = al * bn[kr] / (dy * dy);
+            if (r == c) {
+                double d = -al * ((be[kr] + bw[kr]) / (dx * dx) + (bn[kr] + bs[kr]) / (dy * dy)) + lam[kr];
+                if (i == 0) d -= cW;
+                if (i == M - 1) d -= cE;
+                if (r == 0) d -= cS;
+                if (r == M - 1) d -= cN;
+                a = d;
+            } else if (c == r - 1) a = cS;
+            else if (c == r + 1) a = cN;
+            if (i > 0) a -= cW * prev * sCE[c];
+        }
+        // in-register Gauss-Jordan inverse of the M x M block
+        for (int k = 0; k < M; k++) {
+            const int b = k & 1;
+            if (r == k) sRow[b][c] = a;
+            if (c == k) sCol[b][r] = a;
+            __syncthreads();
+            const double piv = sRow[b][k];
+            const double p = 1.0 / piv;
+            if (threadIdx.x == 0) minp = fmin(minp, fabs(piv));
+            if (r == k) a = (c == k) ? p : a * p;
+            else {
+                const double f = sCol[b][r];
+                a = (c == k) ? -f * p : a - f * p * sRow[b][c];
+            }
+        }
+        P_all[((size_t)leaf * M + i) * M * M + threadIdx.x] = a;
+        prev = a;
+        __syncthreads();
+        if (threadIdx.x < M) sCE[threadIdx.x] = cf[1 * M * M + i * M + threadIdx.x];   // cE[i][.] for the next block
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && min_pivot)
+        atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
+}
+
+// Block-tridiagonal solve for `ncols` right-hand sides of one leaf per CTA (blockIdx.x = leaf,
+// blockIdx.y = column chunk).  mode 0: u = solve(g, f)      (one column; writes u_out)
+//                              mode 1: h = mapD2N(g=0, f)   (one column; writes h_ptrs[leaf])
+//                              mode 2: columns of T: g = e_col, f = 0 (writes T column col)
+// Shared memory: P tile M x (M+1), tmp M x C, Z M*M x C.
+template <int M>
+__global__ void __launch_bounds__(256)
+leaf_var_solve_kernel(const double* __restrict__ coef, const double* __restrict__ P_all, const double* __restrict__ boxes,
+                      const int* __restrict__ leaf_nodes, const double* __restrict__ f, double fscale, double* const* __restrict__ g_ptrs,
+                      double* __restrict__ u_out, double* const* __restrict__ h_ptrs, double* __restrict__ T_all, int mode, int C)
+{
+    extern __shared__ __align__(16) double smv[];
+    double* sP = smv;                       // M x (M+1)
+    double* sT = sP + M * (M + 1);          // M x C
+    double* sZ = sT + M * C;                // M*M x C
+    const int leaf = blockIdx.x, col0 = blockIdx.y * C;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    const double* cW = coef + (size_t)leaf * 4 * M * M;
+    const double* cE = cW + M * M;
+    const double* cS = cE + M * M;
+    const double* cN = cS + M * M;
+    const double* P = P_all + (size_t)leaf * M * M * M;
+    const double* gl = (mode == 0 && g_ptrs) ? g_ptrs[leaf] : nullptr;
+    const double* fl = f ? f + (size_t)leaf * M * M : nullptr;
+
+    // right-hand side of cell (i, j) for local column cc (FiniteVolumeSolver.cpp:100-175: rhs += -2 c_side g)
+    auto rhs = [&](int i, int j, int cc) -> double {
+        double v = 0.0;
+        if (mode == 2) {
+            const int col = col0 + cc, side = col / M, t = col % M;
+            if (side == 0 && i == 0 && j == t) v = -2.0 * cW[j];
+            else if (side == 1 && i == M - 1 && j == t) v = -2.0 * cE[(M - 1) * M + j];
+            else if (side == 2 && j == 0 && i == t) v = -2.0 * cS[i * M];
+            else if (side == 3 && j == M - 1 && i == t) v = -2.0 * cN[i * M + M - 1];
+            return v;
+        }
+        if (fl) v = fscale * fl[i * M + j];
+        if (gl) {
+            if (i == 0) v += -2.0 * cW[j] * gl[j];
+            if (i == M - 1) v += -2.0 * cE[(M - 1) * M + j] * gl[M + j];
+            if (j == 0) v += -2.0 * cS[i * M] * gl[2 * M + i];
+            if (j == M - 1) v += -2.0 * cN[i * M + M - 1] * gl[3 * M + i];
+        }
+        return v;
+    };
+
+    // forward sweep
+    for (int i = 0; i < M; i++) {
+        for (int e = tid; e < M * M; e += NT) sP[(e / M) * (M + 1) + (e % M)] = P[(size_t)i * M * M + e];
+        for (int e = tid; e < M * C; e += NT) {
+            const int j = e / C, cc = e % C;
+            double y = rhs(i, j, cc);
+            if (i > 0) y -= cW[i * M + j] * sZ[((i - 1) * M + j) * C + cc];
+            sT[e] = y;
+        }
+        __syncthreads();
+        for (int e = tid; e < M * C; e += NT) {
+            const int j = e / C, cc = e % C;
+            double z = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < M; k++) z = fma(sP[j * (M + 1) + k], sT[k * C + cc], z);
+            sZ[(i * M + j) * C + cc] = z;
+        }
+        __syncthreads();
+    }
+    // backward sweep (u overwrites z)
+    for (int i = M - 2; i >= 0; i--) {
+        for (int e = tid; e < M * M; e += NT) sP[(e / M) * (M + 1) + (e % M)] = P[(size_t)i * M * M + e];
+        for (int e = tid; e < M * C; e += NT) {
+            const int j = e / C, cc = e % C;
+            sT[e] = cE[i * M + j] * sZ[((i + 1) * M + j) * C + cc];
+        }
+        __syncthreads();
+        for (int e = tid; e < M * C; e += NT) {
+            const int j = e / C, cc = e % C;
+            double z = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < M; k++) z = fma(sP[j * (M + 1) + k], sT[k * C + cc], z);
+            sZ[(i * M + j) * C + cc] -= z;
+        }
+        __syncthreads();
+    }
+    // outputs
+    if (mode == 0) {
+        for (int e = tid; e < M * M; e += NT) u_out[(size_t)leaf * M * M + e] = sZ[e * C];
+    } else if (mode == 1) {
+        double* h = h_ptrs[leaf];
+        for (int e = tid; e < 4 * M; e += NT) {
+            const int side = e / M, t = e % M;
+            double v;
+            if (side == 0) v = (2.0 / dx) * sZ[(0 * M + t) * C];
+            else if (side == 1) v = -(2.0 / dx) * sZ[((M - 1) * M + t) * C];
+            else if (side == 2) v = (2.0 / dy) * sZ[(t * M + 0) * C];
+            else v = -(2.0 / dy) * sZ[(t * M + M - 1) * C];
+            h[e] = v;
+        }
+    } else {
+        double* T = T_all + (size_t)leaf * 16 * M * M;
+        for (int e = tid; e < 4 * M * C; e += NT) {
+            const int row = e / C, cc = e % C, col = col0 + cc;
+            const int side = row / M, t = row % M;
+            double u;
+            if (side == 0) u = sZ[(0 * M + t) * C + cc];
+            else if (side == 1) u = sZ[((M - 1) * M + t) * C + cc];
+            else if (side == 2) u = sZ[(t * M + 0) * C + cc];
+            else u = sZ[(t * M + M - 1) * C + cc];
+            const double gv = (row == col) ? 1.0 : 0.0;
+            const double d = side < 2 ? dx : dy;
+            T[(size_t)row * (4 * M) + col] = side_sign(side) * (2.0 / d) * (u - gv);
+        }
+    }
+}
+
+template <int M>
+static void var_factor_M(const double* const* cin, const double* boxes, const int* leaf_nodes, double* coef, double* P, double* minpiv, int n, cudaStream_t s) {
+    leaf_var_factor_kernel<M><<<n, M * M, 0, s>>>(cin[0], cin[1], cin[2], cin[3], cin[4], cin[5], boxes, leaf_nodes, coef, P, minpiv);
+}
+template <int M>
+static void var_solve_M(const double* coef, const double* P, const double* boxes, const int* leaf_nodes, const double* f, double fscale,
+                        double* const* g_ptrs, double* u_out, double* const* h_ptrs, double* T_all, int mode, int n_leaves, cudaStream_t s) {
+    const int C = mode == 2 ? (M >= 32 ? 16 : (4 * M < 32 ? 4 * M : 32)) : 1;
+    const int smem = (M * (M + 1) + M * C + M * M * C) * (int)sizeof(double);
+    auto kern = leaf_var_solve_kernel<M>;
+    static int attr_done = 0;
+    if (smem > 48 * 1024 && attr_done < smem) {
+        EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = smem;
+    }
+    dim3 grid(n_leaves, mode == 2 ? (4 * M) / C : 1);
+    kern<<<grid, 256, smem, s>>>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, C);
+}
+
+void launch_leaf_var_factor(int M, const double* const* coef_in, const double* boxes, const int* leaf_nodes, double* coef, double* P,
+                            double* min_pivot, int n_leaves, cudaStream_t s)
+{
+    if (n_leaves == 0) return;
+    switch (M) {
+        case 8: var_factor_M<8>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
+        case 16: var_factor_M<16>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
+        case 24: var_factor_M<24>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
+        case 32: var_factor_M<32>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
+        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+    }
+    EF_CUDA(cudaGetLastError());
+}
+
+void launch_leaf_var_solve(int M, const double* coef, const double* P, const double* boxes, const int* leaf_nodes, const double* f, double fscale,
+                           double* const* g_ptrs, double* u_out, double* const* h_ptrs, double* T_all, int mode, int n_leaves, cudaStream_t s)
+{
+    if (n_leaves == 0) return;
+    switch (M) {
+        case 8: var_solve_M<8>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
+        case 16: var_solve_M<16>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
+        case 24: var_solve_M<24>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
+        case 32: var_solve_M<32>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
+        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+    }
+    EF_CUDA(cudaGetLastError());
+}
+
+void launch_broadcast_leaf_T(double* T_all, int M, int n_leaves, cudaStream_t s)
+{
+    if (n_leaves <= 1) return;
+    broadcast_leaf_T_kernel<<<148 * 8, 256, 0, s>>>(T_all, (size_t)16 * M * M, n_leaves);
+    EF_CUDA(cudaGetLastError());
+}
+
 template <int M>
 static void dtn_const_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, double* T_all, int n_build, cudaStream_t s) {
     leaf_dtn_const_kernel<M><<<n_build, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, T_all, n_build);

@@ -34,7 +34,7 @@ def run_gpu(kw, keep_x=True, options=None, scale=1.0):
     return hps
 
 
-@pytest.mark.parametrize("case", [c for c in GOLDEN_CASES if "varcoef" not in c])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_against_reference_dump(case):
     gold = load_golden(case)
     kw = golden_case_args(gold)
@@ -96,6 +96,26 @@ def test_adaptive_m16_against_oracle():
     root = ora.nodes[0]
     assert relerr(hps.operator(0, "T"), root.T) < TOL
     assert relerr(hps.operator(0, "S"), root.S) < TOL
+
+
+@pytest.mark.parametrize("nx,lo,hi", [(16, 2, 2), (8, 1, 3), (32, 1, 1), (24, 1, 2)])
+def test_variable_coefficient_leaves_against_oracle(nx, lo, hi):
+    """FivePointStencil leaves (block-tridiagonal LU per leaf, factored once) vs the oracle's dense LU
+    (FiniteVolumeSolver.cpp:27-223): leaf T, every merged operator, and the solution."""
+    kw = dict(problem_name="varcoef", solver_kind="fivepoint", box=(-10.0, 10.0, -10.0, 10.0), nx=nx,
+              min_level=lo, max_level=hi, threshold=1.2, refine_box=(2.0, 10.0, -3.0, 10.0) if hi > lo else None)
+    hps = run_gpu(kw)
+    ora = O.run(**kw)
+    worst = {}
+    for i, nd in enumerate(ora.nodes):
+        assert hps.mesh.path(i) == nd.path
+        for nm in (["T"] if nd.leaf else ["T", "S", "X", "H"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.operator(i, nm), getattr(nd, nm)))
+        for nm in (["h", "g", "u"] if nd.leaf else ["h", "g", "w"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.vector(i, nm), getattr(nd, nm)))
+    print(nx, lo, hi, {k: "%.1e" % v for k, v in worst.items()})
+    for nm, v in worst.items():
+        assert v < TOL, (nm, v)
 
 
 def test_options_cache_operators_and_homogeneous_rhs():
