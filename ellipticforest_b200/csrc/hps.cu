@@ -101,6 +101,7 @@ struct efgpu_handle {
     int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
     // device state
     DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
+    DevBuf d_robin;                              // workspace of the root boundary solve (efgpu_solve_robin)
     DevBuf d_coef_in[6], d_coef, d_P;            // variable-coefficient leaves: sampled alpha/beta/lambda, stencil coefficients, block-LU inverses
     size_t vec_doubles = 0;
     bool allocated = false, built = false, upwards_done = false;
@@ -784,11 +785,40 @@ int efgpu_solve_robin(efgpu_handle* H, const double* a, const double* b, const d
     if (!H || !a || !b || !r) return EF_ERR_BAD_ARG;
     if (H->roots.size() != 1) { H->last_error = "root boundary solve on a forest handle"; return EF_ERR_STATE; }
     const int len = 4 * H->nodes[0].size;
-    for (int i = 0; i < len; i++)
-        if (b[i] != 0.0) { H->last_error = "Robin/Neumann root data (b != 0) needs the dense root solve, not built yet"; return EF_ERR_UNSUPPORTED; }
-    std::vector<double> g(len);
-    for (int i = 0; i < len; i++) g[i] = r[i] / a[i];   // g = (diag a)^-1 r   (HPSAlgorithm.hpp:402-419 with b = 0)
-    return efgpu_solve_dirichlet(H, g.data(), flags, u_leaves);
+    bool dirichlet = true;
+    for (int i = 0; i < len; i++) if (b[i] != 0.0) { dirichlet = false; break; }
+    if (dirichlet) {
+        std::vector<double> g(len);
+        for (int i = 0; i < len; i++) g[i] = r[i] / a[i];   // g = (diag a)^-1 r   (HPSAlgorithm.hpp:402-419 with b = 0)
+        return efgpu_solve_dirichlet(H, g.data(), flags, u_leaves);
+    }
+    // general case: dense pivoted LU of diag(a) + diag(b) T_root on the device (HPSAlgorithm.hpp:408-419)
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->built) throw Error{EF_ERR_STATE, "solve before build"};
+    const bool homogeneous = (flags & EFGPU_HOMOGENEOUS_RHS) != 0;
+    if (!homogeneous && !H->upwards_done) throw Error{EF_ERR_STATE, "solve before upwards (non-homogeneous right-hand side)"};
+    if (H->nodes[0].leaf && H->external_leaves) throw Error{EF_ERR_STATE, "no root operator"};
+    cudaStream_t s = H->stream;
+    H->d_robin.alloc((robin_workspace_doubles(len) + 4 * (size_t)len) * sizeof(double));
+    double* abr = H->d_robin.as<double>();
+    double* ws = abr + 4 * (size_t)len;
+    EF_CUDA(cudaMemcpyAsync(abr, a, len * sizeof(double), cudaMemcpyHostToDevice, s));
+    EF_CUDA(cudaMemcpyAsync(abr + len, b, len * sizeof(double), cudaMemcpyHostToDevice, s));
+    EF_CUDA(cudaMemcpyAsync(abr + 2 * (size_t)len, r, len * sizeof(double), cudaMemcpyHostToDevice, s));
+    NodeH& root = H->nodes[0];
+    const double* hroot = homogeneous ? nullptr : H->d_vec.as<double>() + root.hbuf[0];   // the reference reads an empty vectorH here and throws
+    int info = 0;
+    EF_CUDA(cudaEventRecord(H->ev0, s));
+    robin_solve(root.Tbuf[0], abr, abr + len, abr + 2 * (size_t)len, hroot, len, ws, abr + 3 * (size_t)len, &info, s);
+    set_root_g(H, abr + 3 * (size_t)len, cudaMemcpyDeviceToDevice);
+    do_solve(H, H->f_cur, H->fscale_cur, flags);
+    EF_CUDA(cudaEventRecord(H->ev1, s));
+    if (u_leaves) EF_CUDA(cudaMemcpyAsync(u_leaves, H->d_u.p, (size_t)H->n_leaves * H->M * H->M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EF_CUDA(cudaStreamSynchronize(s)); collect_profile(H);
+    float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
+    if (info != 0) throw Error{EF_ERR_SINGULAR, "root boundary system is singular (zero pivot at column " + std::to_string(info) + ")"};
+    EF_CATCH(H)
 }
 
 int efgpu_sync(efgpu_handle* H)

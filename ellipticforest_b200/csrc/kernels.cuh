@@ -50,4 +50,9 @@ void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s);     
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s);
 void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s);      // parity/debug: 8n x 4n, reference order
 
+// lu.cu: root boundary system  (diag(a) + diag(b) T) g = r - b .* h  by blocked LU with partial pivoting
+size_t robin_workspace_doubles(int N);
+void robin_solve(const double* T, const double* a, const double* b, const double* r, const double* h, int N, double* ws,
+                 double* g_out, int* info_host, cudaStream_t s);
+
 }  // namespace efgpu

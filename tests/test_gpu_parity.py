@@ -118,6 +118,42 @@ def test_variable_coefficient_leaves_against_oracle(nx, lo, hi):
         assert v < TOL, (nm, v)
 
 
+@pytest.mark.parametrize("nx,level,kind", [(8, 2, "robin"), (8, 3, "mixed"), (24, 1, "robin"), (16, 3, "mixed"), (8, 1, "robin")])
+def test_root_robin_and_mixed_boundary_conditions(nx, level, kind):
+    """solveStage(fn(side,x,y,*a,*b)) with b != 0 (HPSAlgorithm.hpp:402-420): the dense root system
+    (diag a + diag b T) g = r - b h, pivoted LU on the device vs the oracle's dgesv-equivalent."""
+    kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=nx,
+              min_level=level, max_level=level, threshold=1.2, refine_box=None)
+    P = O.problem("helmholtz")
+
+    def bc(side, x, y):
+        u = P["u"](x, y)
+        dudn = np.where(np.asarray(side) < 2, np.cos(x), np.cos(y))   # coordinate derivative, the reference's convention for T
+        if kind == "robin":
+            a, b = 1.0 + 0 * u, 0.25 + 0 * u
+        else:  # examples/thermal/main.cpp:323-349: Dirichlet on W, E; Neumann on S, N
+            a = np.where(np.asarray(side) < 2, 1.0, 0.0)
+            b = 1.0 - a
+        return a * u + b * dudn, a, b
+
+    m = _mesh_for(kw)
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FISHPACK90"
+    s.lambda_function = P["lam"]
+    hps = ef.HPSAlgorithm(m, s)
+    hps.buildStage()
+    hps.upwardsStage(P["f"])
+    u = hps.solveStage(bc)
+    ora = O.HPS(O.build_tree(O.refine_indicator(1.2), kw["box"], nx, level, level), O.Solver(kind="fishpack", lam=P["lam"]))
+    ora.build_stage()
+    ora.upwards_stage(P["f"])
+    ora.solve_stage(lambda sd, x, y: tuple(float(v) for v in bc(sd, x, y)))
+    assert relerr(hps.vector(0, "g"), ora.nodes[0].g) < TOL
+    assert relerr(u, np.stack([v.reshape(nx, nx) for v in ora.leaf_solution()])) < TOL
+    X, Y = hps.mesh.leaf_cell_centres()
+    assert np.max(np.abs(u - P["u"](X, Y))) < 20.0 * (np.pi / (nx * 2 ** level)) ** 2
+
+
 def test_options_cache_operators_and_homogeneous_rhs():
     kw = dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=8,
               min_level=2, max_level=2, threshold=1.2, refine_box=None)
