@@ -14,6 +14,9 @@
 // copy pipeline (cp.async 16-byte, LDGSTS).
 #include "common.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 namespace efgpu {
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -68,30 +71,38 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp / WARPS_N) * C::WM, wn0 = (warp % WARPS_N) * C::WN;
 
-    // flattened (term, k-tile) sequence
+    // flattened (term, k-tile) sequence; the per-term operand bases live in registers so that issuing a
+    // stage costs no descriptor (global memory) reads on the critical path between two barriers
     const int nterms = bd.nterms;
-    int nk_total = 0;
-    for (int t = 0; t < nterms; t++) nk_total += bd.t[t].K / BK;
+    const int nk0 = bd.t[0].K / BK;
+    const int nk_total = nk0 + (nterms > 1 ? bd.t[1].K / BK : 0);
+    const int t1 = nterms > 1 ? 1 : 0;
+    const double* Ab0 = ops[bd.t[0].a_op] + bd.t[0].a_off + (long long)(tm * BM) * bd.t[0].lda;
+    const double* Bb0 = ops[bd.t[0].b_op] + bd.t[0].b_off + tn * BN;
+    const double* Ab1 = ops[bd.t[t1].a_op] + bd.t[t1].a_off + (long long)(tm * BM) * bd.t[t1].lda;
+    const double* Bb1 = ops[bd.t[t1].b_op] + bd.t[t1].b_off + tn * BN;
+    const int lda0 = bd.t[0].lda, ldb0 = bd.t[0].ldb, lda1 = bd.t[t1].lda, ldb1 = bd.t[t1].ldb;
+    const unsigned neg0 = bd.t[0].neg, neg1 = bd.t[t1].neg;
 
     auto load_stage = [&](int s, int buf) {
-        int t = 0, kt = s;
-        while (kt >= bd.t[t].K / BK) { kt -= bd.t[t].K / BK; t++; }
-        const GemmTerm& tr = bd.t[t];
-        const double* Ag = ops[tr.a_op] + tr.a_off + (long long)(tm * BM) * tr.lda + kt * BK;
-        const double* Bg = ops[tr.b_op] + tr.b_off + (long long)(kt * BK) * tr.ldb + tn * BN;
+        const bool second = s >= nk0;
+        const int kt = second ? s - nk0 : s;
+        const int lda = second ? lda1 : lda0, ldb = second ? ldb1 : ldb0;
+        const double* Ag = (second ? Ab1 : Ab0) + kt * BK;
+        const double* Bg = (second ? Bb1 : Bb0) + (long long)(kt * BK) * ldb;
         double* as = As + buf * C::A_STAGE;
         double* bs = Bs + buf * C::B_STAGE;
         constexpr int A_CHUNKS = BM * BK / 2, ACPR = BK / 2;
 #pragma unroll
         for (int c = tid; c < A_CHUNKS; c += C::NT) {
             int r = c / ACPR, cc = (c % ACPR) * 2;
-            cp_async16(as + r * C::LDA_S + cc, Ag + (long long)r * tr.lda + cc);
+            cp_async16(as + r * C::LDA_S + cc, Ag + (long long)r * lda + cc);
         }
         constexpr int B_CHUNKS = BK * BN / 2, BCPR = BN / 2;
 #pragma unroll
         for (int c = tid; c < B_CHUNKS; c += C::NT) {
             int r = c / BCPR, cc = (c % BCPR) * 2;
-            cp_async16(bs + r * C::LDB_S + cc, Bg + (long long)r * tr.ldb + cc);
+            cp_async16(bs + r * C::LDB_S + cc, Bg + (long long)r * ldb + cc);
         }
     };
 
@@ -107,8 +118,6 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
         cp_async_commit();
     }
 
-    int term_of_stage = 0, k_left = bd.t[0].K / BK;   // tracks the sign of the stage being computed
-    unsigned neg = bd.t[0].neg;
     for (int kt = 0; kt < nk_total; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -117,8 +126,7 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
             if (nxt < nk_total) load_stage(nxt, nxt % STAGES);
             cp_async_commit();
         }
-        if (k_left == 0) { term_of_stage++; k_left = bd.t[term_of_stage].K / BK; neg = bd.t[term_of_stage].neg; }
-        k_left--;
+        const unsigned neg = kt >= nk0 ? neg1 : neg0;
         const double* as = As + (kt % STAGES) * C::A_STAGE + (wm0 + (lane >> 2)) * C::LDA_S + (lane & 3);
         const double* bs = Bs + (kt % STAGES) * C::B_STAGE + (lane & 3) * C::LDB_S + wn0 + (lane >> 2);
 #pragma unroll
@@ -156,8 +164,12 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 static void launch_cfg(double* const* ptab, int nops, const GemmBlock* d_blocks, int nblocks, int batch,
-                       int max_tiles, cudaStream_t stream)
+                       int max_tiles, cudaStream_t stream, const GemmBlock* h_blocks = nullptr)
 {
+    if (h_blocks) {   // non-square CTA tiles: recount the tiles of the largest block
+        max_tiles = 0;
+        for (int b = 0; b < nblocks; b++) { int v = (h_blocks[b].rows / BM) * (h_blocks[b].cols / BN); if (v > max_tiles) max_tiles = v; }
+    }
     using C = GemmCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
     auto kern = bgemm_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
     static bool attr_set = false;
@@ -198,7 +210,33 @@ void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, cons
     }
     int mt = tiles_for(tile);
     switch (tile) {
-        case 128: launch_cfg<128, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        case 128: {
+            static const int variant = [] { const char* e = getenv("EFGPU_GEMM_VARIANT"); return e ? atoi(e) : 7; }();
+            switch (variant) {   // tuning variants of the 128 x 128 CTA tile (tools/gemm_bench.py)
+                case 1: launch_cfg<128, 128, 16, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 2: launch_cfg<128, 128, 32, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 3: launch_cfg<128, 128, 32, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 4: launch_cfg<128, 128, 16, 2, 4, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 5: launch_cfg<128, 128, 16, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 6: launch_cfg<128, 128, 32, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 7: launch_cfg<128, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 8: launch_cfg<64, 128, 16, 1, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 9: launch_cfg<128, 64, 32, 2, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 10: launch_cfg<128, 64, 16, 2, 2, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 11: launch_cfg<64, 64, 16, 1, 2, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 12: launch_cfg<128, 64, 32, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 13: launch_cfg<128, 64, 16, 2, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 14: launch_cfg<64, 128, 16, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 15: launch_cfg<128, 64, 16, 4, 1, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 16: launch_cfg<64, 128, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 17: launch_cfg<64, 128, 32, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 0: launch_cfg<128, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                // default (7): 128 x 64 CTA tile, 4 warps of 64 x 32, two CTAs per SM so that one CTA's barrier / fragment-load
+                // phases overlap the other's DMMA phases (measured 31-32 TFLOP/s vs 29-30 for one 128 x 128 CTA per SM)
+                default: launch_cfg<128, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+            }
+            break;
+        }
         case 64: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
         case 32: launch_cfg<32, 32, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
         case 16: launch_cfg<16, 16, 16, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
@@ -249,10 +287,99 @@ invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long lon
     }
 }
 
+// Register-resident variant: 256 threads as a 16 x 16 grid, thread (tr, tc) owns the elements
+// (tr + 16 i, tc + 16 j), i, j < TI (cyclic), N = 16 TI.  Per pivot the owners publish row k and column k
+// through double-buffered shared memory (ONE barrier per pivot) and every thread updates its tile with
+//   row k:      a_kj <- a_kj / a_kk (j != k),  a_kk <- 1 / a_kk
+//   other rows: a_ij <- [j != k] a_ij - a_ik * (new a_kj)
+// compile-time dispatch on a warp-uniform index: calls f(integral_constant<int, I>) for I == idx
+template <int I, int TI, class F>
+__device__ __forceinline__ void dispatch_index(int idx, F&& f)
+{
+    if constexpr (I < TI) {
+        if (idx == I) f(std::integral_constant<int, I>{});
+        else dispatch_index<I + 1, TI>(idx, f);
+    }
+}
+
+template <int TI>
+__global__ void __launch_bounds__(256)
+invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, int ld, double* __restrict__ min_pivot)
+{
+    constexpr int N = 16 * TI;
+    __shared__ double sRow[2][N];
+    __shared__ double sCol[2][N];
+    double* G = ptab[(long long)blockIdx.x * nops + op] + off;
+    const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    double a[TI][TI];
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+        for (int j = 0; j < TI; j++) a[i][j] = G[(long long)(tr + 16 * i) * ld + tc + 16 * j];
+    double minp = 1e300;
+    for (int k = 0; k < N; k++) {
+        const int b = k & 1, ki = k >> 4, kr = k & 15;   // ki, kr are uniform over the CTA
+        // owners publish row k and column k (values before the update)
+        dispatch_index<0, TI>(ki, [&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (tr == kr) {
+#pragma unroll
+                for (int j = 0; j < TI; j++) sRow[b][tc + 16 * j] = a[q][j];
+            }
+            if (tc == kr) {
+#pragma unroll
+                for (int i = 0; i < TI; i++) sCol[b][tr + 16 * i] = a[i][q];
+            }
+        });
+        __syncthreads();
+        const double piv = sRow[b][k];
+        const double p = 1.0 / piv;
+        minp = fmin(minp, fabs(piv));
+        double rk[TI], ck[TI];
+#pragma unroll
+        for (int j = 0; j < TI; j++) rk[j] = sRow[b][tc + 16 * j] * p;
+#pragma unroll
+        for (int i = 0; i < TI; i++) ck[i] = sCol[b][tr + 16 * i];
+        // generic rank-1 update of every element ...
+#pragma unroll
+        for (int i = 0; i < TI; i++)
+#pragma unroll
+            for (int j = 0; j < TI; j++) a[i][j] = fma(-ck[i], rk[j], a[i][j]);
+        // ... then repair column k (wanted -a_ik p; the update gave a_ik - a_ik (a_kk p): rk[k] must act as p with a_ik removed)
+        // and row k (wanted a_kj p, and p on the diagonal)
+        dispatch_index<0, TI>(ki, [&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (tc == kr) {
+#pragma unroll
+                for (int i = 0; i < TI; i++) a[i][q] = -ck[i] * p;
+            }
+            if (tr == kr) {
+#pragma unroll
+                for (int j = 0; j < TI; j++) a[q][j] = rk[j];
+                if (tc == kr) a[q][q] = p;
+            }
+        });
+    }
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+        for (int j = 0; j < TI; j++) G[(long long)(tr + 16 * i) * ld + tc + 16 * j] = a[i][j];
+    if (threadIdx.x == 0 && min_pivot)
+        atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
+}
+
 void launch_invert_small(double* const* ptab, int nops, int op, long long off, int ld, int N, int batch,
                          double* min_pivot, cudaStream_t stream)
 {
     if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "invert_small: N > 128"};
+    switch (N) {
+        case 32: invert_reg_kernel<2><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 48: invert_reg_kernel<3><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 64: invert_reg_kernel<4><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 96: invert_reg_kernel<6><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 128: invert_reg_kernel<8><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        default: break;
+    }
     int smem = (N * (N + 1) + N) * (int)sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {

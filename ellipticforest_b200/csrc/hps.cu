@@ -151,7 +151,7 @@ static void collect_profile(efgpu_handle* H)   // stream must be synchronised
 
 static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int depth, std::vector<long long>& w1_off, long long w2_off)
 {
-    const bool can_split = N > 64 && (N / 2) % 8 == 0;
+    const bool can_split = N > 128 && (N / 2) % 16 == 0;   // base case: one CTA, register-resident Gauss-Jordan (N <= 128)
     if (!can_split) {
         if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
         b.steps.push_back({0, 0, 0, off, N, EFGPU_PROF_INVERT_SMALL});

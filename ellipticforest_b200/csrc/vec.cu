@@ -230,6 +230,116 @@ __global__ void __launch_bounds__(256) solve_split_kernel(const MergeEntry* __re
     }
 }
 
+// ---- short-row variants (child side n <= 256: rows of 2n..8n doubles) ---------------------------
+// One CTA per (parent, row chunk).  The right-hand vector is staged in shared memory once; a row is
+// owned by a group of LW lanes (LW = min(32, L/2), 16-byte loads), so short rows do not idle most of
+// a warp, and every group keeps R rows in flight before reducing (memory-level parallelism).
+template <int LW, int R, class Epilogue>
+__device__ __forceinline__ void gemv_rows_short(const double* __restrict__ A, int L, const double* xs, int r0, int r1, Epilogue epi)
+{
+    const int tid = threadIdx.x;
+    const int grp = tid / LW, gl = tid % LW, ngrp = blockDim.x / LW;
+    const int L2 = L >> 1;
+    const double2* x2 = reinterpret_cast<const double2*>(xs);
+    for (int rb = r0 + grp * R; rb < r1; rb += ngrp * R) {
+        double acc[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) acc[k] = 0.0;
+        for (int c = gl; c < L2; c += LW) {
+            double2 av[R];
+#pragma unroll
+            for (int k = 0; k < R; k++)
+                av[k] = (rb + k < r1) ? __ldcs(reinterpret_cast<const double2*>(A + (size_t)(rb + k) * L) + c) : make_double2(0.0, 0.0);
+            const double2 xv = x2[c];
+#pragma unroll
+            for (int k = 0; k < R; k++) acc[k] = fma(av[k].x, xv.x, fma(av[k].y, xv.y, acc[k]));
+        }
+#pragma unroll
+        for (int o = LW / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < R; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (gl == 0) {
+#pragma unroll
+            for (int k = 0; k < R; k++) if (rb + k < r1) epi(rb + k, acc[k]);
+        }
+    }
+}
+
+// w = X^-1 hd with hd formed on the fly from the children's h (fuses hdiff_kernel)
+template <int LW, int R>
+__global__ void __launch_bounds__(256) upwards_w_short_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
+{
+    extern __shared__ __align__(16) double xs[];
+    const MergeEntry& e = ent[blockIdx.x];
+    const int N = 4 * n;
+    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
+        const int k = idx / n, r = idx % n;
+        const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+        xs[idx] = e.hc[c2][c_iface[c2][k] * n + r] - e.hc[c1][c_iface[c1][k] * n + r];
+    }
+    __syncthreads();
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    double* w = e.w;
+    gemv_rows_short<LW, R>(e.Xinv, N, xs, r0, r1, [&](int row, double v) { w[row] = v; });
+}
+
+// h = pi(H w + h_ext): row `row` of the compact H (length 2n) times [w[k0], w[k1]] of its child
+template <int LW, int R>
+__global__ void __launch_bounds__(256) upwards_h_short_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
+{
+    extern __shared__ __align__(16) double xs[];   // 4n: w
+    const MergeEntry& e = ent[blockIdx.x];
+    for (int idx = threadIdx.x; idx < 4 * n; idx += blockDim.x) xs[idx] = e.w[idx];
+    __syncthreads();
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(8 * n, r0 + rows_per_cta);
+    // rows of one WESN block p share the child and therefore the two w segments; chunks never straddle a block
+    // when rows_per_cta divides n or is a multiple of it, which the launcher guarantees.
+    for (int p0 = r0; p0 < r1; p0 += n) {
+        const int p = p0 / n, pr0 = p0, pr1 = min(r1, (p + 1) * n);
+        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+        const int k0 = c_kk[ch][0], k1 = c_kk[ch][1];
+        const double* hc = e.hc[ch] + side * n;
+        double* h = e.h;
+        // the two segments are contiguous in xs only if k1 == k0 + 1; otherwise two passes over half rows
+        if (k1 == k0 + 1) {
+            gemv_rows_short<LW, R>(e.Hc, 2 * n, xs + k0 * n, pr0, pr1, [&](int row, double v) { h[row] = v + hc[row - p * n]; });
+        } else {
+            __shared__ double xcat[512];
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < 2 * n; idx += blockDim.x) xcat[idx] = idx < n ? xs[k0 * n + idx] : xs[k1 * n + idx - n];
+            __syncthreads();
+            gemv_rows_short<LW, R>(e.Hc, 2 * n, xcat, pr0, pr1, [&](int row, double v) { h[row] = v + hc[row - p * n]; });
+        }
+    }
+}
+
+// u_int = S g (+ w), scattered to the children; exterior segments copied through
+template <int LW, int R>
+__global__ void __launch_bounds__(256) solve_split_short_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta, int add_w)
+{
+    extern __shared__ __align__(16) double xs[];   // 8n: g
+    const MergeEntry& e = ent[blockIdx.x];
+    for (int idx = threadIdx.x; idx < 8 * n; idx += blockDim.x) xs[idx] = e.g[idx];
+    __syncthreads();
+    const int N = 4 * n;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    const double* w = e.w;
+    gemv_rows_short<LW, R>(e.S, 8 * n, xs, r0, r1, [&](int row, double v) {
+        if (add_w) v += w[row];
+        const int k = row / n, r = row % n;
+        const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+        e.gc[c1][c_iface[c1][k] * n + r] = v;
+        e.gc[c2][c_iface[c2][k] * n + r] = v;
+    });
+    const int nct = gridDim.y, per = (8 * n + nct - 1) / nct;
+    const int x0 = blockIdx.y * per, x1 = min(8 * n, x0 + per);
+    for (int idx = x0 + threadIdx.x; idx < x1; idx += blockDim.x) {
+        const int p = idx / n, r = idx % n;
+        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+        e.gc[ch][side * n + r] = xs[idx];
+    }
+}
+
 // ---- launch wrappers ---------------------------------------------------------------------------
 static inline int ew_blocks(long long elems) { long long b = (elems + 255) / 256; return (int)(b < 1 ? 1 : (b > 1024 ? 1024 : b)); }
 static inline void check_count(int count) { if (count > 65535) throw Error{EF_ERR_BAD_SHAPE, "batch too large for grid.y (chunk it)"}; }
@@ -286,9 +396,46 @@ static inline int pick_rows(int rows, int count)
     return rpc;
 }
 
+// chunk of rows per CTA for the short-row kernels: whole parents when there are many, else n-aligned pieces
+static inline int short_rows(int rows, int n, int count)
+{
+    int rpc = rows;
+    while (rpc > n && (long long)count * (rows / rpc) < 148LL * 8) rpc >>= 1;
+    while (rpc > 32 && (long long)count * (rows / rpc) < 148LL * 4) rpc >>= 1;   // below n: still a divisor of n (n = 8 * 2^k or 24 * 2^k ...)
+    return rpc;
+}
+
+template <int R>
+static void launch_upwards_short(const MergeEntry* e, int n, int count, cudaStream_t s)
+{
+    {
+        const int N = 4 * n, rpc = short_rows(N, n, count);
+        dim3 grid(count, N / rpc);
+        const size_t sm = (size_t)N * sizeof(double);
+        if (N / 2 >= 32) upwards_w_short_kernel<32, R><<<grid, 256, sm, s>>>(e, n, rpc);
+        else upwards_w_short_kernel<16, R><<<grid, 256, sm, s>>>(e, n, rpc);
+    }
+    {
+        const int rows = 8 * n;
+        int rpc = short_rows(rows, n, count);
+        if (rpc < n && n % rpc) rpc = n;       // chunks must not straddle WESN blocks
+        dim3 grid(count, rows / rpc);
+        const size_t sm = (size_t)4 * n * sizeof(double);
+        const int L2 = n;                       // row length 2n doubles = n double2
+        if (L2 >= 32) upwards_h_short_kernel<32, R><<<grid, 256, sm, s>>>(e, n, rpc);
+        else if (L2 >= 16) upwards_h_short_kernel<16, R><<<grid, 256, sm, s>>>(e, n, rpc);
+        else upwards_h_short_kernel<8, R><<<grid, 256, sm, s>>>(e, n, rpc);
+    }
+}
+
 void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
 {
     if (!count) return;
+    if (n <= 256 && (n & (n - 1)) == 0 && count <= 65535 * 0 + 2147483647) {
+        launch_upwards_short<4>(e, n, count, s);
+        EF_CUDA(cudaGetLastError());
+        return;
+    }
     for (int off = 0; off < count; off += 65535) {
         int c = count - off < 65535 ? count - off : 65535;
         hdiff_kernel<<<dim3(ew_blocks(4LL * n), c), 256, 0, s>>>(e + off, n);
@@ -303,6 +450,13 @@ void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s)
 {
     if (!count) return;
+    if (n <= 256 && (n & (n - 1)) == 0) {
+        const int N = 4 * n, rpc = short_rows(N, n, count);
+        dim3 grid(count, N / rpc);
+        solve_split_short_kernel<32, 4><<<grid, 256, (size_t)8 * n * sizeof(double), s>>>(e, n, rpc, add_w ? 1 : 0);
+        EF_CUDA(cudaGetLastError());
+        return;
+    }
     int rpc = pick_rows(4 * n, count);
     solve_split_kernel<<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
     EF_CUDA(cudaGetLastError());
