@@ -32,6 +32,11 @@ _I = C.POINTER(C.c_int)
 SIGNATURES = {
     "efgpu_create": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(_P)]),
     "efgpu_create_ex": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(C.c_int32), C.POINTER(_P)]),
+    "efgpu_set_partition": (C.c_int, [_P, C.c_int, C.c_int]),
+    "efgpu_build_begin": (C.c_int, [_P, C.c_uint]),
+    "efgpu_build_level": (C.c_int, [_P, C.c_int, C.c_int]),
+    "efgpu_build_end": (C.c_int, [_P]),
+    "efgpu_max_level": (C.c_int, [_P]),
     "efgpu_destroy": (None, [_P]),
     "efgpu_last_error": (C.c_char_p, [_P]),
     "efgpu_set_leaf_constant": (C.c_int, [_P, C.c_double]),

@@ -89,6 +89,7 @@ struct efgpu_handle {
     std::vector<int> leaf_nodes;                 // node id of each leaf, pre-order (= Morton order)
     std::vector<int> roots;                      // nodes without a parent (one for a tree; several for a forest of subtrees)
     bool external_leaves = false;                // leaf T / h are supplied by the caller (upper tree of a sharded run)
+    int part_rank = 0, part_nranks = 1;          // row partition of S / T among the ranks that replicate this tree
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
     // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
     // (in an unsharded run this is the first thing the leaf's own split1to4 would do, HPSAlgorithm.hpp:1165-1183)
@@ -179,9 +180,28 @@ static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int dep
     gemm(OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W1, W1, h, true);                     // A <- A^-1 - B W1
 }
 
-static void plan_batch_gemms(BatchH& b)
+// Row partition of a replicated upper tree (efgpu_set_partition): this rank computes rows [lo, hi) of the
+// result; a block covering result rows [r0, r0 + rows) is clipped to the overlap (A-side offsets follow).
+static bool clip_rows(GemmBlock& g, long long r0, long long lo, long long hi)
+{
+    const long long a = std::max(r0, lo), e = std::min(r0 + g.rows, hi);
+    if (e <= a) return false;
+    const long long skip = a - r0;
+    g.c_off += skip * g.ldc;
+    if (g.c0_op >= 0) g.c0_off += skip * g.ldc0;
+    for (int t = 0; t < g.nterms; t++) g.t[t].a_off += skip * g.t[t].lda;
+    g.rows = (int)(e - a);
+    return true;
+}
+
+static void plan_batch_gemms(BatchH& b, int rank, int nranks)
 {
     const int n = b.n, N = 4 * n;
+    b.blocks.clear(); b.steps.clear();
+    if (nranks > 1 && ((4 * n) % (8 * nranks) != 0))
+        throw Error{EF_ERR_BAD_SHAPE, "row partition: 4 n must be a multiple of 8 * nranks for every merge of the replicated tree"};
+    const long long s_lo = (long long)rank * (4 * n) / nranks, s_hi = (long long)(rank + 1) * (4 * n) / nranks;
+    const long long t_lo = (long long)rank * (8 * n) / nranks, t_hi = (long long)(rank + 1) * (8 * n) / nranks;
     // workspace layout per entry: W1 blocks per recursion depth (op 7), W2 (op 8)
     std::vector<long long> w1_off; long long acc = 0;
     for (int h = N / 2; h >= 8; h /= 2) { w1_off.push_back(acc); acc += (long long)h * h; }
@@ -202,9 +222,9 @@ static void plan_batch_gemms(BatchH& b)
                 g.t[t] = GemmTerm{OP_XINV, OP_TC0 + c, N, N, (long long)(k * n) * N + k2 * n,
                                   (long long)(h_iface[c][k2] * n) * N + side * n, n, h_sgn[c][k2] < 0 ? 0x80000000u : 0u};
             }
-            b.blocks.push_back(g);
+            if (clip_rows(g, (long long)k * n, s_lo, s_hi)) b.blocks.push_back(g);
         }
-    b.steps.push_back({1, first, 32, 0, 0, EFGPU_PROF_GEMM_S});
+    b.steps.push_back({1, first, (int)b.blocks.size() - first, 0, 0, EFGPU_PROF_GEMM_S});
     // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_)
     first = (int)b.blocks.size();
     for (int qr = 0; qr < 8; qr++)
@@ -221,9 +241,34 @@ static void plan_batch_gemms(BatchH& b)
                 g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n) * N + h_iface[c][k] * n,
                                   (long long)(k * n) * (8 * n) + h_pos[qc] * n, n, 0u};
             }
-            b.blocks.push_back(g);
+            if (clip_rows(g, (long long)h_pos[qr] * n, t_lo, t_hi)) b.blocks.push_back(g);
         }
-    b.steps.push_back({1, first, 64, 0, 0, EFGPU_PROF_GEMM_T});
+    b.steps.push_back({1, first, (int)b.blocks.size() - first, 0, 0, EFGPU_PROF_GEMM_T});
+}
+
+static void compute_flop_model(efgpu_handle* H)
+{
+    const int M = H->M, nn = H->n_nodes;
+    // flop model (SURVEY.md 8(d)): canonical dgesv+dgemm count and the count actually issued
+    double canon = 0, issued = 0, up_bytes = 0, so_bytes = 0;
+    for (auto& b : H->batches) {
+        const double n3 = (double)b.n * b.n * b.n;
+        canon += b.count * 810.0 * n3 + b.count * (2.0 / 3.0) * n3;
+        for (const Step& st : b.steps)
+            if (st.kind == 1)
+                for (int k = st.first; k < st.first + st.count; k++)
+                    for (int t = 0; t < b.blocks[k].nterms; t++) issued += b.count * 2.0 * b.blocks[k].rows * b.blocks[k].cols * b.blocks[k].t[t].K;
+        up_bytes += b.count * 8.0 * (16.0 + 16.0) * b.n * b.n;
+        so_bytes += b.count * 8.0 * 32.0 * b.n * b.n;
+    }
+    H->stats.merge_flops_canonical = canon;
+    H->stats.merge_flops_issued = issued;
+    const double leaf_cells = H->external_leaves ? 0.0 : (double)H->n_leaves * M * M;
+    H->stats.upwards_bytes = up_bytes + 8.0 * leaf_cells;
+    H->stats.solve_bytes = so_bytes + 16.0 * leaf_cells;
+    H->stats.n_leaves = H->n_leaves;
+    H->stats.n_nodes = nn;
+    H->stats.dofs = leaf_cells;
 }
 
 static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* ext_leaf_size)
@@ -291,7 +336,7 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* 
         nd.batch = it->second; nd.slot = (int)b.parents.size();
         b.parents.push_back(i);
     }
-    for (auto& b : H->batches) { b.count = (int)b.parents.size(); plan_batch_gemms(b); }
+    for (auto& b : H->batches) { b.count = (int)b.parents.size(); plan_batch_gemms(b, H->part_rank, H->part_nranks); }
     // vector arena offsets
     size_t off = 0;
     auto take = [&](size_t nd_) { size_t o = off; off += (nd_ + 1) & ~size_t(1); return o; };
@@ -300,23 +345,7 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* 
         if (!nd.leaf) { nd.w_off = take(2 * (size_t)nd.size); nd.hd_off = take(2 * (size_t)nd.size); }
     }
     H->vec_doubles = off;
-    // flop model (SURVEY.md 8(d)): canonical dgesv+dgemm count and the count actually issued
-    double canon = 0, issued = 0, up_bytes = 0, so_bytes = 0;
-    for (auto& b : H->batches) {
-        const double n3 = (double)b.n * b.n * b.n;
-        canon += b.count * 810.0 * n3 + b.count * (2.0 / 3.0) * n3;
-        issued += b.count * (128.0 + 128.0 + 256.0) * n3;
-        up_bytes += b.count * 8.0 * (16.0 + 16.0) * b.n * b.n;
-        so_bytes += b.count * 8.0 * 32.0 * b.n * b.n;
-    }
-    H->stats.merge_flops_canonical = canon;
-    H->stats.merge_flops_issued = issued;
-    const double leaf_cells = H->external_leaves ? 0.0 : (double)H->n_leaves * M * M;
-    H->stats.upwards_bytes = up_bytes + 8.0 * leaf_cells;
-    H->stats.solve_bytes = so_bytes + 16.0 * leaf_cells;
-    H->stats.n_leaves = H->n_leaves;
-    H->stats.n_nodes = nn;
-    H->stats.dofs = leaf_cells;
+    compute_flop_model(H);
 }
 
 static void allocate_device(efgpu_handle* H, unsigned flags)
@@ -471,17 +500,30 @@ static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
                           H->d_leafT.as<double>(), H->n_leaves, (flags & EFGPU_CACHE_OPERATORS) != 0, H->stream);
 }
 
-static void do_build(efgpu_handle* H, unsigned flags)
+// buildStage in pieces, so that a replicated upper tree can exchange row slices between them:
+//   build_begin            allocation, pivot tracker, leaf DtN maps
+//   build_level(lev, 0)    coarsen + assemble X / H + invert X + (this rank's rows of) S for every merge of level `lev`
+//   build_level(lev, 1)    (this rank's rows of) T
+//   build_end              synchronise, singularity report
+static void build_begin(efgpu_handle* H, unsigned flags)
 {
     if (!H->allocated || ((flags ^ H->build_flags) & EFGPU_KEEP_X)) allocate_device(H, flags);
     cudaStream_t s = H->stream;
     const double big = 1e300;
     EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
     EF_CUDA(cudaEventRecord(H->ev0, s));
+    H->built = false;
     timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, flags); });
-    for (int lev = H->max_level; lev >= 0; lev--)
-        for (int bi : H->level_batches[lev]) {
-            BatchH& b = H->batches[bi];
+}
+
+static void build_level(efgpu_handle* H, int lev, int phase)
+{
+    cudaStream_t s = H->stream;
+    if (lev < 0 || lev > H->max_level) throw Error{EF_ERR_BAD_ARG, "bad level"};
+    for (int bi : H->level_batches[lev]) {
+        BatchH& b = H->batches[bi];
+        double* const* ptab = b.d_ptab.as<double*>();
+        if (phase == 0) {
             for (size_t t = 0; t < b.cT.size(); t++)
                 timed(H, EFGPU_PROF_COARSEN_T, 1, [&] { launch_coarsen_T(b.d_cT[t]->as<CoarsenOp>(), (int)b.cT[t].size(), b.cT_max[t], s); });
             const MergeEntry* ent = b.d_entries.as<MergeEntry>();
@@ -489,14 +531,21 @@ static void do_build(efgpu_handle* H, unsigned flags)
                 launch_assemble_X(ent, b.n, b.count, s);
                 launch_assemble_Hc(ent, b.n, b.count, s);
             });
-            double* const* ptab = b.d_ptab.as<double*>();
-            for (const Step& st : b.steps) {
-                timed(H, st.cls, 1, [&] {
-                    if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
-                    else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
-                });
-            }
         }
+        for (const Step& st : b.steps) {
+            const bool is_T = st.cls == EFGPU_PROF_GEMM_T;
+            if (is_T != (phase == 1) || (st.kind == 1 && st.count == 0)) continue;
+            timed(H, st.cls, 1, [&] {
+                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
+                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
+            });
+        }
+    }
+}
+
+static void build_end(efgpu_handle* H)
+{
+    cudaStream_t s = H->stream;
     EF_CUDA(cudaEventRecord(H->ev1, s));
     double minpiv = 0;
     EF_CUDA(cudaMemcpyAsync(&minpiv, H->d_minpiv.p, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -506,6 +555,13 @@ static void do_build(efgpu_handle* H, unsigned flags)
     H->stats.build_ms = ms; H->stats.min_pivot = minpiv;
     H->built = true; H->upwards_done = false;
     if (!(minpiv > 0.0) || !std::isfinite(minpiv)) throw Error{EF_ERR_SINGULAR, "non-positive or non-finite pivot in the merge factorisation"};
+}
+
+static void do_build(efgpu_handle* H, unsigned flags)
+{
+    build_begin(H, flags);
+    for (int lev = H->max_level; lev >= 0; lev--) { build_level(H, lev, 0); build_level(H, lev, 1); }
+    build_end(H);
 }
 
 static void do_upwards(efgpu_handle* H, const double* f_dev, double fscale, unsigned flags)
@@ -645,6 +701,47 @@ int efgpu_build(efgpu_handle* H, unsigned flags)
     do_build(H, flags);
     EF_CATCH(H)
 }
+
+int efgpu_set_partition(efgpu_handle* H, int rank, int nranks)
+{
+    if (!H || nranks < 1 || rank < 0 || rank >= nranks) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    if (H->allocated) throw Error{EF_ERR_STATE, "efgpu_set_partition must precede the first build / device view"};
+    H->part_rank = rank; H->part_nranks = nranks;
+    for (auto& b : H->batches) plan_batch_gemms(b, rank, nranks);
+    compute_flop_model(H);
+    EF_CATCH(H)
+}
+
+int efgpu_build_begin(efgpu_handle* H, unsigned flags)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    build_begin(H, flags);
+    EF_CATCH(H)
+}
+
+int efgpu_build_level(efgpu_handle* H, int level, int phase)
+{
+    if (!H || (phase != 0 && phase != 1)) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->allocated) throw Error{EF_ERR_STATE, "efgpu_build_level before efgpu_build_begin"};
+    build_level(H, level, phase);
+    EF_CATCH(H)
+}
+
+int efgpu_build_end(efgpu_handle* H)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    build_end(H);
+    EF_CATCH(H)
+}
+
+int efgpu_max_level(const efgpu_handle* H) { return H ? H->max_level : -1; }
 
 int efgpu_upwards(efgpu_handle* H, const double* f_leaves, double fscale, unsigned flags)
 {

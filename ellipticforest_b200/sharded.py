@@ -155,6 +155,18 @@ class GpuEngine:
     def build(self, flags):
         check(self._lib.efgpu_build(self._h, flags), self._h)
 
+    def set_partition(self, rank, nranks):
+        check(self._lib.efgpu_set_partition(self._h, int(rank), int(nranks)), self._h)
+
+    def build_begin(self, flags):
+        check(self._lib.efgpu_build_begin(self._h, flags), self._h)
+
+    def build_level(self, level, phase):
+        check(self._lib.efgpu_build_level(self._h, int(level), int(phase)), self._h)
+
+    def build_end(self):
+        check(self._lib.efgpu_build_end(self._h), self._h)
+
     def upwards(self, f_dev_ptr, scale, flags, sync=False):
         check(self._lib.efgpu_upwards_device(self._h, C.c_void_p(f_dev_ptr) if f_dev_ptr else None, float(scale), flags, int(sync)), self._h)
 
@@ -229,6 +241,26 @@ class ShardedExchange:
             for w in self.dist.batch_isend_irecv(ops):
                 w.wait()
 
+    def share(self, local_view, top_view):
+        """Replicated upper tree: every rank ends up with every subtree root's operator / vector in its own
+        upper-tree leaf buffers (owner copies, then broadcasts)."""
+        world = self.dist.get_world_size() if self.dist.is_initialized() else 1
+        for k in range(len(self.plan.cut_nodes)):
+            o = int(self.plan.owner[k])
+            dst = top_view(k)
+            if o == self.rank:
+                dst.copy_(local_view(k))
+            if world > 1:
+                self.dist.broadcast(dst, src=o)
+
+    def allgather_rows(self, full):
+        """In-place all-gather of the contiguous, equally sized row slices of `full` (slice r was computed by rank r)."""
+        world = self.dist.get_world_size() if self.dist.is_initialized() else 1
+        if world == 1:
+            return
+        cnt = full.numel() // world
+        self.dist.all_gather_into_tensor(full, full[self.rank * cnt:(self.rank + 1) * cnt])
+
     def gather_T(self, local, top):
         self._gather(lambda k: local.root_T(k), lambda k: top.leaf_T(k) if top is not None else None)
 
@@ -271,8 +303,9 @@ class _TopGpu:
 class ShardedHPS:
     """Benchmark/driver-facing sharded HPS (same stage names as HPSAlgorithm; inputs/outputs are this rank's share)."""
 
-    def __init__(self, mesh, solver, device=0, rank=0, world=1, options=None, cut=2):
+    def __init__(self, mesh, solver, device=0, rank=0, world=1, options=None, cut=2, top_mode="replicated"):
         import torch
+        self.top_mode = top_mode
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.mesh, self.patch_solver, self.rank, self.world, self._device = mesh, solver, rank, world, device
@@ -287,10 +320,14 @@ class ShardedHPS:
         self._stream = torch.cuda.ExternalStream(self.local.stream())
         self.local_if = _LocalGpu(self.local, roots, self.plan.subtrees_of(rank))
         self.top = self.top_if = None
-        if rank == 0:
+        if rank == 0 or top_mode == "replicated":
             tids, tlev, tch, tbox, ext = self.plan.top_table()
             self.top = GpuEngine(tlev, tch, tbox, mesh.nx, device, ext_sizes=ext, stream=self.local.stream())
+            if top_mode == "replicated":
+                self.top.set_partition(rank, world)     # must precede the first device view
             self.top_if = _TopGpu(self.top, [int(i) for i in np.nonzero(tch[:, 0] < 0)[0]])
+            self._top_level = tlev
+            self._top_interior = [int(i) for i in np.nonzero(tch[:, 0] >= 0)[0]]
         self.xchg = ShardedExchange(self.plan, rank, dist)
         self.leaf_lo, self.leaf_hi = self.plan.local_leaf_range(rank)
         lam = float(solver.lambda_function(np.float64(0.0), np.float64(0.0)))
@@ -305,6 +342,9 @@ class ShardedHPS:
         return (CACHE_OPERATORS if self.options["cache-operators"] else 0) | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0)
 
     def sharding(self):
+        if self.top_mode == "replicated":
+            return ("level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); upper tree replicated: subtree-root T broadcast over NCCL, "
+                    "X^-1 on every rank, rows of S and T split %d ways and all-gathered" % (self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world, self.world))
         return "level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); subtree-root T/h gathered to rank 0 over NCCL, g scattered back" % (
             self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world)
 
@@ -342,17 +382,46 @@ class ShardedHPS:
     def buildStage(self):
         fl = self._flags()
         self.local.build(fl)
+        if self.top_mode != "replicated":
+            with self.torch.cuda.stream(self._stream):
+                self.xchg.gather_T(self.local_if, self.top_if)
+            if self.top is not None:
+                self.top.build(fl)
+            return
         with self.torch.cuda.stream(self._stream):
-            self.xchg.gather_T(self.local_if, self.top_if)
-        if self.top is not None:
-            self.top.build(fl)
+            self.xchg.share(self.local_if.root_T, self.top_if.leaf_T)
+        self.top.build_begin(fl)
+        for lev in range(self.plan.cut - 1, -1, -1):
+            nodes = [i for i in self._top_interior if self._top_level[i] == lev]
+            self.top.build_level(lev, 0)
+            with self.torch.cuda.stream(self._stream):
+                for i in nodes:
+                    self.xchg.allgather_rows(self.top.operator_view(i, "S"))
+            self.top.build_level(lev, 1)
+            if lev > 0:     # the root's DtN map stays row-distributed (only a Robin root solve would need it whole)
+                with self.torch.cuda.stream(self._stream):
+                    for i in nodes:
+                        self.xchg.allgather_rows(self.top.operator_view(i, "T_uncoarsened"))
+        self.top.build_end()
+
+    def gather_root_T(self):
+        """Parity/debug: the root DtN map assembled from its row slices (every rank gets the whole matrix)."""
+        T = self.top.operator_view(0, "T_uncoarsened")
+        if self.top_mode == "replicated":
+            with self.torch.cuda.stream(self._stream):
+                self.xchg.allgather_rows(T)
+            self.local.sync()
+        return T
 
     def upwardsStageDevice(self, f_dev_ptr, scale=1.0, sync=True):
         fl = self._flags()
         self.local.upwards(f_dev_ptr, scale, fl)
         if not (fl & HOMOGENEOUS_RHS):
             with self.torch.cuda.stream(self._stream):
-                self.xchg.gather_h(self.local_if, self.top_if)
+                if self.top_mode == "replicated":
+                    self.xchg.share(self.local_if.root_h, self.top_if.leaf_h)
+                else:
+                    self.xchg.gather_h(self.local_if, self.top_if)
             if self.top is not None:
                 self.top.upwards(0, 1.0, fl)
         if sync:
@@ -366,7 +435,11 @@ class ShardedHPS:
                 groot.copy_(_dev_tensor(g_dev_ptr, groot.numel()))
             self.top.solve_from_roots(0, fl)
         with self.torch.cuda.stream(self._stream):
-            self.xchg.scatter_g(self.top_if, self.local_if)
+            if self.top_mode == "replicated":   # every rank walked the upper tree itself: its subtree roots' g are local
+                for k in self.plan.subtrees_of(self.rank):
+                    self.local_if.root_g(k).copy_(self.top_if.leaf_g(k))
+            else:
+                self.xchg.scatter_g(self.top_if, self.local_if)
         self.local.solve_from_roots(u_dev_ptr, fl, sync=sync)
 
     def upwardsStageHost(self, f_host):

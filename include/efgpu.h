@@ -100,6 +100,18 @@ int efgpu_create_ex(const efgpu_tree_desc* desc, int device, const int32_t* exte
 void efgpu_destroy(efgpu_handle* h);
 const char* efgpu_last_error(const efgpu_handle* h);   /* h may be NULL after a failed create */
 
+/* Replicated upper tree: every rank holds the same (external-leaf) tree and computes only rows
+ * [rank * R / nranks, (rank+1) * R / nranks) of each merge's S (R = 4n) and T (R = 8n); the caller all-gathers the
+ * contiguous row slices (views from efgpu_operator_device) between efgpu_build_level(level, 0) [coarsen, X, X^-1,
+ * S rows] and efgpu_build_level(level, 1) [T rows], levels from the deepest up.  X^-1 is formed by every rank.
+ * efgpu_build == begin; for each level: phase 0, phase 1; end.  Replaces the redundant whole-merge recomputation
+ * on every sharing rank in the reference (Quadtree.hpp:504-506). */
+int efgpu_set_partition(efgpu_handle* h, int rank, int nranks);
+int efgpu_build_begin(efgpu_handle* h, unsigned flags);
+int efgpu_build_level(efgpu_handle* h, int level, int phase);
+int efgpu_build_end(efgpu_handle* h);
+int efgpu_max_level(const efgpu_handle* h);
+
 /* ---- leaf model: replaces FiniteVolumeSolver's public fields (FiniteVolumeSolver.hpp:64-88) ---- */
 /* solver_type = FISHPACK90: constant coefficients, lambda = lambda_function(0,0) (FiniteVolumeSolver.cpp:254) */
 int efgpu_set_leaf_constant(efgpu_handle* h, double lambda);

@@ -34,11 +34,11 @@ def _solver(P):
     return s
 
 
-def _run_sharded(kw, rank, world, device):
+def _run_sharded(kw, rank, world, device, top_mode="replicated"):
     import torch
     P = O.problem(kw["problem_name"])
     m = _mesh_for(kw)
-    hps = ShardedHPS(m, _solver(P), device=device, rank=rank, world=world)
+    hps = ShardedHPS(m, _solver(P), device=device, rank=rank, world=world, top_mode=top_mode)
     f, g = hps.sample_inputs(P["f"], P["u"])
     f_dev = torch.from_numpy(f).cuda(device)
     g_dev = torch.from_numpy(g).cuda(device)
@@ -46,7 +46,7 @@ def _run_sharded(kw, rank, world, device):
     hps.buildStage()
     hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True)
     hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True)
-    rootT = hps.top.operator_view(0, "T").cpu().numpy() if hps.top is not None else None
+    rootT = hps.gather_root_T().cpu().numpy() if hps.top is not None else None
     return hps, u_dev.cpu().numpy(), rootT
 
 
@@ -60,11 +60,12 @@ def _run_single(kw):
     return hps
 
 
+@pytest.mark.parametrize("top_mode", ["replicated", "root"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_forest_and_upper_tree_on_one_gpu(case):
+def test_forest_and_upper_tree_on_one_gpu(case, top_mode):
     kw = CASES[case]
     single = _run_single(kw)
-    hps, u, rootT = _run_sharded(kw, 0, 1, 0)
+    hps, u, rootT = _run_sharded(kw, 0, 1, 0, top_mode)
     assert relerr(u, single.u_leaves.reshape(-1)) < 1e-12
     assert relerr(rootT, single.operator(0, "T").reshape(-1)) < 1e-12
     # and against the oracle, like every other parity test
@@ -72,30 +73,31 @@ def test_forest_and_upper_tree_on_one_gpu(case):
     assert relerr(u, np.concatenate(ora.leaf_solution())) < 1e-10
 
 
-def _worker(rank, world, port, case, out_dir):
+def _worker(rank, world, port, case, out_dir, top_mode):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        hps, u, rootT = _run_sharded(CASES[case], rank, world, rank)
+        hps, u, rootT = _run_sharded(CASES[case], rank, world, rank, top_mode)
         np.save(os.path.join(out_dir, "u_%d.npy" % rank), u)
         np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array([hps.leaf_lo, hps.leaf_hi]))
-        if rootT is not None:
+        if rootT is not None and rank == 0:
             np.save(os.path.join(out_dir, "T_root.npy"), rootT)
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("top_mode", ["replicated", "root"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_two_gpus_over_nccl(case, tmp_path):
+def test_two_gpus_over_nccl(case, top_mode, tmp_path):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path), top_mode), nprocs=2, join=True)
     single = _run_single(CASES[case])
     u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
     for r in range(2):

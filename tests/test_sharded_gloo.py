@@ -141,6 +141,62 @@ CASES = {
 }
 
 
+def _worker_replicated(rank, world, port, case, out_dir):
+    """Replicated upper tree: share() of the subtree roots, then per level the row slices of S and T are
+    all-gathered in place (the oracle computes whole merges; rows a rank does not own are wiped first, so
+    only the exchange can restore them)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kw = CASES[case]
+        P = O.problem(kw["problem_name"])
+        ind = O.refine_box_indicator(kw["refine_box"]) if kw["refine_box"] else O.refine_indicator(1.2)
+        nodes = O.build_tree(ind, kw["box"], kw["nx"], kw["min_level"], kw["max_level"])
+        solver = O.Solver(kind="fishpack", alpha=P["alpha"], beta=P["beta"], lam=P["lam"])
+        plan = ShardPlan(*_tables(nodes), kw["nx"], world)
+        ids, lev, ch, box, roots = plan.local_table(rank)
+        local = OracleEngine(lev, ch, box, kw["nx"], solver)
+        lif = LocalIf(local, roots, plan.subtrees_of(rank))
+        tids, tlev, tch, tbox, ext = plan.top_table()
+        top = OracleEngine(tlev, tch, tbox, kw["nx"], solver, ext_sizes=ext)
+        tif = TopIf(top)
+        x = ShardedExchange(plan, rank, dist)
+        local.build()
+        x.share(lif.root_T, tif.leaf_T)
+        for i in top._post():     # leaves first (from the shared buffers), then merges level by level
+            nd = top.nodes[i]
+            if nd.leaf:
+                nd.T = top.buf[(i, "T")].numpy().reshape(4 * nd.grid.nx, 4 * nd.grid.nx).copy()
+        for level in (1, 0):
+            for i, nd in enumerate(top.nodes):
+                if nd.leaf or nd.level != level:
+                    continue
+                top.hps.merge4to1(nd, *[top.nodes[c] for c in nd.children])
+                for name in ("S", "T"):
+                    full = torch.from_numpy(np.ascontiguousarray(getattr(nd, name))).reshape(-1)
+                    cnt = full.numel() // world
+                    keep = full[rank * cnt:(rank + 1) * cnt].clone()
+                    full.zero_()
+                    full[rank * cnt:(rank + 1) * cnt] = keep
+                    x.allgather_rows(full)
+                    setattr(nd, name, full.numpy().reshape(getattr(nd, name).shape).copy())
+        local.upwards(P["f"])
+        x.share(lif.root_h, tif.leaf_h)
+        top.upwards(None)
+        r, a, b = O.HPS.root_boundary(type("R", (), {"nodes": [top.nodes[0]]})(), lambda s_, xx, yy: (float(P["u"](xx, yy)), 1.0, 0.0))
+        top.nodes[0].g = r / a
+        top.solve()
+        for k in plan.subtrees_of(rank):
+            local.nodes[lif.idx[k]].g = tif.leaf_g(k).numpy().copy()
+        local.solve()
+        np.save(os.path.join(out_dir, "u_%d.npy" % rank), np.concatenate([nd.u for nd in local.nodes if nd.leaf]))
+        np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array(plan.local_leaf_range(rank)))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "T_root.npy"), top.nodes[0].T)
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, case, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -196,10 +252,11 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("mode", ["root", "replicated"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_two_rank_sharded_run_matches_single_process_oracle(case, tmp_path):
+def test_two_rank_sharded_run_matches_single_process_oracle(case, mode, tmp_path):
     kw = CASES[case]
-    mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker if mode == "root" else _worker_replicated, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
     ref = O.run(solver_kind="fishpack", **kw)
     u_ref = ref.leaf_solution()
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
