@@ -333,7 +333,7 @@ def own_arm(a):
 
     gemm_ms = sum(prof[k][0] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
     gemm_launches = sum(prof[k][1] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
-    total_prof_ms = sum(v[0] for v in prof.values())
+    total_prof_ms = sum(v[0] for k, v in prof.items())
     launches = sum(v[1] for v in prof.values())
     flops_issued = stats["merge_flops_issued"] * a.steps      # rank 0's own merges (its subtrees + the upper tree when sharded)
     gemm_tf = flops_issued / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
@@ -360,7 +360,7 @@ def own_arm(a):
                      "flops": "issued to the tensor pipe (512 n^3 per merge; the reference's dgesv+dgemm count is 810.67 n^3)",
                      "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                      "traffic": None},
-        "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0},
+        "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0 or v[0] > 0},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

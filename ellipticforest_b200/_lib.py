@@ -24,6 +24,7 @@ class Stats(C.Structure):
 
 
 REFINE_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_double, C.c_void_p)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p)
 
 # every symbol include/efgpu.h declares: (restype, argtypes)
 _P = C.c_void_p
@@ -33,6 +34,7 @@ SIGNATURES = {
     "efgpu_create": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(_P)]),
     "efgpu_create_ex": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(C.c_int32), C.POINTER(_P)]),
     "efgpu_set_partition": (C.c_int, [_P, C.c_int, C.c_int]),
+    "efgpu_set_allgather": (C.c_int, [_P, ALLGATHER_FN, _P]),
     "efgpu_build_begin": (C.c_int, [_P, C.c_uint]),
     "efgpu_build_level": (C.c_int, [_P, C.c_int, C.c_int]),
     "efgpu_build_end": (C.c_int, [_P]),

@@ -26,7 +26,7 @@ static const int h_tau_side[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
 static const int h_kk[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
 static const int h_pos[8] = {0, 4, 2, 5, 1, 6, 3, 7};  // inverse of pi = {0,4,2,6,1,3,5,7}
 
-enum { OP_TC0 = 0, OP_XINV = 4, OP_S = 5, OP_T = 6, OP_W1 = 7, OP_W2 = 8, NOPS = 10 };
+enum { OP_TC0 = 0, OP_XINV = 4, OP_S = 5, OP_T = 6, OP_W1 = 7, OP_W2 = 8, OP_W3 = 9, NOPS = 10 };
 
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
@@ -62,7 +62,13 @@ struct NodeH {
     size_t w_off = 0, hd_off = 0;
 };
 
-struct Step { int kind; int first, count; long long off; int N; int cls; };  // kind 0: small inverse, 1: gemm; cls: profiling class
+struct Step {
+    int kind; int first, count; long long off; int N; int cls;   // kind 0: small inverse, 1: gemm; cls: profiling class
+    // row-partitioned step of a replicated tree: after the GEMM the h x h result is all-gathered over the ranks.
+    // gk 1: the destination (op g_op, offset g_off) is contiguous (ld == h): in place.  gk 2: the GEMM wrote its rows into
+    // the staging block OP_W3 (ld = h); after the all-gather the block is copied to op g_op, offset g_off, leading dimension g_ld.
+    int gk = 0, g_op = 0, g_h = 0, g_ld = 0; long long g_off = 0;
+};
 
 struct BatchH {
     int level = 0, n = 0, count = 0;
@@ -74,7 +80,8 @@ struct BatchH {
     std::vector<std::vector<CoarsenOp>> cT, cH, cG;  // per step
     std::vector<std::unique_ptr<DevBuf>> d_cT, d_cH, d_cG;
     std::vector<int> cT_max, cH_max, cG_max;
-    size_t ws_per_entry = 0;
+    size_t ws_per_entry = 0, w2_off = 0, w3_off = 0;   // per-entry workspace: [W1 blocks per depth | W2 | W3 staging]
+    std::vector<double*> h_ptab;   // host copy of the operand table (all-gather callbacks need host-side addresses)
 };
 
 }  // namespace efgpu
@@ -90,6 +97,7 @@ struct efgpu_handle {
     std::vector<int> roots;                      // nodes without a parent (one for a tree; several for a forest of subtrees)
     bool external_leaves = false;                // leaf T / h are supplied by the caller (upper tree of a sharded run)
     int part_rank = 0, part_nranks = 1;          // row partition of S / T among the ranks that replicate this tree
+    efgpu_allgather_fn allgather = nullptr; void* allgather_user = nullptr;   // collective supplied by the caller (NCCL)
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
     // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
     // (in an unsharded run this is the first thing the leaf's own split1to4 would do, HPSAlgorithm.hpp:1165-1183)
@@ -150,30 +158,45 @@ static void collect_profile(efgpu_handle* H)   // stream must be synchronised
     H->prof_recs.clear();
 }
 
-static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int depth, std::vector<long long>& w1_off, long long w2_off)
+static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int depth, std::vector<long long>& w1_off, long long w2_off,
+                                int rank, int nranks)
 {
     const bool can_split = N > 128 && (N / 2) % 16 == 0;   // base case: one CTA, register-resident Gauss-Jordan (N <= 128)
     if (!can_split) {
         if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
-        b.steps.push_back({0, 0, 0, off, N, EFGPU_PROF_INVERT_SMALL});
+        Step st{}; st.kind = 0; st.off = off; st.N = N; st.cls = EFGPU_PROF_INVERT_SMALL;
+        b.steps.push_back(st);
         return;
     }
     const int h = N / 2;
     const long long A = off, B = off + h, C = off + (long long)h * ld, D = off + (long long)h * ld + h;
     const long long W1 = w1_off[depth];
+    // products of a replicated tree are split by rows over the ranks when each slice keeps full 128-row tiles
+    const bool split = nranks > 1 && h % (128 * nranks) == 0;
     auto gemm = [&](int c_op, long long c_off, int ldc, int c0_op, long long c0_off, int ldc0,
                     int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb, bool neg) {
         GemmBlock g{};
         g.c_op = c_op; g.c_off = c_off; g.ldc = ldc; g.c0_op = c0_op; g.c0_off = c0_off; g.ldc0 = ldc0;
         g.rows = h; g.cols = h; g.nterms = 1;
         g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, h, neg ? 0x80000000u : 0u};
-        b.steps.push_back({1, (int)b.blocks.size(), 1, 0, 0, EFGPU_PROF_GEMM_XINV});
+        Step st{}; st.kind = 1; st.first = (int)b.blocks.size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
+        if (split) {
+            const long long skip = (long long)rank * (h / nranks);
+            st.g_op = c_op; st.g_off = c_off; st.g_h = h; st.g_ld = ldc;
+            if (ldc == h) st.gk = 1;
+            else { st.gk = 2; g.c_op = OP_W3; g.c_off = 0; g.ldc = h; }   // rows land in the contiguous staging block
+            g.c_off += skip * g.ldc;
+            if (g.c0_op >= 0) g.c0_off += skip * g.ldc0;
+            g.t[0].a_off += skip * lda;
+            g.rows = h / nranks;
+        }
+        b.steps.push_back(st);
         b.blocks.push_back(g);
     };
-    build_inverse_steps(b, A, h, ld, depth + 1, w1_off, w2_off);                                 // A <- A^-1
+    build_inverse_steps(b, A, h, ld, depth + 1, w1_off, w2_off, rank, nranks);                    // A <- A^-1
     gemm(OP_W1, W1, h, -1, 0, 0, OP_XINV, C, ld, OP_XINV, A, ld, false);                          // W1 = C A^-1
     gemm(OP_XINV, D, ld, OP_XINV, D, ld, OP_W1, W1, h, OP_XINV, B, ld, true);                     // D <- D - W1 B   (Schur complement)
-    build_inverse_steps(b, D, h, ld, depth + 1, w1_off, w2_off);                                 // D <- S^-1
+    build_inverse_steps(b, D, h, ld, depth + 1, w1_off, w2_off, rank, nranks);                    // D <- S^-1
     gemm(OP_W2, w2_off, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);                      // W2 = A^-1 B
     gemm(OP_XINV, B, ld, -1, 0, 0, OP_W2, w2_off, h, OP_XINV, D, ld, true);                       // B <- -W2 S^-1
     gemm(OP_XINV, C, ld, -1, 0, 0, OP_XINV, D, ld, OP_W1, W1, h, true);                           // C <- -S^-1 W1
@@ -207,8 +230,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
     for (int h = N / 2; h >= 8; h /= 2) { w1_off.push_back(acc); acc += (long long)h * h; }
     w1_off.push_back(acc);
     const long long w1_total = acc, w2_total = (long long)(N / 2) * (N / 2);
-    b.ws_per_entry = (size_t)(w1_total + w2_total);
-    build_inverse_steps(b, 0, N, N, 0, w1_off, 0);
+    b.w2_off = (size_t)w1_total; b.w3_off = (size_t)(w1_total + w2_total);
+    b.ws_per_entry = (size_t)(w1_total + 2 * w2_total);
+    build_inverse_steps(b, 0, N, N, 0, w1_off, 0, rank, nranks);
     // S = X^-1 S_RHS, written with WESN-permuted columns (mergeS_ + reorderOperators_)
     int first = (int)b.blocks.size();
     for (int k = 0; k < 4; k++)
@@ -224,7 +248,7 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
             }
             if (clip_rows(g, (long long)k * n, s_lo, s_hi)) b.blocks.push_back(g);
         }
-    b.steps.push_back({1, first, (int)b.blocks.size() - first, 0, 0, EFGPU_PROF_GEMM_S});
+    { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_S; b.steps.push_back(st); }
     // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_)
     first = (int)b.blocks.size();
     for (int qr = 0; qr < 8; qr++)
@@ -243,7 +267,7 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
             }
             if (clip_rows(g, (long long)h_pos[qr] * n, t_lo, t_hi)) b.blocks.push_back(g);
         }
-    b.steps.push_back({1, first, (int)b.blocks.size() - first, 0, 0, EFGPU_PROF_GEMM_T});
+    { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_T; b.steps.push_back(st); }
 }
 
 static void compute_flop_model(efgpu_handle* H)
@@ -435,7 +459,8 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             e.hd = vec + P.hd_off; e.h = vec + P.hbuf[0]; e.w = vec + P.w_off; e.g = vec + P.gbuf[0];
             ptab[sl * NOPS + OP_XINV] = e.Xinv; ptab[sl * NOPS + OP_S] = e.S; ptab[sl * NOPS + OP_T] = e.T;
             ptab[sl * NOPS + OP_W1] = H->d_ws.as<double>() + sl * b.ws_per_entry;
-            ptab[sl * NOPS + OP_W2] = H->d_ws.as<double>() + sl * b.ws_per_entry + (b.ws_per_entry - (size_t)(2 * n) * (2 * n));
+            ptab[sl * NOPS + OP_W2] = H->d_ws.as<double>() + sl * b.ws_per_entry + b.w2_off;
+            ptab[sl * NOPS + OP_W3] = H->d_ws.as<double>() + sl * b.ws_per_entry + b.w3_off;
             // this parent's own Dirichlet data arrives coarsened when it was tagged: uncoarsen before the split
             for (int t = P.ncoarsen; t >= 1; t--) {
                 const int step = P.ncoarsen - t;
@@ -444,6 +469,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             }
         }
         b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s);
+        b.h_ptab = ptab;
         auto up = [&](std::vector<std::vector<CoarsenOp>>& v, std::vector<std::unique_ptr<DevBuf>>& dv, std::vector<int>& mx) {
             dv.clear(); mx.clear();
             for (auto& ops : v) {
@@ -532,6 +558,11 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                 launch_assemble_Hc(ent, b.n, b.count, s);
             });
         }
+        auto gather = [&](double* buf, size_t doubles_total) {
+            if (!H->allgather) throw Error{EF_ERR_STATE, "row-partitioned tree without an all-gather callback (efgpu_set_allgather)"};
+            if (H->allgather(buf, doubles_total / H->part_nranks * sizeof(double), H->allgather_user) != 0)
+                throw Error{EF_ERR_STATE, "the all-gather callback failed"};
+        };
         for (const Step& st : b.steps) {
             const bool is_T = st.cls == EFGPU_PROF_GEMM_T;
             if (is_T != (phase == 1) || (st.kind == 1 && st.count == 0)) continue;
@@ -539,7 +570,27 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                 if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
                 else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
             });
+            if (st.gk) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
+                const size_t hh = (size_t)st.g_h * st.g_h;
+                for (int sl = 0; sl < b.count; sl++) {
+                    double* const* ops = b.h_ptab.data() + (size_t)sl * NOPS;
+                    if (st.gk == 1) gather(ops[st.g_op] + st.g_off, hh);
+                    else {
+                        gather(ops[OP_W3], hh);
+                        EF_CUDA(cudaMemcpy2DAsync(ops[st.g_op] + st.g_off, (size_t)st.g_ld * sizeof(double), ops[OP_W3], (size_t)st.g_h * sizeof(double),
+                                                  (size_t)st.g_h * sizeof(double), (size_t)st.g_h, cudaMemcpyDeviceToDevice, s));
+                    }
+                }
+            });
         }
+        // the row slices of S (phase 0) and of the DtN map T (phase 1; the root's stays distributed) become whole on every rank
+        if (H->part_nranks > 1 && H->allgather && (phase == 0 || lev > 0)) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
+            const size_t n2 = (size_t)b.n * b.n;
+            for (int sl = 0; sl < b.count; sl++) {
+                double* const* ops = b.h_ptab.data() + (size_t)sl * NOPS;
+                if (phase == 0) gather(ops[OP_S], 32 * n2); else gather(ops[OP_T], 64 * n2);
+            }
+        });
     }
 }
 
@@ -711,6 +762,13 @@ int efgpu_set_partition(efgpu_handle* H, int rank, int nranks)
     for (auto& b : H->batches) plan_batch_gemms(b, rank, nranks);
     compute_flop_model(H);
     EF_CATCH(H)
+}
+
+int efgpu_set_allgather(efgpu_handle* H, efgpu_allgather_fn fn, void* user)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    H->allgather = fn; H->allgather_user = user;
+    return EF_OK;
 }
 
 int efgpu_build_begin(efgpu_handle* H, unsigned flags)
@@ -1055,7 +1113,7 @@ int efgpu_get_profile(const efgpu_handle* H, int cls, double* ms, double* launch
 const char* efgpu_profile_class_name(int cls)
 {
     static const char* names[EFGPU_PROF_NCLASSES] = {"leaf_dtn", "coarsen_T", "assemble_X_H", "invert_small", "gemm_Xinv", "gemm_S",
-                                                      "gemm_T", "leaf_solve", "upwards_matvec", "solve_matvec", "coarsen_vec", "leaf_lu"};
+                                                      "gemm_T", "leaf_solve", "upwards_matvec", "solve_matvec", "coarsen_vec", "leaf_lu", "allgather"};
     return (cls >= 0 && cls < EFGPU_PROF_NCLASSES) ? names[cls] : "";
 }
 

@@ -155,8 +155,20 @@ class GpuEngine:
     def build(self, flags):
         check(self._lib.efgpu_build(self._h, flags), self._h)
 
-    def set_partition(self, rank, nranks):
+    def set_partition(self, rank, nranks, allgather=None):
+        """Row partition of a replicated tree; `allgather(tensor)` must all-gather the tensor's equal slices in place."""
         check(self._lib.efgpu_set_partition(self._h, int(rank), int(nranks)), self._h)
+        if allgather is not None:
+            def _cb(buf, nbytes, _user):
+                try:
+                    allgather(_dev_tensor(buf, nbytes * nranks // 8))
+                    return 0
+                except Exception as e:  # never unwind through the C frames
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._ag_cb = _lib.ALLGATHER_FN(_cb)      # keep the trampoline alive as long as the handle
+            check(self._lib.efgpu_set_allgather(self._h, self._ag_cb, None), self._h)
 
     def build_begin(self, flags):
         check(self._lib.efgpu_build_begin(self._h, flags), self._h)
@@ -324,7 +336,10 @@ class ShardedHPS:
             tids, tlev, tch, tbox, ext = self.plan.top_table()
             self.top = GpuEngine(tlev, tch, tbox, mesh.nx, device, ext_sizes=ext, stream=self.local.stream())
             if top_mode == "replicated":
-                self.top.set_partition(rank, world)     # must precede the first device view
+                def _ag(t):
+                    with torch.cuda.stream(self._stream):
+                        self.xchg.allgather_rows(t)
+                self.top.set_partition(rank, world, _ag if world > 1 else None)     # must precede the first device view
             self.top_if = _TopGpu(self.top, [int(i) for i in np.nonzero(tch[:, 0] < 0)[0]])
             self._top_level = tlev
             self._top_interior = [int(i) for i in np.nonzero(tch[:, 0] >= 0)[0]]
@@ -390,19 +405,9 @@ class ShardedHPS:
             return
         with self.torch.cuda.stream(self._stream):
             self.xchg.share(self.local_if.root_T, self.top_if.leaf_T)
-        self.top.build_begin(fl)
-        for lev in range(self.plan.cut - 1, -1, -1):
-            nodes = [i for i in self._top_interior if self._top_level[i] == lev]
-            self.top.build_level(lev, 0)
-            with self.torch.cuda.stream(self._stream):
-                for i in nodes:
-                    self.xchg.allgather_rows(self.top.operator_view(i, "S"))
-            self.top.build_level(lev, 1)
-            if lev > 0:     # the root's DtN map stays row-distributed (only a Robin root solve would need it whole)
-                with self.torch.cuda.stream(self._stream):
-                    for i in nodes:
-                        self.xchg.allgather_rows(self.top.operator_view(i, "T_uncoarsened"))
-        self.top.build_end()
+        # levels above the cut: X^-1 products, S and T are computed in row slices and all-gathered by the library
+        # through the callback above (the root's DtN map stays row-distributed)
+        self.top.build(fl)
 
     def gather_root_T(self):
         """Parity/debug: the root DtN map assembled from its row slices (every rank gets the whole matrix)."""

@@ -62,7 +62,7 @@ enum {
     EFGPU_PROF_LEAF_DTN = 0, EFGPU_PROF_COARSEN_T = 1, EFGPU_PROF_ASSEMBLE = 2, EFGPU_PROF_INVERT_SMALL = 3,
     EFGPU_PROF_GEMM_XINV = 4, EFGPU_PROF_GEMM_S = 5, EFGPU_PROF_GEMM_T = 6, EFGPU_PROF_LEAF_SOLVE = 7,
     EFGPU_PROF_UPWARDS_MATVEC = 8, EFGPU_PROF_SOLVE_MATVEC = 9, EFGPU_PROF_COARSEN_VEC = 10, EFGPU_PROF_LEAF_LU = 11,
-    EFGPU_PROF_NCLASSES = 12
+    EFGPU_PROF_ALLGATHER = 12, EFGPU_PROF_NCLASSES = 13
 };
 
 typedef struct efgpu_handle efgpu_handle;
@@ -107,6 +107,13 @@ const char* efgpu_last_error(const efgpu_handle* h);   /* h may be NULL after a 
  * efgpu_build == begin; for each level: phase 0, phase 1; end.  Replaces the redundant whole-merge recomputation
  * on every sharing rank in the reference (Quadtree.hpp:504-506). */
 int efgpu_set_partition(efgpu_handle* h, int rank, int nranks);
+/* With a collective supplied by the caller the library performs every exchange of a partitioned tree itself, inside
+ * efgpu_build / efgpu_build_level: the large products of the block inversion of X are split by rows as well (each rank
+ * computes h / nranks rows of every h x h product, h >= 128 * nranks), and S / T row slices are gathered after their
+ * phase.  fn must all-gather IN PLACE: rank r's bytes_per_rank bytes lie at buf + r * bytes_per_rank; it must be
+ * stream-ordered with efgpu_stream(h) (e.g. ncclAllGather on that stream, or torch.distributed under that stream). */
+typedef int (*efgpu_allgather_fn)(void* buf, size_t bytes_per_rank, void* user);
+int efgpu_set_allgather(efgpu_handle* h, efgpu_allgather_fn fn, void* user);
 int efgpu_build_begin(efgpu_handle* h, unsigned flags);
 int efgpu_build_level(efgpu_handle* h, int level, int phase);
 int efgpu_build_end(efgpu_handle* h);
