@@ -331,6 +331,15 @@ def own_arm(a):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture (never measured under this run)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = {"bytes": tr["traffic_bytes_per_launch"], "algorithmic_bytes": tr["algorithmic_bytes_per_launch"],
+                   "launch": tr["launch"], "source": tr["source"]}
+    except Exception:
+        pass
+
     gemm_ms = sum(prof[k][0] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
     gemm_launches = sum(prof[k][1] for k in ("gemm_Xinv", "gemm_S", "gemm_T"))
     total_prof_ms = sum(v[0] for k, v in prof.items())
@@ -359,7 +368,7 @@ def own_arm(a):
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure; NVIDIA nominal FP64 tensor 37-40 TFLOP/s)",
                      "flops": "issued to the tensor pipe (512 n^3 per merge; the reference's dgesv+dgemm count is 810.67 n^3)",
                      "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
-                     "traffic": None},
+                     "traffic": traffic},
         "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0 or v[0] > 0},
         "cpu_baseline": cpu,
         "clocks": clocks,

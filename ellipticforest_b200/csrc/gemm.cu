@@ -230,6 +230,12 @@ void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, cons
                 case 15: launch_cfg<128, 64, 16, 4, 1, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
                 case 16: launch_cfg<64, 128, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
                 case 17: launch_cfg<64, 128, 32, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                case 18: launch_cfg<128, 64, 16, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // 8 warps of 32 x 32, 2 CTAs / SM
+                case 19: launch_cfg<128, 64, 16, 4, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // ... 2 stages, 3 CTAs / SM
+                case 20: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;    // 4 warps of 32 x 32, 4 CTAs / SM
+                case 21: launch_cfg<128, 64, 32, 4, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // BK 32: half the barriers
+                case 22: launch_cfg<128, 128, 16, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;            // 16 warps of 32 x 32, 1 CTA / SM... 2 if registers allow
+                case 23: launch_cfg<64, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // 8 warps of 32 x 32, wide
                 case 0: launch_cfg<128, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
                 // default (7): 128 x 64 CTA tile, 4 warps of 64 x 32, two CTAs per SM so that one CTA's barrier / fragment-load
                 // phases overlap the other's DMMA phases (measured 31-32 TFLOP/s vs 29-30 for one 128 x 128 CTA per SM)

@@ -77,6 +77,7 @@ struct BatchH {
     std::vector<Step> steps;          // inversion, then S, then T
     DevBuf d_blocks, d_entries, d_ptab;
     DevBuf Xinv, S, Hc, T, Xcopy, Tcoarse;
+    double* Tbase = nullptr;          // this batch's DtN slab: its own buffer T, or a slice of the handle's transient arena (EFGPU_LEAN_T)
     std::vector<std::vector<CoarsenOp>> cT, cH, cG;  // per step
     std::vector<std::unique_ptr<DevBuf>> d_cT, d_cH, d_cG;
     std::vector<int> cT_max, cH_max, cG_max;
@@ -110,6 +111,8 @@ struct efgpu_handle {
     int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
     // device state
     DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
+    DevBuf d_Tarena[2];                          // EFGPU_LEAN_T: DtN maps of even / odd tree levels (a level's maps die when its parents are merged)
+    bool lean_T = false;
     DevBuf d_robin;                              // workspace of the root boundary solve (efgpu_solve_robin)
     DevBuf d_coef_in[6], d_coef, d_P;            // variable-coefficient leaves: sampled alpha/beta/lambda, stencil coefficients, block-LU inverses
     size_t vec_doubles = 0;
@@ -403,20 +406,37 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
     for (int l = 0; l < H->n_leaves; l++) { NodeH& nd = H->nodes[H->leaf_nodes[l]]; lh[l] = vec + nd.hbuf[0]; lg[l] = vec + nd.gbuf[0]; }
     H->d_leaf_h.upload(lh, s); H->d_leaf_g.upload(lg, s);
 
+    // Lean policy: a node's DtN map is only read by its parent's merge, so the maps of tree level l live in
+    // arena[l & 1] and are overwritten when level l - 2 is merged; the roots' maps (written last) stay valid.
+    H->lean_T = (flags & EFGPU_LEAN_T) != 0;
+    if (H->lean_T) {
+        for (int r : H->roots) if (H->nodes[r].level != H->nodes[H->roots[0]].level)
+            throw Error{EF_ERR_UNSUPPORTED, "EFGPU_LEAN_T needs all roots of a forest on one tree level"};
+        size_t need[2] = {0, 0};
+        for (int lev = 0; lev <= H->max_level; lev++) {
+            size_t tot = 0;
+            for (int bi : H->level_batches[lev]) { const BatchH& b = H->batches[bi]; tot += (size_t)b.count * 64 * b.n * b.n; }
+            need[lev & 1] = std::max(need[lev & 1], tot);
+        }
+        for (int p = 0; p < 2; p++) H->d_Tarena[p].alloc(need[p] * sizeof(double));
+    } else { H->d_Tarena[0].release(); H->d_Tarena[1].release(); }
     // per-batch operator storage (deepest level first so children's buffers exist before the parents' tables)
     size_t ws_max = 0;
-    for (int lev = H->max_level; lev >= 0; lev--)
+    for (int lev = H->max_level; lev >= 0; lev--) {
+        size_t arena_off = 0;
         for (int bi : H->level_batches[lev]) {
             BatchH& b = H->batches[bi];
             const size_t n = b.n, cnt = b.count;
             b.Xinv.alloc(cnt * 16 * n * n * sizeof(double));
             b.S.alloc(cnt * 32 * n * n * sizeof(double));
             b.Hc.alloc(cnt * 16 * n * n * sizeof(double));
-            b.T.alloc(cnt * 64 * n * n * sizeof(double));
+            if (H->lean_T) { b.T.release(); b.Tbase = H->d_Tarena[lev & 1].as<double>() + arena_off; arena_off += cnt * 64 * n * n; }
+            else { b.T.alloc(cnt * 64 * n * n * sizeof(double)); b.Tbase = b.T.as<double>(); }
             if (flags & EFGPU_KEEP_X) b.Xcopy.alloc(cnt * 16 * n * n * sizeof(double));
             ws_max = std::max(ws_max, cnt * b.ws_per_entry);
-            for (size_t sl = 0; sl < cnt; sl++) H->nodes[b.parents[sl]].Tbuf.assign(1, b.T.as<double>() + sl * 64 * n * n);
+            for (size_t sl = 0; sl < cnt; sl++) H->nodes[b.parents[sl]].Tbuf.assign(1, b.Tbase + sl * 64 * n * n);
         }
+    }
     H->d_ws.alloc(ws_max * sizeof(double));
     // coarsened copies + tables
     for (auto& b : H->batches) {
@@ -454,7 +474,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             e.Xinv = b.Xinv.as<double>() + sl * 16 * n * n;
             e.S = b.S.as<double>() + sl * 32 * n * n;
             e.Hc = b.Hc.as<double>() + sl * 16 * n * n;
-            e.T = b.T.as<double>() + sl * 64 * n * n;
+            e.T = b.Tbase + sl * 64 * n * n;
             e.Xcopy = (flags & EFGPU_KEEP_X) ? b.Xcopy.as<double>() + sl * 16 * n * n : nullptr;
             e.hd = vec + P.hd_off; e.h = vec + P.hbuf[0]; e.w = vec + P.w_off; e.g = vec + P.gbuf[0];
             ptab[sl * NOPS + OP_XINV] = e.Xinv; ptab[sl * NOPS + OP_S] = e.S; ptab[sl * NOPS + OP_T] = e.T;
@@ -499,7 +519,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
     H->allocated = true; H->build_flags = flags;
     size_t tot = 0;
     for (auto& b : H->batches) tot += b.Xinv.bytes + b.S.bytes + b.Hc.bytes + b.T.bytes + b.Xcopy.bytes + b.Tcoarse.bytes;
-    H->stats.device_bytes = (double)(tot + H->d_leafT.bytes + H->d_vec.bytes + H->d_ws.bytes + H->d_f.bytes + H->d_u.bytes);
+    H->stats.device_bytes = (double)(tot + H->d_Tarena[0].bytes + H->d_Tarena[1].bytes + H->d_leafT.bytes + H->d_vec.bytes + H->d_ws.bytes + H->d_f.bytes + H->d_u.bytes);
 }
 
 static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
@@ -533,7 +553,7 @@ static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
 //   build_end              synchronise, singularity report
 static void build_begin(efgpu_handle* H, unsigned flags)
 {
-    if (!H->allocated || ((flags ^ H->build_flags) & EFGPU_KEEP_X)) allocate_device(H, flags);
+    if (!H->allocated || ((flags ^ H->build_flags) & (EFGPU_KEEP_X | EFGPU_LEAN_T))) allocate_device(H, flags);
     cudaStream_t s = H->stream;
     const double big = 1e300;
     EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
@@ -677,6 +697,14 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
     return EF_OK;
 
 static thread_local std::string g_create_error;
+
+// EFGPU_LEAN_T: only the DtN maps of leaves (own buffer) and of the roots (merged last) outlive the build
+static void require_T_retained(const efgpu_handle* H, int node)
+{
+    const efgpu::NodeH& nd = H->nodes[node];
+    if (H->lean_T && !nd.leaf && nd.parent >= 0)
+        throw efgpu::Error{EF_ERR_STATE, "the DtN map of an interior node is not retained under EFGPU_LEAN_T"};
+}
 
 extern "C" {
 
@@ -901,6 +929,7 @@ int efgpu_operator_device(efgpu_handle* H, int node, int which, double** ptr, in
     if (!H->allocated) { EF_CUDA(cudaSetDevice(H->device)); allocate_device(H, H->build_flags); }
     const NodeH& nd = H->nodes[node];
     const size_t n = nd.size / 2;
+    if (which == EFGPU_OP_T || which == EFGPU_OP_T_UNCOARSENED) require_T_retained(H, node);
     switch (which) {
         case EFGPU_OP_T: *ptr = nd.Tbuf[nd.ncoarsen]; break;
         case EFGPU_OP_T_UNCOARSENED: *ptr = nd.Tbuf[0]; break;
@@ -1037,6 +1066,7 @@ int efgpu_get_operator(efgpu_handle* H, int node, int which, double* out, size_t
     const size_t n = nd.size / 2, bytes = (size_t)rows * cols * sizeof(double);
     const double* src = nullptr;
     DevBuf tmp;
+    if (which == EFGPU_OP_T || which == EFGPU_OP_T_UNCOARSENED) require_T_retained(H, node);
     switch (which) {
         case EFGPU_OP_T: src = nd.Tbuf[nd.ncoarsen]; break;
         case EFGPU_OP_T_UNCOARSENED: src = nd.Tbuf[0]; break;

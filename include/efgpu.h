@@ -48,7 +48,11 @@ enum {
 enum {
     EFGPU_CACHE_OPERATORS = 1u, /* option "cache-operators" (HPSAlgorithm.hpp:134-139): one T_leaf for every leaf */
     EFGPU_HOMOGENEOUS_RHS = 2u, /* option "homogeneous-rhs" (HPSAlgorithm.hpp:532,587,1202) */
-    EFGPU_KEEP_X = 4u           /* parity/debug: retain a copy of X (the product only needs X^-1) */
+    EFGPU_KEEP_X = 4u,          /* parity/debug: retain a copy of X (the product only needs X^-1) */
+    EFGPU_LEAN_T = 8u           /* memory policy: a DtN map T is only read by the parent's merge4to1
+                                   (HPSAlgorithm.hpp:497-518), so the maps of one tree level share a transient arena that is
+                                   reused two levels up; after the build only leaf and root T can be read back.  Halves the
+                                   resident operator bytes (X^-1 + S + H stay: 512 n^2 B per merge instead of 1024 n^2). */
 };
 
 enum { EFGPU_LEAF_CONSTANT = 0, EFGPU_LEAF_VARIABLE = 1 };

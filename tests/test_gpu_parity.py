@@ -176,6 +176,47 @@ def test_options_cache_operators_and_homogeneous_rhs():
     assert relerr(hps.u_leaves, np.stack([u.reshape(8, 8) for u in oh.leaf_solution()])) < TOL
 
 
+@pytest.mark.parametrize("case", ["uniform", "adaptive"])
+def test_lean_T_memory_policy(case):
+    """EFGPU_LEAN_T: interior DtN maps share a two-level transient arena.  Everything that outlives
+    the build (X^-1, S, H, root T, h, w, g, u) must be bit-identical to the retained-T build; reading an interior
+    T afterwards is a state error."""
+    if case == "uniform":
+        kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16,
+                  min_level=3, max_level=3, threshold=1.2, refine_box=None)
+    else:
+        kw = dict(problem_name="poisson", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=8,
+                  min_level=1, max_level=4, threshold=1.2, refine_box=None)
+    full = run_gpu(kw, keep_x=False)
+    P = O.problem(kw["problem_name"])
+    m = _mesh_for(kw)
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FISHPACK90"
+    s.lambda_function = P["lam"]
+    lean = ef.HPSAlgorithm(m, s)
+    lean.lean_T = True
+    lean.buildStage()
+    lean.upwardsStage(P["f"])
+    lean.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0))
+    assert np.array_equal(lean.u_leaves, full.u_leaves)
+    assert np.array_equal(lean.operator(0, "T"), full.operator(0, "T"))
+    interior = [i for i in range(m.n_nodes) if m.child[i, 0] >= 0]
+    for i in interior[:: max(1, len(interior) // 6)]:
+        for which in ("S", "Xinv", "H"):
+            assert np.array_equal(lean.operator(i, which), full.operator(i, which)), (i, which)
+        for which in ("h", "w", "g"):
+            assert np.array_equal(lean.vector(i, which), full.vector(i, which)), (i, which)
+    assert lean.stats()["device_bytes"] < full.stats()["device_bytes"]
+    if len(interior) > 1:
+        with pytest.raises(RuntimeError):
+            lean.operator(interior[1], "T")
+    # a second build + solve on the same handle reuses the arenas
+    lean.buildStage()
+    lean.upwardsStage(P["f"])
+    u2 = lean.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0))
+    assert np.array_equal(u2, full.u_leaves)
+
+
 def test_linearity_and_repeat_solves():
     """Size-independent properties: the solve is linear in (f, g) and repeatable on cached operators."""
     kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16,
