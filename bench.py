@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=16)
     ap.add_argument("--problem", default="poisson", choices=["poisson", "helmholtz"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-symmetry", action="store_true", help="EFGPU_NO_SYMMETRY: general merge plan (A/B against the symmetric one)")
     ap.add_argument("--profile-run", action="store_true", help="for ncu: exactly --warmup/--steps device steps, nothing else, no JSON")
     ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6 own arm, 5 reference arm)")
     return ap.parse_args()
@@ -189,6 +190,7 @@ def own_arm(a):
     f_fn = lambda x, y: (lam - 1.0) * u_exact(x, y)
 
     hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world)
+    hps.no_symmetry = a.no_symmetry
     hps.setupStage()
     f_host, g_host = hps.sample_inputs(f_fn, u_exact)          # numpy, this rank's share
     f_pin = torch.from_numpy(f_host).pin_memory()
@@ -352,7 +354,8 @@ def own_arm(a):
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
-                   "sharding": hps.sharding()},
+                   "sharding": hps.sharding(),
+                   "merge_plan": "general (EFGPU_NO_SYMMETRY)" if a.no_symmetry else "symmetric where the subtree is uniform with constant-coefficient leaves (every merge of this workload)"},
         "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,
                    "build_dofs_per_s": dofs / (build_ms * 1e-3), "solve_dofs_per_s": dofs / ((up_ms + so_ms) * 1e-3),
                    "upwards_gbs": tot["upwards_bytes"] / (up_ms * 1e-3) / 1e9, "solve_gbs": tot["solve_bytes"] / (so_ms * 1e-3) / 1e9,
@@ -366,7 +369,7 @@ def own_arm(a):
         "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)%s" % (" on rank 0" if world > 1 else ""),
                      "achieved": gemm_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": (gemm_tf / dgemm_tf) if (gemm_tf and dgemm_tf) else None,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure; NVIDIA nominal FP64 tensor 37-40 TFLOP/s)",
-                     "flops": "issued to the tensor pipe (512 n^3 per merge; the reference's dgesv+dgemm count is 810.67 n^3)",
+                     "flops": "issued to the tensor pipe (symmetric plan: ~345 n^3 per merge, general plan 484 n^3; the reference's dgesv+dgemm count is 810.67 n^3)",
                      "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                      "traffic": traffic},
         "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0 or v[0] > 0},

@@ -50,6 +50,20 @@ struct GemmBlock {
 void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
                   int nblocks, int batch, cudaStream_t stream, int force_tile = 0);
 
+// Batched out-of-place block transposes  dst (cols x rows) = +-src (rows x cols)^T, addressed like the GEMM operands.
+// Used where the merge matrices are symmetric (uniform, self-adjoint subtrees): the lower blocks of X^-1 and the
+// mirrored blocks of the DtN map T are copies of computed blocks instead of further GEMMs.
+struct TransOp {
+    int src_op, dst_op;
+    int lds, ldd;
+    long long src_off, dst_off;
+    int rows, cols;           // shape of the source block
+    unsigned neg;             // 0 or 0x80000000
+    int pad_;
+};
+void launch_btranspose(double* const* ptab, int nops, const TransOp* d_ops, const TransOp* h_ops, int nt, int batch,
+                       cudaStream_t stream);
+
 // In-place inverse of `batch` small dense N x N matrices (N <= 128) held at
 // ptab[z*nops+op] + off with leading dimension ld; Gauss-Jordan in shared memory, no pivoting
 // (the merge matrices are SPD / diagonally dominant).  min |pivot| is folded

@@ -252,6 +252,49 @@ void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batched block transpose (32 x 32 tiles through shared memory, both sides coalesced).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+btranspose_kernel(double* const* __restrict__ ptab, int nops, const TransOp* __restrict__ tops, int nt, int tiles_per_op)
+{
+    __shared__ double tile[32][33];
+    const long long bid = blockIdx.x;
+    const int t = (int)(bid % tiles_per_op);
+    const int o = (int)((bid / tiles_per_op) % nt);
+    const long long z = bid / ((long long)tiles_per_op * nt);
+    const TransOp op = tops[o];
+    const int tiles_c = (op.cols + 31) >> 5;
+    const int tr = t / tiles_c, tc = t % tiles_c;
+    if (tr >= ((op.rows + 31) >> 5)) return;
+    const double* src = ptab[z * nops + op.src_op] + op.src_off;
+    double* dst = ptab[z * nops + op.dst_op] + op.dst_off;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = tr * 32 + ty + 8 * j, c = tc * 32 + tx;
+        if (r < op.rows && c < op.cols) tile[ty + 8 * j][tx] = src[(long long)r * op.lds + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = tc * 32 + ty + 8 * j, c = tr * 32 + tx;   // destination row = source column
+        if (r < op.cols && c < op.rows) dst[(long long)r * op.ldd + c] = flip_sign(tile[tx][ty + 8 * j], op.neg);
+    }
+}
+
+void launch_btranspose(double* const* ptab, int nops, const TransOp* d_ops, const TransOp* h_ops, int nt, int batch,
+                       cudaStream_t stream)
+{
+    if (nt == 0 || batch == 0) return;
+    int tiles = 0;
+    for (int i = 0; i < nt; i++) { int v = ((h_ops[i].rows + 31) / 32) * ((h_ops[i].cols + 31) / 32); if (v > tiles) tiles = v; }
+    long long grid = (long long)tiles * nt * batch;
+    if (grid > 2147483647LL) throw Error{EF_ERR_BAD_SHAPE, "btranspose grid too large"};
+    btranspose_kernel<<<(unsigned)grid, 256, 0, stream>>>(ptab, nops, d_ops, nt, tiles);
+    EF_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small in-place inverse (base case of the blocked inversion of X): one CTA per matrix,
 // Gauss-Jordan in shared memory.
 // ---------------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <tuple>
 
 namespace efgpu {
 
@@ -57,25 +58,31 @@ struct NodeH {
     int size = 0;       // cells per side of this node's own patch (leaf: M, parent: 2 n)
     int ncoarsen = 0;   // times it is coarsened when merged into its parent (HPSAlgorithm.hpp:676-741)
     int leaf_idx = -1, batch = -1, slot = -1;
+    bool symcand = false;   // see BatchH::symcand
     std::vector<double*> Tbuf;        // [0] own DtN, [t] after t coarsening steps
     std::vector<size_t> hbuf, gbuf;   // offsets into the vector arena, same indexing
     size_t w_off = 0, hd_off = 0;
 };
 
 struct Step {
-    int kind; int first, count; long long off; int N; int cls;   // kind 0: small inverse, 1: gemm; cls: profiling class
-    // row-partitioned step of a replicated tree: after the GEMM the h x h result is all-gathered over the ranks.
-    // gk 1: the destination (op g_op, offset g_off) is contiguous (ld == h): in place.  gk 2: the GEMM wrote its rows into
-    // the staging block OP_W3 (ld = h); after the all-gather the block is copied to op g_op, offset g_off, leading dimension g_ld.
-    int gk = 0, g_op = 0, g_h = 0, g_ld = 0; long long g_off = 0;
+    int kind; int first, count; long long off; int N; int cls;   // kind 0: small inverse, 1: gemm, 2: block transposes; cls: profiling class
+    // row-partitioned step of a replicated tree: after the GEMM the g_rows x g_cols result is all-gathered over the ranks.
+    // gk 1: the destination (op g_op, offset g_off) is contiguous (ld == g_cols): in place.  gk 2: the GEMM wrote its rows into
+    // the staging block OP_W3 (ld = g_cols); after the all-gather the block is copied to op g_op, offset g_off, leading dimension g_ld.
+    int gk = 0, g_op = 0, g_rows = 0, g_cols = 0, g_ld = 0; long long g_off = 0;
 };
 
 struct BatchH {
     int level = 0, n = 0, count = 0;
     std::vector<int> parents;
-    std::vector<GemmBlock> blocks;    // all descriptors of this batch (host copy)
-    std::vector<Step> steps;          // inversion, then S, then T
-    DevBuf d_blocks, d_entries, d_ptab;
+    std::vector<GemmBlock> blocks;    // all descriptors of this batch (host copy), both plans
+    std::vector<TransOp> trans;       // block transposes of the symmetric plan
+    std::vector<Step> steps;          // general plan: inversion, then S, then T
+    std::vector<Step> steps_sym;      // plan for symmetric merge matrices (symcand batches only)
+    bool symcand = false;             // structurally symmetric: square patches, no coarsening anywhere below
+    bool use_sym = false;             // decided at build time (leaf operator self-adjoint, EFGPU_NO_SYMMETRY not set)
+    const std::vector<Step>& active() const { return use_sym ? steps_sym : steps; }
+    DevBuf d_blocks, d_trans, d_entries, d_ptab;
     DevBuf Xinv, S, Hc, T, Xcopy, Tcoarse;
     double* Tbase = nullptr;          // this batch's DtN slab: its own buffer T, or a slice of the handle's transient arena (EFGPU_LEAN_T)
     std::vector<std::vector<CoarsenOp>> cT, cH, cG;  // per step
@@ -109,6 +116,7 @@ struct efgpu_handle {
     std::vector<BatchH> batches;
     // leaf model
     int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
+    bool ext_sym = false;                        // external leaves declared signed-symmetric (efgpu_set_symmetric_leaves)
     // device state
     DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
     DevBuf d_Tarena[2];                          // EFGPU_LEAN_T: DtN maps of even / odd tree levels (a level's maps die when its parents are merged)
@@ -161,50 +169,89 @@ static void collect_profile(efgpu_handle* H)   // stream must be synchronised
     H->prof_recs.clear();
 }
 
-static void build_inverse_steps(BatchH& b, long long off, int N, int ld, int depth, std::vector<long long>& w1_off, long long w2_off,
-                                int rank, int nranks)
-{
-    const bool can_split = N > 128 && (N / 2) % 16 == 0;   // base case: one CTA, register-resident Gauss-Jordan (N <= 128)
-    if (!can_split) {
-        if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
+// Planner of the blocked inversion of X (in place, op OP_XINV).  Two properties of the merge matrix are used:
+//  * structure (always): in the interior ordering [alpha|gamma, beta|omega, alpha|beta, gamma|omega] the two diagonal
+//    2n x 2n blocks of X are block diagonal (mergeX_, HPSAlgorithm.hpp:870-895: the zero blocks), so at the top level
+//    A^-1 = diag(A11^-1, A22^-1) and the products with A^-1 have K = n instead of 2n;
+//  * symmetry (plan `sym`): where every patch below is square, uncoarsened and the leaf operator self-adjoint, X is
+//    symmetric; then C A^-1 = (A^-1 B)^T and the new C block is the transpose of the new B block: four GEMMs and two
+//    transposes per recursion level instead of six GEMMs.
+struct InvPlanner {
+    BatchH& b; std::vector<Step>& steps; const std::vector<long long>& w1_off; int ld, rank, nranks; bool sym;
+
+    void small(long long off, int N) {
         Step st{}; st.kind = 0; st.off = off; st.N = N; st.cls = EFGPU_PROF_INVERT_SMALL;
-        b.steps.push_back(st);
-        return;
+        steps.push_back(st);
     }
-    const int h = N / 2;
-    const long long A = off, B = off + h, C = off + (long long)h * ld, D = off + (long long)h * ld + h;
-    const long long W1 = w1_off[depth];
-    // products of a replicated tree are split by rows over the ranks when each slice keeps full 128-row tiles
-    const bool split = nranks > 1 && h % (128 * nranks) == 0;
-    auto gemm = [&](int c_op, long long c_off, int ldc, int c0_op, long long c0_off, int ldc0,
-                    int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb, bool neg) {
+    // C (rows x cols) = [C0] +- A (rows x K) B (K x cols); split by rows over the ranks when each slice keeps full 128-row tiles
+    void gemm(int rows, int cols, int K, int c_op, long long c_off, int ldc, int c0_op, long long c0_off, int ldc0,
+              int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb, bool neg) {
         GemmBlock g{};
         g.c_op = c_op; g.c_off = c_off; g.ldc = ldc; g.c0_op = c0_op; g.c0_off = c0_off; g.ldc0 = ldc0;
-        g.rows = h; g.cols = h; g.nterms = 1;
-        g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, h, neg ? 0x80000000u : 0u};
+        g.rows = rows; g.cols = cols; g.nterms = 1;
+        g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, K, neg ? 0x80000000u : 0u};
         Step st{}; st.kind = 1; st.first = (int)b.blocks.size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
-        if (split) {
-            const long long skip = (long long)rank * (h / nranks);
-            st.g_op = c_op; st.g_off = c_off; st.g_h = h; st.g_ld = ldc;
-            if (ldc == h) st.gk = 1;
-            else { st.gk = 2; g.c_op = OP_W3; g.c_off = 0; g.ldc = h; }   // rows land in the contiguous staging block
+        if (nranks > 1 && rows % (128 * nranks) == 0) {
+            const long long skip = (long long)rank * (rows / nranks);
+            st.g_op = c_op; st.g_off = c_off; st.g_rows = rows; st.g_cols = cols; st.g_ld = ldc;
+            if (ldc == cols) st.gk = 1;
+            else { st.gk = 2; g.c_op = OP_W3; g.c_off = 0; g.ldc = cols; }   // rows land in the contiguous staging block
             g.c_off += skip * g.ldc;
             if (g.c0_op >= 0) g.c0_off += skip * g.ldc0;
             g.t[0].a_off += skip * lda;
-            g.rows = h / nranks;
+            g.rows = rows / nranks;
         }
-        b.steps.push_back(st);
+        steps.push_back(st);
         b.blocks.push_back(g);
-    };
-    build_inverse_steps(b, A, h, ld, depth + 1, w1_off, w2_off, rank, nranks);                    // A <- A^-1
-    gemm(OP_W1, W1, h, -1, 0, 0, OP_XINV, C, ld, OP_XINV, A, ld, false);                          // W1 = C A^-1
-    gemm(OP_XINV, D, ld, OP_XINV, D, ld, OP_W1, W1, h, OP_XINV, B, ld, true);                     // D <- D - W1 B   (Schur complement)
-    build_inverse_steps(b, D, h, ld, depth + 1, w1_off, w2_off, rank, nranks);                    // D <- S^-1
-    gemm(OP_W2, w2_off, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);                      // W2 = A^-1 B
-    gemm(OP_XINV, B, ld, -1, 0, 0, OP_W2, w2_off, h, OP_XINV, D, ld, true);                       // B <- -W2 S^-1
-    gemm(OP_XINV, C, ld, -1, 0, 0, OP_XINV, D, ld, OP_W1, W1, h, true);                           // C <- -S^-1 W1
-    gemm(OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W1, W1, h, true);                     // A <- A^-1 - B W1
-}
+    }
+    void transpose(int rows, int cols, int s_op, long long s_off, int lds, int d_op, long long d_off, int ldd) {
+        Step st{}; st.kind = 2; st.first = (int)b.trans.size(); st.count = 1; st.cls = EFGPU_PROF_TRANSPOSE;
+        b.trans.push_back(TransOp{s_op, d_op, lds, ldd, s_off, d_off, rows, cols, 0u, 0});
+        steps.push_back(st);
+    }
+    // inverts the N x N block at `off`; depth = log2(size of X / N) selects the W1 slot; `diag2`: the leading and the
+    // trailing half are themselves block diagonal with blocks of N/4 (only the top level of X)
+    void invert(long long off, int N, int depth, bool diag2) {
+        const bool can_split = N > 128 && (N / 2) % 16 == 0;   // base case: one CTA, register-resident Gauss-Jordan (N <= 128)
+        if (!can_split) {
+            if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
+            small(off, N);
+            return;
+        }
+        const int h = N / 2, q = h / 2;
+        const long long A = off, B = off + h, C = off + (long long)h * ld, D = off + (long long)h * ld + h;
+        const long long W1 = w1_off[depth];
+        const bool dg = diag2 && q % 8 == 0;
+        if (dg) { invert(A, q, depth + 2, false); invert(A + (long long)q * ld + q, q, depth + 2, false); }   // A <- diag(A11^-1, A22^-1)
+        else invert(A, h, depth + 1, false);                                                                  // A <- A^-1
+        if (sym) {
+            if (dg) {                                                                                     // W1 = A^-1 B
+                gemm(q, h, q, OP_W1, W1, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
+                gemm(q, h, q, OP_W1, W1 + (long long)q * h, h, -1, 0, 0, OP_XINV, A + (long long)q * ld + q, ld, OP_XINV, B + (long long)q * ld, ld, false);
+            } else gemm(h, h, h, OP_W1, W1, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
+            gemm(h, h, h, OP_XINV, D, ld, OP_XINV, D, ld, OP_XINV, C, ld, OP_W1, W1, h, true);            // D <- D - C W1   (Schur complement)
+            invert(D, h, depth + 1, false);                                                               // D <- S^-1
+            gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true);                  // B <- -W1 S^-1
+            transpose(h, h, OP_XINV, B, ld, OP_XINV, C, ld);                                              // C <- B^T
+            transpose(h, h, OP_W1, W1, h, OP_W2, 0, h);                                                   // W2 = W1^T  (= C A^-1)
+            gemm(h, h, h, OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W2, 0, h, true);             // A <- A^-1 - B W2
+            return;
+        }
+        if (dg) {                                                                                         // W1 = C A^-1
+            gemm(h, q, q, OP_W1, W1, h, -1, 0, 0, OP_XINV, C, ld, OP_XINV, A, ld, false);
+            gemm(h, q, q, OP_W1, W1 + q, h, -1, 0, 0, OP_XINV, C + q, ld, OP_XINV, A + (long long)q * ld + q, ld, false);
+        } else gemm(h, h, h, OP_W1, W1, h, -1, 0, 0, OP_XINV, C, ld, OP_XINV, A, ld, false);
+        gemm(h, h, h, OP_XINV, D, ld, OP_XINV, D, ld, OP_W1, W1, h, OP_XINV, B, ld, true);                // D <- D - W1 B   (Schur complement)
+        invert(D, h, depth + 1, false);                                                                   // D <- S^-1
+        if (dg) {                                                                                         // W2 = A^-1 B
+            gemm(q, h, q, OP_W2, 0, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
+            gemm(q, h, q, OP_W2, (long long)q * h, h, -1, 0, 0, OP_XINV, A + (long long)q * ld + q, ld, OP_XINV, B + (long long)q * ld, ld, false);
+        } else gemm(h, h, h, OP_W2, 0, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
+        gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W2, 0, h, OP_XINV, D, ld, true);                       // B <- -W2 S^-1
+        gemm(h, h, h, OP_XINV, C, ld, -1, 0, 0, OP_XINV, D, ld, OP_W1, W1, h, true);                      // C <- -S^-1 W1
+        gemm(h, h, h, OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W1, W1, h, true);                // A <- A^-1 - B W1
+    }
+};
 
 // Row partition of a replicated upper tree (efgpu_set_partition): this rank computes rows [lo, hi) of the
 // result; a block covering result rows [r0, r0 + rows) is clipped to the overlap (A-side offsets follow).
@@ -223,54 +270,79 @@ static bool clip_rows(GemmBlock& g, long long r0, long long lo, long long hi)
 static void plan_batch_gemms(BatchH& b, int rank, int nranks)
 {
     const int n = b.n, N = 4 * n;
-    b.blocks.clear(); b.steps.clear();
+    b.blocks.clear(); b.trans.clear(); b.steps.clear(); b.steps_sym.clear();
     if (nranks > 1 && ((4 * n) % (8 * nranks) != 0))
         throw Error{EF_ERR_BAD_SHAPE, "row partition: 4 n must be a multiple of 8 * nranks for every merge of the replicated tree"};
     const long long s_lo = (long long)rank * (4 * n) / nranks, s_hi = (long long)(rank + 1) * (4 * n) / nranks;
     const long long t_lo = (long long)rank * (8 * n) / nranks, t_hi = (long long)(rank + 1) * (8 * n) / nranks;
-    // workspace layout per entry: W1 blocks per recursion depth (op 7), W2 (op 8)
+    // workspace layout per entry: W1 blocks per recursion depth (op 7), W2 (op 8), W3 staging (op 9)
     std::vector<long long> w1_off; long long acc = 0;
     for (int h = N / 2; h >= 8; h /= 2) { w1_off.push_back(acc); acc += (long long)h * h; }
-    w1_off.push_back(acc);
+    w1_off.push_back(acc); w1_off.push_back(acc); w1_off.push_back(acc);
     const long long w1_total = acc, w2_total = (long long)(N / 2) * (N / 2);
     b.w2_off = (size_t)w1_total; b.w3_off = (size_t)(w1_total + w2_total);
     b.ws_per_entry = (size_t)(w1_total + 2 * w2_total);
-    build_inverse_steps(b, 0, N, N, 0, w1_off, 0, rank, nranks);
-    // S = X^-1 S_RHS, written with WESN-permuted columns (mergeS_ + reorderOperators_)
-    int first = (int)b.blocks.size();
-    for (int k = 0; k < 4; k++)
-        for (int q = 0; q < 8; q++) {
-            const int c = q >> 1, side = h_tau_side[c][q & 1];
-            GemmBlock g{};
-            g.c_op = OP_S; g.c_off = (long long)(k * n) * (8 * n) + h_pos[q] * n; g.ldc = 8 * n; g.c0_op = -1;
-            g.rows = n; g.cols = n; g.nterms = 2;
-            for (int t = 0; t < 2; t++) {
-                const int k2 = h_kk[c][t];
-                g.t[t] = GemmTerm{OP_XINV, OP_TC0 + c, N, N, (long long)(k * n) * N + k2 * n,
-                                  (long long)(h_iface[c][k2] * n) * N + side * n, n, h_sgn[c][k2] < 0 ? 0x80000000u : 0u};
+    // the root's DtN map of a partitioned tree stays row-distributed (no gather), so it cannot be completed by mirroring
+    const bool mirror_ok = !(nranks > 1 && b.level == 0);
+    for (int variant = 0; variant < (b.symcand ? 2 : 1); variant++) {
+        const bool sym = variant == 1;
+        std::vector<Step>& steps = sym ? b.steps_sym : b.steps;
+        InvPlanner ip{b, steps, w1_off, N, rank, nranks, sym};
+        ip.invert(0, N, 0, true);
+        // S = X^-1 S_RHS, written with WESN-permuted columns (mergeS_ + reorderOperators_)
+        int first = (int)b.blocks.size();
+        for (int k = 0; k < 4; k++)
+            for (int q = 0; q < 8; q++) {
+                const int c = q >> 1, side = h_tau_side[c][q & 1];
+                GemmBlock g{};
+                g.c_op = OP_S; g.c_off = (long long)(k * n) * (8 * n) + h_pos[q] * n; g.ldc = 8 * n; g.c0_op = -1;
+                g.rows = n; g.cols = n; g.nterms = 2;
+                for (int t = 0; t < 2; t++) {
+                    const int k2 = h_kk[c][t];
+                    g.t[t] = GemmTerm{OP_XINV, OP_TC0 + c, N, N, (long long)(k * n) * N + k2 * n,
+                                      (long long)(h_iface[c][k2] * n) * N + side * n, n, h_sgn[c][k2] < 0 ? 0x80000000u : 0u};
+                }
+                if (clip_rows(g, (long long)k * n, s_lo, s_hi)) b.blocks.push_back(g);
             }
-            if (clip_rows(g, (long long)k * n, s_lo, s_hi)) b.blocks.push_back(g);
-        }
-    { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_S; b.steps.push_back(st); }
-    // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_)
-    first = (int)b.blocks.size();
-    for (int qr = 0; qr < 8; qr++)
-        for (int qc = 0; qc < 8; qc++) {
-            const int c = qr >> 1, side_r = h_tau_side[c][qr & 1];
-            const int c2 = qc >> 1, side_c = h_tau_side[c2][qc & 1];
-            GemmBlock g{};
-            g.c_op = OP_T; g.c_off = (long long)(h_pos[qr] * n) * (8 * n) + h_pos[qc] * n; g.ldc = 8 * n;
-            if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n) * N + side_c * n; g.ldc0 = N; }
-            else g.c0_op = -1;
-            g.rows = n; g.cols = n; g.nterms = 2;
-            for (int t = 0; t < 2; t++) {
-                const int k = h_kk[c][t];
-                g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n) * N + h_iface[c][k] * n,
-                                  (long long)(k * n) * (8 * n) + h_pos[qc] * n, n, 0u};
+        { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_S; steps.push_back(st); }
+        // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_).  Symmetric plan: with the sign
+        // d = -1 on the W and S sides (coordinate derivatives instead of outward normals, FiniteVolumeSolver.cpp:332-343)
+        // diag(d) T is symmetric, so of every off-diagonal pair of n x n blocks only one is computed - chosen on a circulant
+        // pattern so that each block row carries 4 or 5 products (row partitions stay balanced) - and the other is its
+        // signed transpose.
+        first = (int)b.blocks.size();
+        const int tfirst = (int)b.trans.size();
+        for (int qr = 0; qr < 8; qr++)
+            for (int qc = 0; qc < 8; qc++) {
+                const int c = qr >> 1, side_r = h_tau_side[c][qr & 1];
+                const int c2 = qc >> 1, side_c = h_tau_side[c2][qc & 1];
+                const int P = h_pos[qr], Q = h_pos[qc];
+                if (sym && mirror_ok && P != Q) {
+                    const int dl = (Q - P) & 7;
+                    if (!(dl < 4 || (dl == 4 && P < 4))) {
+                        const unsigned neg = ((P ^ Q) & 2) ? 0x80000000u : 0u;   // W, W, E, E, S, S, N, N: d = -1 where bit 1 is clear
+                        b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
+                                                  (long long)(P * n) * (8 * n) + Q * n, n, n, neg, 0});
+                        continue;
+                    }
+                }
+                GemmBlock g{};
+                g.c_op = OP_T; g.c_off = (long long)(P * n) * (8 * n) + Q * n; g.ldc = 8 * n;
+                if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n) * N + side_c * n; g.ldc0 = N; }
+                else g.c0_op = -1;
+                g.rows = n; g.cols = n; g.nterms = 2;
+                for (int t = 0; t < 2; t++) {
+                    const int k = h_kk[c][t];
+                    g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n) * N + h_iface[c][k] * n,
+                                      (long long)(k * n) * (8 * n) + Q * n, n, 0u};
+                }
+                if (clip_rows(g, (long long)P * n, t_lo, t_hi)) b.blocks.push_back(g);
             }
-            if (clip_rows(g, (long long)h_pos[qr] * n, t_lo, t_hi)) b.blocks.push_back(g);
+        { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_T; steps.push_back(st); }
+        if ((int)b.trans.size() > tfirst) {   // runs after the row slices of T have been gathered
+            Step st{}; st.kind = 2; st.first = tfirst; st.count = (int)b.trans.size() - tfirst; st.cls = EFGPU_PROF_MIRROR_T; steps.push_back(st);
         }
-    { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_T; b.steps.push_back(st); }
+    }
 }
 
 static void compute_flop_model(efgpu_handle* H)
@@ -281,7 +353,7 @@ static void compute_flop_model(efgpu_handle* H)
     for (auto& b : H->batches) {
         const double n3 = (double)b.n * b.n * b.n;
         canon += b.count * 810.0 * n3 + b.count * (2.0 / 3.0) * n3;
-        for (const Step& st : b.steps)
+        for (const Step& st : b.active())
             if (st.kind == 1)
                 for (int k = st.first; k < st.first + st.count; k++)
                     for (int t = 0; t < b.blocks[k].nterms; t++) issued += b.count * 2.0 * b.blocks[k].rows * b.blocks[k].cols * b.blocks[k].t[t].K;
@@ -344,19 +416,27 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* 
         }
         nd.size = 2 * mn;
     }
-    // batches: parents grouped by (level, child side n)
+    // structural symmetry candidates (bottom-up): square patch, and for a parent four candidate children, none coarsened
+    for (int i = nn - 1; i >= 0; i--) {
+        NodeH& nd = H->nodes[i];
+        const double wx = nd.box[1] - nd.box[0], wy = nd.box[3] - nd.box[2];
+        bool ok = std::fabs(wx - wy) <= 1e-12 * std::max(std::fabs(wx), std::fabs(wy));
+        if (!nd.leaf) for (int c = 0; c < 4; c++) ok = ok && H->nodes[nd.child[c]].symcand && H->nodes[nd.child[c]].ncoarsen == 0;
+        nd.symcand = ok;
+    }
+    // batches: parents grouped by (level, child side n, symmetry candidate)
     H->level_batches.assign(H->max_level + 1, {});
-    std::map<std::pair<int, int>, int> key2batch;
+    std::map<std::tuple<int, int, int>, int> key2batch;
     for (int i = 0; i < nn; i++) {
         NodeH& nd = H->nodes[i];
         if (nd.leaf) continue;
         const int n = nd.size / 2;
-        auto key = std::make_pair(nd.level, n);
+        auto key = std::make_tuple(nd.level, n, nd.symcand ? 1 : 0);
         auto it = key2batch.find(key);
         if (it == key2batch.end()) {
             it = key2batch.emplace(key, (int)H->batches.size()).first;
             H->batches.emplace_back();
-            H->batches.back().level = nd.level; H->batches.back().n = n;
+            H->batches.back().level = nd.level; H->batches.back().n = n; H->batches.back().symcand = nd.symcand;
             H->level_batches[nd.level].push_back(it->second);
         }
         BatchH& b = H->batches[it->second];
@@ -488,7 +568,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
                 b.cG[step].push_back(CoarsenOp{vec + P.gbuf[t], vec + P.gbuf[t - 1], P.size >> (t - 1), 0});
             }
         }
-        b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s);
+        b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s); b.d_trans.upload(b.trans, s);
         b.h_ptab = ptab;
         auto up = [&](std::vector<std::vector<CoarsenOp>>& v, std::vector<std::unique_ptr<DevBuf>>& dv, std::vector<int>& mx) {
             dv.clear(); mx.clear();
@@ -555,6 +635,12 @@ static void build_begin(efgpu_handle* H, unsigned flags)
 {
     if (!H->allocated || ((flags ^ H->build_flags) & (EFGPU_KEEP_X | EFGPU_LEAN_T))) allocate_device(H, flags);
     cudaStream_t s = H->stream;
+    // symmetric plan where the structure allows it and the leaf DtN maps are signed-symmetric: constant-coefficient leaves
+    // (with variable beta the map takes beta-weighted Dirichlet data to unweighted derivatives, FiniteVolumeSolver.cpp:100-175
+    // vs :332-343, and is not symmetric); external leaves: as declared by efgpu_set_symmetric_leaves
+    const bool leaves_sym = H->external_leaves ? H->ext_sym : H->leaf_kind == EFGPU_LEAF_CONSTANT;
+    for (auto& b : H->batches) b.use_sym = b.symcand && leaves_sym && !(flags & EFGPU_NO_SYMMETRY);
+    compute_flop_model(H);
     const double big = 1e300;
     EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
     EF_CUDA(cudaEventRecord(H->ev0, s));
@@ -583,22 +669,27 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             if (H->allgather(buf, doubles_total / H->part_nranks * sizeof(double), H->allgather_user) != 0)
                 throw Error{EF_ERR_STATE, "the all-gather callback failed"};
         };
-        for (const Step& st : b.steps) {
+        auto run_transposes = [&](const Step& st) {
+            timed(H, st.cls, 1, [&] { launch_btranspose(ptab, NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, b.count, s); });
+        };
+        for (const Step& st : b.active()) {
+            if (st.cls == EFGPU_PROF_MIRROR_T) continue;   // after the gather of T, below
             const bool is_T = st.cls == EFGPU_PROF_GEMM_T;
             if (is_T != (phase == 1) || (st.kind == 1 && st.count == 0)) continue;
+            if (st.kind == 2) { run_transposes(st); continue; }
             timed(H, st.cls, 1, [&] {
                 if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
                 else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
             });
             if (st.gk) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
-                const size_t hh = (size_t)st.g_h * st.g_h;
+                const size_t hh = (size_t)st.g_rows * st.g_cols;
                 for (int sl = 0; sl < b.count; sl++) {
                     double* const* ops = b.h_ptab.data() + (size_t)sl * NOPS;
                     if (st.gk == 1) gather(ops[st.g_op] + st.g_off, hh);
                     else {
                         gather(ops[OP_W3], hh);
-                        EF_CUDA(cudaMemcpy2DAsync(ops[st.g_op] + st.g_off, (size_t)st.g_ld * sizeof(double), ops[OP_W3], (size_t)st.g_h * sizeof(double),
-                                                  (size_t)st.g_h * sizeof(double), (size_t)st.g_h, cudaMemcpyDeviceToDevice, s));
+                        EF_CUDA(cudaMemcpy2DAsync(ops[st.g_op] + st.g_off, (size_t)st.g_ld * sizeof(double), ops[OP_W3], (size_t)st.g_cols * sizeof(double),
+                                                  (size_t)st.g_cols * sizeof(double), (size_t)st.g_rows, cudaMemcpyDeviceToDevice, s));
                     }
                 }
             });
@@ -611,6 +702,8 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                 if (phase == 0) gather(ops[OP_S], 32 * n2); else gather(ops[OP_T], 64 * n2);
             }
         });
+        if (phase == 1)
+            for (const Step& st : b.active()) if (st.cls == EFGPU_PROF_MIRROR_T) run_transposes(st);
     }
 }
 
@@ -797,6 +890,62 @@ int efgpu_set_allgather(efgpu_handle* H, efgpu_allgather_fn fn, void* user)
     if (!H) return EF_ERR_BAD_ARG;
     H->allgather = fn; H->allgather_user = user;
     return EF_OK;
+}
+
+int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric, int64_t* steps, int* n_steps,
+                           int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws)
+{
+    if (n < 8 || n % 8 || nranks < 1 || rank < 0 || rank >= nranks || !n_steps || !n_blocks || !n_trans) return EF_ERR_BAD_ARG;
+    try {
+        BatchH b; b.n = n; b.level = level; b.count = 1; b.symcand = symmetric != 0;
+        plan_batch_gemms(b, rank, nranks);
+        const std::vector<Step>& st = symmetric ? b.steps_sym : b.steps;
+        *n_steps = (int)st.size(); *n_blocks = (int)b.blocks.size(); *n_trans = (int)b.trans.size();
+        if (ws) { ws[0] = (int64_t)b.w2_off; ws[1] = (int64_t)(b.w3_off - b.w2_off); ws[2] = (int64_t)(b.ws_per_entry - b.w3_off); }
+        if (steps) for (size_t i = 0; i < st.size(); i++) {
+            int64_t* r = steps + 16 * i; const Step& x = st[i];
+            r[0] = x.kind; r[1] = x.first; r[2] = x.count; r[3] = x.off; r[4] = x.N; r[5] = x.cls; r[6] = x.gk; r[7] = x.g_op;
+            r[8] = x.g_rows; r[9] = x.g_cols; r[10] = x.g_ld; r[11] = x.g_off;
+        }
+        if (blocks && terms) for (size_t i = 0; i < b.blocks.size(); i++) {
+            int64_t* r = blocks + 16 * i; const GemmBlock& g = b.blocks[i];
+            r[0] = g.c_op; r[1] = g.c0_op; r[2] = g.ldc; r[3] = g.ldc0; r[4] = g.c_off; r[5] = g.c0_off; r[6] = g.rows; r[7] = g.cols; r[8] = g.nterms;
+            for (int t = 0; t < 2; t++) {
+                int64_t* q = terms + 16 * i + 8 * t; const GemmTerm& m = g.t[t];
+                q[0] = m.a_op; q[1] = m.b_op; q[2] = m.lda; q[3] = m.ldb; q[4] = m.a_off; q[5] = m.b_off; q[6] = m.K; q[7] = m.neg ? 1 : 0;
+            }
+        }
+        if (trans) for (size_t i = 0; i < b.trans.size(); i++) {
+            int64_t* r = trans + 16 * i; const TransOp& x = b.trans[i];
+            r[0] = x.src_op; r[1] = x.dst_op; r[2] = x.lds; r[3] = x.ldd; r[4] = x.src_off; r[5] = x.dst_off; r[6] = x.rows; r[7] = x.cols; r[8] = x.neg ? 1 : 0;
+        }
+        return EF_OK;
+    } catch (const efgpu::Error& e) { g_create_error = e.msg; return e.code; }
+}
+
+int efgpu_set_tuning(int key, int value)
+{
+    if (key < 0 || key >= 8) return EF_ERR_BAD_ARG;
+    efgpu::set_tuning(key, value);
+    return EF_OK;
+}
+
+int efgpu_set_symmetric_leaves(efgpu_handle* H, int on)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    H->ext_sym = on != 0; H->built = false;
+    return EF_OK;
+}
+
+int efgpu_is_symmetric(const efgpu_handle* H)
+{
+    if (!H || !H->built) return 0;
+    for (int r : H->roots) {
+        const efgpu::NodeH& nd = H->nodes[r];
+        if (nd.leaf) { if (!(nd.symcand && (H->external_leaves ? H->ext_sym : H->leaf_kind == EFGPU_LEAF_CONSTANT))) return 0; }
+        else if (!H->batches[nd.batch].use_sym) return 0;
+    }
+    return 1;
 }
 
 int efgpu_build_begin(efgpu_handle* H, unsigned flags)
@@ -1143,7 +1292,8 @@ int efgpu_get_profile(const efgpu_handle* H, int cls, double* ms, double* launch
 const char* efgpu_profile_class_name(int cls)
 {
     static const char* names[EFGPU_PROF_NCLASSES] = {"leaf_dtn", "coarsen_T", "assemble_X_H", "invert_small", "gemm_Xinv", "gemm_S",
-                                                      "gemm_T", "leaf_solve", "upwards_matvec", "solve_matvec", "coarsen_vec", "leaf_lu", "allgather"};
+                                                      "gemm_T", "leaf_solve", "upwards_matvec", "solve_matvec", "coarsen_vec", "leaf_lu", "allgather",
+                                                      "transpose_Xinv", "mirror_T"};
     return (cls >= 0 && cls < EFGPU_PROF_NCLASSES) ? names[cls] : "";
 }
 

@@ -14,6 +14,12 @@
 
 namespace efgpu {
 
+// ---- tuning (efgpu_set_tuning): kernel-selection knobs for measurements ------------------------------
+// [0] bulk-copy streaming matvec kernels on (1, default) / off (0); [1] long-row kernels: 1 = 8 loads in flight per lane
+// (default 4); [2] CTAs per SM the long-row launcher aims for (default 16)
+static int g_tuning[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+void set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tuning[key] = value; }
+
 // side of child c that faces interior interface k (-1: not adjacent)
 __constant__ int c_iface[4][4] = {{3, -1, 1, -1}, {-1, 3, 0, -1}, {2, -1, -1, 1}, {-1, 2, -1, 0}};
 // sign with which child c enters the jump across interface k (first child -, second +)
@@ -160,16 +166,28 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // row-per-warp dot product, 16-byte loads, streaming (no L1 allocation) on the matrix
+template <int U = 4>
 __device__ __forceinline__ double row_dot(const double* __restrict__ a, const double* __restrict__ x, int len, int lane)
 {
     double s0 = 0.0, s1 = 0.0;
     const double2* a2 = reinterpret_cast<const double2*>(a);
     const double2* x2 = reinterpret_cast<const double2*>(x);
     const int len2 = len >> 1;
-#pragma unroll 4
-    for (int c = lane; c < len2; c += 32) {
-        double2 av = __ldcs(a2 + c);
-        double2 xv = __ldg(x2 + c);
+    int c = lane;
+    for (; c + 32 * (U - 1) < len2; c += 32 * U) {   // U independent 16-byte loads in flight per lane
+        double2 av[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) av[u] = __ldcs(a2 + c + 32 * u);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double2 xv = __ldg(x2 + c + 32 * u);
+            s0 = fma(av[u].x, xv.x, s0);
+            s1 = fma(av[u].y, xv.y, s1);
+        }
+    }
+    for (; c < len2; c += 32) {
+        const double2 av = __ldcs(a2 + c);
+        const double2 xv = __ldg(x2 + c);
         s0 = fma(av.x, xv.x, s0);
         s1 = fma(av.y, xv.y, s1);
     }
@@ -177,18 +195,20 @@ __device__ __forceinline__ double row_dot(const double* __restrict__ a, const do
 }
 
 // w = X^-1 hd
+template <int U>
 __global__ void __launch_bounds__(256) upwards_w_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
 {
     const MergeEntry& e = ent[blockIdx.x];
     const int N = 4 * n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
     for (int r = r0 + warp; r < r1; r += 8) {
-        double s = row_dot(e.Xinv + (size_t)r * N, e.hd, N, lane);
+        double s = row_dot<U>(e.Xinv + (size_t)r * N, e.hd, N, lane);
         if (lane == 0) e.w[r] = s;
     }
 }
 
 // h = pi( H w + h_ext )   with the compact H: row block p of child c multiplies w[k0], w[k1]
+template <int U>
 __global__ void __launch_bounds__(256) upwards_h_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
 {
     const MergeEntry& e = ent[blockIdx.x];
@@ -198,20 +218,21 @@ __global__ void __launch_bounds__(256) upwards_h_kernel(const MergeEntry* __rest
         const int p = row / n, r = row % n;
         const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
         const double* a = e.Hc + (size_t)row * (2 * n);
-        double s = row_dot(a, e.w + c_kk[ch][0] * n, n, lane) + row_dot(a + n, e.w + c_kk[ch][1] * n, n, lane);
+        double s = row_dot<U>(a, e.w + c_kk[ch][0] * n, n, lane) + row_dot<U>(a + n, e.w + c_kk[ch][1] * n, n, lane);
         if (lane == 0) e.h[row] = s + e.hc[ch][side * n + r];
     }
 }
 
 // ---- solve -------------------------------------------------------------------------------------
 // u_int = S g (+ w); children's Dirichlet data assembled in WESN order (HPSAlgorithm.hpp:1206-1227)
+template <int U>
 __global__ void __launch_bounds__(256) solve_split_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta, int add_w)
 {
     const MergeEntry& e = ent[blockIdx.x];
     const int N = 4 * n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
     for (int row = r0 + warp; row < r1; row += 8) {
-        double s = row_dot(e.S + (size_t)row * (8 * n), e.g, 8 * n, lane);
+        double s = row_dot<U>(e.S + (size_t)row * (8 * n), e.g, 8 * n, lane);
         if (lane == 0) {
             if (add_w) s += e.w[row];
             const int k = row / n, r = row % n;
@@ -340,6 +361,186 @@ __global__ void __launch_bounds__(256) solve_split_short_kernel(const MergeEntry
     }
 }
 
+
+// ---- bulk-copy streaming variants (child side n = 16 .. 512, powers of two) ----------------------
+// The matrix rows a CTA owns are one contiguous byte range, so the CTA streams it through a ring of shared-memory
+// stages filled by the bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier): SG_NS x 16 KB in
+// flight per CTA independent of register pressure, 2-3 CTAs per SM.  The right-hand vector is staged in shared memory
+// once.  Warp w reduces the 256 doubles [256 w, 256 w + 256) of every stage: rows of <= 256 entries are finished inside
+// the warp, longer rows (<= 2048 entries = one stage) across the warps through shared memory.
+constexpr int SG_STAGE = 2048;   // doubles per stage
+constexpr int SG_NS = 4;
+constexpr int SG_XMAX = 2048;    // longest staged vector
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SG_DONE;\n"
+        "bra SG_WAIT;\n"
+        "SG_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// dynamic shared memory layout: [SG_NS stages][x: xlen doubles][red: 8][barriers: SG_NS]
+struct SgView {
+    double* stage; double* xs; double* red; unsigned long long* full;
+    __device__ SgView(double* base, int xlen) : stage(base), xs(base + SG_NS * SG_STAGE), red(xs + xlen), full(reinterpret_cast<unsigned long long*>(red + 8)) {}
+};
+static inline size_t sg_smem_bytes(int xlen) { return (size_t)(SG_NS * SG_STAGE + xlen + 8 + SG_NS) * sizeof(double); }
+
+// A: first row of this CTA's chunk; rows of L = 2^logL doubles (32 <= L <= 2048); ntiles stages of SG_STAGE doubles.
+// xfill(i): entry i of the staged vector; xidx(row, col): its index for matrix entry (row, col), row local to the chunk;
+// epi(row, value): row local to the chunk.  All 256 threads must call.
+template <class XFill, class XIdx, class Epi>
+__device__ __forceinline__ void stream_gemv(const double* __restrict__ A, int logL, int ntiles, int xlen, SgView sm, XFill xfill, XIdx xidx, Epi epi)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = 1 << logL;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SG_NS; s++) mbar_init(sm.full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SG_NS; s++)
+            if (s < ntiles) {
+                mbar_expect_tx(sm.full + s, SG_STAGE * 8);
+                bulk_g2s(sm.stage + s * SG_STAGE, A + (size_t)s * SG_STAGE, SG_STAGE * 8, sm.full + s);
+            }
+    }
+    for (int i = tid; i < xlen; i += blockDim.x) sm.xs[i] = xfill(i);
+    __syncthreads();
+    double acc = 0.0;
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % SG_NS;
+        mbar_wait(sm.full + s, (unsigned)((t / SG_NS) & 1));
+        const double* st = sm.stage + s * SG_STAGE + warp * 256 + lane * 2;
+        const int f0 = t * SG_STAGE + warp * 256 + lane * 2;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double2 a = *reinterpret_cast<const double2*>(st + j * 64);
+            const int e = f0 + j * 64, row = e >> logL, col = e & (L - 1);
+            const double2 x = *reinterpret_cast<const double2*>(sm.xs + xidx(row, col));
+            acc = fma(a.x, x.x, fma(a.y, x.y, acc));
+            if (L == 32) {            // two rows per 64 entries: reduce inside half warps
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if ((lane & 15) == 0) epi(row, acc);
+                acc = 0.0;
+            } else if (L <= 256 && (((j + 1) * 64) & (L - 1)) == 0) {   // a row ends inside this warp's slice
+                acc = warp_sum(acc);
+                if (lane == 0) epi(row, acc);
+                acc = 0.0;
+            }
+        }
+        if (L > 256) {                // a row spans L / 256 warps of this stage
+            acc = warp_sum(acc);
+            if (lane == 0) sm.red[warp] = acc;
+            acc = 0.0;
+            __syncthreads();
+            const int wpr = L >> 8, rows = SG_STAGE >> logL;
+            if (tid < rows) {
+                double v = 0.0;
+                for (int k = 0; k < wpr; k++) v += sm.red[tid * wpr + k];
+                epi(t * rows + tid, v);
+            }
+        }
+        __syncthreads();              // every warp is done with stage s (and with red)
+        if (tid == 0 && t + SG_NS < ntiles) {
+            mbar_expect_tx(sm.full + s, SG_STAGE * 8);
+            bulk_g2s(sm.stage + s * SG_STAGE, A + (size_t)(t + SG_NS) * SG_STAGE, SG_STAGE * 8, sm.full + s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sg_upwards_w_kernel(const MergeEntry* __restrict__ ent, int n, int logn, int rows_per_cta)
+{
+    extern __shared__ __align__(128) double sg_smem[];
+    const MergeEntry& e = ent[blockIdx.x];
+    const int N = 4 * n, r0 = blockIdx.y * rows_per_cta;
+    SgView sm(sg_smem, N);
+    double* w = e.w;
+    stream_gemv(e.Xinv + (size_t)r0 * N, logn + 2, rows_per_cta * N / SG_STAGE, N, sm,
+        [&](int idx) {
+            const int k = idx >> logn, r = idx & (n - 1);
+            const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+            return e.hc[c2][c_iface[c2][k] * n + r] - e.hc[c1][c_iface[c1][k] * n + r];
+        },
+        [](int, int col) { return col; },
+        [&](int row, double v) { w[r0 + row] = v; });
+}
+
+__global__ void __launch_bounds__(256) sg_upwards_h_kernel(const MergeEntry* __restrict__ ent, int n, int logn, int rows_per_cta)
+{
+    extern __shared__ __align__(128) double sg_smem[];
+    const MergeEntry& e = ent[blockIdx.x];
+    const int r0 = blockIdx.y * rows_per_cta;
+    SgView sm(sg_smem, 4 * n);
+    double* h = e.h;
+    const double* wv = e.w;
+    stream_gemv(e.Hc + (size_t)r0 * (2 * n), logn + 1, rows_per_cta * 2 * n / SG_STAGE, 4 * n, sm,
+        [&](int idx) { return wv[idx]; },
+        [&](int row, int col) {   // row block p of child ch multiplies [w[k0], w[k1]]
+            const int ch = c_pi[(r0 + row) >> logn] >> 1;
+            return c_kk[ch][col >> logn] * n + (col & (n - 1));
+        },
+        [&](int row, double v) {
+            const int gr = r0 + row, p = gr >> logn, r = gr & (n - 1);
+            const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+            h[gr] = v + e.hc[ch][side * n + r];
+        });
+}
+
+__global__ void __launch_bounds__(256) sg_solve_split_kernel(const MergeEntry* __restrict__ ent, int n, int logn, int rows_per_cta, int add_w)
+{
+    extern __shared__ __align__(128) double sg_smem[];
+    const MergeEntry& e = ent[blockIdx.x];
+    const int r0 = blockIdx.y * rows_per_cta;
+    SgView sm(sg_smem, 8 * n);
+    const double* g = e.g;
+    const double* w = e.w;
+    stream_gemv(e.S + (size_t)r0 * (8 * n), logn + 3, rows_per_cta * 8 * n / SG_STAGE, 8 * n, sm,
+        [&](int idx) { return g[idx]; },
+        [](int, int col) { return col; },
+        [&](int row, double v) {
+            const int gr = r0 + row;
+            if (add_w) v += w[gr];
+            const int k = gr >> logn, r = gr & (n - 1);
+            const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+            e.gc[c1][c_iface[c1][k] * n + r] = v;
+            e.gc[c2][c_iface[c2][k] * n + r] = v;
+        });
+    // exterior segments are copied through: this CTA's share of the 8n entries (xs still holds g)
+    const int nct = gridDim.y, per = (8 * n + nct - 1) / nct;
+    const int x0 = blockIdx.y * per, x1 = min(8 * n, x0 + per);
+    for (int idx = x0 + threadIdx.x; idx < x1; idx += blockDim.x) {
+        const int p = idx >> logn, r = idx & (n - 1);
+        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
+        e.gc[ch][side * n + r] = sm.xs[idx];
+    }
+}
+
+
 // ---- launch wrappers ---------------------------------------------------------------------------
 static inline int ew_blocks(long long elems) { long long b = (elems + 255) / 256; return (int)(b < 1 ? 1 : (b > 1024 ? 1024 : b)); }
 static inline void check_count(int count) { if (count > 65535) throw Error{EF_ERR_BAD_SHAPE, "batch too large for grid.y (chunk it)"}; }
@@ -391,7 +592,8 @@ void launch_uncoarsen_g(const CoarsenOp* ops, int nops, int max_nfine, cudaStrea
 static inline int pick_rows(int rows, int count)
 {
     int rpc = rows;
-    while (rpc > 8 && (long long)count * ((rows + rpc - 1) / rpc) < 148LL * 16) rpc = (rpc + 1) / 2;
+    const long long want = 148LL * (g_tuning[2] > 0 ? g_tuning[2] : 16);
+    while (rpc > 8 && (long long)count * ((rows + rpc - 1) / rpc) < want) rpc = (rpc + 1) / 2;
     if (rpc < 8) rpc = 8;
     return rpc;
 }
@@ -428,9 +630,35 @@ static void launch_upwards_short(const MergeEntry* e, int n, int count, cudaStre
     }
 }
 
+// rows per CTA of the streaming kernels: whole parents when there are many of them, else halved while the grid is short
+// of ~6 CTAs per SM; a chunk is a whole number (>= 1) of stages.
+static inline int sg_rows(int rows, int L, int count)
+{
+    int rpc = rows;
+    while ((long long)count * (rows / rpc) < 148LL * 6 && (long long)(rpc / 2) * L >= 2LL * SG_STAGE) rpc >>= 1;
+    return rpc;
+}
+static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+template <class K>
+static void sg_attr(K kern)
+{
+    EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem_bytes(SG_XMAX)));
+}
+
 void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
 {
     if (!count) return;
+    if (g_tuning[0] && n >= 16 && n <= 512 && (n & (n - 1)) == 0 && count <= 2147483647) {
+        static bool attr = false;
+        if (!attr) { sg_attr(sg_upwards_w_kernel); sg_attr(sg_upwards_h_kernel); attr = true; }
+        const int logn = ilog2(n);
+        int rpc = sg_rows(4 * n, 4 * n, count);
+        sg_upwards_w_kernel<<<dim3(count, 4 * n / rpc), 256, sg_smem_bytes(4 * n), s>>>(e, n, logn, rpc);
+        rpc = sg_rows(8 * n, 2 * n, count);
+        sg_upwards_h_kernel<<<dim3(count, 8 * n / rpc), 256, sg_smem_bytes(4 * n), s>>>(e, n, logn, rpc);
+        EF_CUDA(cudaGetLastError());
+        return;
+    }
     if (n <= 256 && (n & (n - 1)) == 0 && count <= 65535 * 0 + 2147483647) {
         launch_upwards_short<4>(e, n, count, s);
         EF_CUDA(cudaGetLastError());
@@ -441,15 +669,25 @@ void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
         hdiff_kernel<<<dim3(ew_blocks(4LL * n), c), 256, 0, s>>>(e + off, n);
     }
     int rpc = pick_rows(4 * n, count);
-    upwards_w_kernel<<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    if (g_tuning[1] == 1) upwards_w_kernel<8><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    else upwards_w_kernel<4><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
     rpc = pick_rows(8 * n, count);
-    upwards_h_kernel<<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    if (g_tuning[1] == 1) upwards_h_kernel<8><<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    else upwards_h_kernel<4><<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
     EF_CUDA(cudaGetLastError());
 }
 
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s)
 {
     if (!count) return;
+    if (g_tuning[0] && n >= 16 && n <= 256 && (n & (n - 1)) == 0) {
+        static bool attr = false;
+        if (!attr) { sg_attr(sg_solve_split_kernel); attr = true; }
+        const int rpc = sg_rows(4 * n, 8 * n, count);
+        sg_solve_split_kernel<<<dim3(count, 4 * n / rpc), 256, sg_smem_bytes(8 * n), s>>>(e, n, ilog2(n), rpc, add_w ? 1 : 0);
+        EF_CUDA(cudaGetLastError());
+        return;
+    }
     if (n <= 256 && (n & (n - 1)) == 0) {
         const int N = 4 * n, rpc = short_rows(N, n, count);
         dim3 grid(count, N / rpc);
@@ -458,7 +696,8 @@ void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaS
         return;
     }
     int rpc = pick_rows(4 * n, count);
-    solve_split_kernel<<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
+    if (g_tuning[1] == 1) solve_split_kernel<8><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
+    else solve_split_kernel<4><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
     EF_CUDA(cudaGetLastError());
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib
 from ._lib import Stats, TreeDesc, check
 
-CACHE_OPERATORS, HOMOGENEOUS_RHS, KEEP_X, LEAN_T = 1, 2, 4, 8
+CACHE_OPERATORS, HOMOGENEOUS_RHS, KEEP_X, LEAN_T, NO_SYMMETRY = 1, 2, 4, 8, 16
 OP = dict(T=0, S=1, X=2, H=3, Xinv=4, T_uncoarsened=5)
 VEC = dict(h=0, w=1, g=2, u=3, f=4)
 
@@ -160,6 +160,7 @@ class HPSAlgorithm:
             self.options.update(options)
         self.keep_x = False
         self.lean_T = False   # EFGPU_LEAN_T: DtN maps of interior nodes are transient (memory policy)
+        self.no_symmetry = False   # EFGPU_NO_SYMMETRY: general merge plan even where X and diag(d) T are symmetric
         self._lib = _lib.load()
         self._h = C.c_void_p()
         check(self._lib.efgpu_create(C.byref(mesh.desc), device, C.byref(self._h)))
@@ -177,7 +178,11 @@ class HPSAlgorithm:
     def _flags(self):
         return ((CACHE_OPERATORS if self.options["cache-operators"] else 0)
                 | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0) | (KEEP_X if self.keep_x else 0)
-                | (LEAN_T if self.lean_T else 0))
+                | (LEAN_T if self.lean_T else 0) | (NO_SYMMETRY if self.no_symmetry else 0))
+
+    def is_symmetric(self):
+        """True when the root's DtN map was built by the symmetric merge plan (efgpu_is_symmetric)."""
+        return bool(self._lib.efgpu_is_symmetric(self._h))
 
     def buildStage(self):  # HPSAlgorithm.hpp:120-161
         s = self.patch_solver

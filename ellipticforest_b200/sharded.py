@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import TreeDesc, check
-from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, OP, VEC, FiniteVolumeGrid
+from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, NO_SYMMETRY, OP, VEC, FiniteVolumeGrid
 
 
 class ShardPlan:
@@ -154,6 +154,12 @@ class GpuEngine:
 
     def build(self, flags):
         check(self._lib.efgpu_build(self._h, flags), self._h)
+
+    def is_symmetric(self):
+        return bool(self._lib.efgpu_is_symmetric(self._h))
+
+    def set_symmetric_leaves(self, on):
+        check(self._lib.efgpu_set_symmetric_leaves(self._h, int(bool(on))), self._h)
 
     def set_partition(self, rank, nranks, allgather=None):
         """Row partition of a replicated tree; `allgather(tensor)` must all-gather the tensor's equal slices in place."""
@@ -353,8 +359,11 @@ class ShardedHPS:
         self.local_if = self.local = None
 
     # -- helpers -------------------------------------------------------------------------------
+    no_symmetry = False
+
     def _flags(self):
-        return (CACHE_OPERATORS if self.options["cache-operators"] else 0) | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0)
+        return ((CACHE_OPERATORS if self.options["cache-operators"] else 0) | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0)
+                | (NO_SYMMETRY if self.no_symmetry else 0))
 
     def sharding(self):
         if self.top_mode == "replicated":
@@ -397,6 +406,8 @@ class ShardedHPS:
     def buildStage(self):
         fl = self._flags()
         self.local.build(fl)
+        if self.top is not None:   # the subtree roots' DtN maps are signed-symmetric when the forest used the symmetric plan
+            self.top.set_symmetric_leaves(self.local.is_symmetric())
         if self.top_mode != "replicated":
             with self.torch.cuda.stream(self._stream):
                 self.xchg.gather_T(self.local_if, self.top_if)

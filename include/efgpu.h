@@ -49,10 +49,14 @@ enum {
     EFGPU_CACHE_OPERATORS = 1u, /* option "cache-operators" (HPSAlgorithm.hpp:134-139): one T_leaf for every leaf */
     EFGPU_HOMOGENEOUS_RHS = 2u, /* option "homogeneous-rhs" (HPSAlgorithm.hpp:532,587,1202) */
     EFGPU_KEEP_X = 4u,          /* parity/debug: retain a copy of X (the product only needs X^-1) */
-    EFGPU_LEAN_T = 8u           /* memory policy: a DtN map T is only read by the parent's merge4to1
+    EFGPU_LEAN_T = 8u,          /* memory policy: a DtN map T is only read by the parent's merge4to1
                                    (HPSAlgorithm.hpp:497-518), so the maps of one tree level share a transient arena that is
                                    reused two levels up; after the build only leaf and root T can be read back.  Halves the
                                    resident operator bytes (X^-1 + S + H stay: 512 n^2 B per merge instead of 1024 n^2). */
+    EFGPU_NO_SYMMETRY = 16u     /* always use the general merge plan.  By default a merge whose subtree consists of square,
+                                   uncoarsened patches with constant-coefficient (FISHPACK90) leaves uses the symmetry of X and of diag(d) T (d = -1 on W and S: the
+                                   coordinate-derivative convention of FiniteVolumeSolver.cpp:332-343): 4 instead of 6 products
+                                   per level of the block inversion and 36 instead of 64 block products for T. */
 };
 
 enum { EFGPU_LEAF_CONSTANT = 0, EFGPU_LEAF_VARIABLE = 1 };
@@ -66,7 +70,7 @@ enum {
     EFGPU_PROF_LEAF_DTN = 0, EFGPU_PROF_COARSEN_T = 1, EFGPU_PROF_ASSEMBLE = 2, EFGPU_PROF_INVERT_SMALL = 3,
     EFGPU_PROF_GEMM_XINV = 4, EFGPU_PROF_GEMM_S = 5, EFGPU_PROF_GEMM_T = 6, EFGPU_PROF_LEAF_SOLVE = 7,
     EFGPU_PROF_UPWARDS_MATVEC = 8, EFGPU_PROF_SOLVE_MATVEC = 9, EFGPU_PROF_COARSEN_VEC = 10, EFGPU_PROF_LEAF_LU = 11,
-    EFGPU_PROF_ALLGATHER = 12, EFGPU_PROF_NCLASSES = 13
+    EFGPU_PROF_ALLGATHER = 12, EFGPU_PROF_TRANSPOSE = 13, EFGPU_PROF_MIRROR_T = 14, EFGPU_PROF_NCLASSES = 15
 };
 
 typedef struct efgpu_handle efgpu_handle;
@@ -118,6 +122,10 @@ int efgpu_set_partition(efgpu_handle* h, int rank, int nranks);
  * stream-ordered with efgpu_stream(h) (e.g. ncclAllGather on that stream, or torch.distributed under that stream). */
 typedef int (*efgpu_allgather_fn)(void* buf, size_t bytes_per_rank, void* user);
 int efgpu_set_allgather(efgpu_handle* h, efgpu_allgather_fn fn, void* user);
+/* External leaves (efgpu_create_ex): declare that the DtN maps the caller writes are signed-symmetric (diag(d) T symmetric),
+ * e.g. because efgpu_is_symmetric() holds for the forest handle they were built by; enables the symmetric merge plan. */
+int efgpu_set_symmetric_leaves(efgpu_handle* h, int on);
+int efgpu_is_symmetric(const efgpu_handle* h);   /* after a build: 1 when every root's DtN map was built by the symmetric plan */
 int efgpu_build_begin(efgpu_handle* h, unsigned flags);
 int efgpu_build_level(efgpu_handle* h, int level, int phase);
 int efgpu_build_end(efgpu_handle* h);
@@ -181,6 +189,24 @@ int efgpu_mesh_n_leaves(const efgpu_mesh* m);
 const int32_t* efgpu_mesh_leaf_nodes(const efgpu_mesh* m);       /* node id of each leaf, pre-order */
 int efgpu_mesh_path(const efgpu_mesh* m, int node, char* buf, size_t capacity);   /* "0" + child ids (P4est.cpp:35-44) */
 void efgpu_mesh_destroy(efgpu_mesh* m);
+
+/* ---- host-side plan of one merge batch, for CPU tests of the descriptor logic (no device needed) ----
+ * Serialises the step list the build would run for a merge with child side n on tree level `level`, as seen by rank
+ * `rank` of `nranks` (row partition), general (symmetric = 0) or symmetric plan.  Every record is 16 int64:
+ *   steps : kind, first, count, off, N, cls, gk, g_op, g_rows, g_cols, g_ld, g_off
+ *   blocks: c_op, c0_op, ldc, ldc0, c_off, c0_off, rows, cols, nterms   then per term (2 records of 8 int64 follow
+ *           in `terms`): a_op, b_op, lda, ldb, a_off, b_off, K, neg
+ *   trans : src_op, dst_op, lds, ldd, src_off, dst_off, rows, cols, neg
+ * ws[3] receives the per-entry workspace sizes (doubles) of W1, W2 and W3.  Returns the counts through n_*; arrays may
+ * be NULL to query the counts only. */
+int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric, int64_t* steps, int* n_steps,
+                           int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws);
+
+/* Process-wide kernel-selection knobs for measurements (A/B runs of the bandwidth-bound kernels): key 0 = bulk-copy
+ * streaming matvec kernels on (1, default) / off (0); key 1 = long-row matvec variant (0: 4, 1: 8 loads in flight per
+ * lane); key 2 = CTAs per SM the long-row launcher aims for (0: default 16).  Results do not depend on the knobs beyond
+ * floating-point summation order. */
+int efgpu_set_tuning(int key, int value);
 
 /* ---- stand-alone access to the GEMM kernel for unit tests and roofline measurements ------------ */
 int efgpu_dgemm_batched(const double* A_dev, const double* B_dev, double* C_dev, int m, int n, int k, int batch,

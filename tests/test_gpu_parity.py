@@ -19,7 +19,7 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-def run_gpu(kw, keep_x=True, options=None, scale=1.0):
+def run_gpu(kw, keep_x=True, options=None, scale=1.0, no_symmetry=False):
     P = O.problem(kw["problem_name"])
     m = _mesh_for(kw)
     s = ef.FiniteVolumeSolver()
@@ -27,6 +27,7 @@ def run_gpu(kw, keep_x=True, options=None, scale=1.0):
     s.alpha_function, s.beta_function, s.lambda_function = P["alpha"], P["beta"], P["lam"]
     hps = ef.HPSAlgorithm(m, s, options=options)
     hps.keep_x = keep_x
+    hps.no_symmetry = no_symmetry
     hps.setupStage()
     hps.buildStage()
     hps.upwardsStage(P["f"], scale)
@@ -63,12 +64,23 @@ def test_against_reference_dump(case):
         assert v < TOL, (nm, v)
 
 
-@pytest.mark.parametrize("nx,level,problem", [(16, 3, "poisson"), (32, 2, "helmholtz"), (24, 2, "poisson")])
-def test_uniform_against_oracle(nx, level, problem):
+_ORACLE_CACHE = {}
+
+
+@pytest.mark.parametrize("plan", ["symmetric", "general"])
+@pytest.mark.parametrize("nx,level,problem", [(16, 3, "poisson"), (32, 2, "helmholtz"), (24, 2, "poisson"), (16, 4, "poisson"), (24, 3, "helmholtz")])
+def test_uniform_against_oracle(nx, level, problem, plan):
+    """Uniform trees take the symmetric merge plan by default (X and diag(d) T symmetric: 4-GEMM block inversion with
+    transposes, 36 of 64 T blocks computed and 28 mirrored); EFGPU_NO_SYMMETRY forces the general plan.  (16, 4) reaches
+    X of order 512 (two recursion levels of the blocked inversion), (24, 3) has blocks of 48 and 96 rows (no multiple of 32 / 128)."""
     kw = dict(problem_name=problem, solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=nx,
               min_level=level, max_level=level, threshold=1.2, refine_box=None)
-    hps = run_gpu(kw)
-    ora = O.run(**kw)
+    hps = run_gpu(kw, no_symmetry=(plan == "general"))
+    assert hps.is_symmetric() == (plan == "symmetric")
+    key = (nx, level, problem)
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = O.run(**kw)
+    ora = _ORACLE_CACHE[key]
     worst = {}
     for i, nd in enumerate(ora.nodes):
         assert hps.mesh.path(i) == nd.path
@@ -89,6 +101,7 @@ def test_adaptive_m16_against_oracle():
     kw = dict(problem_name="poisson", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=16,
               min_level=0, max_level=4, threshold=1.2, refine_box=None)
     hps = run_gpu(kw)
+    assert not hps.is_symmetric()          # coarsened children: the root merge takes the general plan
     ora = O.run(**kw)
     assert max(nd.n_coarsens for nd in ora.nodes) >= 1
     u_ref = np.stack([u.reshape(16, 16) for u in ora.leaf_solution()])

@@ -1,0 +1,212 @@
+"""CPU tests of the merge planner (host logic of libefgpu.so, no device): the step / descriptor lists that
+efgpu_build would launch are serialised by efgpu_debug_merge_plan, interpreted here with numpy (one state
+per rank, all-gathers included) and the resulting X^-1, S, T compared with the oracle's merge4to1
+(reference src/HPSAlgorithm.hpp:497-518) on the same children."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ellipticforest_b200 import _lib
+import hps_oracle as O
+
+OP_TC0, OP_XINV, OP_S, OP_T, OP_W1, OP_W2, OP_W3 = 0, 4, 5, 6, 7, 8, 9
+CLS_GEMM_T, CLS_MIRROR_T = 6, 14
+
+
+def get_plan(n, level, rank, nranks, sym):
+    lib = _lib.load()
+    ns, nb, nt = C.c_int(), C.c_int(), C.c_int()
+    ws = np.zeros(3, dtype=np.int64)
+    args = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    assert lib.efgpu_debug_merge_plan(n, level, rank, nranks, sym, None, C.byref(ns), None, None, C.byref(nb), None, C.byref(nt), args(ws)) == 0
+    steps = np.zeros((ns.value, 16), dtype=np.int64)
+    blocks = np.zeros((nb.value, 16), dtype=np.int64)
+    terms = np.zeros((nb.value, 2, 8), dtype=np.int64)
+    trans = np.zeros((max(nt.value, 1), 16), dtype=np.int64)
+    assert lib.efgpu_debug_merge_plan(n, level, rank, nranks, sym, args(steps), C.byref(ns), args(blocks), args(terms), C.byref(nb),
+                                      args(trans), C.byref(nt), args(ws)) == 0
+    return steps, blocks, terms, trans[:nt.value], ws
+
+
+def view(buf, off, ld, rows, cols):
+    """rows x cols window of a flat row-major buffer (as_strided: writable, no copy)."""
+    return np.lib.stride_tricks.as_strided(buf[off:], shape=(rows, cols), strides=(ld * 8, 8))
+
+
+class RankState:
+    def __init__(self, n, Tc, X, ws):
+        self.ops = {OP_TC0 + c: np.ascontiguousarray(Tc[c], dtype=np.float64).reshape(-1).copy() for c in range(4)}
+        self.ops[OP_XINV] = np.ascontiguousarray(X).reshape(-1).copy()
+        self.ops[OP_S] = np.full(32 * n * n, np.nan)
+        self.ops[OP_T] = np.full(64 * n * n, np.nan)
+        for k, op in enumerate((OP_W1, OP_W2, OP_W3)):
+            self.ops[op] = np.full(int(ws[k]) + 1, np.nan)
+
+    def gemm(self, blk, trm):
+        c_op, c0_op, ldc, ldc0, c_off, c0_off, rows, cols, nterms = (int(v) for v in blk[:9])
+        acc = np.zeros((rows, cols))
+        if c0_op >= 0:
+            acc += view(self.ops[c0_op], c0_off, ldc0, rows, cols)
+        for t in range(nterms):
+            a_op, b_op, lda, ldb, a_off, b_off, K, neg = (int(v) for v in trm[t])
+            p = view(self.ops[a_op], a_off, lda, rows, K) @ view(self.ops[b_op], b_off, ldb, K, cols)
+            acc += -p if neg else p
+        view(self.ops[c_op], c_off, ldc, rows, cols)[...] = acc
+
+    def run_step(self, st, blocks, terms, trans, n):
+        kind, first, count, off, N = (int(v) for v in st[:5])
+        if kind == 0:
+            v = view(self.ops[OP_XINV], off, 4 * n, N, N)
+            v[...] = np.linalg.inv(v.copy())
+        elif kind == 1:
+            results = []   # one launch: every block reads the state before the launch
+            for k in range(first, first + count):
+                self.gemm(blocks[k], terms[k])
+        else:
+            for k in range(first, first + count):
+                s_op, d_op, lds, ldd, s_off, d_off, rows, cols, neg = (int(v) for v in trans[k][:9])
+                src = view(self.ops[s_op], s_off, lds, rows, cols).copy()
+                view(self.ops[d_op], d_off, ldd, cols, rows)[...] = (-src if neg else src).T
+
+
+def allgather(states, op, off, doubles):
+    nr = len(states)
+    per = doubles // nr
+    full = np.concatenate([states[r].ops[op][off + r * per: off + (r + 1) * per] for r in range(nr)])
+    for s in states:
+        s.ops[op][off: off + doubles] = full
+
+
+def emulate(n, level, nranks, sym, Tc, X):
+    plans = [get_plan(n, level, r, nranks, sym) for r in range(nranks)]
+    states = [RankState(n, Tc, X, plans[r][4]) for r in range(nranks)]
+    nsteps = len(plans[0][0])
+    assert all(len(p[0]) == nsteps for p in plans)
+
+    def run(i):
+        for r in range(nranks):
+            steps, blocks, terms, trans, _ = plans[r]
+            states[r].run_step(steps[i], blocks, terms, trans, n)
+        st = plans[0][0][i]
+        gk, g_op, g_rows, g_cols, g_ld, g_off = (int(v) for v in st[6:12])
+        if gk == 1:
+            allgather(states, g_op, g_off, g_rows * g_cols)
+        elif gk == 2:
+            allgather(states, OP_W3, 0, g_rows * g_cols)
+            for s in states:
+                view(s.ops[g_op], g_off, g_ld, g_rows, g_cols)[...] = s.ops[OP_W3][:g_rows * g_cols].reshape(g_rows, g_cols)
+
+    cls = [int(plans[0][0][i][5]) for i in range(nsteps)]
+    for i in range(nsteps):          # phase 0: everything but T
+        if cls[i] not in (CLS_GEMM_T, CLS_MIRROR_T):
+            run(i)
+    if nranks > 1:
+        allgather(states, OP_S, 0, 32 * n * n)
+    for i in range(nsteps):          # phase 1
+        if cls[i] == CLS_GEMM_T:
+            run(i)
+    if nranks > 1 and level > 0:
+        allgather(states, OP_T, 0, 64 * n * n)
+    for i in range(nsteps):
+        if cls[i] == CLS_MIRROR_T:
+            run(i)
+    flops = 0
+    for steps, blocks, terms, trans, _ in plans:
+        for st in steps:
+            if int(st[0]) == 1:
+                for k in range(int(st[1]), int(st[1]) + int(st[2])):
+                    for t in range(int(blocks[k][8])):
+                        flops += 2 * int(blocks[k][6]) * int(blocks[k][7]) * int(terms[k][t][6])
+    return states, flops
+
+
+def oracle_merge(Tc, n):
+    nodes = [O.Node(path="0", level=0, grid=O.Grid(2 * n, 0.0, 2.0, 0.0, 2.0), leaf=False)]
+    for c in range(4):
+        nd = O.Node(path="0%d" % c, level=1, grid=O.Grid(n, (c & 1) * 1.0, (c & 1) + 1.0, (c >> 1) * 1.0, (c >> 1) + 1.0), leaf=True)
+        nd.T = Tc[c].copy()
+        nodes.append(nd)
+    hps = O.HPS(nodes, None)
+    hps.merge4to1(*nodes)
+    return nodes[0]
+
+
+def uniform_children(n_leaf, depth, name="poisson"):
+    """Four identical-size DtN maps of uniform subtrees (child side n = n_leaf * 2^depth) from the oracle."""
+    r = O.run(problem_name=name, solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=n_leaf, min_level=depth + 1,
+              max_level=depth + 1)
+    root = r.nodes[0]
+    return [r.nodes[c].T for c in root.children], root
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+_CHILDREN = {}
+
+
+@pytest.mark.parametrize("depth", [2, 3])
+@pytest.mark.parametrize("nranks", [1, 2])
+@pytest.mark.parametrize("sym", [0, 1])
+def test_plan_reproduces_oracle_merge_uniform(sym, nranks, depth):
+    # n = 64: X is 256 x 256, blocked inversion with a structured top level and register-resident base cases;
+    # n = 128: two recursion levels, and with 2 ranks the 256-row products are split by rows and all-gathered
+    if depth not in _CHILDREN:
+        _CHILDREN[depth] = uniform_children(16, depth)
+    Tc, root = _CHILDREN[depth]
+    n = 16 << depth
+    for level in ((0, 1) if nranks > 1 else (0,)):
+        states, flops = emulate(n, level, nranks, sym, Tc, root.X)
+        for s in states:
+            assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(root.X)) < 1e-11
+            assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
+        if nranks == 1 or level > 0:
+            for s in states:
+                assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
+        else:   # the root's DtN map of a partitioned tree stays row-distributed
+            T = np.concatenate([states[r].ops[OP_T].reshape(8 * n, 8 * n)[r * 8 * n // nranks:(r + 1) * 8 * n // nranks] for r in range(nranks)])
+            assert rel(T, root.T) < 1e-11
+        n3 = float(n) ** 3
+        if nranks == 1:                      # (small replicated products are issued by every rank of a partition)
+            assert flops < 400 * n3 if sym else flops <= 484 * n3   # symmetric plan: well below the general 484 n^3
+
+
+def test_general_plan_on_nonsymmetric_children():
+    rng = np.random.default_rng(0)
+    n = 40                                       # N = 160: h = 80, q = 40; odd sizes for the transposes / tiles
+    Tc, _ = uniform_children(8, 0)
+    scale = np.max(np.abs(Tc[0]))
+    Tc = []
+    for c in range(4):
+        A = rng.standard_normal((4 * n, 4 * n)) * 0.05 * scale / np.sqrt(n)
+        d = np.ones(4 * n); d[:n] = -1; d[2 * n:3 * n] = -1
+        Tc.append(A + np.diag(d) * scale)       # diagonally dominant with the sign pattern of a DtN map
+    ref = oracle_merge(Tc, n)
+    states, flops = emulate(n, 0, 1, 0, Tc, ref.X)
+    s = states[0]
+    assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(ref.X)) < 1e-11
+    assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), ref.S) < 1e-11
+    assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), ref.T) < 1e-11
+    assert flops <= 484 * n ** 3                 # 100 (structured inverse) + 128 (S) + 256 (T)
+
+
+def test_symmetric_plan_flop_count_and_balance():
+    n = 256
+    steps, blocks, terms, trans, ws = get_plan(n, 1, 0, 1, 1)
+    assert len(trans) >= 28
+    mirror = [t for t in trans if int(t[0]) == OP_T]
+    assert len(mirror) == 28
+    # every off-diagonal block of T is either computed or mirrored, never both
+    tsteps = [st for st in steps if int(st[5]) == CLS_GEMM_T]
+    computed = set()
+    for st in tsteps:
+        for k in range(int(st[1]), int(st[1]) + int(st[2])):
+            off = int(blocks[k][4]); computed.add((off // (8 * n) // n, off % (8 * n) // n))
+    mirrored = {(int(t[5]) // (8 * n) // n, int(t[5]) % (8 * n) // n) for t in mirror}
+    assert len(computed) == 36 and not (computed & mirrored) and len(computed | mirrored) == 64
+    for (p, q) in mirrored:
+        assert (q, p) in computed
+    rows = [sum(1 for (p, q) in computed if p == r) for r in range(8)]
+    assert max(rows) - min(rows) <= 1
