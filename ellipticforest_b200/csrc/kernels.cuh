@@ -48,6 +48,7 @@ void launch_coarsen_h(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_
 void launch_uncoarsen_g(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s);
 void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s);            // hd, w, h
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s);
+int get_tuning(int key);
 void set_tuning(int key, int value);   // efgpu_set_tuning: kernel-selection knobs for measurements
 void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s);      // parity/debug: 8n x 4n, reference order
 

@@ -153,140 +153,218 @@ leaf_solve_const_kernel(const double* __restrict__ Q, const double* __restrict__
 }
 
 
-// Register-tiled variant of leaf_solve_const_kernel for M = 16, 32: (M/4)^2 threads per leaf, each owning
-// a 4 x 4 tile of every M x M product, several leaves per 128-thread CTA.  The one-output-per-thread
-// kernel above is shared-memory-bandwidth bound (two 8-byte loads per FMA); the tile brings that to
-// half a load per FMA.  Same arithmetic, same interface.
+// FP64 tensor-core variant of the leaf solve, M = 8, 16, 24, 32: ONE WARP PER LEAF, the four M x M products of the
+// fast diagonalisation issued as DMMA m8n8k4 (same instruction as csrc/gemm.cu).  The whole M x M result of a product
+// lives in the warp's accumulator registers, so one padded shared-memory tile per warp is enough: read fragments,
+// __syncwarp, write the result over it.  Leading dimension M + 4 == 4 or 12 (mod 16) makes the 8 x 4 (A, row-major), the
+// 4 x 8 (B) and both transposed fragment reads bank-conflict free, so one row-major copy of Q serves Q and Q^T on either
+// side.  No CTA-wide barrier inside the leaf loop: warps stream f / u independently and hide each other's HBM latency.
+// Per FMA it moves 1/8 of the shared-memory bytes of a 4 x 4 register-tiled FMA kernel (measured 1.9x slower, M = 16).
+__device__ __forceinline__ void leaf_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// acc = A B with A(row, k) = A[row * as_r + k * as_k], B(k, col) = B[k * bs_k + col * bs_c]; g = lane / 4, t = lane % 4
 template <int M>
-__device__ __forceinline__ void tile_mm(const double* __restrict__ X, int xs_r, int xs_m, const double* __restrict__ Y, int ys_m, int ys_c,
-                                        int r0, int c0, double acc[4][4])
+__device__ __forceinline__ void warp_mm(const double* __restrict__ A, int as_r, int as_k, const double* __restrict__ B, int bs_k, int bs_c,
+                                        int g, int t, double (&acc)[M / 8][M / 8][2])
 {
+    constexpr int F = M / 8;
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int i = 0; i < F; i++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-#pragma unroll 4
-    for (int m = 0; m < M; m++) {
-        double x[4], y[4];
+        for (int j = 0; j < F; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* a0 = A + g * as_r + t * as_k;
+    const double* b0 = B + t * bs_k + g * bs_c;
 #pragma unroll
-        for (int a = 0; a < 4; a++) x[a] = X[(r0 + a) * xs_r + m * xs_m];
+    for (int kk = 0; kk < M / 4; kk++) {
+        double a[F], b[F];
 #pragma unroll
-        for (int b = 0; b < 4; b++) y[b] = Y[m * ys_m + (c0 + b) * ys_c];
+        for (int i = 0; i < F; i++) a[i] = a0[8 * i * as_r + 4 * kk * as_k];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int j = 0; j < F; j++) b[j] = b0[4 * kk * bs_k + 8 * j * bs_c];
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+        for (int i = 0; i < F; i++)
+#pragma unroll
+            for (int j = 0; j < F; j++) leaf_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
 template <int M>
-__global__ void __launch_bounds__(128)
-leaf_solve_const_tiled_kernel(const double* __restrict__ Q, const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
-                              double lambda, const double* __restrict__ f, double fscale, double* const* __restrict__ g_ptrs,
-                              double* __restrict__ u_out, double* const* __restrict__ h_ptrs, int mode, int n_leaves)
+__device__ __forceinline__ void warp_store(double* __restrict__ buf, int ld, int g, int t, const double (&acc)[M / 8][M / 8][2])
 {
-    constexpr int T = M / 4, TPL = T * T, LPC = 128 / TPL, LD = M + 1;
-    extern __shared__ __align__(16) double smt[];
-    double* sQ = smt;                         // M x LD, sQ[i][k]
-    double* sMu = sQ + M * LD;                // M
-    double* sAB = sMu + M;                    // LPC x 2 x M x LD
-    double* sGall = sAB + LPC * 2 * M * LD;   // LPC x 4M
-    const int tid = threadIdx.x;
-    const int ll = tid / TPL, lt = tid % TPL;             // leaf slot in the CTA, thread within the leaf
-    const int leaf = blockIdx.x * LPC + ll;
-    const bool live = leaf < n_leaves;
-    const int r0 = (lt / T) * 4, c0 = (lt % T) * 4;
-    double* sA = sAB + ll * 2 * M * LD;
-    double* sB = sA + M * LD;
-    double* sG = sGall + ll * 4 * M;
-    for (int e = tid; e < M * M; e += 128) sQ[(e / M) * LD + (e % M)] = Q[e];
-    if (tid < M) sMu[tid] = 2.0 * cospi((double)(tid + 1) / M) - 2.0;
-    double dx = 1.0, dy = 1.0;
-    if (live) {
-        const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
-        dx = (box[1] - box[0]) / M; dy = (box[3] - box[2]) / M;
-        for (int e = lt; e < 4 * M; e += TPL) sG[e] = g_ptrs ? g_ptrs[leaf][e] : 0.0;
+#pragma unroll
+    for (int i = 0; i < M / 8; i++)
+#pragma unroll
+        for (int j = 0; j < M / 8; j++)
+            *reinterpret_cast<double2*>(buf + (8 * i + g) * ld + 8 * j + 2 * t) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// Shared memory per CTA: Q (M x LD) | per warp: 2 tiles (M x LD), 2 x g (4M) | per warp 2 mbarriers.
+// Each warp double-buffers its leaves' inputs with the bulk-copy engine: before it starts the four products of the
+// current leaf, lane i issues a cp.async.bulk of row i of the NEXT leaf's f (M*8 bytes) straight into the padded rows
+// of the other tile, and lane 0 one for g (4M*8 bytes); completion is counted on the slot's mbarrier.
+template <int M, int WARPS>
+struct LeafMmaSmem {
+    static constexpr int LD = M + 4;
+    static constexpr int PER_WARP = 2 * M * LD + 2 * 4 * M;                         // doubles
+    static constexpr int BYTES = (M * LD + WARPS * PER_WARP + WARPS * 2) * 8;
+};
+
+template <int M, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+leaf_solve_const_mma_kernel(const double* __restrict__ Q, const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
+                            double lambda, const double* __restrict__ f, double fscale, double* const* __restrict__ g_ptrs,
+                            double* __restrict__ u_out, double* const* __restrict__ h_ptrs, int mode, int n_leaves)
+{
+    using SM = LeafMmaSmem<M, WARPS>;
+    constexpr int LD = SM::LD, F = M / 8;
+    extern __shared__ __align__(128) double smm[];
+    double* sQ = smm;                                       // M x LD, sQ[i][k] = q_{k+1}(i)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double* tiles = smm + M * LD + warp * SM::PER_WARP;     // [2][M x LD]  f lands here; the products run in place
+    double* gsm = tiles + 2 * M * LD;                       // [2][4M]      Dirichlet data
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smm + M * LD + WARPS * SM::PER_WARP) + warp * 2;
+    for (int e = threadIdx.x; e < M * M; e += WARPS * 32) sQ[(e / M) * LD + (e % M)] = Q[e];
+    if (lane == 0) {
+        mbar_init(bar, 1); mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // eigenvalue numerators of the rows / columns this lane owns in the accumulator layout
+    double muR[F], muC[F][2];
+#pragma unroll
+    for (int i = 0; i < F; i++) muR[i] = 2.0 * cospi((double)(8 * i + g + 1) / M) - 2.0;
+#pragma unroll
+    for (int j = 0; j < F; j++) {
+        muC[j][0] = 2.0 * cospi((double)(8 * j + 2 * t + 1) / M) - 2.0;
+        muC[j][1] = 2.0 * cospi((double)(8 * j + 2 * t + 2) / M) - 2.0;
     }
     __syncthreads();
-    if (live) {
-        // right-hand side with the Dirichlet data folded in (hstcrt.f:412-439); cell (i, j), index j + i*M
-        const double* fl = f ? f + (size_t)leaf * M * M : nullptr;
-        for (int e = lt; e < M * M; e += TPL) {
-            const int i = e / M, j = e % M;
-            double rhs = fl ? fscale * fl[e] : 0.0;
-            if (i == 0) rhs -= 2.0 / (dx * dx) * sG[j];
-            if (i == M - 1) rhs -= 2.0 / (dx * dx) * sG[M + j];
-            if (j == 0) rhs -= 2.0 / (dy * dy) * sG[2 * M + i];
-            if (j == M - 1) rhs -= 2.0 / (dy * dy) * sG[3 * M + i];
-            sA[i * LD + j] = rhs;
+    const int stride = gridDim.x * WARPS;
+    const int leaf0 = blockIdx.x * WARPS + warp;
+    const unsigned tx_bytes = (f ? M * M * 8u : 0u) + (g_ptrs ? 4 * M * 8u : 0u);
+    // start the copies of `leaf` into slot s; gp = that leaf's g pointer (already in a register)
+    auto issue = [&](int leaf, int s, const double* gp) {
+        if (!tx_bytes) return;
+        if (lane == 0) {
+            mbar_expect_tx(bar + s, tx_bytes);
+            if (g_ptrs) bulk_g2s(gsm + s * 4 * M, gp, 4 * M * 8u, bar + s);
         }
+        __syncwarp();
+        if (f && lane < M) bulk_g2s(tiles + s * M * LD + lane * LD, f + (size_t)leaf * M * M + lane * M, M * 8u, bar + s);
+    };
+    const double* gp_next = nullptr;    // g pointer of the leaf after the current one, loaded one iteration ahead
+    if (leaf0 < n_leaves) {
+        issue(leaf0, 0, g_ptrs ? g_ptrs[leaf0] : nullptr);
+        if (g_ptrs && leaf0 + stride < n_leaves) gp_next = g_ptrs[leaf0 + stride];
     }
-    __syncthreads();
-    double acc[4][4];
-    // B = Q^T R : B[k][j] = sum_m Q[m][k] R[m][j]
-    if (live) {
-        tile_mm<M>(sQ, 1, LD, sA, LD, 1, r0, c0, acc);
+    double acc[F][F][2];
+    int it = 0;
+    for (int leaf = leaf0; leaf < n_leaves; leaf += stride, it++) {
+        const int s = it & 1;
+        {   // prefetch: the other slot was last read before the __syncwarp that closed the previous leaf's staging
+            const int next = leaf + stride;
+            if (next < n_leaves) {
+                issue(next, s ^ 1, gp_next);
+                if (g_ptrs && next + stride < n_leaves) gp_next = g_ptrs[next + stride];
+            }
+        }
+        const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+        const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+        const double rx = 1.0 / (dx * dx), ry = 1.0 / (dy * dy);
+        if (tx_bytes) mbar_wait(bar + s, (unsigned)((it >> 1) & 1));
+        double* buf = tiles + s * M * LD;
+        const double* gl = g_ptrs ? gsm + s * 4 * M : nullptr;
+        // right-hand side with the Dirichlet data folded in (hstcrt.f:412-439), in place; cell (i, j) at index j + i*M
+        {
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+            for (int k = 0; k < M * M / 64; k++) {
+                const int e2 = lane + 32 * k;
+                const int i = (2 * e2) / M, j = (2 * e2) % M;   // j even: both entries lie in row i
+                double2 v = make_double2(0.0, 0.0);
+                if (f) { v = *reinterpret_cast<const double2*>(buf + i * LD + j); v.x *= fscale; v.y *= fscale; }
+                if (gl) {
+                    if (i == 0) { v.x -= 2.0 * rx * gl[j]; v.y -= 2.0 * rx * gl[j + 1]; }
+                    if (i == M - 1) { v.x -= 2.0 * rx * gl[M + j]; v.y -= 2.0 * rx * gl[M + j + 1]; }
+                    if (j == 0) v.x -= 2.0 * ry * gl[2 * M + i];
+                    if (j == M - 2) v.y -= 2.0 * ry * gl[3 * M + i];
+                }
+                *reinterpret_cast<double2*>(buf + i * LD + j) = v;
+            }
+        }
+        __syncwarp();
+        // B = Q^T R : A(k, m) = Q[m][k], B(m, j) = R[m][j]
+        warp_mm<M>(sQ, 1, LD, buf, LD, 1, g, t, acc);
+        __syncwarp();
+        warp_store<M>(buf, LD, g, t, acc);
+        __syncwarp();
+        // A = (B Q) / D : A(k, m) = B[k][m], B(m, l) = Q[m][l]
+        warp_mm<M>(buf, LD, 1, sQ, LD, 1, g, t, acc);
 #pragma unroll
-            for (int b = 0; b < 4; b++) sB[(r0 + a) * LD + c0 + b] = acc[a][b];
-    }
-    __syncthreads();
-    // A = (B Q) / D : A[k][l] = sum_m B[k][m] Q[m][l]
-    if (live) {
-        tile_mm<M>(sB, LD, 1, sQ, LD, 1, r0, c0, acc);
+        for (int i = 0; i < F; i++)
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++)
-                sA[(r0 + a) * LD + c0 + b] = acc[a][b] / (sMu[r0 + a] / (dx * dx) + sMu[c0 + b] / (dy * dy) + lambda);
-    }
-    __syncthreads();
-    // B = Q A : B[i][l] = sum_m Q[i][m] A[m][l]
-    if (live) {
-        tile_mm<M>(sQ, LD, 1, sA, LD, 1, r0, c0, acc);
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) sB[(r0 + a) * LD + c0 + b] = acc[a][b];
-    }
-    __syncthreads();
-    // U = B Q^T : U[i][j] = sum_m B[i][m] Q[j][m]
-    if (live) {
-        tile_mm<M>(sB, LD, 1, sQ, 1, LD, r0, c0, acc);
+            for (int j = 0; j < F; j++) {
+                acc[i][j][0] /= (muR[i] * rx + muC[j][0] * ry + lambda);
+                acc[i][j][1] /= (muR[i] * rx + muC[j][1] * ry + lambda);
+            }
+        __syncwarp();
+        warp_store<M>(buf, LD, g, t, acc);
+        __syncwarp();
+        // B = Q A : A(i, m) = Q[i][m], B(m, l) = A[m][l]
+        warp_mm<M>(sQ, LD, 1, buf, LD, 1, g, t, acc);
+        __syncwarp();
+        warp_store<M>(buf, LD, g, t, acc);
+        __syncwarp();
+        // U = B Q^T : A(i, m) = B[i][m], B(m, j) = Q[j][m]
+        warp_mm<M>(buf, LD, 1, sQ, 1, LD, g, t, acc);
         if (mode == 0) {
             double* u = u_out + (size_t)leaf * M * M;
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int i = 0; i < F; i++)
 #pragma unroll
-                for (int b = 0; b < 4; b += 2)
-                    *reinterpret_cast<double2*>(u + (r0 + a) * M + c0 + b) = make_double2(acc[a][b], acc[a][b + 1]);
+                for (int j = 0; j < F; j++)
+                    __stcs(reinterpret_cast<double2*>(u + (8 * i + g) * M + 8 * j + 2 * t), make_double2(acc[i][j][0], acc[i][j][1]));
         } else {
+            // mapD2N (FiniteVolumeSolver.cpp:332-343): coordinate derivatives on the four sides
             double* h = h_ptrs[leaf];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int i = 0; i < F; i++)
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int i = r0 + a, j = c0 + b;
-                    const double t = acc[a][b];
-                    if (i == 0) h[j] = (2.0 / dx) * (t - sG[j]);
-                    if (i == M - 1) h[M + j] = -(2.0 / dx) * (t - sG[M + j]);
-                    if (j == 0) h[2 * M + i] = (2.0 / dy) * (t - sG[2 * M + i]);
-                    if (j == M - 1) h[3 * M + i] = -(2.0 / dy) * (t - sG[3 * M + i]);
-                }
+                for (int j = 0; j < F; j++)
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int ci = 8 * i + g, cj = 8 * j + 2 * t + q;
+                        const double v = acc[i][j][q];
+                        if (ci == 0) h[cj] = (2.0 / dx) * (v - (gl ? gl[cj] : 0.0));
+                        if (ci == M - 1) h[M + cj] = -(2.0 / dx) * (v - (gl ? gl[M + cj] : 0.0));
+                        if (cj == 0) h[2 * M + ci] = (2.0 / dy) * (v - (gl ? gl[2 * M + ci] : 0.0));
+                        if (cj == M - 1) h[3 * M + ci] = -(2.0 / dy) * (v - (gl ? gl[3 * M + ci] : 0.0));
+                    }
         }
+        __syncwarp();   // every lane is done with the tile and with slot s before the next iteration refills them
     }
 }
 
 template <int M>
-static void solve_const_tiled_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, const double* f, double fscale,
-                                double* const* g_ptrs, double* u_out, double* const* h_ptrs, int mode, int n_leaves, cudaStream_t s) {
-    constexpr int T = M / 4, TPL = T * T, LPC = 128 / TPL, LD = M + 1;
-    constexpr int smem = (M * LD + M + LPC * 2 * M * LD + LPC * 4 * M) * (int)sizeof(double);
-    auto kern = leaf_solve_const_tiled_kernel<M>;
-    static bool attr = false;
-    if (!attr) { EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    kern<<<(n_leaves + LPC - 1) / LPC, 128, smem, s>>>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves);
+static void solve_const_mma_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, const double* f, double fscale,
+                              double* const* g_ptrs, double* u_out, double* const* h_ptrs, int mode, int n_leaves, cudaStream_t s) {
+    constexpr int WARPS = M >= 32 ? 4 : 8;
+    constexpr int smem = LeafMmaSmem<M, WARPS>::BYTES;
+    auto kern = leaf_solve_const_mma_kernel<M, WARPS>;
+    static int resident = 0;   // CTAs the device holds at once: the leaves are dealt to them in a grid-stride loop
+    if (!resident) {
+        EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0, sms = 0, per_sm = 0;
+        EF_CUDA(cudaGetDevice(&dev));
+        EF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        EF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    int grid = (n_leaves + WARPS - 1) / WARPS;
+    if (grid > resident) grid = resident;
+    kern<<<grid, WARPS * 32, smem, s>>>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves);
 }
 
 // =================================================================================================
@@ -579,11 +657,23 @@ void launch_leaf_solve_const(int M, const double* Q, const double* boxes, const 
                              int mode, int n_leaves, cudaStream_t s)
 {
     if (n_leaves == 0) return;
-    switch (M) {
+    // default: FP64 tensor-core kernel, one warp per leaf (its bulk copies need f on a 16-byte boundary)
+    if (get_tuning(3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+        switch (M) {
+            case 8: solve_const_mma_M<8>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+            case 16: solve_const_mma_M<16>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+            case 24: solve_const_mma_M<24>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+            case 32: solve_const_mma_M<32>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+            default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+        }
+        EF_CUDA(cudaGetLastError());
+        return;
+    }
+    switch (M) {   // one thread per cell: any alignment of f (a caller-owned device pointer in efgpu_upwards_device)
         case 8: solve_const_M<8>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
-        case 16: solve_const_tiled_M<16>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+        case 16: solve_const_M<16>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
         case 24: solve_const_M<24>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
-        case 32: solve_const_tiled_M<32>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+        case 32: solve_const_M<32>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
         default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
     }
     EF_CUDA(cudaGetLastError());

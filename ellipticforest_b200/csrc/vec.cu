@@ -15,10 +15,13 @@
 namespace efgpu {
 
 // ---- tuning (efgpu_set_tuning): kernel-selection knobs for measurements ------------------------------
-// [0] bulk-copy streaming matvec kernels on (1, default) / off (0); [1] long-row kernels: 1 = 8 loads in flight per lane
-// (default 4); [2] CTAs per SM the long-row launcher aims for (default 16)
-static int g_tuning[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+// [0] 2 = row-batch kernels for rows of <= 256 doubles (default), 0 = one row per warp everywhere
+// [1] compact-H long-row kernel: 0 = 8 loads in flight per lane (default), 1 = 4
+// [2] CTAs per SM the long-row launcher aims for (default 16)
+// [3] leaf solve of constant-coefficient leaves: 0 = DMMA kernel (default), 1 = one thread per cell
+static int g_tuning[8] = {2, 0, 0, 0, 0, 0, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tuning[key] = value; }
+int get_tuning(int key) { return (key >= 0 && key < 8) ? g_tuning[key] : 0; }
 
 // side of child c that faces interior interface k (-1: not adjacent)
 __constant__ int c_iface[4][4] = {{3, -1, 1, -1}, {-1, 3, 0, -1}, {2, -1, -1, 1}, {-1, 2, -1, 0}};
@@ -251,294 +254,210 @@ __global__ void __launch_bounds__(256) solve_split_kernel(const MergeEntry* __re
     }
 }
 
-// ---- short-row variants (child side n <= 256: rows of 2n..8n doubles) ---------------------------
-// One CTA per (parent, row chunk).  The right-hand vector is staged in shared memory once; a row is
-// owned by a group of LW lanes (LW = min(32, L/2), 16-byte loads), so short rows do not idle most of
-// a warp, and every group keeps R rows in flight before reducing (memory-level parallelism).
-template <int LW, int R, class Epilogue>
-__device__ __forceinline__ void gemv_rows_short(const double* __restrict__ A, int L, const double* xs, int r0, int r1, Epilogue epi)
+// ---- row-batch kernels (rows of L = 32 .. 256 doubles) -------------------------------------------
+// Warp-autonomous, no shared memory, no CTA barrier: a warp owns a contiguous range of 4 KB batches of the level's
+// operator slab.  One batch = 8 independent, fully coalesced 512-byte loads per warp (16 bytes per lane, streaming), i.e.
+// 512 / L complete rows.  The lane's slice of the right-hand vector lives in registers (reloaded when the
+// parent - or, for H, the WESN block - changes).  The per-row partial sums of a batch are reduced TOGETHER by a
+// butterfly that halves the number of live values at every exchange (V values over LW lanes cost V - 1 + log2(LW / V)
+// shuffles instead of V log2(LW)), which is what makes short rows cheap: 8 rows of 64 doubles take 9 shuffles, not 40.
+template <int V, int LW>
+__device__ __forceinline__ double butterfly_reduce(double (&v)[V], int lane)
 {
-    const int tid = threadIdx.x;
-    const int grp = tid / LW, gl = tid % LW, ngrp = blockDim.x / LW;
-    const int L2 = L >> 1;
-    const double2* x2 = reinterpret_cast<const double2*>(xs);
-    for (int rb = r0 + grp * R; rb < r1; rb += ngrp * R) {
-        double acc[R];
+    int o = LW / 2;
 #pragma unroll
-        for (int k = 0; k < R; k++) acc[k] = 0.0;
-        for (int c = gl; c < L2; c += LW) {
-            double2 av[R];
+    for (int cnt = V; cnt > 1; cnt >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
 #pragma unroll
-            for (int k = 0; k < R; k++)
-                av[k] = (rb + k < r1) ? __ldcs(reinterpret_cast<const double2*>(A + (size_t)(rb + k) * L) + c) : make_double2(0.0, 0.0);
-            const double2 xv = x2[c];
-#pragma unroll
-            for (int k = 0; k < R; k++) acc[k] = fma(av[k].x, xv.x, fma(av[k].y, xv.y, acc[k]));
-        }
-#pragma unroll
-        for (int o = LW / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int k = 0; k < R; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        if (gl == 0) {
-#pragma unroll
-            for (int k = 0; k < R; k++) if (rb + k < r1) epi(rb + k, acc[k]);
+        for (int i = 0; i < cnt / 2; i++) {
+            const double send = upper ? v[i] : v[i + cnt / 2];
+            const double keep = upper ? v[i + cnt / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
     }
+    double r = v[0];
+#pragma unroll
+    for (; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;   // complete sum of row (lane % LW) / (LW / V) of the group, replicated over LW / V lanes
 }
 
-// w = X^-1 hd with hd formed on the fly from the children's h (fuses hdiff_kernel)
-template <int LW, int R>
-__global__ void __launch_bounds__(256) upwards_w_short_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
+// One batch: 512 doubles at A; xf = this lane's slice of the right-hand vector (double2 per 64 columns).  Returns the row
+// sum this lane ends up holding and sets `row` (within the batch) and `writer` (one lane per row).
+template <int L>
+__device__ __forceinline__ double rb_batch(const double* __restrict__ A, const double2 (&xf)[(L >= 64 ? L / 64 : 1)], int lane, int& row, bool& writer)
 {
-    extern __shared__ __align__(16) double xs[];
-    const MergeEntry& e = ent[blockIdx.x];
-    const int N = 4 * n;
-    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
-        const int k = idx / n, r = idx % n;
-        const int c1 = c_kids[k][0], c2 = c_kids[k][1];
-        xs[idx] = e.hc[c2][c_iface[c2][k] * n + r] - e.hc[c1][c_iface[c1][k] * n + r];
-    }
-    __syncthreads();
-    const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-    double* w = e.w;
-    gemv_rows_short<LW, R>(e.Xinv, N, xs, r0, r1, [&](int row, double v) { w[row] = v; });
-}
-
-// h = pi(H w + h_ext): row `row` of the compact H (length 2n) times [w[k0], w[k1]] of its child
-template <int LW, int R>
-__global__ void __launch_bounds__(256) upwards_h_short_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta)
-{
-    extern __shared__ __align__(16) double xs[];   // 4n: w
-    const MergeEntry& e = ent[blockIdx.x];
-    for (int idx = threadIdx.x; idx < 4 * n; idx += blockDim.x) xs[idx] = e.w[idx];
-    __syncthreads();
-    const int r0 = blockIdx.y * rows_per_cta, r1 = min(8 * n, r0 + rows_per_cta);
-    // rows of one WESN block p share the child and therefore the two w segments; chunks never straddle a block
-    // when rows_per_cta divides n or is a multiple of it, which the launcher guarantees.
-    for (int p0 = r0; p0 < r1; p0 += n) {
-        const int p = p0 / n, pr0 = p0, pr1 = min(r1, (p + 1) * n);
-        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
-        const int k0 = c_kk[ch][0], k1 = c_kk[ch][1];
-        const double* hc = e.hc[ch] + side * n;
-        double* h = e.h;
-        // the two segments are contiguous in xs only if k1 == k0 + 1; otherwise two passes over half rows
-        if (k1 == k0 + 1) {
-            gemv_rows_short<LW, R>(e.Hc, 2 * n, xs + k0 * n, pr0, pr1, [&](int row, double v) { h[row] = v + hc[row - p * n]; });
-        } else {
-            __shared__ double xcat[512];
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < 2 * n; idx += blockDim.x) xcat[idx] = idx < n ? xs[k0 * n + idx] : xs[k1 * n + idx - n];
-            __syncthreads();
-            gemv_rows_short<LW, R>(e.Hc, 2 * n, xcat, pr0, pr1, [&](int row, double v) { h[row] = v + hc[row - p * n]; });
+    const double2* a2 = reinterpret_cast<const double2*>(A) + lane;
+    double2 a[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) a[r] = __ldcs(a2 + 32 * r);
+    if constexpr (L == 32) {           // a load holds two rows (one per half warp): 8 values over 16 lanes
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = fma(a[r].x, xf[0].x, a[r].y * xf[0].y);
+        const double s = butterfly_reduce<8, 16>(v, lane);
+        row = 2 * ((lane & 15) >> 1) + (lane >> 4);
+        writer = (lane & 1) == 0;
+        return s;
+    } else {
+        constexpr int LPR = L / 64, V = 8 / LPR;   // loads per row, rows per batch
+        double v[V];
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < LPR; q++) s = fma(a[i * LPR + q].x, xf[q].x, fma(a[i * LPR + q].y, xf[q].y, s));
+            v[i] = s;
         }
+        const double s = butterfly_reduce<V, 32>(v, lane);
+        row = lane / (32 / V);
+        writer = (lane & (32 / V - 1)) == 0;
+        return s;
     }
 }
 
-// u_int = S g (+ w), scattered to the children; exterior segments copied through
-template <int LW, int R>
-__global__ void __launch_bounds__(256) solve_split_short_kernel(const MergeEntry* __restrict__ ent, int n, int rows_per_cta, int add_w)
+// the warp's contiguous range of batches
+__device__ __forceinline__ void rb_range(long long total, long long& b0, long long& b1)
 {
-    extern __shared__ __align__(16) double xs[];   // 8n: g
-    const MergeEntry& e = ent[blockIdx.x];
-    for (int idx = threadIdx.x; idx < 8 * n; idx += blockDim.x) xs[idx] = e.g[idx];
-    __syncthreads();
-    const int N = 4 * n;
-    const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-    const double* w = e.w;
-    gemv_rows_short<LW, R>(e.S, 8 * n, xs, r0, r1, [&](int row, double v) {
-        if (add_w) v += w[row];
-        const int k = row / n, r = row % n;
-        const int c1 = c_kids[k][0], c2 = c_kids[k][1];
-        e.gc[c1][c_iface[c1][k] * n + r] = v;
-        e.gc[c2][c_iface[c2][k] * n + r] = v;
-    });
-    const int nct = gridDim.y, per = (8 * n + nct - 1) / nct;
-    const int x0 = blockIdx.y * per, x1 = min(8 * n, x0 + per);
-    for (int idx = x0 + threadIdx.x; idx < x1; idx += blockDim.x) {
-        const int p = idx / n, r = idx % n;
-        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
-        e.gc[ch][side * n + r] = xs[idx];
-    }
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5), w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long per = (total + nw - 1) / nw;
+    b0 = w * per; b1 = min(total, b0 + per);
 }
 
-
-// ---- bulk-copy streaming variants (child side n = 16 .. 512, powers of two) ----------------------
-// The matrix rows a CTA owns are one contiguous byte range, so the CTA streams it through a ring of shared-memory
-// stages filled by the bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier): SG_NS x 16 KB in
-// flight per CTA independent of register pressure, 2-3 CTAs per SM.  The right-hand vector is staged in shared memory
-// once.  Warp w reduces the 256 doubles [256 w, 256 w + 256) of every stage: rows of <= 256 entries are finished inside
-// the warp, longer rows (<= 2048 entries = one stage) across the warps through shared memory.
-constexpr int SG_STAGE = 2048;   // doubles per stage
-constexpr int SG_NS = 4;
-constexpr int SG_XMAX = 2048;    // longest staged vector
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+// w = X^-1 hd, hd formed from the children's h; L = 4n
+template <int L>
+__global__ void __launch_bounds__(256) rb_upwards_w_kernel(const MergeEntry* __restrict__ ent, int count, int logn)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SG_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SG_DONE;\n"
-        "bra SG_WAIT;\n"
-        "SG_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// dynamic shared memory layout: [SG_NS stages][x: xlen doubles][red: 8][barriers: SG_NS]
-struct SgView {
-    double* stage; double* xs; double* red; unsigned long long* full;
-    __device__ SgView(double* base, int xlen) : stage(base), xs(base + SG_NS * SG_STAGE), red(xs + xlen), full(reinterpret_cast<unsigned long long*>(red + 8)) {}
-};
-static inline size_t sg_smem_bytes(int xlen) { return (size_t)(SG_NS * SG_STAGE + xlen + 8 + SG_NS) * sizeof(double); }
-
-// A: first row of this CTA's chunk; rows of L = 2^logL doubles (32 <= L <= 2048); ntiles stages of SG_STAGE doubles.
-// xfill(i): entry i of the staged vector; xidx(row, col): its index for matrix entry (row, col), row local to the chunk;
-// epi(row, value): row local to the chunk.  All 256 threads must call.
-template <class XFill, class XIdx, class Epi>
-__device__ __forceinline__ void stream_gemv(const double* __restrict__ A, int logL, int ntiles, int xlen, SgView sm, XFill xfill, XIdx xidx, Epi epi)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = 1 << logL;
-    if (tid == 0) {
+    constexpr int XF = L >= 64 ? L / 64 : 1, ROWS = 512 / L;
+    const int n = 1 << logn, lane = threadIdx.x & 31;
+    const int lbpp = 2 * logn + 4 - 9;                     // log2 of the batches per parent: 16 n^2 / 512
+    long long b0, b1;
+    rb_range((long long)count << lbpp, b0, b1);
+    int cur = -1;
+    double2 xf[XF];
+    const double* A = nullptr; double* w = nullptr;
+    for (long long b = b0; b < b1; b++) {
+        const int p = (int)(b >> lbpp), lb = (int)(b & ((1 << lbpp) - 1));
+        if (p != cur) {
+            cur = p;
+            const MergeEntry& e = ent[p];
+            A = e.Xinv; w = e.w;
 #pragma unroll
-        for (int s = 0; s < SG_NS; s++) mbar_init(sm.full + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < SG_NS; s++)
-            if (s < ntiles) {
-                mbar_expect_tx(sm.full + s, SG_STAGE * 8);
-                bulk_g2s(sm.stage + s * SG_STAGE, A + (size_t)s * SG_STAGE, SG_STAGE * 8, sm.full + s);
-            }
-    }
-    for (int i = tid; i < xlen; i += blockDim.x) sm.xs[i] = xfill(i);
-    __syncthreads();
-    double acc = 0.0;
-    for (int t = 0; t < ntiles; t++) {
-        const int s = t % SG_NS;
-        mbar_wait(sm.full + s, (unsigned)((t / SG_NS) & 1));
-        const double* st = sm.stage + s * SG_STAGE + warp * 256 + lane * 2;
-        const int f0 = t * SG_STAGE + warp * 256 + lane * 2;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const double2 a = *reinterpret_cast<const double2*>(st + j * 64);
-            const int e = f0 + j * 64, row = e >> logL, col = e & (L - 1);
-            const double2 x = *reinterpret_cast<const double2*>(sm.xs + xidx(row, col));
-            acc = fma(a.x, x.x, fma(a.y, x.y, acc));
-            if (L == 32) {            // two rows per 64 entries: reduce inside half warps
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if ((lane & 15) == 0) epi(row, acc);
-                acc = 0.0;
-            } else if (L <= 256 && (((j + 1) * 64) & (L - 1)) == 0) {   // a row ends inside this warp's slice
-                acc = warp_sum(acc);
-                if (lane == 0) epi(row, acc);
-                acc = 0.0;
+            for (int q = 0; q < XF; q++) {
+                const int idx = q * 64 + 2 * lane, k = idx >> logn, r = idx & (n - 1);
+                const int c1 = c_kids[k][0], c2 = c_kids[k][1];
+                const double2 hi = *reinterpret_cast<const double2*>(e.hc[c2] + c_iface[c2][k] * n + r);
+                const double2 lo = *reinterpret_cast<const double2*>(e.hc[c1] + c_iface[c1][k] * n + r);
+                xf[q] = make_double2(hi.x - lo.x, hi.y - lo.y);
             }
         }
-        if (L > 256) {                // a row spans L / 256 warps of this stage
-            acc = warp_sum(acc);
-            if (lane == 0) sm.red[warp] = acc;
-            acc = 0.0;
-            __syncthreads();
-            const int wpr = L >> 8, rows = SG_STAGE >> logL;
-            if (tid < rows) {
-                double v = 0.0;
-                for (int k = 0; k < wpr; k++) v += sm.red[tid * wpr + k];
-                epi(t * rows + tid, v);
-            }
-        }
-        __syncthreads();              // every warp is done with stage s (and with red)
-        if (tid == 0 && t + SG_NS < ntiles) {
-            mbar_expect_tx(sm.full + s, SG_STAGE * 8);
-            bulk_g2s(sm.stage + s * SG_STAGE, A + (size_t)(t + SG_NS) * SG_STAGE, SG_STAGE * 8, sm.full + s);
-        }
+        int row; bool writer;
+        const double s = rb_batch<L>(A + (size_t)lb * 512, xf, lane, row, writer);
+        if (writer) w[lb * ROWS + row] = s;
     }
 }
 
-__global__ void __launch_bounds__(256) sg_upwards_w_kernel(const MergeEntry* __restrict__ ent, int n, int logn, int rows_per_cta)
+// h = pi(H w + h_ext); L = 2n; rows of WESN block p belong to child ch and multiply [w[k0], w[k1]]
+template <int L>
+__global__ void __launch_bounds__(256) rb_upwards_h_kernel(const MergeEntry* __restrict__ ent, int count, int logn)
 {
-    extern __shared__ __align__(128) double sg_smem[];
-    const MergeEntry& e = ent[blockIdx.x];
-    const int N = 4 * n, r0 = blockIdx.y * rows_per_cta;
-    SgView sm(sg_smem, N);
-    double* w = e.w;
-    stream_gemv(e.Xinv + (size_t)r0 * N, logn + 2, rows_per_cta * N / SG_STAGE, N, sm,
-        [&](int idx) {
-            const int k = idx >> logn, r = idx & (n - 1);
-            const int c1 = c_kids[k][0], c2 = c_kids[k][1];
-            return e.hc[c2][c_iface[c2][k] * n + r] - e.hc[c1][c_iface[c1][k] * n + r];
-        },
-        [](int, int col) { return col; },
-        [&](int row, double v) { w[r0 + row] = v; });
+    constexpr int XF = L >= 64 ? L / 64 : 1, ROWS = 512 / L;
+    const int n = 1 << logn, lane = threadIdx.x & 31;
+    const int lbpp = 2 * logn + 4 - 9;                     // 16 n^2 / 512
+    long long b0, b1;
+    rb_range((long long)count << lbpp, b0, b1);
+    int cur = -1, curblk = -1;
+    double2 xf[XF];
+    const double* A = nullptr; const double* wv = nullptr; const double* hext = nullptr; double* h = nullptr;
+    const double* hc[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (long long b = b0; b < b1; b++) {
+        const int p = (int)(b >> lbpp), lb = (int)(b & ((1 << lbpp) - 1));
+        if (p != cur) {
+            cur = p; curblk = -1;
+            const MergeEntry& e = ent[p];
+            A = e.Hc; wv = e.w; h = e.h;
+#pragma unroll
+            for (int c = 0; c < 4; c++) hc[c] = e.hc[c];
+        }
+        const int row0 = lb * ROWS, blk = row0 >> logn;    // a batch never straddles a block: ROWS <= 16 <= n
+        if (blk != curblk) {
+            curblk = blk;
+            const int q8 = c_pi[blk], ch = q8 >> 1, side = c_tau_side[ch][q8 & 1];
+            hext = (ch == 0 ? hc[0] : ch == 1 ? hc[1] : ch == 2 ? hc[2] : hc[3]) + side * n - (blk << logn);
+#pragma unroll
+            for (int q = 0; q < XF; q++) {
+                const int col = q * 64 + 2 * (L == 32 ? (lane & 15) : lane);
+                xf[q] = *reinterpret_cast<const double2*>(wv + c_kk[ch][col >> logn] * n + (col & (n - 1)));
+            }
+        }
+        int row; bool writer;
+        const double s = rb_batch<L>(A + (size_t)lb * 512, xf, lane, row, writer);
+        if (writer) h[row0 + row] = s + hext[row0 + row];
+    }
 }
 
-__global__ void __launch_bounds__(256) sg_upwards_h_kernel(const MergeEntry* __restrict__ ent, int n, int logn, int rows_per_cta)
+// u_int = S g (+ w) scattered to the adjacent children, exterior segments copied through; L = 8n
+template <int L>
+__global__ void __launch_bounds__(256) rb_solve_split_kernel(const MergeEntry* __restrict__ ent, int count, int logn, int add_w)
 {
-    extern __shared__ __align__(128) double sg_smem[];
-    const MergeEntry& e = ent[blockIdx.x];
-    const int r0 = blockIdx.y * rows_per_cta;
-    SgView sm(sg_smem, 4 * n);
-    double* h = e.h;
-    const double* wv = e.w;
-    stream_gemv(e.Hc + (size_t)r0 * (2 * n), logn + 1, rows_per_cta * 2 * n / SG_STAGE, 4 * n, sm,
-        [&](int idx) { return wv[idx]; },
-        [&](int row, int col) {   // row block p of child ch multiplies [w[k0], w[k1]]
-            const int ch = c_pi[(r0 + row) >> logn] >> 1;
-            return c_kk[ch][col >> logn] * n + (col & (n - 1));
-        },
-        [&](int row, double v) {
-            const int gr = r0 + row, p = gr >> logn, r = gr & (n - 1);
-            const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
-            h[gr] = v + e.hc[ch][side * n + r];
-        });
-}
-
-__global__ void __launch_bounds__(256) sg_solve_split_kernel(const MergeEntry* __restrict__ ent, int n, int logn, int rows_per_cta, int add_w)
-{
-    extern __shared__ __align__(128) double sg_smem[];
-    const MergeEntry& e = ent[blockIdx.x];
-    const int r0 = blockIdx.y * rows_per_cta;
-    SgView sm(sg_smem, 8 * n);
-    const double* g = e.g;
-    const double* w = e.w;
-    stream_gemv(e.S + (size_t)r0 * (8 * n), logn + 3, rows_per_cta * 8 * n / SG_STAGE, 8 * n, sm,
-        [&](int idx) { return g[idx]; },
-        [](int, int col) { return col; },
-        [&](int row, double v) {
-            const int gr = r0 + row;
-            if (add_w) v += w[gr];
+    constexpr int XF = L / 64, ROWS = 512 / L;
+    const int n = 1 << logn, lane = threadIdx.x & 31;
+    const int lbpp = 2 * logn + 5 - 9;                     // 32 n^2 / 512
+    long long b0, b1;
+    rb_range((long long)count << lbpp, b0, b1);
+    int cur = -1;
+    double2 xf[XF];
+    const double* A = nullptr; const double* w = nullptr;
+    double* gc[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (long long b = b0; b < b1; b++) {
+        const int p = (int)(b >> lbpp), lb = (int)(b & ((1 << lbpp) - 1));
+        if (p != cur) {
+            cur = p;
+            const MergeEntry& e = ent[p];
+            A = e.S; w = e.w;
+#pragma unroll
+            for (int c = 0; c < 4; c++) gc[c] = e.gc[c];
+#pragma unroll
+            for (int q = 0; q < XF; q++) xf[q] = *reinterpret_cast<const double2*>(e.g + q * 64 + 2 * lane);
+            if (lb == 0) {     // the warp that starts a parent also copies its exterior segments through
+                for (int idx = lane; idx < 8 * n; idx += 32) {
+                    const int pb = idx >> logn, r = idx & (n - 1);
+                    const int q8 = c_pi[pb], ch = q8 >> 1, side = c_tau_side[ch][q8 & 1];
+                    (ch == 0 ? gc[0] : ch == 1 ? gc[1] : ch == 2 ? gc[2] : gc[3])[side * n + r] = e.g[idx];
+                }
+            }
+        }
+        int row; bool writer;
+        double s = rb_batch<L>(A + (size_t)lb * 512, xf, lane, row, writer);
+        if (writer) {
+            const int gr = lb * ROWS + row;
+            if (add_w) s += w[gr];
             const int k = gr >> logn, r = gr & (n - 1);
             const int c1 = c_kids[k][0], c2 = c_kids[k][1];
-            e.gc[c1][c_iface[c1][k] * n + r] = v;
-            e.gc[c2][c_iface[c2][k] * n + r] = v;
-        });
-    // exterior segments are copied through: this CTA's share of the 8n entries (xs still holds g)
-    const int nct = gridDim.y, per = (8 * n + nct - 1) / nct;
-    const int x0 = blockIdx.y * per, x1 = min(8 * n, x0 + per);
-    for (int idx = x0 + threadIdx.x; idx < x1; idx += blockDim.x) {
-        const int p = idx >> logn, r = idx & (n - 1);
-        const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
-        e.gc[ch][side * n + r] = sm.xs[idx];
+            (c1 == 0 ? gc[0] : c1 == 1 ? gc[1] : gc[2])[c_iface[c1][k] * n + r] = s;
+            (c2 == 1 ? gc[1] : c2 == 2 ? gc[2] : gc[3])[c_iface[c2][k] * n + r] = s;
+        }
     }
 }
+
+// grid: as many CTAs as the device holds at once (never more warps than batches)
+template <class K>
+static int rb_grid(K kern, long long batches)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    EF_CUDA(cudaGetDevice(&dev));
+    EF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    EF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    long long g = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    const long long need = (batches + 7) / 8;
+    return (int)(need < g ? need : g);
+}
+#define RB_LAUNCH(KERN, LVAL, batches, ...)                                                        \
+    do {                                                                                           \
+        static int grid_cap_ = 0;                                                                  \
+        if (!grid_cap_) grid_cap_ = rb_grid(KERN<LVAL>, 1LL << 40);                                \
+        const long long need_ = ((batches) + 7) / 8;                                               \
+        KERN<LVAL><<<(int)(need_ < grid_cap_ ? need_ : grid_cap_), 256, 0, s>>>(__VA_ARGS__);      \
+    } while (0)
 
 
 // ---- launch wrappers ---------------------------------------------------------------------------
@@ -598,106 +517,64 @@ static inline int pick_rows(int rows, int count)
     return rpc;
 }
 
-// chunk of rows per CTA for the short-row kernels: whole parents when there are many, else n-aligned pieces
-static inline int short_rows(int rows, int n, int count)
-{
-    int rpc = rows;
-    while (rpc > n && (long long)count * (rows / rpc) < 148LL * 8) rpc >>= 1;
-    while (rpc > 32 && (long long)count * (rows / rpc) < 148LL * 4) rpc >>= 1;   // below n: still a divisor of n (n = 8 * 2^k or 24 * 2^k ...)
-    return rpc;
-}
-
-template <int R>
-static void launch_upwards_short(const MergeEntry* e, int n, int count, cudaStream_t s)
-{
-    {
-        const int N = 4 * n, rpc = short_rows(N, n, count);
-        dim3 grid(count, N / rpc);
-        const size_t sm = (size_t)N * sizeof(double);
-        if (N / 2 >= 32) upwards_w_short_kernel<32, R><<<grid, 256, sm, s>>>(e, n, rpc);
-        else upwards_w_short_kernel<16, R><<<grid, 256, sm, s>>>(e, n, rpc);
-    }
-    {
-        const int rows = 8 * n;
-        int rpc = short_rows(rows, n, count);
-        if (rpc < n && n % rpc) rpc = n;       // chunks must not straddle WESN blocks
-        dim3 grid(count, rows / rpc);
-        const size_t sm = (size_t)4 * n * sizeof(double);
-        const int L2 = n;                       // row length 2n doubles = n double2
-        if (L2 >= 32) upwards_h_short_kernel<32, R><<<grid, 256, sm, s>>>(e, n, rpc);
-        else if (L2 >= 16) upwards_h_short_kernel<16, R><<<grid, 256, sm, s>>>(e, n, rpc);
-        else upwards_h_short_kernel<8, R><<<grid, 256, sm, s>>>(e, n, rpc);
-    }
-}
-
-// rows per CTA of the streaming kernels: whole parents when there are many of them, else halved while the grid is short
-// of ~6 CTAs per SM; a chunk is a whole number (>= 1) of stages.
-static inline int sg_rows(int rows, int L, int count)
-{
-    int rpc = rows;
-    while ((long long)count * (rows / rpc) < 148LL * 6 && (long long)(rpc / 2) * L >= 2LL * SG_STAGE) rpc >>= 1;
-    return rpc;
-}
 static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
-template <class K>
-static void sg_attr(K kern)
-{
-    EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem_bytes(SG_XMAX)));
-}
 
-void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
+static void launch_hdiff(const MergeEntry* e, int n, int count, cudaStream_t s)
 {
-    if (!count) return;
-    if (g_tuning[0] && n >= 16 && n <= 512 && (n & (n - 1)) == 0 && count <= 2147483647) {
-        static bool attr = false;
-        if (!attr) { sg_attr(sg_upwards_w_kernel); sg_attr(sg_upwards_h_kernel); attr = true; }
-        const int logn = ilog2(n);
-        int rpc = sg_rows(4 * n, 4 * n, count);
-        sg_upwards_w_kernel<<<dim3(count, 4 * n / rpc), 256, sg_smem_bytes(4 * n), s>>>(e, n, logn, rpc);
-        rpc = sg_rows(8 * n, 2 * n, count);
-        sg_upwards_h_kernel<<<dim3(count, 8 * n / rpc), 256, sg_smem_bytes(4 * n), s>>>(e, n, logn, rpc);
-        EF_CUDA(cudaGetLastError());
-        return;
-    }
-    if (n <= 256 && (n & (n - 1)) == 0 && count <= 65535 * 0 + 2147483647) {
-        launch_upwards_short<4>(e, n, count, s);
-        EF_CUDA(cudaGetLastError());
-        return;
-    }
     for (int off = 0; off < count; off += 65535) {
         int c = count - off < 65535 ? count - off : 65535;
         hdiff_kernel<<<dim3(ew_blocks(4LL * n), c), 256, 0, s>>>(e + off, n);
     }
-    int rpc = pick_rows(4 * n, count);
-    if (g_tuning[1] == 1) upwards_w_kernel<8><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
-    else upwards_w_kernel<4><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
-    rpc = pick_rows(8 * n, count);
-    if (g_tuning[1] == 1) upwards_h_kernel<8><<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
-    else upwards_h_kernel<4><<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+}
+
+// Kernel choice per operator, by row length L (measured per tree level on B200, profiles/r1d_matvec_levels.md):
+// rows of <= 256 doubles (power-of-two child side >= 16) take the row-batch kernels, longer rows one row per warp
+// with 4 (X^-1, S) or 8 (the two half rows of the compact H) 16-byte loads in flight per lane.
+static inline bool rb_ok(int n, int L) { return g_tuning[0] == 2 && n >= 16 && (n & (n - 1)) == 0 && L <= 256; }
+
+void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s)
+{
+    if (!count) return;
+    const int logn = ilog2(n);
+    const long long batches = (long long)count * 16 * n * n / 512;
+    if (rb_ok(n, 4 * n)) {
+        switch (4 * n) {
+            case 64: RB_LAUNCH(rb_upwards_w_kernel, 64, batches, e, count, logn); break;
+            case 128: RB_LAUNCH(rb_upwards_w_kernel, 128, batches, e, count, logn); break;
+            default: RB_LAUNCH(rb_upwards_w_kernel, 256, batches, e, count, logn); break;
+        }
+    } else {
+        launch_hdiff(e, n, count, s);
+        const int rpc = pick_rows(4 * n, count);
+        upwards_w_kernel<4><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    }
+    if (rb_ok(n, 2 * n)) {
+        switch (2 * n) {
+            case 32: RB_LAUNCH(rb_upwards_h_kernel, 32, batches, e, count, logn); break;
+            case 64: RB_LAUNCH(rb_upwards_h_kernel, 64, batches, e, count, logn); break;
+            case 128: RB_LAUNCH(rb_upwards_h_kernel, 128, batches, e, count, logn); break;
+            default: RB_LAUNCH(rb_upwards_h_kernel, 256, batches, e, count, logn); break;
+        }
+    } else {
+        const int rpc = pick_rows(8 * n, count);
+        if (g_tuning[1] == 0) upwards_h_kernel<8><<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+        else upwards_h_kernel<4><<<dim3(count, (8 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc);
+    }
     EF_CUDA(cudaGetLastError());
 }
 
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s)
 {
     if (!count) return;
-    if (g_tuning[0] && n >= 16 && n <= 256 && (n & (n - 1)) == 0) {
-        static bool attr = false;
-        if (!attr) { sg_attr(sg_solve_split_kernel); attr = true; }
-        const int rpc = sg_rows(4 * n, 8 * n, count);
-        sg_solve_split_kernel<<<dim3(count, 4 * n / rpc), 256, sg_smem_bytes(8 * n), s>>>(e, n, ilog2(n), rpc, add_w ? 1 : 0);
-        EF_CUDA(cudaGetLastError());
-        return;
+    if (rb_ok(n, 8 * n)) {
+        const int logn = ilog2(n);
+        const long long batches = (long long)count * 32 * n * n / 512;
+        if (8 * n == 128) RB_LAUNCH(rb_solve_split_kernel, 128, batches, e, count, logn, add_w ? 1 : 0);
+        else RB_LAUNCH(rb_solve_split_kernel, 256, batches, e, count, logn, add_w ? 1 : 0);
+    } else {
+        const int rpc = pick_rows(4 * n, count);
+        solve_split_kernel<4><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
     }
-    if (n <= 256 && (n & (n - 1)) == 0) {
-        const int N = 4 * n, rpc = short_rows(N, n, count);
-        dim3 grid(count, N / rpc);
-        solve_split_short_kernel<32, 4><<<grid, 256, (size_t)8 * n * sizeof(double), s>>>(e, n, rpc, add_w ? 1 : 0);
-        EF_CUDA(cudaGetLastError());
-        return;
-    }
-    int rpc = pick_rows(4 * n, count);
-    if (g_tuning[1] == 1) solve_split_kernel<8><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
-    else solve_split_kernel<4><<<dim3(count, (4 * n + rpc - 1) / rpc), 256, 0, s>>>(e, n, rpc, add_w ? 1 : 0);
     EF_CUDA(cudaGetLastError());
 }
 

@@ -202,10 +202,11 @@ void efgpu_mesh_destroy(efgpu_mesh* m);
 int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric, int64_t* steps, int* n_steps,
                            int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws);
 
-/* Process-wide kernel-selection knobs for measurements (A/B runs of the bandwidth-bound kernels): key 0 = bulk-copy
- * streaming matvec kernels on (1, default) / off (0); key 1 = long-row matvec variant (0: 4, 1: 8 loads in flight per
- * lane); key 2 = CTAs per SM the long-row launcher aims for (0: default 16).  Results do not depend on the knobs beyond
- * floating-point summation order. */
+/* Process-wide kernel-selection knobs for measurements (A/B runs of the bandwidth-bound kernels): key 0 = matvec kernels
+ * for rows of <= 256 doubles (2, default: row-batch kernels; 0: one row per warp, as for longer rows); key 1 = long-row
+ * kernel of the compact H (0, default: 8 loads in flight per lane; 1: 4); key 2 = CTAs per SM the long-row launcher aims
+ * for (0: default 16); key 3 = leaf solve of constant-coefficient leaves (0, default: FP64 tensor-core kernel, one warp per
+ * leaf; 1: one thread per cell).  Results do not depend on the knobs beyond floating-point summation order. */
 int efgpu_set_tuning(int key, int value);
 
 /* ---- stand-alone access to the GEMM kernel for unit tests and roofline measurements ------------ */

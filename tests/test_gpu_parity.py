@@ -230,6 +230,47 @@ def test_lean_T_memory_policy(case):
     assert np.array_equal(u2, full.u_leaves)
 
 
+@pytest.mark.parametrize("case", ["uniform_m16", "adaptive_m16", "uniform_m32"])
+def test_kernel_variants_agree(case):
+    """The bandwidth-bound stages pick kernels by row length: row-batch kernels for rows of <= 256 doubles (tuning
+    key 0 = 2, default) or one row per warp everywhere (key 0 = 0); the tensor-core leaf solve (key 3 = 0, default) or
+    the one-thread-per-cell kernel (key 3 = 1).  All combinations must reproduce the same h, w, g, u."""
+    lib = ef.load()
+    if case == "adaptive_m16":
+        kw = dict(problem_name="poisson", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=16,
+                  min_level=1, max_level=5, threshold=1.2, refine_box=None)
+    else:
+        kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16 if case == "uniform_m16" else 32,
+                  min_level=4 if case == "uniform_m16" else 3, max_level=4 if case == "uniform_m16" else 3, threshold=1.2, refine_box=None)
+    P = O.problem(kw["problem_name"])
+    bc = lambda side, x, y: (P["u"](x, y), 1.0, 0.0)
+    hps = run_gpu(kw, keep_x=False)
+    m = hps.mesh
+    interior = [i for i in range(m.n_nodes) if m.child[i, 0] >= 0]
+    leaves = [int(i) for i in m.leaf_nodes]
+
+    def snapshot():
+        hps.upwardsStage(P["f"])
+        u = hps.solveStage(bc).copy()
+        vec = {(i, nm): hps.vector(i, nm) for i in interior for nm in ("h", "w", "g")}
+        vec.update({(i, nm): hps.vector(i, nm) for i in leaves[:: max(1, len(leaves) // 16)] for nm in ("h", "g")})
+        return u, vec
+
+    try:
+        assert lib.efgpu_set_tuning(0, 0) == 0 and lib.efgpu_set_tuning(3, 1) == 0     # plain kernels
+        u_ref, v_ref = snapshot()
+        for knobs in ({0: 0, 3: 0}, {0: 2, 3: 1}, {0: 2, 3: 0}):
+            for k, v in knobs.items():
+                assert lib.efgpu_set_tuning(k, v) == 0
+            u, vec = snapshot()
+            assert relerr(u, u_ref) < 1e-12, knobs
+            for key, ref in v_ref.items():
+                assert relerr(vec[key], ref) < TOL, (knobs, key)
+    finally:
+        for k, v in {0: 2, 3: 0}.items():
+            lib.efgpu_set_tuning(k, v)
+
+
 def test_linearity_and_repeat_solves():
     """Size-independent properties: the solve is linear in (f, g) and repeatable on cached operators."""
     kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16,

@@ -18,7 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--level", type=int, default=8)
 ap.add_argument("--nx", type=int, default=16)
 ap.add_argument("--reps", type=int, default=20)
-ap.add_argument("--configs", default="0,0,0;1,0,0;1,1,0;1,1,8;1,1,32;0,1,0")
+ap.add_argument("--configs", default="2;0;2,0,0,1", help="semicolon-separated efgpu_set_tuning values for keys 0, 1, 2, ...")
+ap.add_argument("--ncu", action="store_true", help="one pass per configuration, no warm-up (for an ncu launch list)")
 a = ap.parse_args()
 
 PI = 3.141592653589793
@@ -38,7 +39,7 @@ for cfg in a.configs.split(";"):
     k = [int(v) for v in cfg.split(",")]
     for key, val in enumerate(k):
         assert lib.efgpu_set_tuning(key, val) == 0
-    for _ in range(3):
+    for _ in range(0 if a.ncu else 3):
         hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=False); hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True)
     hps.set_profiling(True)
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
