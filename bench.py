@@ -53,13 +53,17 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-symmetry", action="store_true", help="EFGPU_NO_SYMMETRY: general merge plan (A/B against the symmetric one)")
     ap.add_argument("--profile-run", action="store_true", help="for ncu: exactly --warmup/--steps device steps, nothing else, no JSON")
+    ap.add_argument("--lean-T", action="store_true", help="EFGPU_LEAN_T memory policy (single GPU): interior DtN maps in a transient arena")
+    ap.add_argument("--n-solves", type=int, default=0, help="BASELINE configs[2] pattern: after the timed steps, K x (upwards + solve) on the "
+                    "resident operators with f and the boundary data scaled by (1 + k/K); reported as `repeat_solves`")
     ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6 own arm, 5 reference arm)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "uniform level-%d quadtree, %dx%d FV patches, constant-coefficient %s on [0,pi]^2 (BASELINE configs[1] shape)" % (
-        a.level, a.nx, a.nx, "Poisson" if a.problem == "poisson" else "Helmholtz lambda=-1")
+    shape = "BASELINE configs[1]" if (a.level, a.nx, a.problem) == (8, 16, "poisson") else "BASELINE configs[1] shape at another size"
+    return "uniform level-%d quadtree, %dx%d FV patches, constant-coefficient %s on [0,pi]^2 (%s)" % (
+        a.level, a.nx, a.nx, "Poisson" if a.problem == "poisson" else "Helmholtz lambda=-1", shape)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -177,6 +181,7 @@ def own_arm(a):
         raise RuntimeError("bench.py needs a CUDA device: the HPS path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout for the one JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload (untimed set-up: mesh, plan, host sampling of f and the boundary data) ----
@@ -191,6 +196,10 @@ def own_arm(a):
 
     hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world)
     hps.no_symmetry = a.no_symmetry
+    if a.lean_T:
+        if world > 1:
+            raise SystemExit("--lean-T: single GPU only")
+        hps.lean_T = True
     hps.setupStage()
     f_host, g_host = hps.sample_inputs(f_fn, u_exact)          # numpy, this rank's share
     f_pin = torch.from_numpy(f_host).pin_memory()
@@ -268,6 +277,32 @@ def own_arm(a):
     up_s, _ = timed(lambda: hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True), 1)
     so_s, _ = timed(lambda: hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True), 1)
     build_ms, up_ms, so_ms = 1e3 * build_s, 1e3 * up_s, 1e3 * so_s
+    # ---- repeated solves on the resident operators (the `thermal` usage pattern) ----
+    repeat = None
+    if a.n_solves > 0:
+        K = a.n_solves
+        st = torch.cuda.ExternalStream(hps.stream())
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        checks = {}
+        barrier()
+        for k in range(K):
+            sc = 1.0 + k / K
+            with torch.cuda.stream(st):
+                g_k = g_dev * sc
+            ev[k][0].record(st)
+            hps.upwardsStageDevice(f_dev.data_ptr(), sc, sync=False)
+            hps.solveStageDevice(g_k.data_ptr(), u_dev.data_ptr(), sync=False)
+            ev[k][1].record(st)
+            if k in (0, K // 2, K - 1):          # every solve is checkable against (1 + k/K) u
+                hps.sync()
+                checks[k] = hps.max_error(u_dev, lambda x, y, sc=sc: sc * u_exact(x, y))
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in ev], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.cpu().numpy()
+        repeat = {"n": K, "mean_ms": float(ms.mean()), "min_ms": float(ms.min()), "max_ms": float(ms.max()),
+                  "linf_error_vs_scaled_exact": {str(k): v for k, v in checks.items()}}
     # whole-job totals of the per-rank work models (flops issued, algorithmic bytes, device memory)
     agg = torch.tensor([stats[k] for k in ("merge_flops_issued", "merge_flops_canonical", "upwards_bytes", "solve_bytes", "device_bytes")],
                        dtype=torch.float64, device="cuda")
@@ -373,6 +408,9 @@ def own_arm(a):
                      "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                      "traffic": traffic},
         "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0 or v[0] > 0},
+        "repeat_solves": None if repeat is None else dict(repeat, dofs_per_s_mean=dofs / (repeat["mean_ms"] * 1e-3),
+                                                           gbs_mean=(tot["upwards_bytes"] + tot["solve_bytes"]) / (repeat["mean_ms"] * 1e-3) / 1e9,
+                                                           hbm_frac_mean=(tot["upwards_bytes"] + tot["solve_bytes"]) / (repeat["mean_ms"] * 1e-3) / 1e9 / hbm_peak),
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -337,17 +337,84 @@ invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long lon
 }
 
 // Register-resident variant: 256 threads as a 16 x 16 grid, thread (tr, tc) owns the elements
-// (tr + 16 i, tc + 16 j), i, j < TI (cyclic), N = 16 TI.  Per pivot the owners publish row k and column k
-// through double-buffered shared memory (ONE barrier per pivot) and every thread updates its tile with
+// (tr + 16 i, tc + 16 j), i, j < TI (cyclic), N = 16 TI.  Gauss-Jordan without pivoting:
 //   row k:      a_kj <- a_kj / a_kk (j != k),  a_kk <- 1 / a_kk
 //   other rows: a_ij <- [j != k] a_ij - a_ik * (new a_kj)
-// compile-time dispatch on a warp-uniform index: calls f(integral_constant<int, I>) for I == idx
-template <int I, int TI, class F>
-__device__ __forceinline__ void dispatch_index(int idx, F&& f)
+// Only two warps per scheduler fit (~200 registers), so the serial chain of a pivot must not stall them:
+//  * split barrier: one mbarrier phase per pivot, a warp ARRIVES as soon as it has read row / column k (and published
+//    its share of k+1) and only WAITS at the top of the next pivot, after its rank-1 update; row / column buffers are
+//    double-buffered;
+//  * look-ahead: while pivot k is applied, the owners of row k+1 and column k+1 first form what those will hold after
+//    pivot k (on temporaries), the owner of a_{k+1,k+1} takes the reciprocal ONCE and hands it to its half warp by
+//    shuffle, and the row is published already scaled - nobody else divides or scales, and the division plus the
+//    shared-memory round trip of pivot k+1 overlap the rank-1 update of pivot k;
+//  * the pivot loop is unrolled over the register index k / 16, so every register subscript is a compile-time
+//    constant (no dispatch chains).
+template <int TI, int KI, int K1I>
+__device__ __forceinline__ void gj_pivot(double (&a)[TI][TI], double (*sRow)[16 * TI], double (*sCol)[16 * TI], double (*sPiv)[2],
+                                         unsigned long long* bar, int kr, int tr, int tc, bool last, double& minp)
 {
-    if constexpr (I < TI) {
-        if (idx == I) f(std::integral_constant<int, I>{});
-        else dispatch_index<I + 1, TI>(idx, f);
+    const int b = kr & 1;                                   // N is a multiple of 16: k and kr have the same parity
+    mbar_wait(bar, (unsigned)b);                            // phase k: row / column k are published, buffer b ^ 1 is free
+    const double p = sPiv[b][1];
+    minp = fmin(minp, fabs(sPiv[b][0]));
+    double rk[TI], ck[TI];
+#pragma unroll
+    for (int j = 0; j < TI; j++) rk[j] = sRow[b][tc + 16 * j];   // row k, already divided by the pivot
+#pragma unroll
+    for (int i = 0; i < TI; i++) ck[i] = sCol[b][tr + 16 * i];
+    if (!last) {
+        const int k1r = (kr + 1) & 15;
+        if (tr == k1r) {                                    // one half warp: row k+1 after this pivot
+            double v[TI];
+#pragma unroll
+            for (int j = 0; j < TI; j++) {
+                v[j] = fma(-ck[K1I], rk[j], a[K1I][j]);
+                if (tc == kr && j == KI) v[j] = -ck[K1I] * p;           // its entry in pivot column k
+            }
+            const double diag = v[K1I];                     // meaningful in the lane with tc == k1r
+            const double rinv = 1.0 / diag;
+            const double pn = __shfl_sync(0xffffu << (threadIdx.x & 16), rinv, (threadIdx.x & 16) | k1r);   // within the half warp that owns the row
+            if (tc == k1r) { sPiv[b ^ 1][0] = diag; sPiv[b ^ 1][1] = pn; }
+#pragma unroll
+            for (int j = 0; j < TI; j++) sRow[b ^ 1][tc + 16 * j] = v[j] * pn;
+        }
+        if (tc == k1r) {                                    // column k+1 after this pivot
+#pragma unroll
+            for (int i = 0; i < TI; i++) {
+                double v = fma(-ck[i], rk[K1I], a[i][K1I]);
+                if (tr == kr && i == KI) v = rk[K1I];                   // its entry in pivot row k
+                sCol[b ^ 1][tr + 16 * i] = v;
+            }
+        }
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);          // this warp is done with buffer b and has published its part of b ^ 1
+    // rank-1 update of every element ...
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+        for (int j = 0; j < TI; j++) a[i][j] = fma(-ck[i], rk[j], a[i][j]);
+    // ... then repair column k (wanted -a_ik p) and row k (wanted a_kj p, and p on the diagonal)
+    if (tc == kr) {
+#pragma unroll
+        for (int i = 0; i < TI; i++) a[i][KI] = -ck[i] * p;
+    }
+    if (tr == kr) {
+#pragma unroll
+        for (int j = 0; j < TI; j++) a[KI][j] = rk[j];
+        if (tc == kr) a[KI][KI] = p;
+    }
+}
+
+template <int TI, int KI>
+__device__ __forceinline__ void gj_block(double (&a)[TI][TI], double (*sRow)[16 * TI], double (*sCol)[16 * TI], double (*sPiv)[2],
+                                         unsigned long long* bar, int tr, int tc, double& minp)
+{
+    if constexpr (KI < TI) {
+        for (int kr = 0; kr < 15; kr++) gj_pivot<TI, KI, KI>(a, sRow, sCol, sPiv, bar, kr, tr, tc, false, minp);
+        gj_pivot<TI, KI, (KI + 1 < TI ? KI + 1 : KI)>(a, sRow, sCol, sPiv, bar, 15, tr, tc, KI + 1 == TI, minp);
+        gj_block<TI, KI + 1>(a, sRow, sCol, sPiv, bar, tr, tc, minp);
     }
 }
 
@@ -358,57 +425,36 @@ invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long 
     constexpr int N = 16 * TI;
     __shared__ double sRow[2][N];
     __shared__ double sCol[2][N];
+    __shared__ double sPiv[2][2];   // [buffer][0: pivot, 1: its reciprocal]
+    __shared__ unsigned long long bar;   // one phase per pivot, 8 arrivals (one per warp)
     double* G = ptab[(long long)blockIdx.x * nops + op] + off;
     const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
     double a[TI][TI];
 #pragma unroll
     for (int i = 0; i < TI; i++)
 #pragma unroll
         for (int j = 0; j < TI; j++) a[i][j] = G[(long long)(tr + 16 * i) * ld + tc + 16 * j];
-    double minp = 1e300;
-    for (int k = 0; k < N; k++) {
-        const int b = k & 1, ki = k >> 4, kr = k & 15;   // ki, kr are uniform over the CTA
-        // owners publish row k and column k (values before the update)
-        dispatch_index<0, TI>(ki, [&](auto I) {
-            constexpr int q = decltype(I)::value;
-            if (tr == kr) {
+    // pivot 0 is published from the loaded values
+    if (tr == 0) {
+        const double rinv = 1.0 / a[0][0];
+        const double pn = __shfl_sync(0xffffu, rinv, 0);
 #pragma unroll
-                for (int j = 0; j < TI; j++) sRow[b][tc + 16 * j] = a[q][j];
-            }
-            if (tc == kr) {
-#pragma unroll
-                for (int i = 0; i < TI; i++) sCol[b][tr + 16 * i] = a[i][q];
-            }
-        });
-        __syncthreads();
-        const double piv = sRow[b][k];
-        const double p = 1.0 / piv;
-        minp = fmin(minp, fabs(piv));
-        double rk[TI], ck[TI];
-#pragma unroll
-        for (int j = 0; j < TI; j++) rk[j] = sRow[b][tc + 16 * j] * p;
-#pragma unroll
-        for (int i = 0; i < TI; i++) ck[i] = sCol[b][tr + 16 * i];
-        // generic rank-1 update of every element ...
-#pragma unroll
-        for (int i = 0; i < TI; i++)
-#pragma unroll
-            for (int j = 0; j < TI; j++) a[i][j] = fma(-ck[i], rk[j], a[i][j]);
-        // ... then repair column k (wanted -a_ik p; the update gave a_ik - a_ik (a_kk p): rk[k] must act as p with a_ik removed)
-        // and row k (wanted a_kj p, and p on the diagonal)
-        dispatch_index<0, TI>(ki, [&](auto I) {
-            constexpr int q = decltype(I)::value;
-            if (tc == kr) {
-#pragma unroll
-                for (int i = 0; i < TI; i++) a[i][q] = -ck[i] * p;
-            }
-            if (tr == kr) {
-#pragma unroll
-                for (int j = 0; j < TI; j++) a[q][j] = rk[j];
-                if (tc == kr) a[q][q] = p;
-            }
-        });
+        for (int j = 0; j < TI; j++) sRow[0][tc + 16 * j] = a[0][j] * pn;
+        if (tc == 0) { sPiv[0][0] = a[0][0]; sPiv[0][1] = pn; }
     }
+    if (tc == 0) {
+#pragma unroll
+        for (int i = 0; i < TI; i++) sCol[0][tr + 16 * i] = a[i][0];
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&bar);         // phase 0: row / column 0 are published
+    double minp = 1e300;
+    gj_block<TI, 0>(a, sRow, sCol, sPiv, &bar, tr, tc, minp);
 #pragma unroll
     for (int i = 0; i < TI; i++)
 #pragma unroll

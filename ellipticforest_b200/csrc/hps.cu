@@ -118,6 +118,7 @@ struct efgpu_handle {
     int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
     bool ext_sym = false;                        // external leaves declared signed-symmetric (efgpu_set_symmetric_leaves)
     // device state
+    DevBuf d_leaf_build, d_leaf_src; int n_leaf_build = 0;   // constant-coefficient leaves: one DtN computation per class of identical (dx, dy)
     DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
     DevBuf d_Tarena[2];                          // EFGPU_LEAN_T: DtN maps of even / odd tree levels (a level's maps die when its parents are merged)
     bool lean_T = false;
@@ -470,6 +471,20 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
     for (int i = 0; i < H->n_nodes; i++) std::memcpy(&boxes[4 * (size_t)i], H->nodes[i].box, 4 * sizeof(double));
     H->d_boxes.upload(boxes, s);
     H->d_leaf_nodes.upload(H->leaf_nodes, s);
+    {   // classes of leaves with bit-identical cell sizes (the kernels form dx, dy with the same expression)
+        std::map<std::pair<uint64_t, uint64_t>, int> rep;
+        std::vector<int> build, src(H->n_leaves);
+        for (int l = 0; l < H->n_leaves; l++) {
+            const double* bx = H->nodes[H->leaf_nodes[l]].box;
+            const double dx = (bx[1] - bx[0]) / M, dy = (bx[3] - bx[2]) / M;
+            uint64_t kx, ky; std::memcpy(&kx, &dx, 8); std::memcpy(&ky, &dy, 8);
+            auto it = rep.find({kx, ky});
+            if (it == rep.end()) { it = rep.emplace(std::make_pair(kx, ky), l).first; build.push_back(l); }
+            src[l] = it->second;
+        }
+        H->n_leaf_build = (int)build.size();
+        H->d_leaf_build.upload(build, s); H->d_leaf_src.upload(src, s);
+    }
     H->leafT_off.assign(H->n_leaves + 1, 0);
     for (int l = 0; l < H->n_leaves; l++) { const size_t sz = 4 * (size_t)H->nodes[H->leaf_nodes[l]].size; H->leafT_off[l + 1] = H->leafT_off[l] + sz * sz; }
     H->d_leafT.alloc(H->leafT_off[H->n_leaves] * sizeof(double));
@@ -623,7 +638,8 @@ static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
         return;
     }
     launch_leaf_dtn_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
-                          H->d_leafT.as<double>(), H->n_leaves, (flags & EFGPU_CACHE_OPERATORS) != 0, H->stream);
+                          H->d_leafT.as<double>(), H->n_leaves, (flags & EFGPU_CACHE_OPERATORS) != 0,
+                          H->d_leaf_build.as<int>(), H->n_leaf_build, H->d_leaf_src.as<int>(), H->stream);
 }
 
 // buildStage in pieces, so that a replicated upper tree can exchange row slices between them:

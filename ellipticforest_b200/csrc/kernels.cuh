@@ -25,8 +25,11 @@ struct MergeEntry {
 struct CoarsenOp { const double* src; double* dst; int nfine; int pad_; };
 
 // leaf.cu
+// build_list / n_build: leaf indices whose T is computed (one per class of bit-identical cell sizes; null: every leaf);
+// leaf_src[leaf]: the computed leaf each leaf copies from
 void launch_leaf_dtn_const(int M, const double* Q, const double* boxes, const int* leaf_nodes, double lambda,
-                           double* T_all, int n_leaves, bool cache_operators, cudaStream_t s);
+                           double* T_all, int n_leaves, bool cache_operators, const int* build_list, int n_build, const int* leaf_src,
+                           cudaStream_t s);
 void launch_leaf_solve_const(int M, const double* Q, const double* boxes, const int* leaf_nodes, double lambda,
                              const double* f, double fscale, double* const* g_ptrs, double* u_out, double* const* h_ptrs,
                              int mode, int n_leaves, cudaStream_t s);

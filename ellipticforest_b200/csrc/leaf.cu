@@ -25,15 +25,15 @@ __device__ __forceinline__ double side_sign(int a) { return (a & 1) ? -1.0 : 1.0
 template <int M>
 __global__ void __launch_bounds__(M * M)
 leaf_dtn_const_kernel(const double* __restrict__ Q, const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
-                      double lambda, double* __restrict__ T_all, int n_build)
+                      double lambda, double* __restrict__ T_all, const int* __restrict__ build_list, int n_build)
 {
     __shared__ double sQ[M][M + 1];     // sQ[i][k] = q_{k+1}(i)
     __shared__ double sDinv[M][M + 1];  // 1 / (mu_k/dx^2 + mu_l/dy^2 + lambda), [k][l]
     __shared__ double sZ[M][M + 1];
     __shared__ double sP[M][M + 1];
     __shared__ double sMu[M];
-    const int leaf = blockIdx.x;
-    if (leaf >= n_build) return;
+    if ((int)blockIdx.x >= n_build) return;
+    const int leaf = build_list ? build_list[blockIdx.x] : blockIdx.x;
     const int r = threadIdx.x / M, c = threadIdx.x % M;
     const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
     const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
@@ -86,6 +86,21 @@ __global__ void broadcast_leaf_T_kernel(double* __restrict__ T_all, size_t elems
     const size_t total = elems_per_leaf * (size_t)(n_leaves - 1);
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
         T_all[elems_per_leaf + e] = T_all[e % elems_per_leaf];
+}
+
+// The DtN map of a constant-coefficient leaf depends on (dx, dy, lambda) only: leaves with bit-identical cell sizes share
+// one computation (the launcher builds one representative per class) and the others receive a copy, written at HBM speed
+// from an L2-resident source.  src[leaf] = leaf index of the representative (itself for a representative).
+__global__ void __launch_bounds__(256) copy_leaf_T_kernel(double* __restrict__ T_all, int elems2_per_leaf, const int* __restrict__ src, int n_leaves)
+{
+    double2* T2 = reinterpret_cast<double2*>(T_all);
+    for (int leaf = blockIdx.y; leaf < n_leaves; leaf += gridDim.y) {
+        const int from = src[leaf];
+        if (from == leaf) continue;
+        const double2* in = T2 + (size_t)from * elems2_per_leaf;
+        double2* out = T2 + (size_t)leaf * elems2_per_leaf;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < elems2_per_leaf; e += gridDim.x * blockDim.x) __stcs(out + e, in[e]);
+    }
 }
 
 // mode 0: write u (M*M per leaf);  mode 1: write h (4M per leaf, into h_ptrs[leaf]).
@@ -624,8 +639,8 @@ void launch_broadcast_leaf_T(double* T_all, int M, int n_leaves, cudaStream_t s)
 }
 
 template <int M>
-static void dtn_const_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, double* T_all, int n_build, cudaStream_t s) {
-    leaf_dtn_const_kernel<M><<<n_build, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, T_all, n_build);
+static void dtn_const_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, double* T_all, const int* build_list, int n_build, cudaStream_t s) {
+    leaf_dtn_const_kernel<M><<<n_build, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build);
 }
 template <int M>
 static void solve_const_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, const double* f, double fscale,
@@ -634,20 +649,26 @@ static void solve_const_M(const double* Q, const double* boxes, const int* leaf_
 }
 
 void launch_leaf_dtn_const(int M, const double* Q, const double* boxes, const int* leaf_nodes, double lambda,
-                           double* T_all, int n_leaves, bool cache_operators, cudaStream_t s)
+                           double* T_all, int n_leaves, bool cache_operators, const int* build_list, int n_build, const int* leaf_src,
+                           cudaStream_t s)
 {
     if (n_leaves == 0) return;
-    const int n_build = cache_operators ? 1 : n_leaves;
+    if (cache_operators) { build_list = nullptr; n_build = 1; }   // quirk q1: the first leaf's T for every leaf
+    else if (!build_list) n_build = n_leaves;
     switch (M) {
-        case 8: dtn_const_M<8>(Q, boxes, leaf_nodes, lambda, T_all, n_build, s); break;
-        case 16: dtn_const_M<16>(Q, boxes, leaf_nodes, lambda, T_all, n_build, s); break;
-        case 24: dtn_const_M<24>(Q, boxes, leaf_nodes, lambda, T_all, n_build, s); break;
-        case 32: dtn_const_M<32>(Q, boxes, leaf_nodes, lambda, T_all, n_build, s); break;
+        case 8: dtn_const_M<8>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
+        case 16: dtn_const_M<16>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
+        case 24: dtn_const_M<24>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
+        case 32: dtn_const_M<32>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
         default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
     }
     EF_CUDA(cudaGetLastError());
     if (cache_operators && n_leaves > 1) {
         broadcast_leaf_T_kernel<<<148 * 8, 256, 0, s>>>(T_all, (size_t)16 * M * M, n_leaves);
+        EF_CUDA(cudaGetLastError());
+    } else if (build_list && n_build < n_leaves) {
+        const int e2 = 8 * M * M, bx = (e2 + 255) / 256 < 4 ? (e2 + 255) / 256 : 4;
+        copy_leaf_T_kernel<<<dim3(bx, n_leaves < 148 * 16 ? n_leaves : 148 * 16), 256, 0, s>>>(T_all, e2, leaf_src, n_leaves);
         EF_CUDA(cudaGetLastError());
     }
 }
