@@ -49,7 +49,12 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--level", type=int, default=8)
     ap.add_argument("--nx", type=int, default=16)
-    ap.add_argument("--problem", default="poisson", choices=["poisson", "helmholtz"])
+    ap.add_argument("--problem", default="poisson", choices=["poisson", "helmholtz", "varcoef"],
+                    help="varcoef: alpha = 1, beta = 1 + sin x cos y / 2, lambda = -(1 + cos x cos y / 2), FivePointStencil leaves (BASELINE configs[3])")
+    ap.add_argument("--adaptive", nargs=2, type=int, metavar=("MIN", "MAX"), default=None,
+                    help="adaptive mesh of examples/elliptic-single (refine where |sin x + sin y| > --threshold at a cell centre, 2:1 balanced) "
+                         "on [-10,10]^2: BASELINE configs[0] is --adaptive 0 7, configs[3] --adaptive 4 9 --threshold 1.6 --problem varcoef")
+    ap.add_argument("--threshold", type=float, default=1.2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-symmetry", action="store_true", help="EFGPU_NO_SYMMETRY: general merge plan (A/B against the symmetric one)")
     ap.add_argument("--profile-run", action="store_true", help="for ncu: exactly --warmup/--steps device steps, nothing else, no JSON")
@@ -60,10 +65,16 @@ def parse_args():
     return ap.parse_args()
 
 
+PROBLEM_NAMES = {"poisson": "constant-coefficient Poisson", "helmholtz": "constant-coefficient Helmholtz lambda=-1",
+                 "varcoef": "variable-coefficient alpha/beta/lambda elliptic (FivePointStencil leaves: one block-tridiagonal LU per leaf)"}
+
+
 def workload_name(a):
+    if a.adaptive:
+        return "adaptive quadtree levels %d-%d (|sin x + sin y| > %g, 2:1 balanced), %dx%d FV patches, %s on [-10,10]^2 (BASELINE configs[%d] shape)" % (
+            a.adaptive[0], a.adaptive[1], a.threshold, a.nx, a.nx, PROBLEM_NAMES[a.problem], 3 if a.problem == "varcoef" else 0)
     shape = "BASELINE configs[1]" if (a.level, a.nx, a.problem) == (8, 16, "poisson") else "BASELINE configs[1] shape at another size"
-    return "uniform level-%d quadtree, %dx%d FV patches, constant-coefficient %s on [0,pi]^2 (%s)" % (
-        a.level, a.nx, a.nx, "Poisson" if a.problem == "poisson" else "Helmholtz lambda=-1", shape)
+    return "uniform level-%d quadtree, %dx%d FV patches, %s on [0,pi]^2 (%s)" % (a.level, a.nx, a.nx, PROBLEM_NAMES[a.problem], shape)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -118,13 +129,16 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def run_reference_sample(level, nx, problem, threads):
-    """One run of the unmodified reference on a uniform level-`level` tree; returns its REF_RESULT dict."""
+def run_reference_sample(level, nx, problem, threads, adaptive=None, threshold=1.2):
+    """One run of the unmodified reference on a uniform level-`level` tree (or the adaptive mesh `adaptive` = (min, max));
+    returns its REF_RESULT dict."""
     if not os.path.exists(REF_DRIVER):
         raise RuntimeError("oracle/_ref/ref_driver is missing (built by __graft_entry__.build() where /root/reference exists)")
     env = dict(os.environ, OPENBLAS_NUM_THREADS=str(threads), OMP_NUM_THREADS=str(threads))
-    cmd = [REF_DRIVER, "--problem", problem, "--solver", "fishpack", "--min-level", str(level), "--max-level", str(level),
-           "--nx", str(nx), "--domain", "0", repr(PI), "0", repr(PI), "--ops", "0"]
+    lo, hi = adaptive if adaptive else (level, level)
+    dom = ["-10", "10", "-10", "10"] if adaptive else ["0", repr(PI), "0", repr(PI)]
+    cmd = [REF_DRIVER, "--problem", problem, "--solver", "fivepoint" if problem == "varcoef" else "fishpack", "--min-level", str(lo),
+           "--max-level", str(hi), "--nx", str(nx), "--threshold", repr(threshold), "--domain"] + dom + ["--ops", "0"]
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout
     line = [l for l in out.splitlines() if l.startswith("REF_RESULT")][-1]
     return json.loads(line[len("REF_RESULT "):])
@@ -138,23 +152,35 @@ def host_threads():
     return max(1, min(n, 64))
 
 
+def cpu_sample(a, default_level):
+    """Bounded CPU sample of the workload: (kwargs of run_reference_sample, description)."""
+    if a.problem == "varcoef":
+        default_level -= 1      # the reference factorises a dense M^2 x M^2 matrix in every leaf solve call
+    if a.adaptive:
+        hi = a.cpu_level if a.cpu_level is not None else min(a.adaptive[1], default_level)
+        lo = min(a.adaptive[0], max(hi - 3, 0))
+        return dict(level=hi, adaptive=(lo, hi), threshold=a.threshold), "adaptive levels %d-%d" % (lo, hi)
+    lvl = a.cpu_level if a.cpu_level is not None else min(a.level, default_level)
+    return dict(level=lvl), "uniform level-%d" % lvl
+
+
 def reference_arm(a):
     """`--impl reference`: the reference's own CPU implementation (compiled, unmodified) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    level = a.cpu_level if a.cpu_level is not None else min(a.level, 5)
+    kw, what = cpu_sample(a, 5)
     threads = host_threads()
     for _ in range(a.warmup):
-        run_reference_sample(level, a.nx, a.problem, threads)
+        run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **kw)
     ts, res = [], None
     for _ in range(a.steps):
-        res = run_reference_sample(level, a.nx, a.problem, threads)
+        res = run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **kw)
         ts.append(res["build_s"] + res["upwards_s"] + res["solve_s"])
     t = sum(ts) / len(ts)
     v = res["dofs"] / t
-    sample = "uniform level-%d, %dx%d patches (%d DOFs): build %.3f s, upwards %.3f s, solve %.3f s per step" % (
-        level, a.nx, a.nx, res["dofs"], res["build_s"], res["upwards_s"], res["solve_s"])
+    sample = "%s, %dx%d patches (%d DOFs): build %.3f s, upwards %.3f s, solve %.3f s per step" % (
+        what, a.nx, a.nx, res["dofs"], res["build_s"], res["upwards_s"], res["solve_s"])
     print(json.dumps({
         "impl": "reference", "metric": "HPS build+upwards+solve DOFs/s (FP64)", "value": v, "unit": "DOFs/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
@@ -185,14 +211,31 @@ def own_arm(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload (untimed set-up: mesh, plan, host sampling of f and the boundary data) ----
-    grid = ef.FiniteVolumeGrid(a.nx, 0.0, PI, a.nx, 0.0, PI)
-    mesh = ef.Mesh().refineByFunction(None, 0.0, a.level, a.level, grid)
+    if a.adaptive:
+        if world > 1:
+            raise SystemExit("--adaptive: single GPU only (sharded runs cut a uniform upper tree)")
+        grid = ef.FiniteVolumeGrid(a.nx, -10.0, 10.0, a.nx, -10.0, 10.0)
+        mesh = ef.Mesh().refineByFunction("elliptic-single", a.threshold, a.adaptive[0], a.adaptive[1], grid)
+    else:
+        grid = ef.FiniteVolumeGrid(a.nx, 0.0, PI, a.nx, 0.0, PI)
+        mesh = ef.Mesh().refineByFunction(None, 0.0, a.level, a.level, grid)
     solver = ef.FiniteVolumeSolver()
-    solver.solver_type = "FISHPACK90"
-    lam = 0.0 if a.problem == "poisson" else -1.0
-    solver.lambda_function = lambda x, y: lam + 0.0 * x
     u_exact = lambda x, y: np.sin(x) + np.sin(y)
-    f_fn = lambda x, y: (lam - 1.0) * u_exact(x, y)
+    if a.problem == "varcoef":
+        # manufactured solution u = sin x + sin y of alpha div(beta grad u) + lambda u = f
+        if world > 1:
+            raise SystemExit("--problem varcoef: single GPU only")
+        solver.solver_type = "FivePointStencil"
+        beta = lambda x, y: 1.0 + 0.5 * np.sin(x) * np.cos(y)
+        lamf = lambda x, y: -(1.0 + 0.5 * np.cos(x) * np.cos(y))
+        solver.beta_function, solver.lambda_function = beta, lamf
+        f_fn = lambda x, y: (0.5 * np.cos(x) * np.cos(y) * np.cos(x) - 0.5 * np.sin(x) * np.sin(y) * np.cos(y)
+                             - beta(x, y) * u_exact(x, y) + lamf(x, y) * u_exact(x, y))
+    else:
+        solver.solver_type = "FISHPACK90"
+        lam = 0.0 if a.problem == "poisson" else -1.0
+        solver.lambda_function = lambda x, y: lam + 0.0 * x
+        f_fn = lambda x, y: (lam - 1.0) * u_exact(x, y)
 
     hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world)
     hps.no_symmetry = a.no_symmetry
@@ -217,12 +260,14 @@ def own_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
+    def step_device():      # every input resident in HBM: f, g and (FivePointStencil leaves) the sampled coefficient arrays
+        hps.resample_coefficients = False
         hps.buildStage()
         hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=False)
         hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True)
 
-    def step_host():
+    def step_host():        # host buffers: alpha/beta/lambda sampled and copied by buildStage, f and g copied H2D, u copied D2H
+        hps.resample_coefficients = True
         hps.buildStage()
         hps.upwardsStageHost(f_pin.numpy())
         hps.solveStageHost(g_pin.numpy(), u_pin.numpy())
@@ -266,6 +311,12 @@ def own_arm(a):
 
     # correctness of the timed computation: discretisation error against the manufactured solution
     err = hps.max_error(u_dev, u_exact)
+    mesh_stats = None
+    if a.adaptive:   # leaves per level and the histogram of coarsening tags (HPSAlgorithm.hpp:676-741) over all nodes
+        lv = np.bincount(mesh.level[mesh.leaf_nodes])
+        tags = np.bincount([hps.node_info(i)["n_coarsens"] for i in range(mesh.n_nodes)])
+        mesh_stats = {"leaves_per_level": {str(i): int(c) for i, c in enumerate(lv) if c}, "nodes": mesh.n_nodes,
+                      "n_coarsens_histogram": {str(i): int(c) for i, c in enumerate(tags)}}
 
     # ---- e2e leg: host buffers through the C-ABI, copies inside the timed region ----
     step_host()
@@ -273,6 +324,7 @@ def own_arm(a):
     err_e2e = float(np.max(np.abs(u_pin.numpy() - u_dev.cpu().numpy())))
 
     # ---- stage split (extra passes, not part of the headline): each stage between barriers, max over ranks ----
+    hps.resample_coefficients = False
     build_s, _ = timed(lambda: hps.buildStage(), 1)
     up_s, _ = timed(lambda: hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True), 1)
     so_s, _ = timed(lambda: hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True), 1)
@@ -329,13 +381,13 @@ def own_arm(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            lvl = a.cpu_level if a.cpu_level is not None else min(a.level, 6)
+            kw, what = cpu_sample(a, 6)
             threads = host_threads()
-            r = run_reference_sample(lvl, a.nx, a.problem, threads)
+            r = run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **kw)
             t = r["build_s"] + r["upwards_s"] + r["solve_s"]
             cpu = {"value": r["dofs"] / t, "unit": "DOFs/s", "cores": threads, "kind": "reference",
-                   "sample": "oracle/_ref/ref_driver (unmodified reference, OpenBLAS x%d threads), uniform level-%d %dx%d patches, %d DOFs: "
-                             "build %.2f s, upwards %.2f s, solve %.2f s" % (threads, lvl, a.nx, a.nx, r["dofs"], r["build_s"], r["upwards_s"], r["solve_s"]),
+                   "sample": "oracle/_ref/ref_driver (unmodified reference, OpenBLAS x%d threads), %s %dx%d patches, %d DOFs: "
+                             "build %.2f s, upwards %.2f s, solve %.2f s" % (threads, what, a.nx, a.nx, r["dofs"], r["build_s"], r["upwards_s"], r["solve_s"]),
                    "build_dofs_per_s": r["dofs"] / r["build_s"], "solve_dofs_per_s": r["dofs"] / (r["upwards_s"] + r["solve_s"])}
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             cpu = {"value": None, "unit": "DOFs/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
@@ -388,9 +440,10 @@ def own_arm(a):
         "metric": "HPS build+upwards+solve DOFs/s (FP64)", "value": dofs * a.steps / dev_s, "unit": "DOFs/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
+        "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "mesh": mesh_stats, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
                    "sharding": hps.sharding(),
-                   "merge_plan": "general (EFGPU_NO_SYMMETRY)" if a.no_symmetry else "symmetric where the subtree is uniform with constant-coefficient leaves (every merge of this workload)"},
+                   "merge_plan": "general (EFGPU_NO_SYMMETRY)" if a.no_symmetry else "symmetric where the subtree is uniform with constant-coefficient leaves%s" % (
+                       "" if (a.adaptive or a.problem == "varcoef") else " (every merge of this workload)")},
         "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,
                    "build_dofs_per_s": dofs / (build_ms * 1e-3), "solve_dofs_per_s": dofs / ((up_ms + so_ms) * 1e-3),
                    "upwards_gbs": tot["upwards_bytes"] / (up_ms * 1e-3) / 1e9, "solve_gbs": tot["solve_bytes"] / (so_ms * 1e-3) / 1e9,
@@ -398,7 +451,7 @@ def own_arm(a):
                    "merge_tflops_issued": tot["issued"] / (build_ms * 1e-3) / 1e12,
                    "merge_tflops_canonical": tot["canonical"] / (build_ms * 1e-3) / 1e12},
         "linf_error_vs_exact": err, "e2e_vs_device_max_abs_diff": err_e2e,
-        "e2e": {"value": dofs * a.steps / e2e_wall_s, "unit": "DOFs/s", "h2d_bytes_per_step": int(f_host.nbytes + g_host.nbytes),
+        "e2e": {"value": dofs * a.steps / e2e_wall_s, "unit": "DOFs/s", "h2d_bytes_per_step": int(f_host.nbytes * (7 if a.problem == "varcoef" else 1) + g_host.nbytes),
                 "d2h_bytes_per_step": int(f_host.nbytes), "ms_per_step": 1e3 * e2e_wall_s / a.steps, "timer": "host wall clock between device synchronisations"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)%s" % (" on rank 0" if world > 1 else ""),

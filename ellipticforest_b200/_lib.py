@@ -68,6 +68,7 @@ SIGNATURES = {
     "efgpu_set_profiling": (C.c_int, [_P, C.c_int]),
     "efgpu_get_profile": (C.c_int, [_P, C.c_int, _D, _D]),
     "efgpu_profile_class_name": (C.c_char_p, [C.c_int]),
+    "efgpu_refine_elliptic_single": (C.c_int, [C.c_double, C.c_double, _P]),
     "efgpu_mesh_create": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, REFINE_FN, _P, C.POINTER(_P)]),
     "efgpu_mesh_desc": (C.c_int, [_P, C.POINTER(TreeDesc)]),
     "efgpu_mesh_n_leaves": (C.c_int, [_P]),

@@ -10,6 +10,7 @@
 // unique, so the result is identical to p4est's (pinned against reference dumps in tests/).
 #include "../../include/efgpu.h"
 
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -45,6 +46,11 @@ struct efgpu_mesh {
 };
 
 extern "C" {
+
+int efgpu_refine_elliptic_single(double x, double y, void* user)
+{
+    return std::fabs(-(std::sin(x) + std::sin(y))) > *static_cast<const double*>(user) ? 1 : 0;
+}
 
 int efgpu_mesh_create(double xl, double xu, double yl, double yu, int nx, int min_level, int max_level,
                       efgpu_refine_fn fn, void* user, efgpu_mesh** out)

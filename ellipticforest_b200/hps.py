@@ -85,15 +85,22 @@ class Mesh:
 
     def refineByFunction(self, fn: Optional[Callable[[float, float], bool]], threshold, min_level, max_level,
                          root_grid: FiniteVolumeGrid):
-        """src/Mesh.hpp:111-180.  `fn(x, y) -> bool` is evaluated at the nx*ny cell centres of a quadrant."""
+        """src/Mesh.hpp:111-180.  `fn(x, y) -> bool` is evaluated at the nx*ny cell centres of a quadrant; the string
+        "elliptic-single" selects the library's built-in |-(sin x + sin y)| > threshold (examples/elliptic-single)."""
         lib = _lib.load()
         if root_grid.nx != root_grid.ny:
             raise ValueError("square patches only (nx == ny), as the reference's merge assumes")
         self.root_grid = root_grid
-        cb = _lib.REFINE_FN(lambda x, y, _u: 1 if fn(x, y) else 0) if fn is not None else _lib.REFINE_FN()
+        user = None
+        if fn == "elliptic-single":
+            thr = C.c_double(float(threshold))
+            cb = C.cast(lib.efgpu_refine_elliptic_single, _lib.REFINE_FN)
+            user = C.cast(C.pointer(thr), C.c_void_p)
+        else:
+            cb = _lib.REFINE_FN(lambda x, y, _u: 1 if fn(x, y) else 0) if fn is not None else _lib.REFINE_FN()
         out = C.c_void_p()
         check(lib.efgpu_mesh_create(root_grid.x_lower, root_grid.x_upper, root_grid.y_lower, root_grid.y_upper,
-                                    root_grid.nx, min_level, max_level, cb, None, C.byref(out)))
+                                    root_grid.nx, min_level, max_level, cb, user, C.byref(out)))
         self._m = out
         d = TreeDesc()
         check(lib.efgpu_mesh_desc(self._m, C.byref(d)))
@@ -161,6 +168,10 @@ class HPSAlgorithm:
         self.keep_x = False
         self.lean_T = False   # EFGPU_LEAN_T: DtN maps of interior nodes are transient (memory policy)
         self.no_symmetry = False   # EFGPU_NO_SYMMETRY: general merge plan even where X and diag(d) T are symmetric
+        # FivePointStencil leaves: the reference evaluates alpha/beta/lambda inside every leaf solve; here they are sampled on
+        # the host once per buildStage.  False keeps the coefficient arrays already resident in HBM (same functions).
+        self.resample_coefficients = True
+        self._coefficients_set = False
         self._lib = _lib.load()
         self._h = C.c_void_p()
         check(self._lib.efgpu_create(C.byref(mesh.desc), device, C.byref(self._h)))
@@ -190,7 +201,9 @@ class HPSAlgorithm:
             lam = float(s.lambda_function(np.float64(0.0), np.float64(0.0)))  # FiniteVolumeSolver.cpp:254
             check(self._lib.efgpu_set_leaf_constant(self._h, lam), self._h)
         elif s.solver_type == "FivePointStencil":
-            self._set_variable_coefficients()
+            if self.resample_coefficients or not self._coefficients_set:
+                self._set_variable_coefficients()
+                self._coefficients_set = True
         else:
             raise ValueError("unknown solver_type")
         check(self._lib.efgpu_build(self._h, self._flags()), self._h)

@@ -182,6 +182,9 @@ const char* efgpu_profile_class_name(int cls);
  * so that the library is usable stand-alone.  A reference-side caller passes its own p4est-derived table. */
 typedef int (*efgpu_refine_fn)(double x, double y, void* user);   /* non-zero: refine the patch containing (x,y) */
 typedef struct efgpu_mesh efgpu_mesh;
+/* built-in callback: the indicator of examples/elliptic-single/main.cpp:165-175, |-(sin x + sin y)| > *(const double*)user
+ * (saves the per-point trip through a foreign-language callback when large adaptive meshes are built from Python) */
+int efgpu_refine_elliptic_single(double x, double y, void* user);
 int efgpu_mesh_create(double x_lower, double x_upper, double y_lower, double y_upper, int nx, int min_level,
                       int max_level, efgpu_refine_fn fn, void* user, efgpu_mesh** out);
 int efgpu_mesh_desc(const efgpu_mesh* m, efgpu_tree_desc* out);   /* pointers stay owned by the mesh */
