@@ -38,8 +38,11 @@ __device__ __forceinline__ double flip_sign(double x, unsigned neg) {
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 struct GemmCfg {
     static constexpr int NT = WARPS_M * WARPS_N * 32;
-    static constexpr int LDA_S = BK + 4;   // == 4 (mod 8): conflict-free 8x4 fragment reads
-    static constexpr int LDB_S = BN + 4;   // == 4 (mod 16): conflict-free 4x8 fragment reads
+    // Fragment loads: the four k slots of a DMMA may hold any four k as long as A and B agree, so lane t takes the PAIR
+    // k = 2t, 2t+1 of each group of 8 with one 16-byte load of A and feeds it to two consecutive DMMAs (slots {0,2,4,6}
+    // and {1,3,5,7}); B rows 2t and 2t+1 are read separately.  Paddings make both patterns bank-conflict free.
+    static constexpr int LDA_S = BK + 8;   // == 8 (mod 16): rows g, g+1 of a quarter warp's 16-byte reads fall into disjoint bank halves
+    static constexpr int LDB_S = BN + 2;   // == 2 (mod 8): rows 2t (and 2t+1), t < 4, start 4 banks apart
     static constexpr int A_STAGE = BM * LDA_S;
     static constexpr int B_STAGE = BK * LDB_S;
     static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
@@ -53,6 +56,9 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
              int nblocks, int tiles_per_block)
 {
     using C = GemmCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
+    // column slots of the B / C fragments: with an even number of 8-column tiles per warp, slot g of the tile pair (2 jg,
+    // 2 jg + 1) stands for the adjacent columns 2g, 2g + 1 of a 16-column group, so one 16-byte load feeds both tiles
+    constexpr bool PAIRED_N = C::FN % 2 == 0;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * C::A_STAGE;
@@ -118,6 +124,10 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
         cp_async_commit();
     }
 
+    // The sign of a term is applied to the accumulators, not to every A fragment: raw products are accumulated, the
+    // accumulators are negated where the sign changes between the two terms and once more at the end if the last term is
+    // negative (exact, so the result is bit-identical to flipping A; saves one LOP3 per fragment on the LDS -> DMMA path).
+    const bool flip_mid = nterms > 1 && neg0 != neg1;
     for (int kt = 0; kt < nk_total; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -126,40 +136,85 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
             if (nxt < nk_total) load_stage(nxt, nxt % STAGES);
             cp_async_commit();
         }
-        const unsigned neg = kt >= nk0 ? neg1 : neg0;
-        const double* as = As + (kt % STAGES) * C::A_STAGE + (wm0 + (lane >> 2)) * C::LDA_S + (lane & 3);
-        const double* bs = Bs + (kt % STAGES) * C::B_STAGE + (lane & 3) * C::LDB_S + wn0 + (lane >> 2);
-#pragma unroll
-        for (int kk = 0; kk < BK / 4; kk++) {
-            double a[C::FM], b[C::FN];
-#pragma unroll
-            for (int i = 0; i < C::FM; i++) a[i] = flip_sign(as[i * 8 * C::LDA_S + kk * 4], neg);
-#pragma unroll
-            for (int j = 0; j < C::FN; j++) b[j] = bs[kk * 4 * C::LDB_S + j * 8];
+        if (flip_mid && kt == nk0) {
 #pragma unroll
             for (int i = 0; i < C::FM; i++)
 #pragma unroll
-                for (int j = 0; j < C::FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < C::FN; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
+        }
+        const double* as = As + (kt % STAGES) * C::A_STAGE + (wm0 + (lane >> 2)) * C::LDA_S + 2 * (lane & 3);
+        const double* bs = Bs + (kt % STAGES) * C::B_STAGE + 2 * (lane & 3) * C::LDB_S + wn0 + (PAIRED_N ? 2 : 1) * (lane >> 2);
+#pragma unroll
+        for (int kp = 0; kp < BK / 8; kp++) {
+            double2 a[C::FM];
+            double b0[C::FN], b1[C::FN];
+#pragma unroll
+            for (int i = 0; i < C::FM; i++) a[i] = *reinterpret_cast<const double2*>(as + i * 8 * C::LDA_S + kp * 8);
+            if constexpr (PAIRED_N) {
+#pragma unroll
+                for (int jg = 0; jg < C::FN / 2; jg++) {
+                    const double2 v0 = *reinterpret_cast<const double2*>(bs + kp * 8 * C::LDB_S + jg * 16);
+                    const double2 v1 = *reinterpret_cast<const double2*>(bs + (kp * 8 + 1) * C::LDB_S + jg * 16);
+                    b0[2 * jg] = v0.x; b0[2 * jg + 1] = v0.y; b1[2 * jg] = v1.x; b1[2 * jg + 1] = v1.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < C::FN; j++) {
+                    b0[j] = bs[kp * 8 * C::LDB_S + j * 8];
+                    b1[j] = bs[(kp * 8 + 1) * C::LDB_S + j * 8];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < C::FM; i++)
+#pragma unroll
+                for (int j = 0; j < C::FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b0[j]);
+#pragma unroll
+            for (int i = 0; i < C::FM; i++)
+#pragma unroll
+                for (int j = 0; j < C::FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b1[j]);
         }
     }
     cp_async_wait<0>();
+    if (neg1) {
+#pragma unroll
+        for (int i = 0; i < C::FM; i++)
+#pragma unroll
+            for (int j = 0; j < C::FN; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
+    }
 
-    // epilogue: C = acc (+ C0); each thread owns rows (lane/4), column pairs (lane%4)*2
-    double* Cg = ops[bd.c_op] + bd.c_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc + tn * BN + wn0 + (lane & 3) * 2;
+    // epilogue: C = acc (+ C0); each thread owns rows lane/4 + 8 i.  Unpaired columns: the pair (lane%4)*2 of every 8-column
+    // tile; paired: the four adjacent columns 4 (lane%4) .. + 3 of every 16-column group (slots 0/1 of its two tiles interleaved)
+    const int col0 = tn * BN + wn0 + (PAIRED_N ? 4 : 2) * (lane & 3);
+    double* Cg = ops[bd.c_op] + bd.c_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc + col0;
     const double* C0g = nullptr;
-    if (bd.c0_op >= 0)
-        C0g = ops[bd.c0_op] + bd.c0_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc0 + tn * BN + wn0 + (lane & 3) * 2;
+    if (bd.c0_op >= 0) C0g = ops[bd.c0_op] + bd.c0_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc0 + col0;
 #pragma unroll
-    for (int i = 0; i < C::FM; i++)
+    for (int i = 0; i < C::FM; i++) {
+        if constexpr (PAIRED_N) {
 #pragma unroll
-        for (int j = 0; j < C::FN; j++) {
-            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-            if (C0g) {
-                double2 c0 = *reinterpret_cast<const double2*>(C0g + (long long)(i * 8) * bd.ldc0 + j * 8);
-                v.x += c0.x; v.y += c0.y;
+            for (int jg = 0; jg < C::FN / 2; jg++) {
+                double2 lo = make_double2(acc[i][2 * jg][0], acc[i][2 * jg + 1][0]);
+                double2 hi = make_double2(acc[i][2 * jg][1], acc[i][2 * jg + 1][1]);
+                if (C0g) {
+                    const double2* c0 = reinterpret_cast<const double2*>(C0g + (long long)(i * 8) * bd.ldc0 + jg * 16);
+                    const double2 c0l = c0[0], c0h = c0[1];
+                    lo.x += c0l.x; lo.y += c0l.y; hi.x += c0h.x; hi.y += c0h.y;
+                }
+                double2* c = reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + jg * 16);
+                c[0] = lo; c[1] = hi;
             }
-            *reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + j * 8) = v;
+        } else {
+#pragma unroll
+            for (int j = 0; j < C::FN; j++) {
+                double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                if (C0g) {
+                    double2 c0 = *reinterpret_cast<const double2*>(C0g + (long long)(i * 8) * bd.ldc0 + j * 8);
+                    v.x += c0.x; v.y += c0.y;
+                }
+                *reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + j * 8) = v;
+            }
         }
+    }
 }
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
