@@ -36,36 +36,46 @@ __constant__ int c_kids[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
 // WESN block permutation (HPSAlgorithm.hpp:984): permuted position p holds pre-permutation block c_pi[p]
 __constant__ int c_pi[8] = {0, 4, 2, 6, 1, 3, 5, 7};
 
-// X[k][k'] = - sum_c sgn_c(k) T^c[iface_c(k), iface_c(k')]   (16 n x n blocks, 4 of them zero)
-__global__ void assemble_X_kernel(const MergeEntry* __restrict__ ent, int n)
+// X[k][k'] = - sum_c sgn_c(k) T^c[iface_c(k), iface_c(k')]   (16 n x n blocks, 4 of them zero); two entries per thread
+__global__ void __launch_bounds__(256) assemble_X_kernel(const MergeEntry* __restrict__ ent, int n)
 {
     const MergeEntry& e = ent[blockIdx.y];
-    const int N = 4 * n;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * N; idx += gridDim.x * blockDim.x) {
-        const int row = idx / N, col = idx % N;
-        const int k = row / n, r = row % n, k2 = col / n, c = col % n;
-        double v = 0.0;
+    const int N = 4 * n, N2 = N / 2;
+    const double* Tc[4] = {e.Tc[0], e.Tc[1], e.Tc[2], e.Tc[3]};
+    double2* X2 = reinterpret_cast<double2*>(e.Xinv);
+    double2* Xc2 = reinterpret_cast<double2*>(e.Xcopy);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * N2; idx += gridDim.x * blockDim.x) {
+        const int row = idx / N2, col = 2 * (idx - row * N2);        // col even: both entries lie in one block (n is even)
+        const int k = row / n, r = row - k * n, k2 = col / n, c = col - k2 * n;
+        double2 v = make_double2(0.0, 0.0);
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) {
             const int sa = c_iface[ch][k], sb = c_iface[ch][k2];
-            if (sa >= 0 && sb >= 0) v -= c_sgn[ch][k] * e.Tc[ch][(size_t)(sa * n + r) * N + sb * n + c];
+            if (sa >= 0 && sb >= 0) {
+                const double2 t = *reinterpret_cast<const double2*>(Tc[ch] + (size_t)(sa * n + r) * N + sb * n + c);
+                const double s = c_sgn[ch][k];
+                v.x -= s * t.x; v.y -= s * t.y;
+            }
         }
-        e.Xinv[idx] = v;
-        if (e.Xcopy) e.Xcopy[idx] = v;
+        X2[idx] = v;
+        if (Xc2) Xc2[idx] = v;
     }
 }
 
-// Hc row block p (WESN position) of child c = [ T^c[side, iface_c(k0)] | T^c[side, iface_c(k1)] ]
-__global__ void assemble_Hc_kernel(const MergeEntry* __restrict__ ent, int n)
+// Hc row block p (WESN position) of child c = [ T^c[side, iface_c(k0)] | T^c[side, iface_c(k1)] ]; two entries per thread
+__global__ void __launch_bounds__(256) assemble_Hc_kernel(const MergeEntry* __restrict__ ent, int n)
 {
     const MergeEntry& e = ent[blockIdx.y];
-    const int N = 4 * n, W = 2 * n;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 8 * n * W; idx += gridDim.x * blockDim.x) {
-        const int row = idx / W, col = idx % W;
-        const int p = row / n, r = row % n, t = col / n, c = col % n;
+    const int N = 4 * n;
+    const double* Tc[4] = {e.Tc[0], e.Tc[1], e.Tc[2], e.Tc[3]};
+    double2* H2 = reinterpret_cast<double2*>(e.Hc);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 8 * n * n; idx += gridDim.x * blockDim.x) {
+        const int row = idx / n, col = 2 * (idx - row * n);           // row of 2n entries = n pairs
+        const int p = row / n, r = row - p * n, t = col / n, c = col - t * n;
         const int q = c_pi[p], ch = q >> 1, side = c_tau_side[ch][q & 1];
         const int sb = c_iface[ch][c_kk[ch][t]];
-        e.Hc[idx] = e.Tc[ch][(size_t)(side * n + r) * N + sb * n + c];
+        const double* T = ch == 0 ? Tc[0] : ch == 1 ? Tc[1] : ch == 2 ? Tc[2] : Tc[3];
+        H2[idx] = *reinterpret_cast<const double2*>(T + (size_t)(side * n + r) * N + sb * n + c);
     }
 }
 
@@ -468,7 +478,7 @@ void launch_assemble_X(const MergeEntry* e, int n, int count, cudaStream_t s)
 {
     for (int off = 0; off < count; off += 65535) {
         int c = count - off < 65535 ? count - off : 65535;
-        assemble_X_kernel<<<dim3(ew_blocks(16LL * n * n), c), 256, 0, s>>>(e + off, n);
+        assemble_X_kernel<<<dim3(ew_blocks(8LL * n * n), c), 256, 0, s>>>(e + off, n);
     }
     EF_CUDA(cudaGetLastError());
 }
@@ -476,7 +486,7 @@ void launch_assemble_Hc(const MergeEntry* e, int n, int count, cudaStream_t s)
 {
     for (int off = 0; off < count; off += 65535) {
         int c = count - off < 65535 ? count - off : 65535;
-        assemble_Hc_kernel<<<dim3(ew_blocks(16LL * n * n), c), 256, 0, s>>>(e + off, n);
+        assemble_Hc_kernel<<<dim3(ew_blocks(8LL * n * n), c), 256, 0, s>>>(e + off, n);
     }
     EF_CUDA(cudaGetLastError());
 }
