@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -192,7 +193,11 @@ struct InvPlanner {
         g.rows = rows; g.cols = cols; g.nterms = 1;
         g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, K, neg ? 0x80000000u : 0u};
         Step st{}; st.kind = 1; st.first = (int)b.blocks.size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
-        if (nranks > 1 && rows % (128 * nranks) == 0) {
+        // A product is split only where the flops saved outweigh the all-gather that follows (tens of microseconds of
+        // latency per collective): 2048-row products take ~0.6 ms, 1024-row ones 70 us; the deep, small products of the
+        // recursion are recomputed by every rank (6 % of the inversion flops).
+        static const int split_min = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 2048; }();
+        if (nranks > 1 && rows % (128 * nranks) == 0 && rows >= split_min) {
             const long long skip = (long long)rank * (rows / nranks);
             st.g_op = c_op; st.g_off = c_off; st.g_rows = rows; st.g_cols = cols; st.g_ld = ldc;
             if (ldc == cols) st.gk = 1;
