@@ -67,8 +67,8 @@ void launch_btranspose(double* const* ptab, int nops, const TransOp* d_ops, cons
 // In-place inverse of `batch` small dense N x N matrices (N <= 128) held at
 // ptab[z*nops+op] + off with leading dimension ld; Gauss-Jordan in shared memory, no pivoting
 // (the merge matrices are SPD / diagonally dominant).  min |pivot| is folded
-// into *min_pivot (device scalar) for singularity reporting.
-void launch_invert_small(double* const* ptab, int nops, int op, long long off, int ld, int N, int batch,
+// into *min_pivot (device scalar) for singularity reporting.  off2 >= 0: a second block per entry in the same launch.
+void launch_invert_small(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int N, int batch,
                          double* min_pivot, cudaStream_t stream);
 
 #ifdef __CUDACC__

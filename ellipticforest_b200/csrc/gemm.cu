@@ -354,14 +354,15 @@ void launch_btranspose(double* const* ptab, int nops, const TransOp* d_ops, cons
 // Gauss-Jordan in shared memory.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, int ld, int N,
+invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, int N,
                     double* __restrict__ min_pivot)
 {
+    const int nmat = off2 >= 0 ? 2 : 1;
     extern __shared__ __align__(16) double sm[];
     const int LDS = N + 1;
     double* A = sm;                 // N x (N+1)
     double* colk = sm + N * LDS;    // N  (column k before the update)
-    double* G = ptab[(long long)blockIdx.x * nops + op] + off;
+    double* G = ptab[(long long)(blockIdx.x / nmat) * nops + op] + ((blockIdx.x % nmat) ? off2 : off);
     const int tid = threadIdx.x, NT = blockDim.x;
     for (int e = tid; e < N * N; e += NT) { int r = e / N, c = e % N; A[r * LDS + c] = G[(long long)r * ld + c]; }
     __syncthreads();
@@ -475,14 +476,15 @@ __device__ __forceinline__ void gj_block(double (&a)[TI][TI], double (*sRow)[16 
 
 template <int TI>
 __global__ void __launch_bounds__(256)
-invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, int ld, double* __restrict__ min_pivot)
+invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, double* __restrict__ min_pivot)
 {
     constexpr int N = 16 * TI;
+    const int nmat = off2 >= 0 ? 2 : 1;
     __shared__ double sRow[2][N];
     __shared__ double sCol[2][N];
     __shared__ double sPiv[2][2];   // [buffer][0: pivot, 1: its reciprocal]
     __shared__ unsigned long long bar;   // one phase per pivot, 8 arrivals (one per warp)
-    double* G = ptab[(long long)blockIdx.x * nops + op] + off;
+    double* G = ptab[(long long)(blockIdx.x / nmat) * nops + op] + ((blockIdx.x % nmat) ? off2 : off);
     const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 8);
@@ -518,16 +520,17 @@ invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long 
         atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
 }
 
-void launch_invert_small(double* const* ptab, int nops, int op, long long off, int ld, int N, int batch,
+void launch_invert_small(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int N, int batch,
                          double* min_pivot, cudaStream_t stream)
 {
+    batch *= off2 >= 0 ? 2 : 1;   // CTAs: two blocks per entry
     if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "invert_small: N > 128"};
     switch (N) {
-        case 32: invert_reg_kernel<2><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
-        case 48: invert_reg_kernel<3><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
-        case 64: invert_reg_kernel<4><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
-        case 96: invert_reg_kernel<6><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
-        case 128: invert_reg_kernel<8><<<batch, 256, 0, stream>>>(ptab, nops, op, off, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 32: invert_reg_kernel<2><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 48: invert_reg_kernel<3><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 64: invert_reg_kernel<4><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 96: invert_reg_kernel<6><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 128: invert_reg_kernel<8><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
         default: break;
     }
     int smem = (N * (N + 1) + N) * (int)sizeof(double);
@@ -536,7 +539,7 @@ void launch_invert_small(double* const* ptab, int nops, int op, long long off, i
         EF_CUDA(cudaFuncSetAttribute(invert_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 128) * 8));
         attr_set = true;
     }
-    invert_small_kernel<<<batch, 256, smem, stream>>>(ptab, nops, op, off, ld, N, min_pivot);
+    invert_small_kernel<<<batch, 256, smem, stream>>>(ptab, nops, op, off, off2, ld, N, min_pivot);
     EF_CUDA(cudaGetLastError());
 }
 

@@ -67,6 +67,7 @@ struct NodeH {
 
 struct Step {
     int kind; int first, count; long long off; int N; int cls;   // kind 0: small inverse, 1: gemm, 2: block transposes; cls: profiling class
+    long long off2 = -1;              // kind 0: a second, independent N x N block inverted by the same launch (-1: none)
     // row-partitioned step of a replicated tree: after the GEMM the g_rows x g_cols result is all-gathered over the ranks.
     // gk 1: the destination (op g_op, offset g_off) is contiguous (ld == g_cols): in place.  gk 2: the GEMM wrote its rows into
     // the staging block OP_W3 (ld = g_cols); after the all-gather the block is copied to op g_op, offset g_off, leading dimension g_ld.
@@ -178,8 +179,17 @@ static void collect_profile(efgpu_handle* H)   // stream must be synchronised
 //  * symmetry (plan `sym`): where every patch below is square, uncoarsened and the leaf operator self-adjoint, X is
 //    symmetric; then C A^-1 = (A^-1 B)^T and the new C block is the transpose of the new B block: four GEMMs and two
 //    transposes per recursion level instead of six GEMMs.
+// The two diagonal blocks of A at the top level are independent and of the same shape: their recursions are planned
+// separately (second one on its own workspace slots w1b / w2b) and zipped step by step into launches that carry both,
+// which shortens the serial chain of small launches of the top tree levels by a quarter.
 struct InvPlanner {
     BatchH& b; std::vector<Step>& steps; const std::vector<long long>& w1_off; int ld, rank, nranks; bool sym;
+    std::vector<GemmBlock>* blk = nullptr;      // where descriptors go (default: the batch's vectors)
+    std::vector<TransOp>* trn = nullptr;
+    const std::vector<long long>* w1b = nullptr; // workspace of a zipped second branch (null: no zipping below this planner)
+    long long w2 = 0, w2b = 0;                   // W2 base of this planner / of a zipped second branch
+    std::vector<GemmBlock>& B_() { return blk ? *blk : b.blocks; }
+    std::vector<TransOp>& T_() { return trn ? *trn : b.trans; }
 
     void small(long long off, int N) {
         Step st{}; st.kind = 0; st.off = off; st.N = N; st.cls = EFGPU_PROF_INVERT_SMALL;
@@ -192,7 +202,7 @@ struct InvPlanner {
         g.c_op = c_op; g.c_off = c_off; g.ldc = ldc; g.c0_op = c0_op; g.c0_off = c0_off; g.ldc0 = ldc0;
         g.rows = rows; g.cols = cols; g.nterms = 1;
         g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, K, neg ? 0x80000000u : 0u};
-        Step st{}; st.kind = 1; st.first = (int)b.blocks.size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
+        Step st{}; st.kind = 1; st.first = (int)B_().size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
         // A product is split only where the flops saved outweigh the all-gather that follows (tens of microseconds of
         // latency per collective): 2048-row products take ~0.6 ms, 1024-row ones 70 us; the deep, small products of the
         // recursion are recomputed by every rank (6 % of the inversion flops).
@@ -208,12 +218,40 @@ struct InvPlanner {
             g.rows = rows / nranks;
         }
         steps.push_back(st);
-        b.blocks.push_back(g);
+        B_().push_back(g);
     }
     void transpose(int rows, int cols, int s_op, long long s_off, int lds, int d_op, long long d_off, int ldd) {
-        Step st{}; st.kind = 2; st.first = (int)b.trans.size(); st.count = 1; st.cls = EFGPU_PROF_TRANSPOSE;
-        b.trans.push_back(TransOp{s_op, d_op, lds, ldd, s_off, d_off, rows, cols, 0u, 0});
+        Step st{}; st.kind = 2; st.first = (int)T_().size(); st.count = 1; st.cls = EFGPU_PROF_TRANSPOSE;
+        T_().push_back(TransOp{s_op, d_op, lds, ldd, s_off, d_off, rows, cols, 0u, 0});
         steps.push_back(st);
+    }
+    // appends the steps of a sub-plan (descriptor indices rebased)
+    void append(const std::vector<Step>& ss, const std::vector<GemmBlock>& bb, const std::vector<TransOp>& tt) {
+        for (Step st : ss) {
+            if (st.kind == 1) { const int f = (int)B_().size(); for (int k = 0; k < st.count; k++) B_().push_back(bb[st.first + k]); st.first = f; }
+            if (st.kind == 2) { const int f = (int)T_().size(); for (int k = 0; k < st.count; k++) T_().push_back(tt[st.first + k]); st.first = f; }
+            steps.push_back(st);
+        }
+    }
+    // inverts the two q x q blocks at offA and offB: zipped into common launches when a second workspace is available
+    void invert_pair(long long offA, long long offB, int q, int depth) {
+        if (!w1b) { invert(offA, q, depth, false); invert(offB, q, depth, false); return; }
+        std::vector<Step> sA, sB; std::vector<GemmBlock> bA, bB; std::vector<TransOp> tA, tB;
+        InvPlanner pa{b, sA, w1_off, ld, rank, nranks, sym}; pa.blk = &bA; pa.trn = &tA; pa.w2 = w2;
+        InvPlanner pb{b, sB, *w1b, ld, rank, nranks, sym}; pb.blk = &bB; pb.trn = &tB; pb.w2 = w2b;
+        pa.invert(offA, q, depth, false);
+        pb.invert(offB, q, depth, false);
+        bool zip = sA.size() == sB.size();
+        for (size_t i = 0; zip && i < sA.size(); i++)
+            zip = sA[i].kind == sB[i].kind && sA[i].count == sB[i].count && sA[i].count <= 1 && !sA[i].gk && !sB[i].gk && sA[i].N == sB[i].N;
+        if (!zip) { append(sA, bA, tA); append(sB, bB, tB); return; }
+        for (size_t i = 0; i < sA.size(); i++) {
+            Step st = sA[i];
+            if (st.kind == 0) st.off2 = sB[i].off;
+            else if (st.kind == 1) { st.first = (int)B_().size(); st.count = 2; B_().push_back(bA[sA[i].first]); B_().push_back(bB[sB[i].first]); }
+            else { st.first = (int)T_().size(); st.count = 2; T_().push_back(tA[sA[i].first]); T_().push_back(tB[sB[i].first]); }
+            steps.push_back(st);
+        }
     }
     // inverts the N x N block at `off`; depth = log2(size of X / N) selects the W1 slot; `diag2`: the leading and the
     // trailing half are themselves block diagonal with blocks of N/4 (only the top level of X)
@@ -228,7 +266,7 @@ struct InvPlanner {
         const long long A = off, B = off + h, C = off + (long long)h * ld, D = off + (long long)h * ld + h;
         const long long W1 = w1_off[depth];
         const bool dg = diag2 && q % 8 == 0;
-        if (dg) { invert(A, q, depth + 2, false); invert(A + (long long)q * ld + q, q, depth + 2, false); }   // A <- diag(A11^-1, A22^-1)
+        if (dg) invert_pair(A, A + (long long)q * ld + q, q, depth + 2);                                      // A <- diag(A11^-1, A22^-1)
         else invert(A, h, depth + 1, false);                                                                  // A <- A^-1
         if (sym) {
             if (dg) {                                                                                     // W1 = A^-1 B
@@ -239,8 +277,8 @@ struct InvPlanner {
             invert(D, h, depth + 1, false);                                                               // D <- S^-1
             gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true);                  // B <- -W1 S^-1
             transpose(h, h, OP_XINV, B, ld, OP_XINV, C, ld);                                              // C <- B^T
-            transpose(h, h, OP_W1, W1, h, OP_W2, 0, h);                                                   // W2 = W1^T  (= C A^-1)
-            gemm(h, h, h, OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W2, 0, h, true);             // A <- A^-1 - B W2
+            transpose(h, h, OP_W1, W1, h, OP_W2, w2, h);                                                   // W2 = W1^T  (= C A^-1)
+            gemm(h, h, h, OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W2, w2, h, true);             // A <- A^-1 - B W2
             return;
         }
         if (dg) {                                                                                         // W1 = C A^-1
@@ -250,10 +288,10 @@ struct InvPlanner {
         gemm(h, h, h, OP_XINV, D, ld, OP_XINV, D, ld, OP_W1, W1, h, OP_XINV, B, ld, true);                // D <- D - W1 B   (Schur complement)
         invert(D, h, depth + 1, false);                                                                   // D <- S^-1
         if (dg) {                                                                                         // W2 = A^-1 B
-            gemm(q, h, q, OP_W2, 0, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
-            gemm(q, h, q, OP_W2, (long long)q * h, h, -1, 0, 0, OP_XINV, A + (long long)q * ld + q, ld, OP_XINV, B + (long long)q * ld, ld, false);
-        } else gemm(h, h, h, OP_W2, 0, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
-        gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W2, 0, h, OP_XINV, D, ld, true);                       // B <- -W2 S^-1
+            gemm(q, h, q, OP_W2, w2, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
+            gemm(q, h, q, OP_W2, w2 + (long long)q * h, h, -1, 0, 0, OP_XINV, A + (long long)q * ld + q, ld, OP_XINV, B + (long long)q * ld, ld, false);
+        } else gemm(h, h, h, OP_W2, w2, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
+        gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W2, w2, h, OP_XINV, D, ld, true);                       // B <- -W2 S^-1
         gemm(h, h, h, OP_XINV, C, ld, -1, 0, 0, OP_XINV, D, ld, OP_W1, W1, h, true);                      // C <- -S^-1 W1
         gemm(h, h, h, OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W1, W1, h, true);                // A <- A^-1 - B W1
     }
@@ -285,6 +323,11 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
     std::vector<long long> w1_off; long long acc = 0;
     for (int h = N / 2; h >= 8; h /= 2) { w1_off.push_back(acc); acc += (long long)h * h; }
     w1_off.push_back(acc); w1_off.push_back(acc); w1_off.push_back(acc);
+    // second set of W1 slots for depths >= 2 (the zipped sub-inversion of the second diagonal block of A); its W2 use
+    // ((N/8)^2 doubles) sits in the upper half of W2
+    std::vector<long long> w1b_off(w1_off.size(), acc);
+    for (size_t d = 2; d < w1_off.size(); d++) w1b_off[d] = acc + (w1_off[d] - w1_off[2]);
+    acc += acc - w1_off[2];
     const long long w1_total = acc, w2_total = (long long)(N / 2) * (N / 2);
     b.w2_off = (size_t)w1_total; b.w3_off = (size_t)(w1_total + w2_total);
     b.ws_per_entry = (size_t)(w1_total + 2 * w2_total);
@@ -294,6 +337,7 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
         const bool sym = variant == 1;
         std::vector<Step>& steps = sym ? b.steps_sym : b.steps;
         InvPlanner ip{b, steps, w1_off, N, rank, nranks, sym};
+        ip.w1b = &w1b_off; ip.w2b = w2_total / 2;
         ip.invert(0, N, 0, true);
         // S = X^-1 S_RHS, written with WESN-permuted columns (mergeS_ + reorderOperators_)
         int first = (int)b.blocks.size();
@@ -699,7 +743,7 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             if (is_T != (phase == 1) || (st.kind == 1 && st.count == 0)) continue;
             if (st.kind == 2) { run_transposes(st); continue; }
             timed(H, st.cls, 1, [&] {
-                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
+                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
                 else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
             });
             if (st.gk) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
@@ -926,7 +970,7 @@ int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric
         if (steps) for (size_t i = 0; i < st.size(); i++) {
             int64_t* r = steps + 16 * i; const Step& x = st[i];
             r[0] = x.kind; r[1] = x.first; r[2] = x.count; r[3] = x.off; r[4] = x.N; r[5] = x.cls; r[6] = x.gk; r[7] = x.g_op;
-            r[8] = x.g_rows; r[9] = x.g_cols; r[10] = x.g_ld; r[11] = x.g_off;
+            r[8] = x.g_rows; r[9] = x.g_cols; r[10] = x.g_ld; r[11] = x.g_off; r[12] = x.off2;
         }
         if (blocks && terms) for (size_t i = 0; i < b.blocks.size(); i++) {
             int64_t* r = blocks + 16 * i; const GemmBlock& g = b.blocks[i];

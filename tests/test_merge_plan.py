@@ -57,8 +57,9 @@ class RankState:
     def run_step(self, st, blocks, terms, trans, n):
         kind, first, count, off, N = (int(v) for v in st[:5])
         if kind == 0:
-            v = view(self.ops[OP_XINV], off, 4 * n, N, N)
-            v[...] = np.linalg.inv(v.copy())
+            for o in [off] + ([int(st[12])] if int(st[12]) >= 0 else []):    # a launch may invert two independent blocks
+                v = view(self.ops[OP_XINV], o, 4 * n, N, N)
+                v[...] = np.linalg.inv(v.copy())
         elif kind == 1:
             results = []   # one launch: every block reads the state before the launch
             for k in range(first, first + count):
@@ -171,6 +172,24 @@ def test_plan_reproduces_oracle_merge_uniform(sym, nranks, depth):
         n3 = float(n) ** 3
         if nranks == 1:                      # (small replicated products are issued by every rank of a partition)
             assert flops < 400 * n3 if sym else flops <= 484 * n3   # symmetric plan: well below the general 484 n^3
+
+
+@pytest.mark.parametrize("sym", [0, 1])
+def test_zipped_diagonal_subinversions(sym):
+    """n = 256: X is 1024 x 1024, the two 256 x 256 diagonal blocks of its leading block recurse (products inside), and
+    their step lists are zipped into launches that carry both blocks (second branch on its own workspace slots)."""
+    if 4 not in _CHILDREN:
+        _CHILDREN[4] = uniform_children(16, 4)
+    Tc, root = _CHILDREN[4]
+    n = 256
+    steps, blocks, terms, trans, ws = get_plan(n, 0, 0, 1, sym)
+    assert sum(1 for st in steps if int(st[0]) == 0 and int(st[12]) >= 0) == 2        # two paired base-case launches
+    assert any(int(st[0]) == 1 and int(st[2]) == 2 and int(st[5]) == 4 for st in steps)  # paired products of the inversion
+    states, flops = emulate(n, 0, 1, sym, Tc, root.X)
+    s = states[0]
+    assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(root.X)) < 1e-11
+    assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
+    assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
 
 
 def test_general_plan_on_nonsymmetric_children():
