@@ -35,6 +35,7 @@ SIGNATURES = {
     "efgpu_create_ex": (C.c_int, [C.POINTER(TreeDesc), C.c_int, C.POINTER(C.c_int32), C.POINTER(_P)]),
     "efgpu_set_partition": (C.c_int, [_P, C.c_int, C.c_int]),
     "efgpu_set_allgather": (C.c_int, [_P, ALLGATHER_FN, _P]),
+    "efgpu_complete_root_dtn": (C.c_int, [_P]),
     "efgpu_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "efgpu_set_symmetric_leaves": (C.c_int, [_P, C.c_int]),
     "efgpu_is_symmetric": (C.c_int, [_P]),

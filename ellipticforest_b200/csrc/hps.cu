@@ -107,6 +107,7 @@ struct efgpu_handle {
     std::vector<int> roots;                      // nodes without a parent (one for a tree; several for a forest of subtrees)
     bool external_leaves = false;                // leaf T / h are supplied by the caller (upper tree of a sharded run)
     int part_rank = 0, part_nranks = 1;          // row partition of S / T among the ranks that replicate this tree
+    bool root_T_distributed = false;             // partitioned tree after a build: the roots' T rows are not gathered / mirrored yet
     efgpu_allgather_fn allgather = nullptr; void* allgather_user = nullptr;   // collective supplied by the caller (NCCL)
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
     // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
@@ -331,8 +332,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
     const long long w1_total = acc, w2_total = (long long)(N / 2) * (N / 2);
     b.w2_off = (size_t)w1_total; b.w3_off = (size_t)(w1_total + w2_total);
     b.ws_per_entry = (size_t)(w1_total + 2 * w2_total);
-    // the root's DtN map of a partitioned tree stays row-distributed (no gather), so it cannot be completed by mirroring
-    const bool mirror_ok = !(nranks > 1 && b.level == 0);
+    // (the root's DtN map of a partitioned tree stays row-distributed: its mirrored blocks are completed on demand,
+    // efgpu_complete_root_dtn, so that the root merge also issues 36 instead of 64 block products)
+    const bool mirror_ok = true;
     for (int variant = 0; variant < (b.symcand ? 2 : 1); variant++) {
         const bool sym = variant == 1;
         std::vector<Step>& steps = sym ? b.steps_sym : b.steps;
@@ -709,7 +711,7 @@ static void build_begin(efgpu_handle* H, unsigned flags)
     const double big = 1e300;
     EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
     EF_CUDA(cudaEventRecord(H->ev0, s));
-    H->built = false;
+    H->built = false; H->root_T_distributed = false;
     timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, flags); });
 }
 
@@ -767,9 +769,34 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                 if (phase == 0) gather(ops[OP_S], 32 * n2); else gather(ops[OP_T], 64 * n2);
             }
         });
-        if (phase == 1)
-            for (const Step& st : b.active()) if (st.cls == EFGPU_PROF_MIRROR_T) run_transposes(st);
+        if (phase == 1) {
+            if (H->part_nranks > 1 && lev == 0) H->root_T_distributed = true;   // completed by complete_root_T when somebody needs it
+            else for (const Step& st : b.active()) if (st.cls == EFGPU_PROF_MIRROR_T) run_transposes(st);
+        }
     }
+}
+
+// Partitioned tree: the root's DtN map is only needed by the Robin solve and by parity readers, so its row slices stay
+// where they were computed until this (collective) call gathers them and mirrors the blocks of the symmetric plan.
+static void complete_root_T(efgpu_handle* H)
+{
+    if (!H->root_T_distributed) return;
+    if (!H->allgather) throw Error{EF_ERR_STATE, "row-partitioned tree without an all-gather callback (efgpu_set_allgather)"};
+    cudaStream_t s = H->stream;
+    for (int bi : H->level_batches[0]) {
+        BatchH& b = H->batches[bi];
+        const size_t n2 = (size_t)b.n * b.n;
+        for (int sl = 0; sl < b.count; sl++) {
+            double* T = b.h_ptab[(size_t)sl * NOPS + OP_T];
+            if (H->allgather(T, 64 * n2 / H->part_nranks * sizeof(double), H->allgather_user) != 0)
+                throw Error{EF_ERR_STATE, "the all-gather callback failed"};
+        }
+        for (const Step& st : b.active())
+            if (st.cls == EFGPU_PROF_MIRROR_T)
+                launch_btranspose(b.d_ptab.as<double*>(), NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, b.count, s);
+    }
+    EF_CUDA(cudaStreamSynchronize(s));
+    H->root_T_distributed = false;
 }
 
 static void build_end(efgpu_handle* H)
@@ -860,6 +887,8 @@ static thread_local std::string g_create_error;
 static void require_T_retained(const efgpu_handle* H, int node)
 {
     const efgpu::NodeH& nd = H->nodes[node];
+    if (H->root_T_distributed && nd.parent < 0 && !nd.leaf)
+        throw efgpu::Error{EF_ERR_STATE, "the root's DtN map of a partitioned tree is row-distributed: call efgpu_complete_root_dtn on every rank first"};
     if (H->lean_T && !nd.leaf && nd.parent >= 0)
         throw efgpu::Error{EF_ERR_STATE, "the DtN map of an interior node is not retained under EFGPU_LEAN_T"};
 }
@@ -1041,6 +1070,15 @@ int efgpu_build_end(efgpu_handle* H)
     EF_CATCH(H)
 }
 
+int efgpu_complete_root_dtn(efgpu_handle* H)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    efgpu::complete_root_T(H);
+    EF_CATCH(H)
+}
+
 int efgpu_max_level(const efgpu_handle* H) { return H ? H->max_level : -1; }
 
 int efgpu_upwards(efgpu_handle* H, const double* f_leaves, double fscale, unsigned flags)
@@ -1197,6 +1235,7 @@ int efgpu_solve_robin(efgpu_handle* H, const double* a, const double* b, const d
     const bool homogeneous = (flags & EFGPU_HOMOGENEOUS_RHS) != 0;
     if (!homogeneous && !H->upwards_done) throw Error{EF_ERR_STATE, "solve before upwards (non-homogeneous right-hand side)"};
     if (H->nodes[0].leaf && H->external_leaves) throw Error{EF_ERR_STATE, "no root operator"};
+    if (H->root_T_distributed) throw Error{EF_ERR_STATE, "the root's DtN map of a partitioned tree is row-distributed: call efgpu_complete_root_dtn on every rank first"};
     cudaStream_t s = H->stream;
     H->d_robin.alloc((robin_workspace_doubles(len) + 4 * (size_t)len) * sizeof(double));
     double* abr = H->d_robin.as<double>();

@@ -176,6 +176,10 @@ class GpuEngine:
             self._ag_cb = _lib.ALLGATHER_FN(_cb)      # keep the trampoline alive as long as the handle
             check(self._lib.efgpu_set_allgather(self._h, self._ag_cb, None), self._h)
 
+    def complete_root_T(self):
+        """Collective: gather the row slices of the root's DtN map and mirror the blocks of the symmetric plan."""
+        check(self._lib.efgpu_complete_root_dtn(self._h), self._h)
+
     def build_begin(self, flags):
         check(self._lib.efgpu_build_begin(self._h, flags), self._h)
 
@@ -422,12 +426,9 @@ class ShardedHPS:
 
     def gather_root_T(self):
         """Parity/debug: the root DtN map assembled from its row slices (every rank gets the whole matrix)."""
-        T = self.top.operator_view(0, "T_uncoarsened")
         if self.top_mode == "replicated":
-            with self.torch.cuda.stream(self._stream):
-                self.xchg.allgather_rows(T)
-            self.local.sync()
-        return T
+            self.top.complete_root_T()
+        return self.top.operator_view(0, "T_uncoarsened")
 
     def upwardsStageDevice(self, f_dev_ptr, scale=1.0, sync=True):
         fl = self._flags()

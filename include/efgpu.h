@@ -115,6 +115,11 @@ const char* efgpu_last_error(const efgpu_handle* h);   /* h may be NULL after a 
  * efgpu_build == begin; for each level: phase 0, phase 1; end.  Replaces the redundant whole-merge recomputation
  * on every sharing rank in the reference (Quadtree.hpp:504-506). */
 int efgpu_set_partition(efgpu_handle* h, int rank, int nranks);
+/* After a build the root's DtN map of a partitioned tree is left row-distributed (nothing on the Dirichlet path reads it; the
+ * reference's merge computes it all the same, HPSAlgorithm.hpp:940-968).  This COLLECTIVE call (every rank of the partition)
+ * gathers the row slices and completes the mirrored blocks of the symmetric plan; it is required before efgpu_solve_robin,
+ * efgpu_get_operator / efgpu_operator_device of the root's T.  No-op on unpartitioned handles and when already complete. */
+int efgpu_complete_root_dtn(efgpu_handle* h);
 /* With a collective supplied by the caller the library performs every exchange of a partitioned tree itself, inside
  * efgpu_build / efgpu_build_level: the large products of the block inversion of X are split by rows as well (each rank
  * computes h / nranks rows of every h x h product, h >= 128 * nranks), and S / T row slices are gathered after their
