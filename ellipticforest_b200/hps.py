@@ -80,7 +80,10 @@ class Mesh:
 
     def __del__(self):
         if getattr(self, "_m", None):
-            _lib.load().efgpu_mesh_destroy(self._m)
+            try:
+                _lib.load().efgpu_mesh_destroy(self._m)
+            except TypeError:      # interpreter shutdown: the module globals are already gone, the process frees the mesh
+                pass
             self._m = None
 
     def refineByFunction(self, fn: Optional[Callable[[float, float], bool]], threshold, min_level, max_level,

@@ -23,6 +23,16 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
+def test_builtin_refine_indicator_matches_the_callback():
+    """efgpu_refine_elliptic_single (used for large adaptive meshes built from Python) = the per-point callback."""
+    g = ef.FiniteVolumeGrid(16, -10.0, 10.0, 16, -10.0, 10.0)
+    for thr, lo, hi in [(1.2, 0, 5), (1.6, 2, 5)]:
+        a = ef.Mesh().refineByFunction("elliptic-single", thr, lo, hi, g)
+        b = ef.Mesh().refineByFunction(lambda x, y: abs(-(np.sin(x) + np.sin(y))) > thr, thr, lo, hi, g)
+        assert np.array_equal(a.level, b.level) and np.array_equal(a.child, b.child) and np.array_equal(a.box, b.box)
+        assert np.array_equal(a.leaf_nodes, b.leaf_nodes)
+
+
 def _mesh_for(kw):
     ind = O.refine_box_indicator(kw["refine_box"]) if kw["refine_box"] is not None else O.refine_indicator(kw["threshold"])
     g = ef.FiniteVolumeGrid(kw["nx"], kw["box"][0], kw["box"][1], kw["nx"], kw["box"][2], kw["box"][3])

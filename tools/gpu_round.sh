@@ -13,7 +13,7 @@ if [ "$2" != "noncu" ]; then
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --profile-run --steps 1 --warmup 0 > $OUT/ncu_list_$TAG.log 2>&1
 python tools/pick_launch.py $OUT/launches_$TAG.csv --summary > $OUT/launch_summary_$TAG.md; cat $OUT/launch_summary_$TAG.md
-for K in ${KERNELS:-bgemm_kernel solve_split_short_kernel upwards_h_short_kernel upwards_w_short_kernel invert_reg_kernel leaf_solve_const_tiled_kernel}; do
+for K in ${KERNELS:-bgemm_kernel rb_upwards_w_kernel rb_upwards_h_kernel rb_solve_split_kernel solve_split_kernel leaf_solve_const_mma_kernel invert_reg_kernel assemble_X_kernel}; do
   IDX=$(python tools/pick_launch.py $OUT/launches_$TAG.csv $K)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s $IDX -c 1 -f -o $OUT/prof_${K}_$TAG \
       python bench.py --profile-run --steps 1 --warmup 0 > $OUT/ncu_full_${K}_$TAG.log 2>&1
