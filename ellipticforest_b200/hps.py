@@ -17,6 +17,7 @@ reference's host code does (src/HPSAlgorithm.hpp:241-249, :375-400).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -175,6 +176,7 @@ class HPSAlgorithm:
         # the host once per buildStage.  False keeps the coefficient arrays already resident in HBM (same functions).
         self.resample_coefficients = True
         self._coefficients_set = False
+        self.sampling_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         self._lib = _lib.load()
         self._h = C.c_void_p()
         check(self._lib.efgpu_create(C.byref(mesh.desc), device, C.byref(self._h)))
@@ -213,16 +215,34 @@ class HPSAlgorithm:
         self.isBuilt = True
 
     def _set_variable_coefficients(self):
-        """Sample alpha, beta, lambda where FiniteVolumeSolver.cpp:63-79 samples them."""
+        """Sample alpha, beta, lambda where FiniteVolumeSolver.cpp:63-79 samples them (alpha, lambda at the cell centres,
+        beta at the four face midpoints).  The callbacks are vectorised numpy functions; blocks of leaves are evaluated on
+        `sampling_threads` host threads (numpy releases the GIL inside its kernels) - set it to 1 for callbacks that are not
+        thread-safe.  The reference calls them point by point, serially, inside every leaf solve."""
         s, m = self.patch_solver, self.mesh
         X, Y = m.leaf_cell_centres()
         b = m.box[m.leaf_nodes]
         dx = ((b[:, 1] - b[:, 0]) / m.nx)[:, None, None]
         dy = ((b[:, 3] - b[:, 2]) / m.nx)[:, None, None]
-        arrs = [s.alpha_function(X, Y), s.beta_function(X - dx / 2.0, Y), s.beta_function(X + dx / 2.0, Y),
-                s.beta_function(X, Y - dy / 2.0), s.beta_function(X, Y + dy / 2.0), s.lambda_function(X, Y)]
-        arrs = [np.ascontiguousarray(np.broadcast_to(a, X.shape), dtype=np.float64) for a in arrs]
-        check(self._lib.efgpu_set_leaf_variable(self._h, *[a.ctypes.data for a in arrs]), self._h)
+        out = [np.empty(X.shape, dtype=np.float64) for _ in range(6)]
+
+        def block(lo, hi):
+            x, y, hx, hy = X[lo:hi], Y[lo:hi], dx[lo:hi] / 2.0, dy[lo:hi] / 2.0
+            vals = (s.alpha_function(x, y), s.beta_function(x - hx, y), s.beta_function(x + hx, y),
+                    s.beta_function(x, y - hy), s.beta_function(x, y + hy), s.lambda_function(x, y))
+            for o, v in zip(out, vals):
+                o[lo:hi] = v          # broadcasts scalar / lower-dimensional results
+
+        nl = m.n_leaves
+        nthreads = max(1, min(int(self.sampling_threads), nl))
+        if nthreads == 1:
+            block(0, nl)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            step = max(1, -(-nl // (4 * nthreads)))
+            with ThreadPoolExecutor(max_workers=nthreads) as ex:
+                list(ex.map(lambda lo: block(lo, min(nl, lo + step)), range(0, nl, step)))
+        check(self._lib.efgpu_set_leaf_variable(self._h, *[a.ctypes.data for a in out]), self._h)
 
     def upwardsStage(self, rhs, scale: float = 1.0):
         """HPSAlgorithm.hpp:178-272.  `rhs` is f(x, y) (sampled at leaf cell centres) or a ready
