@@ -462,7 +462,7 @@ def own_arm(a):
         "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)%s" % (" on rank 0" if world > 1 else ""),
                      "achieved": gemm_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": (gemm_tf / dgemm_tf) if (gemm_tf and dgemm_tf) else None,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure; NVIDIA nominal FP64 tensor 37-40 TFLOP/s)",
-                     "flops": "issued to the tensor pipe (symmetric plan: ~345 n^3 per merge, general plan 484 n^3; the reference's dgesv+dgemm count is 810.67 n^3)",
+                     "flops": "issued to the tensor pipe (symmetric plan: ~327 n^3 per merge, general plan 484 n^3; the reference's dgesv+dgemm count is 810.67 n^3)",
                      "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                      "timing": "CUDA events around every launch on the library's stream, over a second pass of the same %d steps (%.2f ms per step with "
                                "the events, %.2f without)" % (a.steps, 1e3 * prof_dev_s / a.steps, ms_per_step),

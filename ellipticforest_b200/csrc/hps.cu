@@ -226,6 +226,30 @@ struct InvPlanner {
         T_().push_back(TransOp{s_op, d_op, lds, ldd, s_off, d_off, rows, cols, 0u, 0});
         steps.push_back(st);
     }
+    // C = C0 - A B with a SYMMETRIC h x h result (Schur complement and the update of the leading block of a symmetric X):
+    // only the upper triangle of a 2 x 2 or 4 x 4 block partition is multiplied (3 of 4 / 10 of 16 sub-blocks, one
+    // launch), the lower blocks are transposes.  Row-partitioned products keep the plain form (their slices are gathered).
+    void gemm_sym(int h, int K, int c_op, long long c_off, int ldc, int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb) {
+        static const int split_min = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 2048; }();
+        const bool row_split = nranks > 1 && h % (128 * nranks) == 0 && h >= split_min;
+        const int nb = row_split ? 1 : ((h % 64 == 0 && h / 4 >= 128) ? 4 : ((h % 32 == 0 && h / 2 >= 128) ? 2 : 1));
+        if (nb == 1) { gemm(h, h, K, c_op, c_off, ldc, c_op, c_off, ldc, a_op, a_off, lda, b_op, b_off, ldb, true); return; }
+        const int sb = h / nb;
+        Step st{}; st.kind = 1; st.first = (int)B_().size(); st.cls = EFGPU_PROF_GEMM_XINV;
+        Step tr{}; tr.kind = 2; tr.first = (int)T_().size(); tr.cls = EFGPU_PROF_TRANSPOSE;
+        for (int I = 0; I < nb; I++)
+            for (int J = I; J < nb; J++) {
+                GemmBlock g{};
+                const long long cij = c_off + (long long)I * sb * ldc + (long long)J * sb;
+                g.c_op = c_op; g.c_off = cij; g.ldc = ldc; g.c0_op = c_op; g.c0_off = cij; g.ldc0 = ldc;
+                g.rows = sb; g.cols = sb; g.nterms = 1;
+                g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off + (long long)I * sb * lda, b_off + (long long)J * sb, K, 0x80000000u};
+                B_().push_back(g); st.count++;
+                if (J > I) { T_().push_back(TransOp{c_op, c_op, ldc, ldc, cij, c_off + (long long)J * sb * ldc + (long long)I * sb, sb, sb, 0u, 0}); tr.count++; }
+            }
+        steps.push_back(st);
+        steps.push_back(tr);
+    }
     // appends the steps of a sub-plan (descriptor indices rebased)
     void append(const std::vector<Step>& ss, const std::vector<GemmBlock>& bb, const std::vector<TransOp>& tt) {
         for (Step st : ss) {
@@ -244,13 +268,20 @@ struct InvPlanner {
         pb.invert(offB, q, depth, false);
         bool zip = sA.size() == sB.size();
         for (size_t i = 0; zip && i < sA.size(); i++)
-            zip = sA[i].kind == sB[i].kind && sA[i].count == sB[i].count && sA[i].count <= 1 && !sA[i].gk && !sB[i].gk && sA[i].N == sB[i].N;
+            zip = sA[i].kind == sB[i].kind && sA[i].count == sB[i].count && !sA[i].gk && !sB[i].gk && sA[i].N == sB[i].N;
         if (!zip) { append(sA, bA, tA); append(sB, bB, tB); return; }
         for (size_t i = 0; i < sA.size(); i++) {
             Step st = sA[i];
             if (st.kind == 0) st.off2 = sB[i].off;
-            else if (st.kind == 1) { st.first = (int)B_().size(); st.count = 2; B_().push_back(bA[sA[i].first]); B_().push_back(bB[sB[i].first]); }
-            else { st.first = (int)T_().size(); st.count = 2; T_().push_back(tA[sA[i].first]); T_().push_back(tB[sB[i].first]); }
+            else if (st.kind == 1) {
+                st.first = (int)B_().size(); st.count = 2 * sA[i].count;
+                for (int k = 0; k < sA[i].count; k++) B_().push_back(bA[sA[i].first + k]);
+                for (int k = 0; k < sB[i].count; k++) B_().push_back(bB[sB[i].first + k]);
+            } else {
+                st.first = (int)T_().size(); st.count = 2 * sA[i].count;
+                for (int k = 0; k < sA[i].count; k++) T_().push_back(tA[sA[i].first + k]);
+                for (int k = 0; k < sB[i].count; k++) T_().push_back(tB[sB[i].first + k]);
+            }
             steps.push_back(st);
         }
     }
@@ -274,12 +305,12 @@ struct InvPlanner {
                 gemm(q, h, q, OP_W1, W1, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
                 gemm(q, h, q, OP_W1, W1 + (long long)q * h, h, -1, 0, 0, OP_XINV, A + (long long)q * ld + q, ld, OP_XINV, B + (long long)q * ld, ld, false);
             } else gemm(h, h, h, OP_W1, W1, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
-            gemm(h, h, h, OP_XINV, D, ld, OP_XINV, D, ld, OP_XINV, C, ld, OP_W1, W1, h, true);            // D <- D - C W1   (Schur complement)
+            gemm_sym(h, h, OP_XINV, D, ld, OP_XINV, C, ld, OP_W1, W1, h);                                 // D <- D - C W1   (Schur complement, symmetric)
             invert(D, h, depth + 1, false);                                                               // D <- S^-1
             gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true);                  // B <- -W1 S^-1
             transpose(h, h, OP_XINV, B, ld, OP_XINV, C, ld);                                              // C <- B^T
             transpose(h, h, OP_W1, W1, h, OP_W2, w2, h);                                                   // W2 = W1^T  (= C A^-1)
-            gemm(h, h, h, OP_XINV, A, ld, OP_XINV, A, ld, OP_XINV, B, ld, OP_W2, w2, h, true);             // A <- A^-1 - B W2
+            gemm_sym(h, h, OP_XINV, A, ld, OP_XINV, B, ld, OP_W2, w2, h);                                  // A <- A^-1 - B W2 (symmetric)
             return;
         }
         if (dg) {                                                                                         // W1 = C A^-1
