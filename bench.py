@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--lean-T", action="store_true", help="EFGPU_LEAN_T memory policy (single GPU): interior DtN maps in a transient arena")
     ap.add_argument("--n-solves", type=int, default=0, help="BASELINE configs[2] pattern: after the timed steps, K x (upwards + solve) on the "
                     "resident operators with f and the boundary data scaled by (1 + k/K); reported as `repeat_solves`")
+    ap.add_argument("--tuning", action="append", default=[], metavar="KEY=VALUE",
+                    help="efgpu_set_tuning knob for A/B runs (include/efgpu.h), e.g. --tuning 5=1; recorded in config.tuning")
     ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6 own arm, 5 reference arm)")
     return ap.parse_args()
 
@@ -210,6 +212,11 @@ def own_arm(a):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout for the one JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    for kv in a.tuning:
+        k, v = kv.split("=")
+        if ef.load().efgpu_set_tuning(int(k), int(v)) != 0:
+            raise SystemExit("bad --tuning %s" % kv)
 
     # ---- workload (untimed set-up: mesh, plan, host sampling of f and the boundary data) ----
     if a.adaptive:
@@ -446,7 +453,7 @@ def own_arm(a):
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "mesh": mesh_stats, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
-                   "sharding": hps.sharding(),
+                   "sharding": hps.sharding(), "tuning": a.tuning,
                    "merge_plan": "general (EFGPU_NO_SYMMETRY)" if a.no_symmetry else "symmetric where the subtree is uniform with constant-coefficient leaves%s" % (
                        "" if (a.adaptive or a.problem == "varcoef") else " (every merge of this workload)")},
         "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,

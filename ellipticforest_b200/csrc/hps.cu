@@ -409,17 +409,28 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
                         continue;
                     }
                 }
-                GemmBlock g{};
-                g.c_op = OP_T; g.c_off = (long long)(P * n) * (8 * n) + Q * n; g.ldc = 8 * n;
-                if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n) * N + side_c * n; g.ldc0 = N; }
-                else g.c0_op = -1;
-                g.rows = n; g.cols = n; g.nterms = 2;
-                for (int t = 0; t < 2; t++) {
-                    const int k = h_kk[c][t];
-                    g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n) * N + h_iface[c][k] * n,
-                                      (long long)(k * n) * (8 * n) + Q * n, n, 0u};
-                }
-                if (clip_rows(g, (long long)P * n, t_lo, t_hi)) b.blocks.push_back(g);
+                // a diagonal block of the signed-symmetric T is itself symmetric: optionally (efgpu_set_tuning key 5; off by
+                // default until measured on the GPU) only the upper triangle of its 2 x 2 / 4 x 4 sub-blocks is multiplied
+                const int nb = (sym && mirror_ok && P == Q && get_tuning(5) == 1)
+                                   ? ((n % 64 == 0 && n / 4 >= 128) ? 4 : ((n % 32 == 0 && n / 2 >= 128) ? 2 : 1)) : 1;
+                const int sb = n / nb;
+                for (int I = 0; I < nb; I++)
+                    for (int J = I; J < nb; J++) {
+                        GemmBlock g{};
+                        g.c_op = OP_T; g.c_off = (long long)(P * n + I * sb) * (8 * n) + Q * n + J * sb; g.ldc = 8 * n;
+                        if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n + I * sb) * N + side_c * n + J * sb; g.ldc0 = N; }
+                        else g.c0_op = -1;
+                        g.rows = sb; g.cols = sb; g.nterms = 2;
+                        for (int t = 0; t < 2; t++) {
+                            const int k = h_kk[c][t];
+                            g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n + I * sb) * N + h_iface[c][k] * n,
+                                              (long long)(k * n) * (8 * n) + Q * n + J * sb, n, 0u};
+                        }
+                        if (clip_rows(g, (long long)P * n + I * sb, t_lo, t_hi)) b.blocks.push_back(g);
+                        if (J > I)
+                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(P * n + I * sb) * (8 * n) + Q * n + J * sb,
+                                                      (long long)(P * n + J * sb) * (8 * n) + Q * n + I * sb, sb, sb, 0u, 0});
+                    }
             }
         { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_T; steps.push_back(st); }
         if ((int)b.trans.size() > tfirst) {   // runs after the row slices of T have been gathered

@@ -214,7 +214,9 @@ int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric
  * for rows of <= 256 doubles (2, default: row-batch kernels; 0: one row per warp, as for longer rows); key 1 = long-row
  * kernel of the compact H (0, default: 8 loads in flight per lane; 1: 4); key 2 = CTAs per SM the long-row launcher aims
  * for (0: default 16); key 3 = leaf solve of constant-coefficient leaves (0, default: FP64 tensor-core kernel, one warp per
- * leaf; 1: one thread per cell).  Results do not depend on the knobs beyond floating-point summation order. */
+ * leaf; 1: one thread per cell); key 5 = symmetric merge plan, diagonal blocks of T: 1 = multiply only the upper triangle of
+ * their 2 x 2 / 4 x 4 sub-blocks and mirror the rest (0, default: whole blocks; read when a handle is created / partitioned).
+ * Results do not depend on the knobs beyond floating-point summation order. */
 int efgpu_set_tuning(int key, int value);
 
 /* ---- stand-alone access to the GEMM kernel for unit tests and roofline measurements ------------ */

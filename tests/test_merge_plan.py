@@ -188,6 +188,30 @@ def test_zipped_diagonal_subinversions(sym):
     assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
 
 
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_symmetric_diagonal_blocks_of_T(nranks):
+    """Tuning key 5: the eight diagonal n x n blocks of the signed-symmetric T are symmetric themselves; with the knob on they
+    are multiplied as upper-triangular sub-blocks (n = 256: 2 x 2 of 128) and completed by transposes in the mirror step."""
+    from ellipticforest_b200 import _lib
+    lib = _lib.load()
+    if 4 not in _CHILDREN:
+        _CHILDREN[4] = uniform_children(16, 4)
+    Tc, root = _CHILDREN[4]
+    n = 256
+    base = get_plan(n, 1, 0, nranks, 1)
+    assert lib.efgpu_set_tuning(5, 1) == 0
+    try:
+        split = get_plan(n, 1, 0, nranks, 1)
+        assert len(split[3]) == len(base[3]) + 8             # one mirrored sub-block per diagonal block
+        for level in ((0, 1) if nranks > 1 else (0,)):
+            states, flops = emulate(n, level, nranks, 1, Tc, root.X)
+            for s in states:
+                assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
+                assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
+    finally:
+        lib.efgpu_set_tuning(5, 0)
+
+
 def test_general_plan_on_nonsymmetric_children():
     rng = np.random.default_rng(0)
     n = 40                                       # N = 160: h = 80, q = 40; odd sizes for the transposes / tiles
