@@ -48,6 +48,11 @@ SIGNATURES = {
     "efgpu_last_error": (C.c_char_p, [_P]),
     "efgpu_set_leaf_constant": (C.c_int, [_P, C.c_double]),
     "efgpu_set_leaf_variable": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "efgpu_set_leaf_variable_device": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "efgpu_leaf_points_device": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
+    "efgpu_leaf_points": (C.c_int, [_P, C.c_int, _P, _P]),
+    "efgpu_error_norms_device": (C.c_int, [_P, _P, _P, _D, _D, _D]),
+    "efgpu_error_norms": (C.c_int, [_P, _P, _D, _D, _D]),
     "efgpu_build": (C.c_int, [_P, C.c_uint]),
     "efgpu_upwards": (C.c_int, [_P, _P, C.c_double, C.c_uint]),
     "efgpu_upwards_device": (C.c_int, [_P, _P, C.c_double, C.c_uint, C.c_int]),

@@ -126,6 +126,8 @@ struct efgpu_handle {
     DevBuf d_Tarena[2];                          // EFGPU_LEAN_T: DtN maps of even / odd tree levels (a level's maps die when its parents are merged)
     bool lean_T = false;
     DevBuf d_robin;                              // workspace of the root boundary solve (efgpu_solve_robin)
+    DevBuf d_pts, d_err;                         // staging of efgpu_leaf_points / efgpu_error_norms (sample.cu)
+    bool solve_done = false;                     // d_u holds the solution of a solve stage
     DevBuf d_coef_in[6], d_coef, d_P;            // variable-coefficient leaves: sampled alpha/beta/lambda, stencil coefficients, block-LU inverses
     size_t vec_doubles = 0;
     bool allocated = false, built = false, upwards_done = false;
@@ -909,6 +911,7 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
             launch_leaf_solve_const(H->M, H->d_Q.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->lambda,
                                     homogeneous ? nullptr : f_dev, fscale, H->d_leaf_g.as<double*>(), H->d_u.as<double>(), nullptr, 0, H->n_leaves, s);
     });
+    H->solve_done = !H->external_leaves;
 }
 
 }  // namespace efgpu
@@ -997,6 +1000,24 @@ int efgpu_set_leaf_variable(efgpu_handle* H, const double* alpha, const double* 
         EF_CUDA(cudaMemcpyAsync(H->d_coef_in[k].p, src[k], bytes, cudaMemcpyHostToDevice, H->stream));
     }
     EF_CUDA(cudaStreamSynchronize(H->stream));
+    H->leaf_kind = EFGPU_LEAF_VARIABLE; H->built = false;
+    EF_CATCH(H)
+}
+
+int efgpu_set_leaf_variable_device(efgpu_handle* H, const double* alpha, const double* beta_w, const double* beta_e, const double* beta_s,
+                                   const double* beta_n, const double* lambda)
+{
+    if (!H || !alpha || !beta_w || !beta_e || !beta_s || !beta_n || !lambda) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    if (H->external_leaves) throw Error{EF_ERR_STATE, "external leaves have no coefficients"};
+    EF_CUDA(cudaSetDevice(H->device));
+    const double* src[6] = {alpha, beta_w, beta_e, beta_s, beta_n, lambda};
+    const size_t bytes = (size_t)H->n_leaves * H->M * H->M * sizeof(double);
+    for (int k = 0; k < 6; k++) {
+        H->d_coef_in[k].alloc(bytes);
+        EF_CUDA(cudaMemcpyAsync(H->d_coef_in[k].p, src[k], bytes, cudaMemcpyDeviceToDevice, H->stream));
+    }
+    EF_CUDA(cudaStreamSynchronize(H->stream));   // the caller's arrays are borrowed for the call only
     H->leaf_kind = EFGPU_LEAF_VARIABLE; H->built = false;
     EF_CATCH(H)
 }
@@ -1297,6 +1318,92 @@ int efgpu_solve_robin(efgpu_handle* H, const double* a, const double* b, const d
     EF_CUDA(cudaStreamSynchronize(s)); collect_profile(H);
     float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1)); H->stats.solve_ms = ms;
     if (info != 0) throw Error{EF_ERR_SINGULAR, "root boundary system is singular (zero pivot at column " + std::to_string(info) + ")"};
+    EF_CATCH(H)
+}
+
+// ---- sampling coordinates and error norms on the device (sample.cu) ----------
+static void points_tables(efgpu_handle* H)
+{
+    if (H->external_leaves) throw Error{EF_ERR_STATE, "external leaves have no cells"};
+    EF_CUDA(cudaSetDevice(H->device));
+    if (H->d_boxes.p && H->d_leaf_nodes.p) return;
+    // before the first build only the two small tables are needed (allocate_device uploads the same contents again)
+    std::vector<double> boxes((size_t)4 * H->n_nodes);
+    for (int i = 0; i < H->n_nodes; i++) std::memcpy(&boxes[4 * (size_t)i], H->nodes[i].box, 4 * sizeof(double));
+    H->d_boxes.upload(boxes, H->stream);
+    H->d_leaf_nodes.upload(H->leaf_nodes, H->stream);
+    EF_CUDA(cudaStreamSynchronize(H->stream));   // the host vectors go out of scope
+}
+
+int efgpu_leaf_points_device(efgpu_handle* H, int which, double* x_dev, double* y_dev, int sync)
+{
+    if (!H || which < 0 || which > 4 || (!x_dev && !y_dev)) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    points_tables(H);
+    launch_leaf_points(H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->M, which, x_dev, y_dev, H->n_leaves, H->stream);
+    EF_CUDA(cudaGetLastError());
+    if (sync) EF_CUDA(cudaStreamSynchronize(H->stream));
+    EF_CATCH(H)
+}
+
+int efgpu_leaf_points(efgpu_handle* H, int which, double* x, double* y)
+{
+    if (!H || which < 0 || which > 4 || (!x && !y)) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    points_tables(H);
+    const size_t cells = (size_t)H->n_leaves * H->M * H->M;
+    H->d_pts.alloc(2 * cells * sizeof(double));
+    double* dx = H->d_pts.as<double>();
+    double* dy = dx + cells;
+    launch_leaf_points(H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->M, which, x ? dx : nullptr, y ? dy : nullptr, H->n_leaves, H->stream);
+    EF_CUDA(cudaGetLastError());
+    if (x) EF_CUDA(cudaMemcpyAsync(x, dx, cells * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+    if (y) EF_CUDA(cudaMemcpyAsync(y, dy, cells * sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    H->d_pts.release();   // 16 B per cell: not kept between calls
+    EF_CATCH(H)
+}
+
+static void error_norms(efgpu_handle* H, const double* u_dev, const double* exact_dev, double* l1, double* l2, double* linf)
+{
+    if (!u_dev) {
+        if (!H->solve_done) throw Error{EF_ERR_STATE, "error norms of the handle's solution before a solve stage"};
+        u_dev = H->d_u.as<double>();
+    }
+    double area = 0.0;   // (x_upper - x_lower) * (y_upper - y_lower) of the domain (main.cpp:368); a forest: sum over its roots
+    for (int r : H->roots) area += (H->nodes[r].box[1] - H->nodes[r].box[0]) * (H->nodes[r].box[3] - H->nodes[r].box[2]);
+    H->d_err.alloc((3 * (size_t)H->n_leaves + 3) * sizeof(double));
+    double* part = H->d_err.as<double>();
+    double* out = part + 3 * (size_t)H->n_leaves;
+    launch_error_norms(u_dev, exact_dev, H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->M, H->n_leaves, area, part, out, H->stream);
+    EF_CUDA(cudaGetLastError());
+    double res[3];
+    EF_CUDA(cudaMemcpyAsync(res, out, sizeof(res), cudaMemcpyDeviceToHost, H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    if (l1) *l1 = res[0];
+    if (l2) *l2 = res[1];
+    if (linf) *linf = res[2];
+}
+
+int efgpu_error_norms_device(efgpu_handle* H, const double* u_dev, const double* exact_dev, double* l1, double* l2, double* linf)
+{
+    if (!H || !exact_dev) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    points_tables(H);
+    error_norms(H, u_dev, exact_dev, l1, l2, linf);
+    EF_CATCH(H)
+}
+
+int efgpu_error_norms(efgpu_handle* H, const double* exact, double* l1, double* l2, double* linf)
+{
+    if (!H || !exact) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    points_tables(H);
+    const size_t bytes = (size_t)H->n_leaves * H->M * H->M * sizeof(double);
+    H->d_pts.alloc(bytes);
+    EF_CUDA(cudaMemcpyAsync(H->d_pts.p, exact, bytes, cudaMemcpyHostToDevice, H->stream));
+    error_norms(H, nullptr, H->d_pts.as<double>(), l1, l2, linf);
+    H->d_pts.release();
     EF_CATCH(H)
 }
 

@@ -55,6 +55,12 @@ int get_tuning(int key);
 void set_tuning(int key, int value);   // efgpu_set_tuning: kernel-selection knobs for measurements
 void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s);      // parity/debug: 8n x 4n, reference order
 
+// sample.cu: sampling coordinates of every leaf (which: 0 cell centres, 1..4 W, E, S, N face midpoints; x or y may be null) and the
+// error norms of the reference's drivers; part = 3 * n_leaves doubles of scratch, out = {l1, l2, linf} (device)
+void launch_leaf_points(const double* boxes, const int* leaf_nodes, int M, int which, double* x, double* y, int n_leaves, cudaStream_t s);
+void launch_error_norms(const double* u, const double* v, const double* boxes, const int* leaf_nodes, int M, int n_leaves, double area,
+                        double* part, double* out, cudaStream_t s);
+
 // lu.cu: root boundary system  (diag(a) + diag(b) T) g = r - b .* h  by blocked LU with partial pivoting
 size_t robin_workspace_doubles(int N);
 void robin_solve(const double* T, const double* a, const double* b, const double* r, const double* h, int N, double* ws,

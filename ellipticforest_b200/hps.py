@@ -313,6 +313,46 @@ class HPSAlgorithm:
         check(self._lib.efgpu_solve_dirichlet_device(self._h, C.c_void_p(g_dev_ptr), self._flags(),
                                                      C.c_void_p(u_dev_ptr) if u_dev_ptr else None, int(sync)), self._h)
 
+    # -- callers either side of the path: sampling coordinates and error norms on the device ----
+    POINTS = {"centre": 0, "W": 1, "E": 2, "S": 3, "N": 4}
+
+    def leafPoints(self, which="centre"):
+        """(x, y) of the sampling points of every leaf, shape (n_leaves, nx, ny), computed on the device: the cell centres
+        (load, alpha, lambda) or the W / E / S / N face midpoints (beta) - bit-identical to Mesh.leaf_cell_centres()."""
+        m = self.mesh
+        x, y = (np.empty((m.n_leaves, m.nx, m.nx)) for _ in range(2))
+        check(self._lib.efgpu_leaf_points(self._h, self.POINTS[which], x.ctypes.data, y.ctypes.data), self._h)
+        return x, y
+
+    def leafPointsDevice(self, which, x_dev_ptr: int, y_dev_ptr: int, sync: bool = True):
+        check(self._lib.efgpu_leaf_points_device(self._h, self.POINTS[which], C.c_void_p(x_dev_ptr) if x_dev_ptr else None,
+                                                 C.c_void_p(y_dev_ptr) if y_dev_ptr else None, int(sync)), self._h)
+
+    def setVariableCoefficientsDevice(self, alpha, beta_w, beta_e, beta_s, beta_n, lam):
+        """FivePointStencil leaves from six device arrays (pointers) the caller evaluated on leafPointsDevice coordinates;
+        the following buildStage keeps them (no host sampling)."""
+        check(self._lib.efgpu_set_leaf_variable_device(self._h, *[C.c_void_p(int(p)) for p in (alpha, beta_w, beta_e, beta_s, beta_n, lam)]), self._h)
+        self._coefficients_set = True
+        self.resample_coefficients = False
+
+    def errorNorms(self, exact):
+        """(l1, l2, linf) of the last solveStage against `exact` (a function of (x, y) sampled at the cell centres, or a
+        ready (n_leaves, nx, ny) array), as the reference's drivers compute them (examples/elliptic-multiple/main.cpp:346-371)
+        but reduced on the device."""
+        if callable(exact):
+            X, Y = self.mesh.leaf_cell_centres()
+            exact = exact(X, Y)
+        e = np.ascontiguousarray(np.broadcast_to(exact, (self.mesh.n_leaves, self.mesh.nx, self.mesh.nx)), dtype=np.float64)
+        out = [C.c_double() for _ in range(3)]
+        check(self._lib.efgpu_error_norms(self._h, e.ctypes.data, *[C.byref(v) for v in out]), self._h)
+        return tuple(v.value for v in out)
+
+    def errorNormsDevice(self, exact_dev_ptr: int, u_dev_ptr: int = 0):
+        out = [C.c_double() for _ in range(3)]
+        check(self._lib.efgpu_error_norms_device(self._h, C.c_void_p(u_dev_ptr) if u_dev_ptr else None, C.c_void_p(exact_dev_ptr),
+                                                 *[C.byref(v) for v in out]), self._h)
+        return tuple(v.value for v in out)
+
     def sync(self):
         check(self._lib.efgpu_sync(self._h), self._h)
 

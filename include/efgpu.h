@@ -145,6 +145,11 @@ int efgpu_set_leaf_constant(efgpu_handle* h, double lambda);
 int efgpu_set_leaf_variable(efgpu_handle* h, const double* alpha, const double* beta_w, const double* beta_e,
                             const double* beta_s, const double* beta_n, const double* lambda);
 
+/* the same arrays already resident in device memory (e.g. evaluated by the caller's own device code on the coordinates of
+ * efgpu_leaf_points_device); copied, borrowed for the call only */
+int efgpu_set_leaf_variable_device(efgpu_handle* h, const double* alpha_dev, const double* beta_w_dev, const double* beta_e_dev,
+                                   const double* beta_s_dev, const double* beta_n_dev, const double* lambda_dev);
+
 /* ---- stages ------------------------------------------------------------------------------------ */
 /* buildStage (HPSAlgorithm.hpp:120-161): leaf buildD2N + every merge4to1. */
 int efgpu_build(efgpu_handle* h, unsigned flags);
@@ -163,6 +168,22 @@ int efgpu_operator_device(efgpu_handle* h, int node, int which, double** ptr, in
 int efgpu_vector_device(efgpu_handle* h, int node, int which, double** ptr, int* len);
 int efgpu_solve_robin(efgpu_handle* h, const double* a, const double* b, const double* r, unsigned flags, double* u_leaves);
 int efgpu_sync(efgpu_handle* h);
+
+/* ---- callers either side of the path ------------------------------------
+ * Sampling coordinates of every leaf, leaf-major, cell index j + i*ny: what grid(XDIM, i), grid(YDIM, j) yield in the
+ * reference's sampling loops (HPSAlgorithm.hpp:241-249: load at the cell centres; FiniteVolumeSolver.cpp:63-79: alpha and
+ * lambda at the centres, beta at the four face midpoints of each cell).  The reference calls a std::function per point on
+ * the host; here the caller evaluates its functions on these arrays with its own (device) code and passes the results to
+ * efgpu_upwards_device / efgpu_set_leaf_variable_device.  x or y may be NULL.  n_leaves * nx * ny doubles each. */
+enum { EFGPU_POINTS_CENTRE = 0, EFGPU_POINTS_FACE_W = 1, EFGPU_POINTS_FACE_E = 2, EFGPU_POINTS_FACE_S = 3, EFGPU_POINTS_FACE_N = 4 };
+int efgpu_leaf_points_device(efgpu_handle* h, int which, double* x_dev, double* y_dev, int sync);
+int efgpu_leaf_points(efgpu_handle* h, int which, double* x, double* y);   /* host arrays */
+/* The error norms of the reference's drivers (examples/elliptic-multiple/main.cpp:346-371) reduced on the device:
+ *   l1 = sum dx dy |u - exact| / area,  l2 = sqrt(sum dx dy (u - exact)^2 / area),  linf = max |u - exact|
+ * over every cell of every leaf; area = area of the root patch(es).  u_dev == NULL: the solution of the last solve stage,
+ * resident in the handle.  Deterministic (fixed reduction order); any of l1 / l2 / linf may be NULL. */
+int efgpu_error_norms_device(efgpu_handle* h, const double* u_dev, const double* exact_dev, double* l1, double* l2, double* linf);
+int efgpu_error_norms(efgpu_handle* h, const double* exact, double* l1, double* l2, double* linf);   /* exact: host array */
 void* efgpu_stream(efgpu_handle* h);   /* the cudaStream_t all work of this handle is issued on */
 int efgpu_set_stream(efgpu_handle* h, void* stream);   /* adopt a caller-owned cudaStream_t (e.g. share one stream between two handles) */
 
