@@ -17,6 +17,7 @@ underneath through the same small interface.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -263,17 +264,44 @@ class ShardedExchange:
             for w in self.dist.batch_isend_irecv(ops):
                 w.wait()
 
-    def share(self, local_view, top_view):
+    def share(self, local_view, top_view, flat=None):
         """Replicated upper tree: every rank ends up with every subtree root's operator / vector in its own
-        upper-tree leaf buffers (owner copies, then broadcasts)."""
+        upper-tree leaf buffers (owner copies, then broadcasts).
+
+        `flat(first, total)`: optional - returns ONE tensor of `total` elements aliasing the destination buffers from
+        `first` on.  When the K buffers lie back to back in subtree order with equal sizes (libefgpu keeps the leaf DtN maps
+        of the upper tree that way) and every rank owns an equal Morton block, the K broadcasts collapse into one in-place
+        all-gather.  Opt-in (EFGPU_SHARE_ALLGATHER=1) until it has been timed over NCCL."""
         world = self.dist.get_world_size() if self.dist.is_initialized() else 1
-        for k in range(len(self.plan.cut_nodes)):
-            o = int(self.plan.owner[k])
-            dst = top_view(k)
-            if o == self.rank:
-                dst.copy_(local_view(k))
-            if world > 1:
-                self.dist.broadcast(dst, src=o)
+        K = len(self.plan.cut_nodes)
+        dsts = [top_view(k) for k in range(K)]
+        for k in range(K):
+            if int(self.plan.owner[k]) == self.rank:
+                dsts[k].copy_(local_view(k))
+        if world == 1:
+            return
+        full = self._back_to_back(dsts, flat, world) if os.environ.get("EFGPU_SHARE_ALLGATHER") == "1" else None
+        if full is not None:
+            cnt = full.numel() // world
+            self.dist.all_gather_into_tensor(full, full[self.rank * cnt:(self.rank + 1) * cnt])
+            return
+        for k in range(K):
+            self.dist.broadcast(dsts[k], src=int(self.plan.owner[k]))
+
+    def _back_to_back(self, dsts, flat, world):
+        """The flat tensor over `dsts` when one all-gather can replace the broadcasts, else None (same answer on every rank:
+        it depends on the plan and on the library's deterministic layout only)."""
+        K = len(dsts)
+        if flat is None or K % world:
+            return None
+        per = K // world
+        n = dsts[0].numel()
+        for k in range(K):
+            if int(self.plan.owner[k]) != k // per or dsts[k].numel() != n:
+                return None
+            if dsts[k].data_ptr() != dsts[0].data_ptr() + k * n * dsts[0].element_size():
+                return None
+        return flat(dsts[0], K * n)
 
     def allgather_rows(self, full):
         """In-place all-gather of the contiguous, equally sized row slices of `full` (slice r was computed by rank r)."""
@@ -371,8 +399,10 @@ class ShardedHPS:
 
     def sharding(self):
         if self.top_mode == "replicated":
-            return ("level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); upper tree replicated: subtree-root T broadcast over NCCL, "
-                    "X^-1 on every rank, rows of S and T split %d ways and all-gathered" % (self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world, self.world))
+            how = "all-gathered in place (one collective)" if os.environ.get("EFGPU_SHARE_ALLGATHER") == "1" else "broadcast"
+            return ("level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); upper tree replicated: subtree-root T %s over NCCL, "
+                    "X^-1 on every rank, rows of S and T split %d ways and all-gathered" % (
+                        self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world, how, self.world))
         return "level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); subtree-root T/h gathered to rank 0 over NCCL, g scattered back" % (
             self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world)
 
@@ -419,7 +449,7 @@ class ShardedHPS:
                 self.top.build(fl)
             return
         with self.torch.cuda.stream(self._stream):
-            self.xchg.share(self.local_if.root_T, self.top_if.leaf_T)
+            self.xchg.share(self.local_if.root_T, self.top_if.leaf_T, flat=lambda first, total: _dev_tensor(first.data_ptr(), total))
         # levels above the cut: X^-1 products, S and T are computed in row slices and all-gathered by the library
         # through the callback above (the root's DtN map stays row-distributed)
         self.top.build(fl)

@@ -118,9 +118,21 @@ class LocalIf:
 
 
 class TopIf:
-    def __init__(self, eng):
+    def __init__(self, eng, back_to_back=False):
         self.eng = eng
         self.leaves = [i for i, nd in enumerate(eng.nodes) if nd.leaf]
+        self.big = None
+        if back_to_back:   # the layout libefgpu gives the leaf DtN maps of the upper tree: one slab, leaf order
+            sizes = [(4 * eng.nodes[i].grid.nx) ** 2 for i in self.leaves]
+            self.big = torch.zeros(sum(sizes), dtype=torch.float64)
+            off = 0
+            for i, n in zip(self.leaves, sizes):
+                eng.buf[(i, "T")] = self.big[off:off + n]
+                off += n
+
+    def flat(self, first, total):
+        assert first.data_ptr() == self.big.data_ptr()
+        return self.big[:total]
 
     def leaf_T(self, j):
         i = self.leaves[j]
@@ -141,7 +153,7 @@ CASES = {
 }
 
 
-def _worker_replicated(rank, world, port, case, out_dir):
+def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False):
     """Replicated upper tree: share() of the subtree roots, then per level the row slices of S and T are
     all-gathered in place (the oracle computes whole merges; rows a rank does not own are wiped first, so
     only the exchange can restore them)."""
@@ -159,10 +171,20 @@ def _worker_replicated(rank, world, port, case, out_dir):
         lif = LocalIf(local, roots, plan.subtrees_of(rank))
         tids, tlev, tch, tbox, ext = plan.top_table()
         top = OracleEngine(tlev, tch, tbox, kw["nx"], solver, ext_sizes=ext)
-        tif = TopIf(top)
+        tif = TopIf(top, back_to_back=one_allgather)
         x = ShardedExchange(plan, rank, dist)
         local.build()
-        x.share(lif.root_T, tif.leaf_T)
+        if one_allgather:
+            os.environ["EFGPU_SHARE_ALLGATHER"] = "1"
+            calls = []
+            real = dist.broadcast
+            dist.broadcast = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+        x.share(lif.root_T, tif.leaf_T, flat=tif.flat if one_allgather else None)
+        if one_allgather:
+            dist.broadcast = real
+            # equal subtree roots in equal Morton blocks travel as ONE all-gather; anything else falls back to broadcasts
+            sizes = {tif.leaf_T(j).numel() for j in range(len(tif.leaves))}
+            assert (len(calls) == 0) == (len(sizes) == 1), (len(calls), sizes)
         for i in top._post():     # leaves first (from the shared buffers), then merges level by level
             nd = top.nodes[i]
             if nd.leaf:
@@ -252,11 +274,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("mode", ["root", "replicated"])
+@pytest.mark.parametrize("mode", ["root", "replicated", "replicated-one-allgather"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_two_rank_sharded_run_matches_single_process_oracle(case, mode, tmp_path):
     kw = CASES[case]
-    mp.spawn(_worker if mode == "root" else _worker_replicated, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    if mode == "root":
+        mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    else:
+        mp.spawn(_worker_replicated, args=(2, _free_port(), case, str(tmp_path), mode == "replicated-one-allgather"), nprocs=2, join=True)
     ref = O.run(solver_kind="fishpack", **kw)
     u_ref = ref.leaf_solution()
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
