@@ -24,10 +24,14 @@
 #include <EllipticForest.hpp>
 #include <Patches/FiniteVolume/FiniteVolume.hpp>
 
+#include <algorithm>
 #include <cmath>
+#include <exception>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "efgpu.h"
@@ -45,6 +49,11 @@ public:
     // the patches, as the reference leaves them.  Off by default: only leaf vectorU()/vectorF(),
     // grid() and n_coarsens are written, which is all the reference's drivers read.
     bool copy_back_operators = false;
+    // The reference calls rhs_function / alpha / beta / lambda point by point on the calling thread
+    // (HPSAlgorithm.hpp:241-249, FiniteVolumeSolver.cpp:63-79); at 1e7+ cells that loop, not the stages, is the wall
+    // clock.  > 1: the leaves are sampled in contiguous blocks on this many host threads - only for callbacks that are
+    // thread-safe, hence opt-in.  The values and where they are stored do not depend on it.
+    int sampling_threads = 1;
 
     HPSAlgorithmB200(MPI::Communicator comm, Mesh<PatchT>& mesh, FiniteVolumeSolver& solver, int device = 0)
         : Base(comm, mesh, solver), device(device) {}
@@ -117,7 +126,7 @@ public:
         app.timers["upwards-stage"].start();
         const size_t cells = (size_t)nx_ * nx_;
         f_.resize(leaves_.size() * cells);
-        for (size_t l = 0; l < leaves_.size(); l++) {
+        for_leaves_([&](size_t l) {
             PatchT& patch = nodes_[leaves_[l]]->data;
             FiniteVolumeGrid& grid = patch.grid();
             patch.vectorF() = Vector<double>(cells);
@@ -129,7 +138,7 @@ public:
                     f_[l * cells + j + (size_t)i * nx_] = v;
                 }
             }
-        }
+        });
         run_upwards_();
         app.timers["upwards-stage"].stop();
     }
@@ -254,12 +263,30 @@ private:
         }
     }
 
+    // body(l) for every leaf l, serially or in contiguous blocks on `sampling_threads` host threads
+    template <class F>
+    void for_leaves_(F&& body) {
+        const size_t n = leaves_.size();
+        const size_t nt = std::min<size_t>((size_t)std::max(1, sampling_threads), n);
+        if (nt <= 1) { for (size_t l = 0; l < n; l++) body(l); return; }
+        std::vector<std::thread> pool;
+        std::exception_ptr err;
+        std::mutex guard;
+        for (size_t t = 0; t < nt; t++)
+            pool.emplace_back([&, t] {
+                try { for (size_t l = n * t / nt; l < n * (t + 1) / nt; l++) body(l); }
+                catch (...) { std::lock_guard<std::mutex> lock(guard); if (!err) err = std::current_exception(); }
+            });
+        for (auto& th : pool) th.join();
+        if (err) std::rethrow_exception(err);
+    }
+
     // alpha, lambda at cell centres; beta at face midpoints: the sampling points of FiniteVolumeSolver.cpp:63-79
     void sample_coefficients_() {
         const size_t cells = (size_t)nx_ * nx_, tot = leaves_.size() * cells;
         std::vector<double> al(tot), bw(tot), be(tot), bs(tot), bn(tot), la(tot);
         FiniteVolumeSolver& s = this->patch_solver;
-        for (size_t l = 0; l < leaves_.size(); l++) {
+        for_leaves_([&](size_t l) {
             FiniteVolumeGrid& grid = nodes_[leaves_[l]]->data.grid();
             const double dx = grid.dx(), dy = grid.dy();
             for (int i = 0; i < nx_; i++)
@@ -273,7 +300,7 @@ private:
                     bs[k] = s.beta_function(xi, yj - dy / 2.0);
                     la[k] = s.lambda_function(xi, yj);
                 }
-        }
+        });
         check_(efgpu_set_leaf_variable(h_, al.data(), bw.data(), be.data(), bs.data(), bn.data(), la.data()), "efgpu_set_leaf_variable");
     }
 

@@ -45,6 +45,7 @@ int main(int argc, char** argv) {
     int min_level = 0, max_level = 2, nx = 8; bool homogeneous = false, cache = false, robin = false;
     double xl = -10, xu = 10, yl = -10, yu = 10, threshold = 1.2;
     bool use_box = false; double rb[4] = {0, 0, 0, 0};
+    int threads = 1; bool sampling_only = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() { return std::string(argv[++i]); };
@@ -57,6 +58,8 @@ int main(int argc, char** argv) {
         else if (a == "--homogeneous") homogeneous = std::stoi(next());
         else if (a == "--cache") cache = std::stoi(next());
         else if (a == "--robin") robin = std::stoi(next());
+        else if (a == "--threads") threads = std::stoi(next());
+        else if (a == "--sampling-only") sampling_only = true;
         else if (a == "--refine-box") { use_box = true; for (int k = 0; k < 4; k++) rb[k] = std::stod(next()); }
         else if (a == "--domain") { xl = std::stod(next()); xu = std::stod(next()); yl = std::stod(next()); yu = std::stod(next()); }
         else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
@@ -111,6 +114,29 @@ int main(int argc, char** argv) {
 
     HPSAlgorithmB200 gpu(MPI_COMM_WORLD, mesh_b, solver);
     gpu.copy_back_operators = true; gpu.keep_x = true;
+    gpu.sampling_threads = threads;
+    if (sampling_only) {
+        // host logic of the binding without a device: setupStage flattens the quadtree before efgpu_create fails, and
+        // upwardsStage samples the load into every leaf's vectorF before efgpu_upwards is reached; both must throw (no
+        // CPU fallback), and the sampled loads must equal the reference's bit for bit at any thread count
+        int threw = 0;
+        try { gpu.setupStage(); } catch (const std::exception&) { threw++; }
+        try { gpu.upwardsStage(rhs); } catch (const std::exception&) { threw++; }
+        std::vector<NodeT*> A, B;
+        mesh_a.quadtree.traversePreOrder([&](NodeT* n) { A.push_back(n); return 1; });
+        mesh_b.quadtree.traversePreOrder([&](NodeT* n) { B.push_back(n); return 1; });
+        bool same = A.size() == B.size(); long leaves = 0, cells = 0;
+        for (size_t i = 0; same && i < A.size(); i++) {
+            if (!A[i]->leaf) continue;
+            auto& fa = A[i]->data.vectorF(); auto& fb = B[i]->data.vectorF();
+            same = same && fa.size() == fb.size() && fa.size() == (size_t)nx * nx;
+            for (int c = 0; same && c < (int)fa.size(); c++) same = fa[c] == fb[c];
+            leaves++; cells += (long)fa.size();
+        }
+        printf("DROPIN_SAMPLING {\"same\": %s, \"threw\": %d, \"leaves\": %ld, \"cells\": %ld, \"threads\": %d}\n", same ? "true" : "false", threw, leaves, cells, threads);
+        fflush(stdout);
+        _exit(same ? 0 : 1);
+    }
     try {
         gpu.setupStage(); gpu.buildStage(); gpu.upwardsStage(rhs);
         if (homogeneous) gpu.solveStage(bc_patch); else gpu.solveStage(bc_fn);

@@ -23,6 +23,9 @@ CASES = {
                            "--homogeneous", "1", "--cache", "1"],
     "varcoef_fivepoint_m8": ["--problem", "varcoef", "--solver", "fivepoint", "--min-level", "1", "--max-level", "3", "--nx", "8", "--domain", "-10", "10", "-10", "10",
                              "--refine-box", "2", "10", "-3", "10"],
+    # the binding's opt-in threaded sampling of the std::function callbacks (sampling_threads = 4)
+    "varcoef_fivepoint_m8_threads4": ["--problem", "varcoef", "--solver", "fivepoint", "--min-level", "1", "--max-level", "3", "--nx", "8", "--domain", "-10", "10", "-10", "10",
+                                      "--refine-box", "2", "10", "-3", "10", "--threads", "4"],
     "robin_root_m8": ["--problem", "helmholtz", "--solver", "fishpack", "--min-level", "2", "--max-level", "2", "--nx", "8", "--domain", "0", PI, "0", PI, "--robin", "1"],
 }
 

@@ -87,3 +87,24 @@ def test_bad_arguments_are_rejected():
     assert lib.efgpu_mesh_create(0.0, 1.0, 0.0, 1.0, 8, 3, 2, _lib.REFINE_FN(), None, ctypes.byref(out)) == 2
     assert lib.efgpu_mesh_create(1.0, 0.0, 0.0, 1.0, 8, 0, 1, _lib.REFINE_FN(), None, ctypes.byref(out)) == 2
     assert lib.efgpu_build(None, 0) == 2
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_cpp_binding_samples_like_the_reference_and_has_no_cpu_fallback(threads):
+    """include/EllipticForestB200.hpp compiled against the unmodified reference (oracle/_ref/dropin_driver), without a
+    device: setupStage and upwardsStage must throw (nothing falls back to the reference's CPU stages), and the load the
+    binding samples into every leaf's vectorF - serially or on `sampling_threads` host threads - is bit-identical to what
+    the reference's own upwardsStage stored (HPSAlgorithm.hpp:241-249)."""
+    import json
+    import subprocess
+    driver = os.path.join(ROOT, "oracle", "_ref", "dropin_driver")
+    if not os.path.exists(driver):
+        pytest.skip("oracle/_ref/dropin_driver not built (needs /root/reference at build time)")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([driver, "--problem", "poisson", "--solver", "fishpack", "--min-level", "1", "--max-level", "4", "--nx", "8",
+                        "--domain", "-10", "10", "-10", "10", "--sampling-only", "--threads", str(threads)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    line = [l for l in p.stdout.splitlines() if l.startswith("DROPIN_SAMPLING")]
+    assert line, p.stdout[-2000:] + p.stderr[-2000:]
+    res = json.loads(line[-1][len("DROPIN_SAMPLING "):])
+    assert res["same"] and res["threw"] == 2 and res["threads"] == threads and res["cells"] == res["leaves"] * 64 > 0, res
