@@ -212,6 +212,23 @@ def test_symmetric_diagonal_blocks_of_T(nranks):
         lib.efgpu_set_tuning(5, 0)
 
 
+@pytest.mark.parametrize("n,nranks,split_min,plans", [(256, 4, 256, "1,0"), (512, 8, 256, "1")])
+def test_partitions_of_4_and_8_ranks_with_row_split_inversion(n, nranks, split_min, plans):
+    """The shapes of the 4- and 8-GPU runs: products of the block inversion split by rows over the ranks (512 rows over 4,
+    1024 rows over 8) with in-place and staged all-gathers, S / T row slices of n / 2 and n rows, tree levels 1 (T gathered
+    after the merge) and 0 (root: gathered and mirrored on demand).  Own process: the split threshold is read once."""
+    import os
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "plan_partition_check.py"),
+                        str(n), str(nranks), str(split_min), plans], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("n ")]
+    assert len(lines) == 2 * len(plans.split(",")), p.stdout
+    for l in lines:
+        assert int(l.split("gathers")[1].split()[0]) >= 3, l      # the inversion's products really were split
+
+
 def test_general_plan_on_nonsymmetric_children():
     rng = np.random.default_rng(0)
     n = 40                                       # N = 160: h = 80, q = 40; odd sizes for the transposes / tiles
