@@ -1,7 +1,7 @@
 """Helper of tests/test_merge_plan.py, run as a subprocess because EFGPU_SPLIT_MIN_ROWS is read once per process: emulates the
 merge plan of one batch at `nranks` ranks (row-partitioned products of the block inversion, S and T rows, all-gathers) on
 synthetic signed-symmetric children and compares X^-1, S, T with the oracle's merge4to1.
-usage: plan_partition_check.py n nranks split_min_rows [plans, default "1,0"]"""
+usage: plan_partition_check.py n nranks split_min_rows [plans, default "1,0"] [tuning KEY=VALUE]"""
 import os, sys, time
 os.environ["EFGPU_SPLIT_MIN_ROWS"] = sys.argv[3] if len(sys.argv) > 3 else "256"
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -10,6 +10,9 @@ for p in (os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "oracle"), 
 import numpy as np
 import test_merge_plan as tm
 n, nranks = int(sys.argv[1]), int(sys.argv[2])
+if len(sys.argv) > 5:      # "KEY=VALUE": efgpu_set_tuning before the plans are made
+    from ellipticforest_b200 import _lib
+    assert _lib.load().efgpu_set_tuning(*[int(v) for v in sys.argv[5].split("=")]) == 0
 rng = np.random.default_rng(1)
 d = np.ones(4 * n); d[:n] = -1; d[2 * n:3 * n] = -1      # W, E, S, N: d = -1 on W and S
 A = rng.standard_normal((4 * n, 4 * n)) / np.sqrt(4 * n)
