@@ -393,8 +393,8 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
         // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_).  Symmetric plan: with the sign
         // d = -1 on the W and S sides (coordinate derivatives instead of outward normals, FiniteVolumeSolver.cpp:332-343)
         // diag(d) T is symmetric, so of every off-diagonal pair of n x n blocks only one is computed - chosen on a circulant
-        // pattern so that each block row carries 4 or 5 products (row partitions stay balanced) - and the other is its
-        // signed transpose.
+        // pattern so that each block row carries 4 or 5 products and every half / quarter of the rows the same number (row
+        // partitions over 2 and 4 ranks are balanced exactly, over 8 ranks to 5 : 4) - and the other is its signed transpose.
         first = (int)b.blocks.size();
         const int tfirst = (int)b.trans.size();
         for (int qr = 0; qr < 8; qr++)
@@ -404,7 +404,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
                 const int P = h_pos[qr], Q = h_pos[qc];
                 if (sym && mirror_ok && P != Q) {
                     const int dl = (Q - P) & 7;
-                    if (!(dl < 4 || (dl == 4 && P < 4))) {
+                    // (of the opposite pair P, P + 4 the even one of rows 0..3 / the odd one of rows 4..7 computes: block rows 0, 2, 5, 7
+                    // carry 5 products and 1, 3, 4, 6 carry 4, so halves and quarters of the rows - 2 and 4 ranks - get 18 and 9 each)
+                    if (!(dl < 4 || (dl == 4 && ((P < 4) != ((P & 1) != 0))))) {
                         const unsigned neg = ((P ^ Q) & 2) ? 0x80000000u : 0u;   // W, W, E, E, S, S, N, N: d = -1 where bit 1 is clear
                         b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
                                                   (long long)(P * n) * (8 * n) + Q * n, n, n, neg, 0});
