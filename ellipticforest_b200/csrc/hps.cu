@@ -368,6 +368,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
     // (the root's DtN map of a partitioned tree stays row-distributed: its mirrored blocks are completed on demand,
     // efgpu_complete_root_dtn, so that the root merge also issues 36 instead of 64 block products)
     const bool mirror_ok = true;
+    // partitions with at most one block row of T per rank (8 ranks and more): the four opposite pairs are shared half and half,
+    // 4.5 instead of 5 : 4 block products per row (halves of >= 128 rows / columns: full GEMM tiles)
+    const bool split_opposite = nranks >= 8 && n % 256 == 0;
     for (int variant = 0; variant < (b.symcand ? 2 : 1); variant++) {
         const bool sym = variant == 1;
         std::vector<Step>& steps = sym ? b.steps_sym : b.steps;
@@ -404,6 +407,31 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
                 const int P = h_pos[qr], Q = h_pos[qc];
                 if (sym && mirror_ok && P != Q) {
                     const int dl = (Q - P) & 7;
+                    if (dl == 4 && split_opposite) {
+                        // one block row per rank: both rows of an opposite pair compute HALF of their block - rows 0..3 the upper
+                        // n/2 rows of (P, P + 4), rows 4..7 the right n/2 columns of (P, P - 4) - and receive the other half as
+                        // the transpose of what the partner computed (no sign: both sides lie on the same kind of axis)
+                        const int hn = n / 2;
+                        const int r0 = 0, c0 = P < 4 ? 0 : hn, nr_ = P < 4 ? hn : n, nc_ = P < 4 ? n : hn;
+                        GemmBlock g{};
+                        g.c_op = OP_T; g.c_off = (long long)(P * n + r0) * (8 * n) + Q * n + c0; g.ldc = 8 * n;
+                        if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n + r0) * N + side_c * n + c0; g.ldc0 = N; }
+                        else g.c0_op = -1;
+                        g.rows = nr_; g.cols = nc_; g.nterms = 2;
+                        for (int t = 0; t < 2; t++) {
+                            const int k = h_kk[c][t];
+                            g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n + r0) * N + h_iface[c][k] * n,
+                                              (long long)(k * n) * (8 * n) + Q * n + c0, n, 0u};
+                        }
+                        if (clip_rows(g, (long long)P * n + r0, t_lo, t_hi)) b.blocks.push_back(g);
+                        if (P < 4)   // lower half of (P, Q) <- transpose of the right half of (Q, P)
+                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n + hn,
+                                                      (long long)(P * n + hn) * (8 * n) + Q * n, n, hn, 0u, 0});
+                        else         // left half of (P, Q) <- transpose of the upper half of (Q, P)
+                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
+                                                      (long long)(P * n) * (8 * n) + Q * n, hn, n, 0u, 0});
+                        continue;
+                    }
                     // (of the opposite pair P, P + 4 the even one of rows 0..3 / the odd one of rows 4..7 computes: block rows 0, 2, 5, 7
                     // carry 5 products and 1, 3, 4, 6 carry 4, so halves and quarters of the rows - 2 and 4 ranks - get 18 and 9 each)
                     if (!(dl < 4 || (dl == 4 && ((P < 4) != ((P & 1) != 0))))) {

@@ -266,3 +266,20 @@ def test_symmetric_plan_flop_count_and_balance():
         assert (q, p) in computed
     rows = [sum(1 for (p, q) in computed if p == r) for r in range(8)]
     assert max(rows) - min(rows) <= 1
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_T_products_are_balanced_over_the_ranks(nranks):
+    """Symmetric plan: 36 block products of n^3 x 4 flops; halves / quarters of the rows carry 18 / 9 of them, and with one
+    block row per rank (8 ranks) the opposite pairs are shared half and half: 4.5 each."""
+    n = 1024
+    per_rank = []
+    for r in range(nranks):
+        steps, blocks, terms, trans, ws = get_plan(n, 1, r, nranks, 1)
+        f = 0
+        for st in steps:
+            if int(st[0]) == 1 and int(st[5]) == CLS_GEMM_T:
+                for k in range(int(st[1]), int(st[1]) + int(st[2])):
+                    f += sum(2 * int(blocks[k][6]) * int(blocks[k][7]) * int(terms[k][t][6]) for t in range(int(blocks[k][8])))
+        per_rank.append(f / n ** 3)
+    assert per_rank == [144.0 / nranks] * nranks, per_rank
