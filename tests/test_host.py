@@ -87,6 +87,12 @@ def test_bad_arguments_are_rejected():
     assert lib.efgpu_mesh_create(0.0, 1.0, 0.0, 1.0, 8, 3, 2, _lib.REFINE_FN(), None, ctypes.byref(out)) == 2
     assert lib.efgpu_mesh_create(1.0, 0.0, 0.0, 1.0, 8, 0, 1, _lib.REFINE_FN(), None, ctypes.byref(out)) == 2
     assert lib.efgpu_build(None, 0) == 2
+    d = ctypes.c_double()
+    assert lib.efgpu_leaf_points(None, 0, None, None) == 2
+    assert lib.efgpu_leaf_points_device(None, 9, None, None, 1) == 2
+    assert lib.efgpu_error_norms(None, None, ctypes.byref(d), ctypes.byref(d), ctypes.byref(d)) == 2
+    assert lib.efgpu_error_norms_device(None, None, None, None, None, None) == 2
+    assert lib.efgpu_set_leaf_variable_device(None, None, None, None, None, None, None) == 2
 
 
 @pytest.mark.parametrize("threads", [1, 4])
