@@ -30,7 +30,13 @@ from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, NO_SYMMETRY, OP, VEC, FiniteV
 class ShardPlan:
     """Static ownership of the subtrees below `cut` and the node tables of every piece."""
 
-    def __init__(self, level, child, box, nx, world, cut=2):
+    def __init__(self, level, child, box, nx, world, cut=2, balance="count"):
+        """balance: how the 4^cut subtrees (Morton order) are dealt to the ranks, always as contiguous blocks of whole subtrees:
+        "count" - equally many per rank (p4est_partition on a uniform tree; needs world | 4^cut);
+        "leaves" - blocks with the smallest possible maximum number of leaves (p4est_partition weights leaves uniformly,
+                   src/Mesh.hpp:169-170; here whole subtrees stay together);
+        "work"  - the same with the merge work below the cut as the weight (sum of n^3 over the subtree's merges, n = child
+                   side, plus nx^3 per leaf for its DtN map): what balances the build stage of an adaptive tree."""
         self.level = np.asarray(level, dtype=np.int32)
         self.child = np.asarray(child, dtype=np.int32).reshape(-1, 4)
         self.box = np.asarray(box, dtype=np.float64).reshape(-1, 4)
@@ -41,9 +47,11 @@ class ShardPlan:
             raise ValueError("tree too shallow to shard: a leaf lies above the cut level %d" % cut)
         self.cut_nodes = np.nonzero(self.level == cut)[0]            # pre-order = Morton order
         ncut = len(self.cut_nodes)
-        if ncut != 4 ** cut or ncut % world:
+        if balance not in ("count", "leaves", "work"):
+            raise ValueError("balance must be 'count', 'leaves' or 'work'")
+        if ncut != 4 ** cut or world < 1 or world > ncut or (balance == "count" and ncut % world):
             raise ValueError("%d subtrees cannot be dealt to %d ranks" % (ncut, world))
-        self.owner = (np.arange(ncut) * world) // ncut                # contiguous Morton blocks, as p4est_partition
+        self.balance = balance
         # subtree extents: the table is in pre-order, so a subtree is a contiguous id range
         self.sub_end = np.empty(ncut, dtype=np.int64)
         for k, r in enumerate(self.cut_nodes):
@@ -57,6 +65,41 @@ class ShardPlan:
             self.size[i] = self.nx if leaf[i] else 2 * min(self.size[c] for c in self.child[i])
         self.leaf = leaf
         self.leaf_index = np.cumsum(leaf) - 1                        # global leaf numbering (pre-order)
+        # weights of the subtrees and their owners
+        self.weight = np.ones(ncut)
+        if balance != "count":
+            for k, r in enumerate(self.cut_nodes):
+                ids = np.arange(r, self.sub_end[k])
+                if balance == "leaves":
+                    self.weight[k] = float(np.sum(leaf[ids]))
+                else:
+                    half = self.size[ids] / 2.0
+                    self.weight[k] = float(np.sum(np.where(leaf[ids], float(self.nx) ** 3, half ** 3)))
+        # "count": contiguous Morton blocks of equal length, as p4est_partition on a uniform tree
+        self.owner = self._contiguous_blocks(self.weight, world) if balance != "count" else (np.arange(ncut) * world) // ncut
+
+    @staticmethod
+    def _contiguous_blocks(w, parts):
+        """Owner of each item when the sequence is cut into `parts` non-empty contiguous blocks with the smallest possible
+        maximum block weight (dynamic programme over the prefix sums; ties resolved towards earlier cuts: deterministic)."""
+        n = len(w)
+        pre = np.concatenate([[0.0], np.cumsum(w)])
+        best = np.full((parts + 1, n + 1), np.inf)
+        arg = np.zeros((parts + 1, n + 1), dtype=np.int64)
+        best[0, 0] = 0.0
+        for p in range(1, parts + 1):
+            for i in range(p, n - (parts - p) + 1):
+                for j in range(p - 1, i):
+                    v = max(best[p - 1, j], pre[i] - pre[j])
+                    if v < best[p, i]:
+                        best[p, i], arg[p, i] = v, j
+        owner = np.zeros(n, dtype=np.int64)
+        i = n
+        for p in range(parts, 0, -1):
+            j = arg[p, i]
+            owner[j:i] = p - 1
+            i = j
+        return owner
 
     # -- pieces ------------------------------------------------------------------------------
     def subtrees_of(self, rank) -> List[int]:
@@ -353,7 +396,7 @@ class _TopGpu:
 class ShardedHPS:
     """Benchmark/driver-facing sharded HPS (same stage names as HPSAlgorithm; inputs/outputs are this rank's share)."""
 
-    def __init__(self, mesh, solver, device=0, rank=0, world=1, options=None, cut=2, top_mode="replicated"):
+    def __init__(self, mesh, solver, device=0, rank=0, world=1, options=None, cut=2, top_mode="replicated", balance="count"):
         import torch
         self.top_mode = top_mode
         import torch.distributed as dist
@@ -364,7 +407,7 @@ class ShardedHPS:
             self.options.update(options)
         if solver.solver_type != "FISHPACK90":
             raise NotImplementedError("sharded runs: constant-coefficient leaves only for now")
-        self.plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, cut)
+        self.plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, cut, balance=balance)
         ids, lev, ch, box, roots = self.plan.local_table(rank)
         self.local = GpuEngine(lev, ch, box, mesh.nx, device)
         self._stream = torch.cuda.ExternalStream(self.local.stream())
@@ -398,13 +441,15 @@ class ShardedHPS:
                 | (NO_SYMMETRY if self.no_symmetry else 0))
 
     def sharding(self):
+        K = len(self.plan.cut_nodes)
+        per = ("%d per GPU" % (K // self.world) if self.plan.balance == "count" else
+               "%s per GPU, balanced by %s" % ("/".join(str(len(self.plan.subtrees_of(r))) for r in range(self.world)), self.plan.balance))
         if self.top_mode == "replicated":
             how = "all-gathered in place (one collective)" if os.environ.get("EFGPU_SHARE_ALLGATHER") == "1" else "broadcast"
-            return ("level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); upper tree replicated: subtree-root T %s over NCCL, "
-                    "X^-1 on every rank, rows of S and T split %d ways and all-gathered" % (
-                        self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world, how, self.world))
-        return "level-%d subtrees in Morton blocks over %d GPUs (%d per GPU); subtree-root T/h gathered to rank 0 over NCCL, g scattered back" % (
-            self.plan.cut, self.world, len(self.plan.cut_nodes) // self.world)
+            return ("level-%d subtrees in Morton blocks over %d GPUs (%s); upper tree replicated: subtree-root T %s over NCCL, "
+                    "X^-1 on every rank, rows of S and T split %d ways and all-gathered" % (self.plan.cut, self.world, per, how, self.world))
+        return "level-%d subtrees in Morton blocks over %d GPUs (%s); subtree-root T/h gathered to rank 0 over NCCL, g scattered back" % (
+            self.plan.cut, self.world, per)
 
     def stream(self):
         return self.local.stream()

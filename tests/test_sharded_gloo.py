@@ -153,7 +153,7 @@ CASES = {
 }
 
 
-def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False):
+def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False, balance="count"):
     """Replicated upper tree: share() of the subtree roots, then per level the row slices of S and T are
     all-gathered in place (the oracle computes whole merges; rows a rank does not own are wiped first, so
     only the exchange can restore them)."""
@@ -165,7 +165,7 @@ def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False):
         ind = O.refine_box_indicator(kw["refine_box"]) if kw["refine_box"] else O.refine_indicator(1.2)
         nodes = O.build_tree(ind, kw["box"], kw["nx"], kw["min_level"], kw["max_level"])
         solver = O.Solver(kind="fishpack", alpha=P["alpha"], beta=P["beta"], lam=P["lam"])
-        plan = ShardPlan(*_tables(nodes), kw["nx"], world)
+        plan = ShardPlan(*_tables(nodes), kw["nx"], world, balance=balance)
         ids, lev, ch, box, roots = plan.local_table(rank)
         local = OracleEngine(lev, ch, box, kw["nx"], solver)
         lif = LocalIf(local, roots, plan.subtrees_of(rank))
@@ -274,14 +274,15 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("mode", ["root", "replicated", "replicated-one-allgather"])
+@pytest.mark.parametrize("mode", ["root", "replicated", "replicated-one-allgather", "replicated-balanced"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_two_rank_sharded_run_matches_single_process_oracle(case, mode, tmp_path):
     kw = CASES[case]
     if mode == "root":
         mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
     else:
-        mp.spawn(_worker_replicated, args=(2, _free_port(), case, str(tmp_path), mode == "replicated-one-allgather"), nprocs=2, join=True)
+        mp.spawn(_worker_replicated, args=(2, _free_port(), case, str(tmp_path), mode == "replicated-one-allgather",
+                                           "leaves" if mode == "replicated-balanced" else "count"), nprocs=2, join=True)
     ref = O.run(solver_kind="fishpack", **kw)
     u_ref = ref.leaf_solution()
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
@@ -316,6 +317,21 @@ def test_shard_plan_tables():
         assert len(tids) == 21 and list(ext) == [16] * 16 and plan.root_size() == 64
     with pytest.raises(ValueError):
         ShardPlan(level, child, box, 8, 3)
+    # weighted dealing (adaptive trees): contiguous Morton blocks of whole subtrees, smallest possible maximum weight
+    assert ShardPlan._contiguous_blocks(np.array([1, 1, 1, 1, 10, 1, 1, 1.0]), 3).tolist() == [0, 0, 0, 0, 1, 2, 2, 2]
+    assert ShardPlan(level, child, box, 8, 4, balance="leaves").owner.tolist() == ShardPlan(level, child, box, 8, 4).owner.tolist()
+    lop = O.build_tree(O.refine_box_indicator((-10.0, 0.5, -10.0, 0.5)), (-10.0, 10.0, -10.0, 10.0), 8, 2, 5)
+    for world in (2, 3, 4):
+        count = ShardPlan(*_tables(lop), 8, world if world != 3 else 4)
+        for bal in ("leaves", "work"):
+            plan = ShardPlan(*_tables(lop), 8, world, balance=bal)
+            assert list(plan.owner) == sorted(plan.owner) and set(plan.owner) == set(range(world))      # contiguous, nobody idle
+            load = [sum(plan.weight[k] for k in plan.subtrees_of(r)) for r in range(world)]
+            if world != 3:
+                even = [sum(plan.weight[k] for k in count.subtrees_of(r)) for r in range(world)]
+                assert max(load) < max(even)                                                         # and better than equal counts
+            ranges = [plan.local_leaf_range(r) for r in range(world)]
+            assert ranges[0][0] == 0 and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
     shallow = O.build_tree(O.refine_indicator(1.2), (0.0, 1.0, 0.0, 1.0), 8, 1, 1)
     with pytest.raises(ValueError):
         ShardPlan(*_tables(shallow), 8, 2)
