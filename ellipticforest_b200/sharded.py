@@ -323,13 +323,31 @@ class ShardedExchange:
                 dsts[k].copy_(local_view(k))
         if world == 1:
             return
-        full = self._back_to_back(dsts, flat, world) if os.environ.get("EFGPU_SHARE_ALLGATHER") == "1" else None
-        if full is not None:
-            cnt = full.numel() // world
-            self.dist.all_gather_into_tensor(full, full[self.rank * cnt:(self.rank + 1) * cnt])
-            return
+        if os.environ.get("EFGPU_SHARE_ALLGATHER") == "1":
+            full = self._back_to_back(dsts, flat, world)
+            if full is not None:
+                cnt = full.numel() // world
+                self.dist.all_gather_into_tensor(full, full[self.rank * cnt:(self.rank + 1) * cnt])
+                return
+            if self._equal_blocks(dsts, world):
+                # scattered destinations of equal size (the subtree roots' h: 16 small vectors): pack this rank's share, ONE
+                # all-gather into a staging tensor, one multi-tensor copy into the leaf buffers - 3 launches instead of K
+                import torch
+                n = dsts[0].numel()
+                mine = torch.cat([dsts[k].reshape(-1) for k in range(K) if int(self.plan.owner[k]) == self.rank])
+                staged = torch.empty(K * n, dtype=mine.dtype, device=mine.device)
+                self.dist.all_gather_into_tensor(staged, mine)
+                torch._foreach_copy_([d.reshape(-1) for d in dsts], list(staged.split(n)))
+                return
         for k in range(K):
             self.dist.broadcast(dsts[k], src=int(self.plan.owner[k]))
+
+    def _equal_blocks(self, dsts, world):
+        K = len(dsts)
+        if K % world:
+            return False
+        per, n = K // world, dsts[0].numel()
+        return all(int(self.plan.owner[k]) == k // per and dsts[k].numel() == n for k in range(K))
 
     def _back_to_back(self, dsts, flat, world):
         """The flat tensor over `dsts` when one all-gather can replace the broadcasts, else None (same answer on every rank:

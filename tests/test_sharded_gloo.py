@@ -203,7 +203,13 @@ def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False, ba
                     x.allgather_rows(full)
                     setattr(nd, name, full.numpy().reshape(getattr(nd, name).shape).copy())
         local.upwards(P["f"])
+        if one_allgather:   # scattered equal-size vectors: packed into one all-gather as well (no broadcast), else the fallback
+            calls = []
+            dist.broadcast = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
         x.share(lif.root_h, tif.leaf_h)
+        if one_allgather:
+            dist.broadcast = real
+            assert (len(calls) == 0) == (len({tif.leaf_h(j).numel() for j in range(len(tif.leaves))}) == 1), len(calls)
         top.upwards(None)
         r, a, b = O.HPS.root_boundary(type("R", (), {"nodes": [top.nodes[0]]})(), lambda s_, xx, yy: (float(P["u"](xx, yy)), 1.0, 0.0))
         top.nodes[0].g = r / a
