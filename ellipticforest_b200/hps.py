@@ -159,6 +159,41 @@ class Mesh:
         return X, Y
 
 
+def sample_leaf_coefficients(solver, leaf_boxes, nx, threads=1):
+    """alpha, beta_w, beta_e, beta_s, beta_n, lambda of every leaf in `leaf_boxes` (rows x_lower, x_upper, y_lower, y_upper), each
+    (n_leaves, nx, nx): alpha and lambda at the cell centres, beta at the four face midpoints (FiniteVolumeSolver.cpp:63-79).
+    The callbacks are vectorised numpy functions; blocks of leaves are evaluated on `threads` host threads (numpy releases the
+    GIL inside its kernels) - 1 for callbacks that are not thread-safe.  The reference calls them point by point, serially,
+    inside every leaf solve."""
+    b = np.asarray(leaf_boxes, dtype=np.float64).reshape(-1, 4)
+    nl, M = len(b), int(nx)
+    dx1, dy1 = (b[:, 1] - b[:, 0]) / M, (b[:, 3] - b[:, 2]) / M
+    k = np.arange(M)
+    xs = (b[:, 0] + dx1 / 2)[:, None] + k[None, :] * dx1[:, None]
+    ys = (b[:, 2] + dy1 / 2)[:, None] + k[None, :] * dy1[:, None]
+    X = np.broadcast_to(xs[:, :, None], (nl, M, M))
+    Y = np.broadcast_to(ys[:, None, :], (nl, M, M))
+    dx, dy = dx1[:, None, None], dy1[:, None, None]
+    out = [np.empty((nl, M, M), dtype=np.float64) for _ in range(6)]
+
+    def block(lo, hi):
+        x, y, hx, hy = X[lo:hi], Y[lo:hi], dx[lo:hi] / 2.0, dy[lo:hi] / 2.0
+        vals = (solver.alpha_function(x, y), solver.beta_function(x - hx, y), solver.beta_function(x + hx, y),
+                solver.beta_function(x, y - hy), solver.beta_function(x, y + hy), solver.lambda_function(x, y))
+        for o, v in zip(out, vals):
+            o[lo:hi] = v          # broadcasts scalar / lower-dimensional results
+
+    nthreads = max(1, min(int(threads), nl))
+    if nthreads == 1:
+        block(0, nl)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        step = max(1, -(-nl // (4 * nthreads)))
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(lambda lo: block(lo, min(nl, lo + step)), range(0, nl, step)))
+    return out
+
+
 class HPSAlgorithm:
     """src/HPSAlgorithm.hpp:26-596 for <FiniteVolumeGrid, FiniteVolumeSolver, FiniteVolumePatch, double>."""
 
@@ -215,33 +250,10 @@ class HPSAlgorithm:
         self.isBuilt = True
 
     def _set_variable_coefficients(self):
-        """Sample alpha, beta, lambda where FiniteVolumeSolver.cpp:63-79 samples them (alpha, lambda at the cell centres,
-        beta at the four face midpoints).  The callbacks are vectorised numpy functions; blocks of leaves are evaluated on
-        `sampling_threads` host threads (numpy releases the GIL inside its kernels) - set it to 1 for callbacks that are not
-        thread-safe.  The reference calls them point by point, serially, inside every leaf solve."""
-        s, m = self.patch_solver, self.mesh
-        X, Y = m.leaf_cell_centres()
-        b = m.box[m.leaf_nodes]
-        dx = ((b[:, 1] - b[:, 0]) / m.nx)[:, None, None]
-        dy = ((b[:, 3] - b[:, 2]) / m.nx)[:, None, None]
-        out = [np.empty(X.shape, dtype=np.float64) for _ in range(6)]
-
-        def block(lo, hi):
-            x, y, hx, hy = X[lo:hi], Y[lo:hi], dx[lo:hi] / 2.0, dy[lo:hi] / 2.0
-            vals = (s.alpha_function(x, y), s.beta_function(x - hx, y), s.beta_function(x + hx, y),
-                    s.beta_function(x, y - hy), s.beta_function(x, y + hy), s.lambda_function(x, y))
-            for o, v in zip(out, vals):
-                o[lo:hi] = v          # broadcasts scalar / lower-dimensional results
-
-        nl = m.n_leaves
-        nthreads = max(1, min(int(self.sampling_threads), nl))
-        if nthreads == 1:
-            block(0, nl)
-        else:
-            from concurrent.futures import ThreadPoolExecutor
-            step = max(1, -(-nl // (4 * nthreads)))
-            with ThreadPoolExecutor(max_workers=nthreads) as ex:
-                list(ex.map(lambda lo: block(lo, min(nl, lo + step)), range(0, nl, step)))
+        """Sample alpha, beta, lambda where FiniteVolumeSolver.cpp:63-79 samples them (sample_leaf_coefficients) and hand the
+        six leaf-major arrays to the library."""
+        m = self.mesh
+        out = sample_leaf_coefficients(self.patch_solver, m.box[m.leaf_nodes], m.nx, self.sampling_threads)
         check(self._lib.efgpu_set_leaf_variable(self._h, *[a.ctypes.data for a in out]), self._h)
 
     def upwardsStage(self, rhs, scale: float = 1.0):

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import TreeDesc, check
-from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, NO_SYMMETRY, OP, VEC, FiniteVolumeGrid
+from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, NO_SYMMETRY, OP, VEC, FiniteVolumeGrid, sample_leaf_coefficients
 
 
 class ShardPlan:
@@ -184,6 +184,11 @@ class GpuEngine:
 
     def set_leaf_constant(self, lam):
         check(self._lib.efgpu_set_leaf_constant(self._h, float(lam)), self._h)
+
+    def set_leaf_variable(self, arrays):
+        """FivePointStencil leaves: alpha, beta_w, beta_e, beta_s, beta_n, lambda of this handle's leaves (host arrays, leaf-major)."""
+        arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
+        check(self._lib.efgpu_set_leaf_variable(self._h, *[a.ctypes.data for a in arrays]), self._h)
 
     def operator_view(self, node, which):
         p, r, c = C.c_void_p(), C.c_int(), C.c_int()
@@ -423,8 +428,8 @@ class ShardedHPS:
         self.options = {"cache-operators": False, "homogeneous-rhs": False}
         if options:
             self.options.update(options)
-        if solver.solver_type != "FISHPACK90":
-            raise NotImplementedError("sharded runs: constant-coefficient leaves only for now")
+        if solver.solver_type not in ("FISHPACK90", "FivePointStencil"):
+            raise ValueError("unknown solver_type")
         self.plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, cut, balance=balance)
         ids, lev, ch, box, roots = self.plan.local_table(rank)
         self.local = GpuEngine(lev, ch, box, mesh.nx, device)
@@ -444,8 +449,13 @@ class ShardedHPS:
             self._top_interior = [int(i) for i in np.nonzero(tch[:, 0] >= 0)[0]]
         self.xchg = ShardedExchange(self.plan, rank, dist)
         self.leaf_lo, self.leaf_hi = self.plan.local_leaf_range(rank)
-        lam = float(solver.lambda_function(np.float64(0.0), np.float64(0.0)))
-        self.local.set_leaf_constant(lam)
+        if solver.solver_type == "FISHPACK90":
+            lam = float(solver.lambda_function(np.float64(0.0), np.float64(0.0)))      # FiniteVolumeSolver.cpp:254
+            self.local.set_leaf_constant(lam)
+        else:   # this rank's leaves only: sampled where FiniteVolumeSolver.cpp:63-79 samples (general merge plan above them)
+            boxes = mesh.box[mesh.leaf_nodes[self.leaf_lo:self.leaf_hi]]
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            self.local.set_leaf_variable(sample_leaf_coefficients(solver, boxes, mesh.nx, max(1, threads // max(1, world))))
 
     def __del__(self):
         self.top_if = self.top = None      # the upper-tree handle borrows the forest handle's stream: release it first

@@ -23,22 +23,31 @@ CASES = {
 }
 
 
+# two GPUs only (not run by the single-GPU parts of this file): variable-coefficient leaves below the cut - the subtree roots'
+# DtN maps are not signed-symmetric, so the upper tree takes the general plan - on a lopsided tree dealt by merge work
+EXTRA_CASES = {
+    "adaptive_l2_4_m8_varcoef": dict(problem_name="varcoef", solver_kind="fivepoint", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=2, max_level=4,
+                                     threshold=1.2, refine_box=(-10.0, 0.5, -10.0, 0.5)),
+}
+ALL_CASES = dict(CASES, **EXTRA_CASES)
+
+
 def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-def _solver(P):
+def _solver(P, kind="fishpack"):
     s = ef.FiniteVolumeSolver()
-    s.solver_type = "FISHPACK90"
+    s.solver_type = "FISHPACK90" if kind == "fishpack" else "FivePointStencil"
     s.alpha_function, s.beta_function, s.lambda_function = P["alpha"], P["beta"], P["lam"]
     return s
 
 
-def _run_sharded(kw, rank, world, device, top_mode="replicated"):
+def _run_sharded(kw, rank, world, device, top_mode="replicated", balance="count"):
     import torch
     P = O.problem(kw["problem_name"])
     m = _mesh_for(kw)
-    hps = ShardedHPS(m, _solver(P), device=device, rank=rank, world=world, top_mode=top_mode)
+    hps = ShardedHPS(m, _solver(P, kw["solver_kind"]), device=device, rank=rank, world=world, top_mode=top_mode, balance=balance)
     f, g = hps.sample_inputs(P["f"], P["u"])
     f_dev = torch.from_numpy(f).cuda(device)
     g_dev = torch.from_numpy(g).cuda(device)
@@ -53,7 +62,7 @@ def _run_sharded(kw, rank, world, device, top_mode="replicated"):
 def _run_single(kw):
     P = O.problem(kw["problem_name"])
     m = _mesh_for(kw)
-    hps = ef.HPSAlgorithm(m, _solver(P))
+    hps = ef.HPSAlgorithm(m, _solver(P, kw["solver_kind"]))
     hps.buildStage()
     hps.upwardsStage(P["f"])
     hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0))
@@ -73,14 +82,14 @@ def test_forest_and_upper_tree_on_one_gpu(case, top_mode):
     assert relerr(u, np.concatenate(ora.leaf_solution())) < 1e-10
 
 
-def _worker(rank, world, port, case, out_dir, top_mode):
+def _worker(rank, world, port, case, out_dir, top_mode, balance="count"):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        hps, u, rootT = _run_sharded(CASES[case], rank, world, rank, top_mode)
+        hps, u, rootT = _run_sharded(ALL_CASES[case], rank, world, rank, top_mode, balance)
         np.save(os.path.join(out_dir, "u_%d.npy" % rank), u)
         np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array([hps.leaf_lo, hps.leaf_hi]))
         if rootT is not None and rank == 0:
@@ -104,3 +113,21 @@ def test_two_gpus_over_nccl(case, top_mode, tmp_path):
         lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
         assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-12
     assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12
+
+
+@pytest.mark.parametrize("top_mode", ["replicated", "root"])
+def test_two_gpus_variable_coefficients_balanced_by_work(top_mode, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = "adaptive_l2_4_m8_varcoef"
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path), top_mode, "work"), nprocs=2, join=True)
+    single = _run_single(ALL_CASES[case])
+    u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
+    ranges = [tuple(np.load(tmp_path / ("range_%d.npy" % r))) for r in range(2)]
+    assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == single.mesh.n_leaves
+    for r, (lo, hi) in enumerate(ranges):
+        assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-10
+    assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-10
