@@ -21,6 +21,18 @@ struct Error { int code; std::string msg; };
                                  std::string(#call) + ": " + cudaGetErrorString(e__)};             \
     } while (0)
 
+// Function attributes (opt-in shared memory above 48 KB) and occupancy figures are per DEVICE: a launch site keeps a bit mask of
+// the devices it has prepared.  True the first time the site is reached with the current device.
+inline bool first_use_on_device(unsigned long long& seen)
+{
+    int dev = 0;
+    EF_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 // ---- descriptor-driven batched DGEMM (gemm.cu) ----------------------------------------------
 // One launch computes, for every batch entry z and every block descriptor d:
 //     C_d = [C0_d] + sum_t  sign_t * A_{d,t} (rows x K_t) * B_{d,t} (K_t x cols)

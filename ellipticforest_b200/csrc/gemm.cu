@@ -227,11 +227,9 @@ static void launch_cfg(double* const* ptab, int nops, const GemmBlock* d_blocks,
     }
     using C = GemmCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
     auto kern = bgemm_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long prepared = 0;
+    if (first_use_on_device(prepared))
         EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
     long long grid = (long long)max_tiles * nblocks * batch;
     if (grid <= 0) return;
     if (grid > 2147483647LL) throw Error{EF_ERR_BAD_SHAPE, "bgemm grid too large"};
@@ -534,11 +532,9 @@ void launch_invert_small(double* const* ptab, int nops, int op, long long off, l
         default: break;
     }
     int smem = (N * (N + 1) + N) * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long prepared = 0;
+    if (first_use_on_device(prepared))
         EF_CUDA(cudaFuncSetAttribute(invert_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 128) * 8));
-        attr_set = true;
-    }
     invert_small_kernel<<<batch, 256, smem, stream>>>(ptab, nops, op, off, off2, ld, N, min_pivot);
     EF_CUDA(cudaGetLastError());
 }

@@ -369,7 +369,8 @@ static void solve_const_mma_M(const double* Q, const double* boxes, const int* l
     constexpr int smem = LeafMmaSmem<M, WARPS>::BYTES;
     auto kern = leaf_solve_const_mma_kernel<M, WARPS>;
     static int resident = 0;   // CTAs the device holds at once: the leaves are dealt to them in a grid-stride loop
-    if (!resident) {
+    static unsigned long long prepared = 0;
+    if (first_use_on_device(prepared)) {   // (the devices of one box are identical: `resident` is the same for all of them)
         EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int dev = 0, sms = 0, per_sm = 0;
         EF_CUDA(cudaGetDevice(&dev));
@@ -594,11 +595,8 @@ static void var_solve_M(const double* coef, const double* P, const double* boxes
     const int C = mode == 2 ? (M >= 32 ? 16 : (4 * M < 32 ? 4 * M : 32)) : 1;
     const int smem = (M * (M + 1) + M * C + M * M * C) * (int)sizeof(double);
     auto kern = leaf_var_solve_kernel<M>;
-    static int attr_done = 0;
-    if (smem > 48 * 1024 && attr_done < smem) {
+    if (smem > 48 * 1024)   // per device, and the size depends on the mode: set on every such launch (a host-side table write)
         EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = smem;
-    }
     dim3 grid(n_leaves, mode == 2 ? (4 * M) / C : 1);
     kern<<<grid, 256, smem, s>>>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, C);
 }

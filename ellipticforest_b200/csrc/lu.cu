@@ -260,11 +260,10 @@ void robin_solve(const double* T, const double* a, const double* b, const double
         EF_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(GemmBlock) * blocks.size(), cudaMemcpyHostToDevice, s));
     }
     const int tri_smem = 2 * NB * (NB + 1) * (int)sizeof(double);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long prepared = 0;
+    if (first_use_on_device(prepared)) {
         EF_CUDA(cudaFuncSetAttribute(tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
         EF_CUDA(cudaFuncSetAttribute(tri_solve_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 65 + 64) * 8));
-        attr = true;
     }
     for (int p = 0; p < np; p++) {
         int k0 = p * NB;
