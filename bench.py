@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--lean-T", action="store_true", help="EFGPU_LEAN_T memory policy (single GPU): interior DtN maps in a transient arena")
     ap.add_argument("--n-solves", type=int, default=0, help="BASELINE configs[2] pattern: after the timed steps, K x (upwards + solve) on the "
                     "resident operators with f and the boundary data scaled by (1 + k/K); reported as `repeat_solves`")
+    ap.add_argument("--lazy-root-dtn", action="store_true", help="EFGPU_LAZY_ROOT_DTN: the DtN map of the whole domain (read by nothing on the Dirichlet "
+                    "path) is left to its first reader; recorded in config.root_dtn - not the reference's buildStage, which always forms it")
     ap.add_argument("--tuning", action="append", default=[], metavar="KEY=VALUE",
                     help="efgpu_set_tuning knob for A/B runs (include/efgpu.h), e.g. --tuning 5=1; recorded in config.tuning")
     ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6 own arm, 5 reference arm)")
@@ -247,6 +249,7 @@ def own_arm(a):
 
     hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world)
     hps.no_symmetry = a.no_symmetry
+    hps.lazy_root_dtn = a.lazy_root_dtn
     if a.lean_T:
         if world > 1:
             raise SystemExit("--lean-T: single GPU only")
@@ -453,7 +456,7 @@ def own_arm(a):
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "mesh": mesh_stats, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
-                   "sharding": hps.sharding(), "tuning": a.tuning,
+                   "sharding": hps.sharding(), "tuning": a.tuning, "root_dtn": "deferred to its first reader (EFGPU_LAZY_ROOT_DTN)" if a.lazy_root_dtn else "formed by the build",
                    "merge_plan": "general (EFGPU_NO_SYMMETRY)" if a.no_symmetry else "symmetric where the subtree is uniform with constant-coefficient leaves%s" % (
                        "" if (a.adaptive or a.problem == "varcoef") else " (every merge of this workload)")},
         "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,

@@ -108,6 +108,8 @@ struct efgpu_handle {
     bool external_leaves = false;                // leaf T / h are supplied by the caller (upper tree of a sharded run)
     int part_rank = 0, part_nranks = 1;          // row partition of S / T among the ranks that replicate this tree
     bool root_T_distributed = false;             // partitioned tree after a build: the roots' T rows are not gathered / mirrored yet
+    bool root_T_pending = false;                 // EFGPU_LAZY_ROOT_DTN: the level-0 DtN products have not been issued yet
+    unsigned cur_flags = 0;                      // flags of the build in progress / of the last build
     efgpu_allgather_fn allgather = nullptr; void* allgather_user = nullptr;   // collective supplied by the caller (NCCL)
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
     // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
@@ -480,7 +482,7 @@ static void compute_flop_model(efgpu_handle* H)
         const double n3 = (double)b.n * b.n * b.n;
         canon += b.count * 810.0 * n3 + b.count * (2.0 / 3.0) * n3;
         for (const Step& st : b.active())
-            if (st.kind == 1)
+            if (st.kind == 1 && !(st.cls == EFGPU_PROF_GEMM_T && b.level == 0 && (H->cur_flags & EFGPU_LAZY_ROOT_DTN)))
                 for (int k = st.first; k < st.first + st.count; k++)
                     for (int t = 0; t < b.blocks[k].nterms; t++) issued += b.count * 2.0 * b.blocks[k].rows * b.blocks[k].cols * b.blocks[k].t[t].K;
         up_bytes += b.count * 8.0 * (16.0 + 16.0) * b.n * b.n;
@@ -781,11 +783,12 @@ static void build_begin(efgpu_handle* H, unsigned flags)
     // vs :332-343, and is not symmetric); external leaves: as declared by efgpu_set_symmetric_leaves
     const bool leaves_sym = H->external_leaves ? H->ext_sym : H->leaf_kind == EFGPU_LEAF_CONSTANT;
     for (auto& b : H->batches) b.use_sym = b.symcand && leaves_sym && !(flags & EFGPU_NO_SYMMETRY);
+    H->cur_flags = flags;
     compute_flop_model(H);
     const double big = 1e300;
     EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
     EF_CUDA(cudaEventRecord(H->ev0, s));
-    H->built = false; H->root_T_distributed = false;
+    H->built = false; H->root_T_distributed = false; H->root_T_pending = false;
     timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, flags); });
 }
 
@@ -793,6 +796,12 @@ static void build_level(efgpu_handle* H, int lev, int phase)
 {
     cudaStream_t s = H->stream;
     if (lev < 0 || lev > H->max_level) throw Error{EF_ERR_BAD_ARG, "bad level"};
+    if (lev == 0 && phase == 1 && (H->cur_flags & EFGPU_LAZY_ROOT_DTN) && !H->level_batches[0].empty()) {
+        // the DtN map of the whole domain is read by nothing on the Dirichlet path (only by the root's Robin system, a parent
+        // that does not exist, and parity readers): its products are issued by complete_root_T when somebody asks for it
+        H->root_T_pending = true;
+        return;
+    }
     for (int bi : H->level_batches[lev]) {
         BatchH& b = H->batches[bi];
         double* const* ptab = b.d_ptab.as<double*>();
@@ -854,6 +863,16 @@ static void build_level(efgpu_handle* H, int lev, int phase)
 // where they were computed until this (collective) call gathers them and mirrors the blocks of the symmetric plan.
 static void complete_root_T(efgpu_handle* H)
 {
+    if (H->root_T_pending) {   // EFGPU_LAZY_ROOT_DTN: phase 1 of level 0 now (on every rank of a partition: this call is collective)
+        if (!H->built) throw Error{EF_ERR_STATE, "root DtN map requested before the build has finished"};
+        H->root_T_pending = false;
+        H->cur_flags &= ~(unsigned)EFGPU_LAZY_ROOT_DTN;
+        build_level(H, 0, 1);
+        // the map exists from now on: the flop model counts its products again
+        compute_flop_model(H);
+        EF_CUDA(cudaStreamSynchronize(H->stream));
+        collect_profile(H);
+    }
     if (!H->root_T_distributed) return;
     if (!H->allgather) throw Error{EF_ERR_STATE, "row-partitioned tree without an all-gather callback (efgpu_set_allgather)"};
     cudaStream_t s = H->stream;
@@ -959,9 +978,15 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
 static thread_local std::string g_create_error;
 
 // EFGPU_LEAN_T: only the DtN maps of leaves (own buffer) and of the roots (merged last) outlive the build
-static void require_T_retained(const efgpu_handle* H, int node)
+static void require_T_retained(efgpu_handle* H, int node)
 {
     const efgpu::NodeH& nd = H->nodes[node];
+    if (H->root_T_pending && nd.parent < 0 && !nd.leaf && nd.level == 0) {   // EFGPU_LAZY_ROOT_DTN: first reader
+        if (H->part_nranks > 1)
+            throw efgpu::Error{EF_ERR_STATE, "the root's DtN map of a partitioned tree has not been formed (EFGPU_LAZY_ROOT_DTN): call efgpu_complete_root_dtn on every rank first"};
+        EF_CUDA(cudaSetDevice(H->device));
+        efgpu::complete_root_T(H);
+    }
     if (H->root_T_distributed && nd.parent < 0 && !nd.leaf)
         throw efgpu::Error{EF_ERR_STATE, "the root's DtN map of a partitioned tree is row-distributed: call efgpu_complete_root_dtn on every rank first"};
     if (H->lean_T && !nd.leaf && nd.parent >= 0)
@@ -1328,7 +1353,7 @@ int efgpu_solve_robin(efgpu_handle* H, const double* a, const double* b, const d
     const bool homogeneous = (flags & EFGPU_HOMOGENEOUS_RHS) != 0;
     if (!homogeneous && !H->upwards_done) throw Error{EF_ERR_STATE, "solve before upwards (non-homogeneous right-hand side)"};
     if (H->nodes[0].leaf && H->external_leaves) throw Error{EF_ERR_STATE, "no root operator"};
-    if (H->root_T_distributed) throw Error{EF_ERR_STATE, "the root's DtN map of a partitioned tree is row-distributed: call efgpu_complete_root_dtn on every rank first"};
+    if (!H->nodes[0].leaf) require_T_retained(H, 0);   // forms a lazily deferred root map (EFGPU_LAZY_ROOT_DTN); throws while it is row-distributed
     cudaStream_t s = H->stream;
     H->d_robin.alloc((robin_workspace_doubles(len) + 4 * (size_t)len) * sizeof(double));
     double* abr = H->d_robin.as<double>();

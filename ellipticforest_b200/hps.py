@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from ._lib import Stats, TreeDesc, check
 
-CACHE_OPERATORS, HOMOGENEOUS_RHS, KEEP_X, LEAN_T, NO_SYMMETRY = 1, 2, 4, 8, 16
+CACHE_OPERATORS, HOMOGENEOUS_RHS, KEEP_X, LEAN_T, NO_SYMMETRY, LAZY_ROOT_DTN = 1, 2, 4, 8, 16, 32
 OP = dict(T=0, S=1, X=2, H=3, Xinv=4, T_uncoarsened=5)
 VEC = dict(h=0, w=1, g=2, u=3, f=4)
 
@@ -207,6 +207,9 @@ class HPSAlgorithm:
         self.keep_x = False
         self.lean_T = False   # EFGPU_LEAN_T: DtN maps of interior nodes are transient (memory policy)
         self.no_symmetry = False   # EFGPU_NO_SYMMETRY: general merge plan even where X and diag(d) T are symmetric
+        # EFGPU_LAZY_ROOT_DTN: the DtN map of the whole domain is formed by its first reader (Robin solve, operator(0, "T")) instead
+        # of by buildStage - nothing on the Dirichlet path reads it
+        self.lazy_root_dtn = False
         # FivePointStencil leaves: the reference evaluates alpha/beta/lambda inside every leaf solve; here they are sampled on
         # the host once per buildStage.  False keeps the coefficient arrays already resident in HBM (same functions).
         self.resample_coefficients = True
@@ -229,7 +232,8 @@ class HPSAlgorithm:
     def _flags(self):
         return ((CACHE_OPERATORS if self.options["cache-operators"] else 0)
                 | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0) | (KEEP_X if self.keep_x else 0)
-                | (LEAN_T if self.lean_T else 0) | (NO_SYMMETRY if self.no_symmetry else 0))
+                | (LEAN_T if self.lean_T else 0) | (NO_SYMMETRY if self.no_symmetry else 0)
+                | (LAZY_ROOT_DTN if self.lazy_root_dtn else 0))
 
     def is_symmetric(self):
         """True when the root's DtN map was built by the symmetric merge plan (efgpu_is_symmetric)."""

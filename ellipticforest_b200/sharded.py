@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import TreeDesc, check
-from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, NO_SYMMETRY, OP, VEC, FiniteVolumeGrid, sample_leaf_coefficients
+from .hps import CACHE_OPERATORS, HOMOGENEOUS_RHS, LAZY_ROOT_DTN, NO_SYMMETRY, OP, VEC, FiniteVolumeGrid, sample_leaf_coefficients
 
 
 class ShardPlan:
@@ -463,10 +463,11 @@ class ShardedHPS:
 
     # -- helpers -------------------------------------------------------------------------------
     no_symmetry = False
+    lazy_root_dtn = False      # EFGPU_LAZY_ROOT_DTN on the upper tree (the forests have no level-0 merge)
 
     def _flags(self):
         return ((CACHE_OPERATORS if self.options["cache-operators"] else 0) | (HOMOGENEOUS_RHS if self.options["homogeneous-rhs"] else 0)
-                | (NO_SYMMETRY if self.no_symmetry else 0))
+                | (NO_SYMMETRY if self.no_symmetry else 0) | (LAZY_ROOT_DTN if self.lazy_root_dtn else 0))
 
     def sharding(self):
         K = len(self.plan.cut_nodes)

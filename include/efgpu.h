@@ -53,10 +53,15 @@ enum {
                                    (HPSAlgorithm.hpp:497-518), so the maps of one tree level share a transient arena that is
                                    reused two levels up; after the build only leaf and root T can be read back.  Halves the
                                    resident operator bytes (X^-1 + S + H stay: 512 n^2 B per merge instead of 1024 n^2). */
-    EFGPU_NO_SYMMETRY = 16u     /* always use the general merge plan.  By default a merge whose subtree consists of square,
+    EFGPU_NO_SYMMETRY = 16u,    /* always use the general merge plan.  By default a merge whose subtree consists of square,
                                    uncoarsened patches with constant-coefficient (FISHPACK90) leaves uses the symmetry of X and of diag(d) T (d = -1 on W and S: the
                                    coordinate-derivative convention of FiniteVolumeSolver.cpp:332-343): 4 instead of 6 products
                                    per level of the block inversion and 36 instead of 64 block products for T. */
+    EFGPU_LAZY_ROOT_DTN = 32u   /* the DtN map of the whole domain (tree level 0) is read by nothing on the Dirichlet path - no parent merges it, the
+                                   upwards and solve sweeps use X^-1, H and S only (HPSAlgorithm.hpp:529-577) - yet it is 22 % of the flops of a
+                                   uniform build.  With this flag efgpu_build leaves its block products unissued; the first reader (efgpu_solve_robin
+                                   with b != 0, efgpu_get_operator / efgpu_operator_device of the root's T, efgpu_complete_root_dtn) forms it then,
+                                   with identical results.  Off by default: the reference's buildStage always forms it (mergeT_ :940-968). */
 };
 
 enum { EFGPU_LEAF_CONSTANT = 0, EFGPU_LEAF_VARIABLE = 1 };

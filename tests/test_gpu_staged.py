@@ -1,0 +1,98 @@
+"""Staged GPU tests: switches written after the round's GPU budget was spent (all off by default).  They run with
+EFGPU_TEST_STAGED=1 - tools/gpu_round2.sh sets it - and move into the regular parity files once they have passed on a B200.
+Each compares the switched path with the default path of the same library on the same inputs, which the regular parity
+tests tie to the reference."""
+import os
+
+import numpy as np
+import pytest
+
+import ellipticforest_b200 as ef
+import hps_oracle as O
+from ellipticforest_b200 import _lib
+from test_host import _mesh_for
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("EFGPU_TEST_STAGED") != "1", reason="staged: not yet run on a GPU (set EFGPU_TEST_STAGED=1)")]
+
+CASES = {
+    "uniform_l3_m16": dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16, min_level=3, max_level=3,
+                           threshold=1.2, refine_box=None),
+    "adaptive_l1_4_m8": dict(problem_name="helmholtz", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=1, max_level=4,
+                             threshold=1.2, refine_box=None),
+    "uniform_l4_m32": dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=32, min_level=4, max_level=4,
+                           threshold=1.2, refine_box=None),
+}
+
+
+def _hps(kw, **attrs):
+    P = O.problem(kw["problem_name"])
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FISHPACK90"
+    s.lambda_function = P["lam"]
+    hps = ef.HPSAlgorithm(_mesh_for(kw), s)
+    for k, v in attrs.items():
+        setattr(hps, k, v)
+    return P, hps
+
+
+def _robin(P):
+    def bc(side, x, y):
+        u = P["u"](x, y)
+        dudn = np.where(np.asarray(side) < 2, np.cos(x), np.cos(y))
+        return u + 0.25 * dudn, 1.0 + 0 * u, 0.25 + 0 * u
+    return bc
+
+
+@pytest.mark.parametrize("case", ["uniform_l3_m16", "adaptive_l1_4_m8"])
+def test_lazy_root_dtn(case):
+    """EFGPU_LAZY_ROOT_DTN: buildStage leaves the DtN map of the whole domain unformed; the Dirichlet path gives the same bits,
+    and the first reader of the map (operator(0, "T"), a Robin solve) gets the same bits as from a regular build."""
+    kw = CASES[case]
+    P, ref = _hps(kw)
+    ref.buildStage(); ref.upwardsStage(P["f"])
+    dirichlet = lambda side, x, y: (P["u"](x, y), 1.0, 0.0)
+    u_ref = ref.solveStage(dirichlet).copy()
+    T_ref = ref.operator(0, "T")
+    u_robin_ref = ref.solveStage(_robin(P)).copy()
+    full = ref.stats()["merge_flops_issued"]
+
+    P, lazy = _hps(kw, lazy_root_dtn=True)
+    lazy.buildStage(); lazy.upwardsStage(P["f"])
+    saved = full - lazy.stats()["merge_flops_issued"]
+    assert saved > (0.15 if case.startswith("uniform") else 0.0) * full      # the root's T products: ~22 % of a uniform build
+    assert np.array_equal(lazy.solveStage(dirichlet), u_ref)
+    assert lazy.stats()["merge_flops_issued"] == full - saved    # still unformed after a Dirichlet solve
+    assert np.array_equal(lazy.operator(0, "T"), T_ref)          # formed by its first reader
+    assert lazy.stats()["merge_flops_issued"] == full
+    assert np.array_equal(lazy.solveStage(_robin(P)), u_robin_ref)
+
+    P, lazy2 = _hps(kw, lazy_root_dtn=True)                      # first reader = the Robin system of the root
+    lazy2.buildStage(); lazy2.upwardsStage(P["f"])
+    assert np.array_equal(lazy2.solveStage(_robin(P)), u_robin_ref)
+    lazy2.buildStage()                                           # a rebuild defers it again
+    assert lazy2.stats()["merge_flops_issued"] == full - saved
+
+
+@pytest.mark.parametrize("case", ["uniform_l3_m16", "uniform_l4_m32"])
+def test_symmetric_diagonal_blocks_of_T_as_block_triangles(case):
+    """efgpu_set_tuning(5, 1): the diagonal blocks of the signed-symmetric T multiply only their upper sub-block triangle
+    (active from child side 256: uniform_l4_m32 reaches n = 256 at the root; uniform_l3_m16 checks that small merges are
+    untouched).  Same operators and solution as the default plan up to summation order."""
+    kw = CASES[case]
+    P, ref = _hps(kw)
+    ref.buildStage(); ref.upwardsStage(P["f"])
+    u_ref = ref.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+    T_ref, S_ref, flops_ref = ref.operator(0, "T"), ref.operator(0, "S"), ref.stats()["merge_flops_issued"]
+    lib = _lib.load()
+    assert lib.efgpu_set_tuning(5, 1) == 0
+    try:
+        P, tri = _hps(kw)
+        tri.buildStage(); tri.upwardsStage(P["f"])
+        u = tri.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0))
+        rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+        assert rel(tri.operator(0, "T"), T_ref) < 1e-12 and rel(tri.operator(0, "S"), S_ref) < 1e-12 and rel(u, u_ref) < 1e-12
+        flops = tri.stats()["merge_flops_issued"]
+        assert flops < flops_ref if case == "uniform_l4_m32" else flops == flops_ref
+    finally:
+        lib.efgpu_set_tuning(5, 0)

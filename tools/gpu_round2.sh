@@ -4,11 +4,12 @@
 #   gpurun --gpus 8 --timeout 1200 -- 'bash tools/gpu_round2.sh r2a multi "1 2 4 8"'
 TAG=${1:-r2a}; MODE=${2:-single}; NS=${3:-"2 4 8"}
 OUT=gpurun_out; mkdir -p $OUT
+export EFGPU_TEST_STAGED=1     # tests/test_gpu_staged.py: the switches below, against the default path
 if [ "$MODE" = "single" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest exit $?"; tail -4 $OUT/pytest_$TAG.log
   # A/B: symmetric diagonal blocks of T as block triangles (327 -> 315 n^3 per merge; CPU-emulated at 1 / 4 / 8 ranks)
-  for T in "" "--tuning 5=1"; do
-    N=$(echo "$T" | tr -dc '0-9'); timeout 600 python bench.py --no-cpu-baseline $T > $OUT/bench_${TAG}_t${N:-0}.json 2> $OUT/bench_${TAG}_t${N:-0}.err
+  for T in "" "--tuning 5=1" "--lazy-root-dtn" "--tuning 5=1 --lazy-root-dtn"; do
+    N=$(echo "$T" | tr -dc '0-9a-z'); timeout 600 python bench.py --no-cpu-baseline $T > $OUT/bench_${TAG}_t${N:-0}.json 2> $OUT/bench_${TAG}_t${N:-0}.err
     echo "bench [$T] exit $?"; python -c "import json,sys; d=json.load(open('$OUT/bench_${TAG}_t${N:-0}.json')); print(d['ms_per_step'], d['roofline']['frac'], d['kernel_ms_per_step'])"
   done
   timeout 300 python tools/sample_bench.py > $OUT/sample_bench_$TAG.log 2>&1; tail -2 $OUT/sample_bench_$TAG.log
