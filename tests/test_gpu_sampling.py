@@ -1,5 +1,5 @@
-"""SURVEY 8(f) rank 1 - the callers either side of the path: sampling coordinates written by the device, coefficient
-arrays handed over in device memory, and the error norms of the reference's drivers reduced on the device.
+"""SURVEY 8(f) rank 1 - the callers either side of the path: sampling coordinates written by the device and the error norms of
+the reference's drivers reduced on the device (coefficient arrays handed over in device memory: tests/test_gpu_staged.py).
 
 Oracle: the host formulas of the Python mirror (pinned to the compiled reference through the golden dumps) and a numpy
 restatement of the driver loop examples/elliptic-multiple/main.cpp:346-371.  Coordinates: bit-exact.  Norms: linf exact,
@@ -72,46 +72,3 @@ def test_error_norms_match_the_reference_driver_loop(case):
     assert abs(g1 - l1) <= 1e-12 * l1 and abs(g2 - l2) <= 1e-12 * l2, (g1, l1, g2, l2)
     assert hps.errorNorms(exact) == (g1, g2, gi)      # array form, and deterministic
     assert np.isfinite(gi) and 0.0 < g1 <= g2 <= gi   # area-weighted means: l1 <= l2 <= linf
-
-
-def test_device_resident_coefficients_and_load():
-    """FivePointStencil leaves whose alpha / beta / lambda and load never exist on the host: evaluated by device code
-    (torch here) on the coordinates the library writes, handed back as device pointers."""
-    torch = pytest.importorskip("torch")
-    kw = dict(problem_name="varcoef", solver_kind="fivepoint", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=1, max_level=3,
-              threshold=1.2, refine_box=(2.0, 10.0, -3.0, 10.0))
-    m = _mesh_for(kw)
-    P, s = _solver(kw)
-    host = ef.HPSAlgorithm(m, s)
-    host.buildStage()
-    host.upwardsStage(P["f"])
-    u_host = host.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
-
-    dev = ef.HPSAlgorithm(m, s)
-    shape = (m.n_leaves, m.nx, m.nx)
-    x, y = (torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(2))
-
-    def on_points(which, fn):
-        dev.leafPointsDevice(which, x.data_ptr(), y.data_ptr())
-        return torch.from_numpy(np.ascontiguousarray(np.broadcast_to(fn(x.cpu().numpy(), y.cpu().numpy()), shape))).cuda()
-
-    # (the functions of the oracle are numpy callables: evaluated on the device-written coordinates, uploaded once)
-    arrays = [on_points("centre", P["alpha"]), on_points("W", P["beta"]), on_points("E", P["beta"]), on_points("S", P["beta"]),
-              on_points("N", P["beta"]), on_points("centre", P["lam"])]
-    dev.setVariableCoefficientsDevice(*[a.data_ptr() for a in arrays])
-    dev.buildStage()
-    f = on_points("centre", P["f"])
-    dev.upwardsStageDevice(f.data_ptr())
-    side, bx, by = dev.root_boundary_points()
-    g = torch.from_numpy(np.ascontiguousarray(P["u"](bx, by))).cuda()
-    u = torch.empty(shape, dtype=torch.float64, device="cuda")
-    dev.solveStageDevice(g.data_ptr(), u.data_ptr())
-    # same coordinates and kernels; numpy may evaluate sin / cos of a full array and of a broadcast view through different
-    # (SIMD / scalar) loops, so the sampled values can differ in the last bit
-    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
-    assert rel(u.cpu().numpy(), u_host) < 1e-10
-    assert rel(dev.operator(0, "T"), host.operator(0, "T")) < 1e-10
-    exact = on_points("centre", P["u"])
-    n_dev = dev.errorNormsDevice(exact.data_ptr(), u.data_ptr())
-    assert n_dev == dev.errorNormsDevice(exact.data_ptr())        # u_dev = NULL: the handle's own solution
-    assert np.allclose(n_dev, host.errorNorms(P["u"]), rtol=1e-8, atol=0.0)

@@ -96,3 +96,49 @@ def test_symmetric_diagonal_blocks_of_T_as_block_triangles(case):
         assert flops < flops_ref if case == "uniform_l4_m32" else flops == flops_ref
     finally:
         lib.efgpu_set_tuning(5, 0)
+
+
+def test_device_resident_coefficients_and_load():
+    """FivePointStencil leaves whose alpha / beta / lambda and load never exist on the host: evaluated by device code
+    (torch here) on the coordinates the library writes, handed back as device pointers."""
+    torch = pytest.importorskip("torch")
+    kw = dict(problem_name="varcoef", solver_kind="fivepoint", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=1, max_level=3,
+              threshold=1.2, refine_box=(2.0, 10.0, -3.0, 10.0))
+    m = _mesh_for(kw)
+    P = O.problem(kw["problem_name"])
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FivePointStencil"
+    s.alpha_function, s.beta_function, s.lambda_function = P["alpha"], P["beta"], P["lam"]
+    host = ef.HPSAlgorithm(m, s)
+    host.buildStage()
+    host.upwardsStage(P["f"])
+    u_host = host.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+
+    dev = ef.HPSAlgorithm(m, s)
+    shape = (m.n_leaves, m.nx, m.nx)
+    x, y = (torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(2))
+
+    def on_points(which, fn):
+        dev.leafPointsDevice(which, x.data_ptr(), y.data_ptr())
+        return torch.from_numpy(np.ascontiguousarray(np.broadcast_to(fn(x.cpu().numpy(), y.cpu().numpy()), shape))).cuda()
+
+    # (the functions of the oracle are numpy callables: evaluated on the device-written coordinates, uploaded once)
+    arrays = [on_points("centre", P["alpha"]), on_points("W", P["beta"]), on_points("E", P["beta"]), on_points("S", P["beta"]),
+              on_points("N", P["beta"]), on_points("centre", P["lam"])]
+    dev.setVariableCoefficientsDevice(*[a.data_ptr() for a in arrays])
+    dev.buildStage()
+    f = on_points("centre", P["f"])
+    dev.upwardsStageDevice(f.data_ptr())
+    side, bx, by = dev.root_boundary_points()
+    g = torch.from_numpy(np.ascontiguousarray(P["u"](bx, by))).cuda()
+    u = torch.empty(shape, dtype=torch.float64, device="cuda")
+    dev.solveStageDevice(g.data_ptr(), u.data_ptr())
+    # same coordinates and kernels; numpy may evaluate sin / cos of a full array and of a broadcast view through different
+    # (SIMD / scalar) loops, so the sampled values can differ in the last bit
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    assert rel(u.cpu().numpy(), u_host) < 1e-10
+    assert rel(dev.operator(0, "T"), host.operator(0, "T")) < 1e-10
+    exact = on_points("centre", P["u"])
+    n_dev = dev.errorNormsDevice(exact.data_ptr(), u.data_ptr())
+    assert n_dev == dev.errorNormsDevice(exact.data_ptr())        # u_dev = NULL: the handle's own solution
+    assert np.allclose(n_dev, host.errorNorms(P["u"]), rtol=1e-8, atol=0.0)
