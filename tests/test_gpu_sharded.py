@@ -115,6 +115,7 @@ def test_two_gpus_over_nccl(case, top_mode, tmp_path):
     assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12
 
 
+@pytest.mark.skipif(os.environ.get("EFGPU_TEST_STAGED") != "1", reason="staged: not yet run on GPUs (set EFGPU_TEST_STAGED=1)")
 @pytest.mark.parametrize("top_mode", ["replicated", "root"])
 def test_two_gpus_variable_coefficients_balanced_by_work(top_mode, tmp_path):
     import torch
