@@ -341,3 +341,19 @@ def test_shard_plan_tables():
     shallow = O.build_tree(O.refine_indicator(1.2), (0.0, 1.0, 0.0, 1.0), 8, 1, 1)
     with pytest.raises(ValueError):
         ShardPlan(*_tables(shallow), 8, 2)
+
+
+def test_sharding_description_strings():
+    """ShardedHPS.sharding() feeds bench.py's config line on every multi-GPU run: formatted without a device here."""
+    from ellipticforest_b200.sharded import ShardedHPS
+    nodes = O.build_tree(O.refine_box_indicator((-10.0, 0.5, -10.0, 0.5)), (-10.0, 10.0, -10.0, 10.0), 8, 2, 4)
+
+    class Fake:
+        pass
+    for world, balance in ((2, "count"), (4, "count"), (8, "count"), (4, "work"), (3, "leaves")):
+        for top_mode in ("replicated", "root"):
+            f = Fake()
+            f.plan, f.world, f.top_mode = ShardPlan(*_tables(nodes), 8, world, balance=balance), world, top_mode
+            text = ShardedHPS.sharding(f)
+            assert "over %d GPUs" % world in text and "%" not in text, text
+            assert ("balanced by " + balance in text) == (balance != "count"), text
