@@ -48,8 +48,10 @@ class SingleGpuHPS(HPSAlgorithm):
         return float(np.max(np.abs(u - u_fn(X, Y))))
 
 
-def make_hps(mesh, solver, device=0, rank=0, world=1, options=None):
+def make_hps(mesh, solver, device=0, rank=0, world=1, options=None, cut=2):
+    """cut: tree level whose 4^cut subtrees are dealt to the ranks (2: the 16 subtrees of SURVEY 8(e); 1: four subtrees, for 2 or 4
+    ranks - the level-1 merges then run whole on their owners and only the root merge is row-partitioned)."""
     if world == 1:
         return SingleGpuHPS(mesh, solver, device=device, options=options)
     from .sharded import ShardedHPS
-    return ShardedHPS(mesh, solver, device=device, rank=rank, world=world, options=options)
+    return ShardedHPS(mesh, solver, device=device, rank=rank, world=world, options=options, cut=cut)

@@ -43,11 +43,11 @@ def _solver(P, kind="fishpack"):
     return s
 
 
-def _run_sharded(kw, rank, world, device, top_mode="replicated", balance="count"):
+def _run_sharded(kw, rank, world, device, top_mode="replicated", balance="count", cut=2):
     import torch
     P = O.problem(kw["problem_name"])
     m = _mesh_for(kw)
-    hps = ShardedHPS(m, _solver(P, kw["solver_kind"]), device=device, rank=rank, world=world, top_mode=top_mode, balance=balance)
+    hps = ShardedHPS(m, _solver(P, kw["solver_kind"]), device=device, rank=rank, world=world, top_mode=top_mode, balance=balance, cut=cut)
     f, g = hps.sample_inputs(P["f"], P["u"])
     f_dev = torch.from_numpy(f).cuda(device)
     g_dev = torch.from_numpy(g).cuda(device)
@@ -82,14 +82,14 @@ def test_forest_and_upper_tree_on_one_gpu(case, top_mode):
     assert relerr(u, np.concatenate(ora.leaf_solution())) < 1e-10
 
 
-def _worker(rank, world, port, case, out_dir, top_mode, balance="count"):
+def _worker(rank, world, port, case, out_dir, top_mode, balance="count", cut=2):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        hps, u, rootT = _run_sharded(ALL_CASES[case], rank, world, rank, top_mode, balance)
+        hps, u, rootT = _run_sharded(ALL_CASES[case], rank, world, rank, top_mode, balance, cut)
         np.save(os.path.join(out_dir, "u_%d.npy" % rank), u)
         np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array([hps.leaf_lo, hps.leaf_hi]))
         if rootT is not None and rank == 0:
@@ -132,3 +132,35 @@ def test_two_gpus_variable_coefficients_balanced_by_work(top_mode, tmp_path):
     for r, (lo, hi) in enumerate(ranges):
         assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-10
     assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-10
+
+
+STAGED = pytest.mark.skipif(os.environ.get("EFGPU_TEST_STAGED") != "1", reason="staged: not yet run on GPUs (set EFGPU_TEST_STAGED=1)")
+
+
+@STAGED
+@pytest.mark.parametrize("top_mode", ["replicated", "root"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_cut_at_level_1_on_one_gpu(case, top_mode):
+    """cut = 1: four subtrees; the level-1 merges belong to the forests and the upper tree is the root merge alone."""
+    kw = CASES[case]
+    single = _run_single(kw)
+    hps, u, rootT = _run_sharded(kw, 0, 1, 0, top_mode, cut=1)
+    assert relerr(u, single.u_leaves.reshape(-1)) < 1e-12
+    assert relerr(rootT, single.operator(0, "T").reshape(-1)) < 1e-12
+
+
+@STAGED
+@pytest.mark.parametrize("case", list(CASES))
+def test_cut_at_level_1_on_two_gpus(case, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path), "replicated", "count", 1), nprocs=2, join=True)
+    single = _run_single(CASES[case])
+    u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
+    for r in range(2):
+        lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
+        assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-12
+    assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12

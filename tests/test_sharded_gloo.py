@@ -153,7 +153,7 @@ CASES = {
 }
 
 
-def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False, balance="count"):
+def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False, balance="count", cut=2):
     """Replicated upper tree: share() of the subtree roots, then per level the row slices of S and T are
     all-gathered in place (the oracle computes whole merges; rows a rank does not own are wiped first, so
     only the exchange can restore them)."""
@@ -165,7 +165,7 @@ def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False, ba
         ind = O.refine_box_indicator(kw["refine_box"]) if kw["refine_box"] else O.refine_indicator(1.2)
         nodes = O.build_tree(ind, kw["box"], kw["nx"], kw["min_level"], kw["max_level"])
         solver = O.Solver(kind="fishpack", alpha=P["alpha"], beta=P["beta"], lam=P["lam"])
-        plan = ShardPlan(*_tables(nodes), kw["nx"], world, balance=balance)
+        plan = ShardPlan(*_tables(nodes), kw["nx"], world, cut=cut, balance=balance)
         ids, lev, ch, box, roots = plan.local_table(rank)
         local = OracleEngine(lev, ch, box, kw["nx"], solver)
         lif = LocalIf(local, roots, plan.subtrees_of(rank))
@@ -189,7 +189,7 @@ def _worker_replicated(rank, world, port, case, out_dir, one_allgather=False, ba
             nd = top.nodes[i]
             if nd.leaf:
                 nd.T = top.buf[(i, "T")].numpy().reshape(4 * nd.grid.nx, 4 * nd.grid.nx).copy()
-        for level in (1, 0):
+        for level in range(cut - 1, -1, -1):
             for i, nd in enumerate(top.nodes):
                 if nd.leaf or nd.level != level:
                     continue
@@ -280,7 +280,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("mode", ["root", "replicated", "replicated-one-allgather", "replicated-balanced"])
+@pytest.mark.parametrize("mode", ["root", "replicated", "replicated-one-allgather", "replicated-balanced", "replicated-cut1"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_two_rank_sharded_run_matches_single_process_oracle(case, mode, tmp_path):
     kw = CASES[case]
@@ -288,7 +288,8 @@ def test_two_rank_sharded_run_matches_single_process_oracle(case, mode, tmp_path
         mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
     else:
         mp.spawn(_worker_replicated, args=(2, _free_port(), case, str(tmp_path), mode == "replicated-one-allgather",
-                                           "leaves" if mode == "replicated-balanced" else "count"), nprocs=2, join=True)
+                                           "leaves" if mode == "replicated-balanced" else "count", 1 if mode == "replicated-cut1" else 2),
+                 nprocs=2, join=True)
     ref = O.run(solver_kind="fishpack", **kw)
     u_ref = ref.leaf_solution()
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))

@@ -16,6 +16,11 @@ if [ "$MODE" = "single" ]; then
   timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"; cat $OUT/bench_$TAG.json
 else
   timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q > $OUT/pytest_sharded_$TAG.log 2>&1; echo "pytest exit $?"; tail -4 $OUT/pytest_sharded_$TAG.log
+  for N in 2 4; do   # cut at level 1: four subtrees, level-1 merges whole on their owners (model: -5 % / -11 % at 2 / 4 GPUs)
+    F=$OUT/bench_${TAG}_n${N}_cut1
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --cut 1 > $F.json 2> $F.err
+    echo "bench N=$N cut=1 exit $?"; [ -s $F.json ] && python -c "import json; d=json.load(open('$F.json')); print(d['ms_per_step'], d['stages'], d['config']['sharding'])"
+  done
   for N in $NS; do
     for AG in 0 1; do
       F=$OUT/bench_${TAG}_n${N}_ag$AG
