@@ -64,6 +64,8 @@ def parse_args():
                     "resident operators with f and the boundary data scaled by (1 + k/K); reported as `repeat_solves`")
     ap.add_argument("--cut", type=int, default=2, help="multi-GPU: tree level of the subtrees dealt to the ranks (2: 16 subtrees, the default of "
                     "SURVEY 8(e); 1: four subtrees for 2 or 4 GPUs, level-1 merges whole on their owners)")
+    ap.add_argument("--grouped", action="store_true", help="multi-GPU (4 or 8): level-1 merges row-split inside rank groups, root merge over all ranks "
+                    "(GroupedShardedHPS; not yet run on GPUs)")
     ap.add_argument("--lazy-root-dtn", action="store_true", help="EFGPU_LAZY_ROOT_DTN: the DtN map of the whole domain (read by nothing on the Dirichlet "
                     "path) is left to its first reader; recorded in config.root_dtn - not the reference's buildStage, which always forms it")
     ap.add_argument("--tuning", action="append", default=[], metavar="KEY=VALUE",
@@ -249,7 +251,7 @@ def own_arm(a):
         solver.lambda_function = lambda x, y: lam + 0.0 * x
         f_fn = lambda x, y: (lam - 1.0) * u_exact(x, y)
 
-    hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world, cut=a.cut)
+    hps = efdist.make_hps(mesh, solver, device=local, rank=rank, world=world, cut=a.cut, grouped=a.grouped)
     hps.no_symmetry = a.no_symmetry
     hps.lazy_root_dtn = a.lazy_root_dtn
     if a.lean_T:

@@ -624,3 +624,169 @@ class ShardedHPS:
         if self.world > 1:
             self.dist.all_reduce(e, op=self.dist.ReduceOp.MAX)
         return float(e[0])
+
+
+class GroupedShardedHPS(ShardedHPS):
+    """Three tiers for world = 4 * gs ranks (gs = 1, 2 or 4; eight GPUs: gs = 2) on a tree whose 16 level-2 subtrees have equal
+    roots.  The four subtrees under level-1 node k belong to the ranks of group k = [k gs, (k + 1) gs) (Morton blocks), and in
+    the solve a rank only descends through its own level-1 parent.  So
+
+      local  the forest of this rank's subtrees (no communication);
+      mid    level-1 node k alone, its four subtree roots as external leaves, row-partitioned over the gs ranks of the group:
+             the subtree roots' DtN maps and every all-gather of that merge stay inside the group;
+      top    the root merge alone, the four level-1 nodes as external leaves, row-partitioned over all ranks: only the level-1
+             DtN maps are exchanged between groups (one in-place all-gather, each rank sending 1 / gs of its group's map).
+
+    Against the replicated upper tree of ShardedHPS this removes the 16 world-wide broadcasts of the subtree roots' maps, gathers
+    the level-1 S and the products of its inversion over gs instead of 4 gs ranks, and no rank repeats another group's small
+    products (model estimate -4.5 of 52 ms at eight GPUs).  Not yet run on GPUs."""
+
+    def __init__(self, mesh, solver, device=0, rank=0, world=4, options=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.top_mode = "grouped"
+        self.mesh, self.patch_solver, self.rank, self.world, self._device = mesh, solver, rank, world, device
+        self.options = {"cache-operators": False, "homogeneous-rhs": False}
+        if options:
+            self.options.update(options)
+        if world % 4 or world // 4 not in (1, 2, 4):
+            raise ValueError("grouped sharding needs 4, 8 or 16 ranks")
+        if solver.solver_type != "FISHPACK90":
+            raise NotImplementedError("grouped sharding: constant-coefficient leaves only")
+        self.gs = gs = world // 4
+        self.group_id, self.group_rank = rank // gs, rank % gs
+        self.plan = plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, 2)
+        l1 = np.nonzero(plan.level == 1)[0]                              # the four level-1 nodes, Morton order
+        if len(set(int(v) for v in plan.size[plan.cut_nodes])) != 1 or len(set(int(v) for v in plan.size[l1])) != 1:
+            raise ValueError("grouped sharding needs equal subtree roots (uniform upper levels)")
+        ids, lev, ch, box, roots = plan.local_table(rank)
+        self.local = GpuEngine(lev, ch, box, mesh.nx, device)
+        self._stream = torch.cuda.ExternalStream(self.local.stream())
+        self.local_if = _LocalGpu(self.local, roots, plan.subtrees_of(rank))
+        self.xchg = ShardedExchange(plan, rank, dist)
+        self.leaf_lo, self.leaf_hi = plan.local_leaf_range(rank)
+        self.local.set_leaf_constant(float(solver.lambda_function(np.float64(0.0), np.float64(0.0))))
+        # every rank creates every group (new_group is collective); ranks keep their own
+        self.group = None
+        for k in range(4):
+            g = dist.new_group(list(range(k * gs, (k + 1) * gs))) if gs > 1 else None
+            if k == self.group_id:
+                self.group = g
+        star = np.array([[1, 2, 3, 4]] + [[-1] * 4] * 4, dtype=np.int32)   # one merge, four external leaves
+        me1 = int(l1[self.group_id])
+        kids = [int(c) for c in plan.child[me1]]
+        assert kids == [int(plan.cut_nodes[4 * self.group_id + j]) for j in range(4)]
+        self.mid = GpuEngine(np.array([1, 2, 2, 2, 2], dtype=np.int32), star, plan.box[[me1] + kids], mesh.nx, device,
+                             ext_sizes=plan.size[kids].astype(np.int32), stream=self.local.stream())
+
+        def _ag_group(t):
+            with torch.cuda.stream(self._stream):
+                cnt = t.numel() // gs
+                dist.all_gather_into_tensor(t, t[self.group_rank * cnt:(self.group_rank + 1) * cnt], group=self.group)
+
+        def _ag_world(t):
+            with torch.cuda.stream(self._stream):
+                cnt = t.numel() // world
+                dist.all_gather_into_tensor(t, t[rank * cnt:(rank + 1) * cnt])
+        if gs > 1:
+            self.mid.set_partition(self.group_rank, gs, _ag_group)
+        self.top = GpuEngine(np.array([0, 1, 1, 1, 1], dtype=np.int32), star, plan.box[[0] + [int(i) for i in l1]], mesh.nx, device,
+                             ext_sizes=plan.size[l1].astype(np.int32), stream=self.local.stream())
+        self.top.set_partition(rank, world, _ag_world)
+        self.top_if = None
+
+    def __del__(self):
+        self.top = self.mid = None         # both borrow the forest handle's stream: release them first
+        self.local_if = self.local = None
+
+    def sharding(self):
+        return ("level-2 subtrees in Morton blocks over %d GPUs (%d per GPU); level-1 merges row-split inside groups of %d GPUs, root merge over "
+                "all %d; between groups only the level-1 DtN maps travel (one in-place all-gather)" % (self.world, 16 // self.world, self.gs, self.world))
+
+    def _slab(self, eng, which):
+        """One tensor over the four leaf buffers of a star handle (libefgpu lays the leaf DtN maps out back to back)."""
+        v = [eng.operator_view(1 + j, which) for j in range(4)]
+        n = v[0].numel()
+        if any(v[j].data_ptr() != v[0].data_ptr() + 8 * j * n or v[j].numel() != n for j in range(4)):
+            raise RuntimeError("leaf DtN maps are not contiguous")
+        return _dev_tensor(v[0].data_ptr(), 4 * n), n
+
+    def buildStage(self):
+        t, dist, fl = self.torch, self.dist, self._flags()
+        self.local.build(fl)
+        self.mid.set_symmetric_leaves(self.local.is_symmetric())
+        with t.cuda.stream(self._stream):
+            slab, n = self._slab(self.mid, "T_uncoarsened")
+            for k in self.plan.subtrees_of(self.rank):
+                j = k - 4 * self.group_id
+                slab[j * n:(j + 1) * n].copy_(self.local_if.root_T(k))
+            if self.gs > 1:      # rank q of the group owns leaves [4 q / gs, 4 (q + 1) / gs): equal contiguous chunks
+                cnt = slab.numel() // self.gs
+                dist.all_gather_into_tensor(slab, slab[self.group_rank * cnt:(self.group_rank + 1) * cnt], group=self.group)
+        self.mid.build(fl & ~LAZY_ROOT_DTN)      # its root is a level-1 node: gathered and mirrored inside the group by the library
+        self.top.set_symmetric_leaves(self.mid.is_symmetric())
+        with t.cuda.stream(self._stream):
+            Tk = self.mid.operator_view(0, "T_uncoarsened")
+            slab, n = self._slab(self.top, "T_uncoarsened")
+            cnt = slab.numel() // self.world          # = n / gs: chunk r of the slab is part r % gs of leaf r // gs
+            slab[self.rank * cnt:(self.rank + 1) * cnt].copy_(Tk[self.group_rank * cnt:(self.group_rank + 1) * cnt])
+            dist.all_gather_into_tensor(slab, slab[self.rank * cnt:(self.rank + 1) * cnt])
+        self.top.build(fl)
+
+    def gather_root_T(self):
+        self.top.complete_root_T()
+        return self.top.operator_view(0, "T_uncoarsened")
+
+    def upwardsStageDevice(self, f_dev_ptr, scale=1.0, sync=True):
+        t, dist, fl = self.torch, self.dist, self._flags()
+        self.local.upwards(f_dev_ptr, scale, fl)
+        if not (fl & HOMOGENEOUS_RHS):
+            per = 4 // self.gs
+            with t.cuda.stream(self._stream):
+                for k in self.plan.subtrees_of(self.rank):
+                    self.mid.vector_view(1 + k - 4 * self.group_id, "h0").copy_(self.local_if.root_h(k))
+                if self.gs > 1:
+                    for j in range(4):
+                        dist.broadcast(self.mid.vector_view(1 + j, "h0"), src=self.group_id * self.gs + j // per, group=self.group)
+            self.mid.upwards(0, 1.0, fl)
+            with t.cuda.stream(self._stream):
+                self.top.vector_view(1 + self.group_id, "h0").copy_(self.mid.vector_view(0, "h0"))
+                for k in range(4):        # every rank of group k holds that node's h: its first rank sends
+                    dist.broadcast(self.top.vector_view(1 + k, "h0"), src=k * self.gs)
+            self.top.upwards(0, 1.0, fl)
+        if sync:
+            self.local.sync()
+
+    def solveStageDevice(self, g_dev_ptr, u_dev_ptr=0, sync=True):
+        t, fl = self.torch, self._flags()
+        groot = self.top.vector_view(0, "g")
+        with t.cuda.stream(self._stream):
+            groot.copy_(_dev_tensor(g_dev_ptr, groot.numel()))
+        self.top.solve_from_roots(0, fl)
+        with t.cuda.stream(self._stream):
+            self.mid.vector_view(0, "g").copy_(self.top.vector_view(1 + self.group_id, "g"))
+        self.mid.solve_from_roots(0, fl)
+        with t.cuda.stream(self._stream):
+            for k in self.plan.subtrees_of(self.rank):
+                self.local_if.root_g(k).copy_(self.mid.vector_view(1 + k - 4 * self.group_id, "g"))
+        self.local.solve_from_roots(u_dev_ptr, fl, sync=sync)
+
+    def set_profiling(self, on=True):
+        for e in (self.local, self.mid, self.top):
+            e.set_profiling(on)
+
+    def profile(self):
+        p = self.local.profile()
+        for e in (self.mid, self.top):
+            for k, (ms, n) in e.profile().items():
+                p[k] = (p[k][0] + ms, p[k][1] + n)
+        return p
+
+    def stats(self):
+        s = self.local.stats()
+        for e in (self.mid, self.top):
+            ts = e.stats()
+            for k in ("merge_flops_canonical", "merge_flops_issued", "upwards_bytes", "solve_bytes", "device_bytes", "build_ms", "upwards_ms", "solve_ms"):
+                s[k] += ts[k]
+        return s

@@ -164,3 +164,48 @@ def test_cut_at_level_1_on_two_gpus(case, tmp_path):
         lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
         assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-12
     assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12
+
+
+def _worker_grouped(rank, world, port, case, out_dir):
+    import torch
+    import torch.distributed as dist
+    from ellipticforest_b200.sharded import GroupedShardedHPS
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        kw = CASES[case]
+        P = O.problem(kw["problem_name"])
+        hps = GroupedShardedHPS(_mesh_for(kw), _solver(P, kw["solver_kind"]), device=rank, rank=rank, world=world)
+        f, g = hps.sample_inputs(P["f"], P["u"])
+        f_dev, g_dev = torch.from_numpy(f).cuda(rank), torch.from_numpy(g).cuda(rank)
+        u_dev = torch.empty_like(f_dev)
+        hps.buildStage()
+        hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True)
+        hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True)
+        rootT = hps.gather_root_T().cpu().numpy()
+        np.save(os.path.join(out_dir, "u_%d.npy" % rank), u_dev.cpu().numpy())
+        np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array([hps.leaf_lo, hps.leaf_hi]))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "T_root.npy"), rootT)
+    finally:
+        dist.destroy_process_group()
+
+
+@STAGED
+@pytest.mark.parametrize("world", [4, 8])
+def test_grouped_level_1_merges(world, tmp_path):
+    """GroupedShardedHPS: forests, level-1 merges inside rank groups (1 rank at 4 GPUs, 2 at 8), root merge over all ranks."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    case = "uniform_l3_m16"
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker_grouped, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    single = _run_single(CASES[case])
+    u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
+    for r in range(world):
+        lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
+        assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-12
+    assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12

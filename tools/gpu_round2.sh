@@ -21,6 +21,12 @@ else
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --cut 1 > $F.json 2> $F.err
     echo "bench N=$N cut=1 exit $?"; [ -s $F.json ] && python -c "import json; d=json.load(open('$F.json')); print(d['ms_per_step'], d['stages'], d['config']['sharding'])"
   done
+  for N in 4 8; do   # three tiers: level-1 merges inside rank groups (model: -4.5 of 52 ms at 8 GPUs)
+    [ $(nvidia-smi -L | wc -l) -ge $N ] || continue
+    F=$OUT/bench_${TAG}_n${N}_grouped
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --grouped > $F.json 2> $F.err
+    echo "bench N=$N grouped exit $?"; [ -s $F.json ] && python -c "import json; d=json.load(open('$F.json')); print(d['ms_per_step'], d['stages'], d['config']['sharding'])"
+  done
   for N in $NS; do
     for AG in 0 1; do
       F=$OUT/bench_${TAG}_n${N}_ag$AG
