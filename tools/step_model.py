@@ -29,6 +29,7 @@ ap.add_argument("--gpus", default="1,2,4,8")
 ap.add_argument("--cut", type=int, default=2)
 ap.add_argument("--tuning5", type=int, default=0)
 ap.add_argument("--lazy-root-dtn", action="store_true")
+ap.add_argument("--grouped", action="store_true", help="GroupedShardedHPS: level-1 merges inside groups of gpus / 4 ranks")
 ap.add_argument("--gemm", type=float, default=32.5, help="TFLOP/s of the large products (S, T)")
 ap.add_argument("--gemm-small", type=float, default=22.0, help="TFLOP/s of the products of the block inversion")
 ap.add_argument("--base-us", type=float, default=73.0)
@@ -92,13 +93,22 @@ def merge_cost(n, level, nranks, count):
 def step(nranks):
     L, M = a.level, a.nx
     tot = dict(gemm_ST=0.0, gemm_Xinv=0.0, base=0.0, launch=0.0, gather=0.0)
+    grouped = a.grouped and nranks >= 4
+    gs = nranks // 4
     for lev in range(L - 1, -1, -1):
         n = M << (L - 1 - lev)
         merges = 4 ** lev
-        c = merge_cost(n, lev, 1, merges // nranks) if (nranks > 1 and lev >= a.cut) else merge_cost(n, lev, nranks, merges)
+        if grouped and lev == 1:
+            c = merge_cost(n, lev, gs, 1)            # one level-1 merge per group, row-split over its gs ranks
+        else:
+            c = merge_cost(n, lev, 1, merges // nranks) if (nranks > 1 and lev >= a.cut) else merge_cost(n, lev, nranks, merges)
         for k, v in c.items():
             tot[k] += v
-    if nranks > 1:
+    if grouped:      # subtree roots' T inside the group, then the four level-1 T's all-gathered over everybody
+        n2, n1 = M << (L - 2), M << (L - 1)
+        tot["gather"] += 8.0 * 4 * (4 * n2) ** 2 * (gs - 1) / gs / (a.nvlink * 1e6) + (a.gather_us * 1e-3 if gs > 1 else 0.0)
+        tot["gather"] += 8.0 * 4 * (4 * n1) ** 2 * (nranks - 1) / nranks / (a.nvlink * 1e6) + a.gather_us * 1e-3
+    elif nranks > 1:
         n2 = M << (L - a.cut)
         tot["gather"] += 8.0 * (4 ** a.cut) * (4 * n2) ** 2 * (nranks - 1) / nranks / (a.nvlink * 1e6) + 16 * a.gather_us * 1e-3
     tot["other"] = a.other_ms / nranks
