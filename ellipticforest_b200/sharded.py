@@ -626,6 +626,70 @@ class ShardedHPS:
         return float(e[0])
 
 
+class GroupedExchange:
+    """The exchanges of GroupedShardedHPS on plain tensors (device views over NCCL on the GPUs; CPU tensors over gloo in
+    tests/test_sharded_gloo.py): world = 4 gs ranks, group k = ranks [k gs, (k + 1) gs) owns the four level-2 subtrees
+    4 k .. 4 k + 3 under level-1 node k, rank q of a group the subtrees [4 q / gs, 4 (q + 1) / gs) of those four."""
+
+    def __init__(self, plan: ShardPlan, rank: int, world: int, dist):
+        if world % 4 or world // 4 not in (1, 2, 4):
+            raise ValueError("grouped sharding needs 4, 8 or 16 ranks")
+        self.plan, self.rank, self.world, self.dist = plan, rank, world, dist
+        self.gs = gs = world // 4
+        self.group_id, self.group_rank = rank // gs, rank % gs
+        self.group = None
+        for k in range(4):      # every rank creates every group (new_group is collective); ranks keep their own
+            g = dist.new_group(list(range(k * gs, (k + 1) * gs))) if gs > 1 else None
+            if k == self.group_id:
+                self.group = g
+
+    def local_index(self, k):
+        """Leaf slot (0..3) of global subtree k under this rank's level-1 node."""
+        j = k - 4 * self.group_id
+        if not 0 <= j < 4:
+            raise ValueError("subtree %d does not belong to group %d" % (k, self.group_id))
+        return j
+
+    def allgather_group(self, t):
+        """In place: equal contiguous chunks of t, chunk q from rank q of this rank's group."""
+        if self.gs > 1:
+            cnt = t.numel() // self.gs
+            self.dist.all_gather_into_tensor(t, t[self.group_rank * cnt:(self.group_rank + 1) * cnt], group=self.group)
+
+    def allgather_world(self, t):
+        cnt = t.numel() // self.world
+        self.dist.all_gather_into_tensor(t, t[self.rank * cnt:(self.rank + 1) * cnt])
+
+    def subtree_T_to_group(self, slab, n, root_T):
+        """slab: the four leaf DtN maps (n doubles each, back to back) of the level-1 handle; root_T(k): this rank's subtree roots."""
+        for k in self.plan.subtrees_of(self.rank):
+            j = self.local_index(k)
+            slab[j * n:(j + 1) * n].copy_(root_T(k))
+        self.allgather_group(slab)      # rank q owns leaves [4 q / gs, 4 (q + 1) / gs): equal contiguous chunks
+
+    def level1_T_to_world(self, Tk, slab):
+        """Tk: this group's level-1 DtN map (whole on every rank of the group); slab: the four leaf maps of the root handle.
+        Chunk r of the slab is part r % gs of leaf r // gs: every rank sends 1 / gs of its group's map."""
+        cnt = slab.numel() // self.world
+        slab[self.rank * cnt:(self.rank + 1) * cnt].copy_(Tk[self.group_rank * cnt:(self.group_rank + 1) * cnt])
+        self.allgather_world(slab)
+
+    def subtree_h_to_group(self, leaf_h, root_h):
+        """leaf_h(j): leaf vector j (0..3) of the level-1 handle; root_h(k): this rank's subtree roots."""
+        per = 4 // self.gs
+        for k in self.plan.subtrees_of(self.rank):
+            leaf_h(self.local_index(k)).copy_(root_h(k))
+        if self.gs > 1:
+            for j in range(4):
+                self.dist.broadcast(leaf_h(j), src=self.group_id * self.gs + j // per, group=self.group)
+
+    def level1_h_to_world(self, own_h, leaf_h):
+        """own_h: h of this group's level-1 node (every rank of the group holds it: its first rank sends); leaf_h(k) of the root handle."""
+        leaf_h(self.group_id).copy_(own_h)
+        for k in range(4):
+            self.dist.broadcast(leaf_h(k), src=k * self.gs)
+
+
 class GroupedShardedHPS(ShardedHPS):
     """Three tiers for world = 4 * gs ranks (gs = 1, 2 or 4; eight GPUs: gs = 2) on a tree whose 16 level-2 subtrees have equal
     roots.  The four subtrees under level-1 node k belong to the ranks of group k = [k gs, (k + 1) gs) (Morton blocks), and in
@@ -654,8 +718,6 @@ class GroupedShardedHPS(ShardedHPS):
             raise ValueError("grouped sharding needs 4, 8 or 16 ranks")
         if solver.solver_type != "FISHPACK90":
             raise NotImplementedError("grouped sharding: constant-coefficient leaves only")
-        self.gs = gs = world // 4
-        self.group_id, self.group_rank = rank // gs, rank % gs
         self.plan = plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, 2)
         l1 = np.nonzero(plan.level == 1)[0]                              # the four level-1 nodes, Morton order
         if len(set(int(v) for v in plan.size[plan.cut_nodes])) != 1 or len(set(int(v) for v in plan.size[l1])) != 1:
@@ -665,14 +727,11 @@ class GroupedShardedHPS(ShardedHPS):
         self._stream = torch.cuda.ExternalStream(self.local.stream())
         self.local_if = _LocalGpu(self.local, roots, plan.subtrees_of(rank))
         self.xchg = ShardedExchange(plan, rank, dist)
+        self.gx = GroupedExchange(plan, rank, world, dist)
+        self.gs, self.group_id, self.group_rank, self.group = self.gx.gs, self.gx.group_id, self.gx.group_rank, self.gx.group
+        gs = self.gs
         self.leaf_lo, self.leaf_hi = plan.local_leaf_range(rank)
         self.local.set_leaf_constant(float(solver.lambda_function(np.float64(0.0), np.float64(0.0))))
-        # every rank creates every group (new_group is collective); ranks keep their own
-        self.group = None
-        for k in range(4):
-            g = dist.new_group(list(range(k * gs, (k + 1) * gs))) if gs > 1 else None
-            if k == self.group_id:
-                self.group = g
         star = np.array([[1, 2, 3, 4]] + [[-1] * 4] * 4, dtype=np.int32)   # one merge, four external leaves
         me1 = int(l1[self.group_id])
         kids = [int(c) for c in plan.child[me1]]
@@ -682,13 +741,11 @@ class GroupedShardedHPS(ShardedHPS):
 
         def _ag_group(t):
             with torch.cuda.stream(self._stream):
-                cnt = t.numel() // gs
-                dist.all_gather_into_tensor(t, t[self.group_rank * cnt:(self.group_rank + 1) * cnt], group=self.group)
+                self.gx.allgather_group(t)
 
         def _ag_world(t):
             with torch.cuda.stream(self._stream):
-                cnt = t.numel() // world
-                dist.all_gather_into_tensor(t, t[rank * cnt:(rank + 1) * cnt])
+                self.gx.allgather_world(t)
         if gs > 1:
             self.mid.set_partition(self.group_rank, gs, _ag_group)
         self.top = GpuEngine(np.array([0, 1, 1, 1, 1], dtype=np.int32), star, plan.box[[0] + [int(i) for i in l1]], mesh.nx, device,
@@ -718,20 +775,12 @@ class GroupedShardedHPS(ShardedHPS):
         self.mid.set_symmetric_leaves(self.local.is_symmetric())
         with t.cuda.stream(self._stream):
             slab, n = self._slab(self.mid, "T_uncoarsened")
-            for k in self.plan.subtrees_of(self.rank):
-                j = k - 4 * self.group_id
-                slab[j * n:(j + 1) * n].copy_(self.local_if.root_T(k))
-            if self.gs > 1:      # rank q of the group owns leaves [4 q / gs, 4 (q + 1) / gs): equal contiguous chunks
-                cnt = slab.numel() // self.gs
-                dist.all_gather_into_tensor(slab, slab[self.group_rank * cnt:(self.group_rank + 1) * cnt], group=self.group)
+            self.gx.subtree_T_to_group(slab, n, self.local_if.root_T)
         self.mid.build(fl & ~LAZY_ROOT_DTN)      # its root is a level-1 node: gathered and mirrored inside the group by the library
         self.top.set_symmetric_leaves(self.mid.is_symmetric())
         with t.cuda.stream(self._stream):
-            Tk = self.mid.operator_view(0, "T_uncoarsened")
             slab, n = self._slab(self.top, "T_uncoarsened")
-            cnt = slab.numel() // self.world          # = n / gs: chunk r of the slab is part r % gs of leaf r // gs
-            slab[self.rank * cnt:(self.rank + 1) * cnt].copy_(Tk[self.group_rank * cnt:(self.group_rank + 1) * cnt])
-            dist.all_gather_into_tensor(slab, slab[self.rank * cnt:(self.rank + 1) * cnt])
+            self.gx.level1_T_to_world(self.mid.operator_view(0, "T_uncoarsened"), slab)
         self.top.build(fl)
 
     def gather_root_T(self):
@@ -742,18 +791,11 @@ class GroupedShardedHPS(ShardedHPS):
         t, dist, fl = self.torch, self.dist, self._flags()
         self.local.upwards(f_dev_ptr, scale, fl)
         if not (fl & HOMOGENEOUS_RHS):
-            per = 4 // self.gs
             with t.cuda.stream(self._stream):
-                for k in self.plan.subtrees_of(self.rank):
-                    self.mid.vector_view(1 + k - 4 * self.group_id, "h0").copy_(self.local_if.root_h(k))
-                if self.gs > 1:
-                    for j in range(4):
-                        dist.broadcast(self.mid.vector_view(1 + j, "h0"), src=self.group_id * self.gs + j // per, group=self.group)
+                self.gx.subtree_h_to_group(lambda j: self.mid.vector_view(1 + j, "h0"), self.local_if.root_h)
             self.mid.upwards(0, 1.0, fl)
             with t.cuda.stream(self._stream):
-                self.top.vector_view(1 + self.group_id, "h0").copy_(self.mid.vector_view(0, "h0"))
-                for k in range(4):        # every rank of group k holds that node's h: its first rank sends
-                    dist.broadcast(self.top.vector_view(1 + k, "h0"), src=k * self.gs)
+                self.gx.level1_h_to_world(self.mid.vector_view(0, "h0"), lambda k: self.top.vector_view(1 + k, "h0"))
             self.top.upwards(0, 1.0, fl)
         if sync:
             self.local.sync()
@@ -769,7 +811,7 @@ class GroupedShardedHPS(ShardedHPS):
         self.mid.solve_from_roots(0, fl)
         with t.cuda.stream(self._stream):
             for k in self.plan.subtrees_of(self.rank):
-                self.local_if.root_g(k).copy_(self.mid.vector_view(1 + k - 4 * self.group_id, "g"))
+                self.local_if.root_g(k).copy_(self.mid.vector_view(1 + self.gx.local_index(k), "g"))
         self.local.solve_from_roots(u_dev_ptr, fl, sync=sync)
 
     def set_profiling(self, on=True):

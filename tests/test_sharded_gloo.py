@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import hps_oracle as O
-from ellipticforest_b200.sharded import ShardPlan, ShardedExchange
+from ellipticforest_b200.sharded import GroupedExchange, ShardPlan, ShardedExchange
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -270,6 +270,103 @@ def _worker(rank, world, port, case, out_dir):
             np.save(os.path.join(out_dir, "T_root.npy"), top.nodes[0].T)
     finally:
         dist.destroy_process_group()
+
+
+def _worker_grouped(rank, world, port, case, out_dir):
+    """GroupedShardedHPS's three tiers with the numpy oracle as the engine: forest -> level-1 star merge inside the rank group ->
+    root star merge over all ranks, every exchange through GroupedExchange (the object the GPU class uses).  The row partition of a
+    tier is emulated as in _worker_replicated: a rank keeps its row slice of S and T, wipes the rest, and the tier's in-place
+    all-gather (group / world) has to restore it."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kw = CASES[case]
+        P = O.problem(kw["problem_name"])
+        nodes = O.build_tree(O.refine_indicator(1.2), kw["box"], kw["nx"], kw["min_level"], kw["max_level"])
+        solver = O.Solver(kind="fishpack", alpha=P["alpha"], beta=P["beta"], lam=P["lam"])
+        plan = ShardPlan(*_tables(nodes), kw["nx"], world, cut=2)
+        gx = GroupedExchange(plan, rank, world, dist)
+        assert (gx.gs, gx.group_id, gx.group_rank) == (world // 4, rank // (world // 4), rank % (world // 4))
+        ids, lev, ch, box, roots = plan.local_table(rank)
+        local = OracleEngine(lev, ch, box, kw["nx"], solver)
+        lif = LocalIf(local, roots, plan.subtrees_of(rank))
+        star = np.array([[1, 2, 3, 4]] + [[-1] * 4] * 4, dtype=np.int32)
+        l1 = np.nonzero(plan.level == 1)[0]
+        me1 = int(l1[gx.group_id])
+        kids = [int(c) for c in plan.child[me1]]
+        assert kids == [int(plan.cut_nodes[4 * gx.group_id + j]) for j in range(4)]
+        mid = OracleEngine(np.array([1, 2, 2, 2, 2]), star, plan.box[[me1] + kids], kw["nx"], solver, ext_sizes=plan.size[kids])
+        top = OracleEngine(np.array([0, 1, 1, 1, 1]), star, plan.box[[0] + [int(i) for i in l1]], kw["nx"], solver, ext_sizes=plan.size[l1])
+        mif, tif = TopIf(mid, back_to_back=True), TopIf(top, back_to_back=True)
+
+        def merge_partitioned(eng, part_rank, nranks, allgather, gather_T):
+            nd = eng.nodes[0]
+            for j in range(4):
+                leaf = eng.nodes[1 + j]
+                leaf.T = eng.buf[(1 + j, "T")].numpy().reshape(4 * leaf.grid.nx, 4 * leaf.grid.nx).copy()
+            eng.hps.merge4to1(nd, *[eng.nodes[c] for c in nd.children])
+            for name in ("S", "T"):
+                full = torch.from_numpy(np.ascontiguousarray(getattr(nd, name))).reshape(-1)
+                if nranks > 1 and (name == "S" or gather_T):
+                    cnt = full.numel() // nranks
+                    keep = full[part_rank * cnt:(part_rank + 1) * cnt].clone()
+                    full.zero_()
+                    full[part_rank * cnt:(part_rank + 1) * cnt] = keep
+                    allgather(full)
+                setattr(nd, name, full.numpy().reshape(getattr(nd, name).shape).copy())
+
+        # build
+        local.build()
+        n = mif.leaf_T(0).numel()
+        gx.subtree_T_to_group(mif.big, n, lif.root_T)
+        merge_partitioned(mid, gx.group_rank, gx.gs, gx.allgather_group, True)
+        Tk = torch.from_numpy(np.ascontiguousarray(mid.nodes[0].T)).reshape(-1)
+        own = Tk.clone()
+        cnt = Tk.numel() // gx.gs      # only this rank's part of the group's map may travel: wipe the rest of the source
+        Tk.zero_()
+        Tk[gx.group_rank * cnt:(gx.group_rank + 1) * cnt] = own[gx.group_rank * cnt:(gx.group_rank + 1) * cnt]
+        gx.level1_T_to_world(Tk, tif.big)
+        assert torch.equal(tif.leaf_T(gx.group_id), own)
+        merge_partitioned(top, rank, world, gx.allgather_world, True)
+        # upwards
+        local.upwards(P["f"])
+        gx.subtree_h_to_group(mif.leaf_h, lif.root_h)
+        mid.upwards(None)
+        gx.level1_h_to_world(torch.from_numpy(np.ascontiguousarray(mid.nodes[0].h)), tif.leaf_h)
+        top.upwards(None)
+        # solve: no exchange - a rank descends through its own level-1 node only
+        r, a, b = O.HPS.root_boundary(type("R", (), {"nodes": [top.nodes[0]]})(), lambda s_, xx, yy: (float(P["u"](xx, yy)), 1.0, 0.0))
+        top.nodes[0].g = r / a
+        top.solve()
+        mid.nodes[0].g = tif.leaf_g(gx.group_id).numpy().copy()
+        mid.solve()
+        for k in plan.subtrees_of(rank):
+            local.nodes[lif.idx[k]].g = mif.leaf_g(gx.local_index(k)).numpy().copy()
+        local.solve()
+        np.save(os.path.join(out_dir, "u_%d.npy" % rank), np.concatenate([nd.u for nd in local.nodes if nd.leaf]))
+        np.save(os.path.join(out_dir, "range_%d.npy" % rank), np.array(plan.local_leaf_range(rank)))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "T_root.npy"), top.nodes[0].T)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_grouped_three_tier_run_matches_single_process_oracle(world, tmp_path):
+    """world = 4 gs: groups of gs ranks per level-1 merge (gs = 2: sub-groups, group all-gathers and broadcasts)."""
+    kw = CASES["uniform"]
+    mp.spawn(_worker_grouped, args=(world, _free_port(), "uniform", str(tmp_path)), nprocs=world, join=True)
+    ref = O.run(solver_kind="fishpack", **kw)
+    u_ref = ref.leaf_solution()
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    lo_seen = 0
+    for r in range(world):
+        lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
+        assert lo == lo_seen
+        lo_seen = hi
+        assert rel(np.load(tmp_path / ("u_%d.npy" % r)), np.concatenate(u_ref[lo:hi])) < 1e-11
+    assert lo_seen == len(u_ref)
+    assert rel(np.load(tmp_path / "T_root.npy"), ref.nodes[0].T) < 1e-11
 
 
 def _free_port():
