@@ -440,11 +440,12 @@ def own_arm(a):
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
     # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture (never measured under this run)
-    traffic = None
+    traffic = traffic_bytes = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = {"bytes": tr["traffic_bytes_per_launch"], "algorithmic_bytes": tr["algorithmic_bytes_per_launch"],
                    "launch": tr["launch"], "source": tr["source"]}
+        traffic_bytes = tr["traffic_bytes_per_launch"]
     except Exception:
         pass
 
@@ -480,7 +481,7 @@ def own_arm(a):
                      "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                      "timing": "CUDA events around every launch on the library's stream, over a second pass of the same %d steps (%.2f ms per step with "
                                "the events, %.2f without)" % (a.steps, 1e3 * prof_dev_s / a.steps, ms_per_step),
-                     "traffic": traffic},
+                     "traffic": traffic_bytes, "traffic_detail": traffic},
         "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items() if v[1] > 0 or v[0] > 0},
         "repeat_solves": None if repeat is None else dict(repeat, dofs_per_s_mean=dofs / (repeat["mean_ms"] * 1e-3),
                                                            gbs_mean=(tot["upwards_bytes"] + tot["solve_bytes"]) / (repeat["mean_ms"] * 1e-3) / 1e9,
