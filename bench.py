@@ -70,7 +70,7 @@ def parse_args():
                     "path) is left to its first reader; recorded in config.root_dtn - not the reference's buildStage, which always forms it")
     ap.add_argument("--tuning", action="append", default=[], metavar="KEY=VALUE",
                     help="efgpu_set_tuning knob for A/B runs (include/efgpu.h), e.g. --tuning 5=1; recorded in config.tuning")
-    ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6 own arm, 5 reference arm)")
+    ap.add_argument("--cpu-level", type=int, default=None, help="tree depth of the CPU sample (default 6; the reference arm lowers it until warmup + steps runs fit EFGPU_REF_BUDGET_S)")
     return ap.parse_args()
 
 
@@ -153,6 +153,22 @@ def run_reference_sample(level, nx, problem, threads, adaptive=None, threshold=1
     return json.loads(line[len("REF_RESULT "):])
 
 
+def run_binding_timing(a, threads, passes=2):
+    """The same step through the reference-side C++ binding (include/EllipticForestB200.hpp: the reference's own Mesh / Quadtree /
+    FiniteVolumeSolver objects, std::function callbacks sampled per cell, Vector copies of f and u per leaf), timed by the
+    reference's stage timers: oracle/_ref/dropin_driver --time-only (compiled against the unmodified reference)."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "dropin_driver")
+    if not os.path.exists(drv):
+        raise RuntimeError("oracle/_ref/dropin_driver is missing")
+    lo, hi = a.adaptive if a.adaptive else (a.level, a.level)
+    dom = ["-10", "10", "-10", "10"] if a.adaptive else ["0", repr(PI), "0", repr(PI)]
+    cmd = [drv, "--problem", a.problem, "--solver", "fivepoint" if a.problem == "varcoef" else "fishpack", "--min-level", str(lo), "--max-level", str(hi),
+           "--nx", str(a.nx), "--threshold", repr(a.threshold), "--domain"] + dom + ["--time-only", str(passes), "--threads", str(threads)]
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("DROPIN_TIMING")][-1]
+    return json.loads(line[len("DROPIN_TIMING "):])
+
+
 def host_threads():
     try:
         n = len(os.sched_getaffinity(0))
@@ -173,16 +189,49 @@ def cpu_sample(a, default_level):
     return dict(level=lvl), "uniform level-%d" % lvl
 
 
+def extrapolate_reference(a, t_lo, t_hi, lvl_hi):
+    """Estimate of the reference's step time on the full workload from two timed levels of the same uniform family (labelled as
+    an extrapolation wherever it is printed): t(L) = t(lvl_hi) * r^(L - lvl_hi) with the MEASURED growth r = t(lvl_hi) / t(lvl_hi - 1)
+    per level.  DOFs grow 4x per level and the dense root merge 8x (810.67 n^3), so r lies between 4 and 8 and grows
+    with L: the estimate is optimistic for the reference."""
+    if a.adaptive or t_lo is None or a.level <= lvl_hi:
+        return None
+    r = t_hi / t_lo
+    t = t_hi * r ** (a.level - lvl_hi)
+    dofs = float(4 ** a.level * a.nx * a.nx)
+    return {"to": "uniform level-%d (the workload of the repo arm)" % a.level, "ms_per_step": 1e3 * t, "value": dofs / t, "unit": "DOFs/s",
+            "method": "t(L) = t(%d) * r^(L-%d), r = t(%d)/t(%d) = %.2f measured in this run; not a measurement" % (lvl_hi, lvl_hi, lvl_hi, lvl_hi - 1, r)}
+
+
 def reference_arm(a):
-    """`--impl reference`: the reference's own CPU implementation (compiled, unmodified) on the host cores."""
+    """`--impl reference`: the reference's own CPU implementation (compiled, unmodified) on the host cores.  Every step is one
+    full build + upwards + solve of a BOUNDED sample of the workload: the largest uniform level (6 by default) whose
+    warmup + steps runs fit EFGPU_REF_BUDGET_S (600 s); the level actually timed is a top-level config field, the line says
+    same_config false, and an extrapolation to the full workload is printed next to it, labelled as such."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kw, what = cpu_sample(a, 5)
     threads = host_threads()
-    for _ in range(a.warmup):
+    budget = float(os.environ.get("EFGPU_REF_BUDGET_S", "600"))
+    kw, what = cpu_sample(a, 6)
+    runs = a.warmup + a.steps
+    t_first = None
+    while True:   # first warm-up run decides whether this level fits the budget
+        res = run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **kw)
+        t_first = res["build_s"] + res["upwards_s"] + res["solve_s"]
+        if a.cpu_level is not None or t_first * runs <= budget or kw["level"] <= 3:
+            break
+        if a.adaptive:
+            kw["level"] -= 1; kw["adaptive"] = (min(kw["adaptive"][0], max(kw["level"] - 3, 0)), kw["level"]); what = "adaptive levels %d-%d" % kw["adaptive"]
+        else:
+            kw["level"] -= 1; what = "uniform level-%d" % kw["level"]
+    t_lower = None
+    if not a.adaptive and kw["level"] >= 2:   # one run a level below: the measured growth per level for the extrapolation
+        lo = run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **dict(kw, level=kw["level"] - 1))
+        t_lower = lo["build_s"] + lo["upwards_s"] + lo["solve_s"]
+    for _ in range(max(a.warmup - 1, 0)):
         run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **kw)
-    ts, res = [], None
+    ts = []
     for _ in range(a.steps):
         res = run_reference_sample(nx=a.nx, problem=a.problem, threads=threads, **kw)
         ts.append(res["build_s"] + res["upwards_s"] + res["solve_s"])
@@ -190,11 +239,16 @@ def reference_arm(a):
     v = res["dofs"] / t
     sample = "%s, %dx%d patches (%d DOFs): build %.3f s, upwards %.3f s, solve %.3f s per step" % (
         what, a.nx, a.nx, res["dofs"], res["build_s"], res["upwards_s"], res["solve_s"])
+    full = (not a.adaptive) and kw["level"] == a.level
     print(json.dumps({
         "impl": "reference", "metric": "HPS build+upwards+solve DOFs/s (FP64)", "value": v, "unit": "DOFs/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": sample},
+        "config": {"workload": workload_name(a), "timed": what, "level_timed": kw["level"], "dofs_timed": res["dofs"],
+                   "same_config": bool(full), "sample": sample,
+                   "note": None if full else "the reference's DOFs/s falls as the tree grows (dense root merge): a ratio against this line is a "
+                                             "cross-config figure that favours the reference; see `extrapolated`",
+                   "extrapolated": None if full else extrapolate_reference(a, t_lower, t, kw["level"])},
         "cpu_baseline": {"value": v, "unit": "DOFs/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "DOFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -312,12 +366,16 @@ def own_arm(a):
         return
 
     # ---- warm-up, then the device-resident leg under the clock sampler ----
-    for _ in range(max(a.warmup, 3)):
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(a.warmup, 3) or time.perf_counter() - t_w < 0.5:    # short steps (adaptive trees: ms) also get the clocks up
         step_device()
+        n_w += 1
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     dev_s, wall_s = timed(step_device, a.steps)
+    ms_per_step_hint = 1e3 * dev_s / a.steps
     # Per-kernel CUDA events (two cudaEventRecord per launch on the library's stream, ~900 launches per step) are taken
     # over a second, identical pass of the same K steps: in the launch-bound top tree levels the event records themselves
     # cost 3 % of a step at N = 1 and 10 % at N = 8, which must not sit in the headline time.
@@ -337,17 +395,95 @@ def own_arm(a):
         mesh_stats = {"leaves_per_level": {str(i): int(c) for i, c in enumerate(lv) if c}, "nodes": mesh.n_nodes,
                       "n_coarsens_histogram": {str(i): int(c) for i, c in enumerate(tags)}}
 
+    # ---- sharded runs: parity against a single-GPU build of the SAME tree, measured here so that every driver-run line carries it
+    # (each rank rebuilds the whole tree on its own GPU when it fits next to its shard, and compares its leaves' u; rank 0
+    # compares the root's DtN map after the collective that gathers its row slices).  Reference: the per-node parity tests tie the
+    # single-GPU path to the reference (tests/test_gpu_parity.py, tests/test_gpu_refscale.py).
+    parity = None
+    if world > 1:
+        parity = {"linf_error_vs_exact": err}
+        free_b, _tot_b = torch.cuda.mem_get_info()
+        single_bytes = dofs * (256.0 * a.level + 300.0)      # 1 KiB n^2 per merge, sum of n^2 per level = DOFs / 4; + leaf maps, vectors, workspace
+        fits = torch.tensor([1 if single_bytes < 0.85 * free_b else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+        if int(fits[0]) and not a.adaptive and a.problem != "varcoef":
+            rootT = hps.gather_root_T()                       # collective: completes the row-distributed root map
+            one = ef.HPSAlgorithm(mesh, solver, device=local)
+            one.no_symmetry = a.no_symmetry
+            one.buildStage()
+            Xc, Yc = mesh.leaf_cell_centres()
+            one.upwardsStage(f_fn(Xc, Yc))
+            _s, bx, by = one.root_boundary_points()
+            u_one = one.solveStage(np.ascontiguousarray(u_exact(bx, by)))
+            lo, hi = hps.leaf_lo, hps.leaf_hi
+            mine = u_dev.cpu().numpy().reshape(hi - lo, a.nx, a.nx)
+            du = torch.tensor([float(np.max(np.abs(mine - u_one[lo:hi]))), float(np.max(np.abs(u_one[lo:hi])))], dtype=torch.float64, device="cuda")
+            dist.all_reduce(du, op=dist.ReduceOp.MAX)
+            parity["u_vs_single_gpu_rel_max"] = float(du[0] / du[1])
+            if rank == 0:
+                T1 = one.operator(0, "T").reshape(-1)
+                Tn = rootT.cpu().numpy()
+                parity["root_T_vs_single_gpu_rel_max"] = float(np.max(np.abs(Tn - T1)) / np.max(np.abs(T1)))
+                del T1, Tn
+            del one, u_one, mine
+        else:
+            parity["note"] = "tree does not fit one GPU next to the shard: no single-GPU rebuild; error against the exact solution only"
+
     # ---- e2e leg: host buffers through the C-ABI, copies inside the timed region ----
     step_host()
     e2e_dev_s, e2e_wall_s = timed(step_host, a.steps)
     err_e2e = float(np.max(np.abs(u_pin.numpy() - u_dev.cpu().numpy())))
 
+    # ---- variable coefficients: the same end-to-end step through the device-functor entry points ----
+    # The reference calls alpha / beta / lambda / f as std::function per point on the host (FiniteVolumeSolver.cpp:63-79,
+    # HPSAlgorithm.hpp:241-249); the host-array e2e leg above pays for that sampling (numpy on all host threads) plus 7 arrays of
+    # H2D.  Here the library writes the sampling coordinates on the device (efgpu_leaf_points_device), the caller's functions are
+    # evaluated there by its own device code (torch elementwise kernels stand in for the user's functors) and handed over as
+    # device pointers (efgpu_set_leaf_variable_device, efgpu_upwards_device); g still comes from the host, u still goes back.
+    e2e_devsample = None
+    if a.problem == "varcoef" and world == 1:
+        st_lib = torch.cuda.ExternalStream(hps.stream())
+        shape = (mesh.n_leaves, a.nx, a.nx)
+        xd, yd = (torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(2))
+        t_u = lambda x, y: torch.sin(x) + torch.sin(y)
+        t_beta = lambda x, y: 1.0 + 0.5 * torch.sin(x) * torch.cos(y)
+        t_lam = lambda x, y: -(1.0 + 0.5 * torch.cos(x) * torch.cos(y))
+        t_f = lambda x, y: (0.5 * torch.cos(x) * torch.cos(y) * torch.cos(x) - 0.5 * torch.sin(x) * torch.sin(y) * torch.cos(y)
+                            - t_beta(x, y) * t_u(x, y) + t_lam(x, y) * t_u(x, y))
+
+        def step_devsample():
+            with torch.cuda.stream(st_lib):
+                arrs = []
+                for which, fn in (("centre", None), ("W", t_beta), ("E", t_beta), ("S", t_beta), ("N", t_beta), ("centre", t_lam)):
+                    hps.leafPointsDevice(which, xd.data_ptr(), yd.data_ptr(), sync=False)
+                    arrs.append(torch.ones(shape, dtype=torch.float64, device="cuda") if fn is None else fn(xd, yd))
+                f_t = t_f(xd, yd)                  # xd, yd hold the cell centres again (last request)
+                hps.setVariableCoefficientsDevice(*[t.data_ptr() for t in arrs])
+                hps.buildStage()
+                hps.upwardsStageDevice(f_t.data_ptr(), 1.0, sync=False)
+                g_dev.copy_(g_pin, non_blocking=True)
+                hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=False)
+                u_pin.copy_(u_dev, non_blocking=True)
+            hps.sync()
+
+        u_host_leg = u_pin.numpy().copy()
+        step_devsample()
+        ds_dev_s, ds_wall_s = timed(step_devsample, a.steps)
+        e2e_devsample = {"value": dofs * a.steps / ds_wall_s, "unit": "DOFs/s", "ms_per_step": 1e3 * ds_wall_s / a.steps,
+                         "h2d_bytes_per_step": int(g_host.nbytes), "d2h_bytes_per_step": int(f_host.nbytes),
+                         "max_abs_diff_vs_host_sampled": float(np.max(np.abs(u_pin.numpy() - u_host_leg))),
+                         "what": "coordinates written by efgpu_leaf_points_device, alpha/beta/lambda/f evaluated on the device by the caller's "
+                                 "elementwise kernels, efgpu_set_leaf_variable_device + efgpu_upwards_device; g H2D and u D2H as in e2e"}
+        hps.resample_coefficients = True
+        hps._coefficients_set = False
+
     # ---- stage split (extra passes, not part of the headline): each stage between barriers, max over ranks ----
     hps.resample_coefficients = False
-    build_s, _ = timed(lambda: hps.buildStage(), 1)
-    up_s, _ = timed(lambda: hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True), 1)
-    so_s, _ = timed(lambda: hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True), 1)
-    build_ms, up_ms, so_ms = 1e3 * build_s, 1e3 * up_s, 1e3 * so_s
+    med = lambda v: sorted(v)[len(v) // 2]
+    reps = 5 if ms_per_step_hint < 400.0 else 3          # median of several samples per stage
+    build_ms = 1e3 * med([timed(lambda: hps.buildStage(), 1)[0] for _ in range(reps)])
+    up_ms = 1e3 * med([timed(lambda: hps.upwardsStageDevice(f_dev.data_ptr(), 1.0, sync=True), 1)[0] for _ in range(reps)])
+    so_ms = 1e3 * med([timed(lambda: hps.solveStageDevice(g_dev.data_ptr(), u_dev.data_ptr(), sync=True), 1)[0] for _ in range(reps)])
     # ---- repeated solves on the resident operators (the `thermal` usage pattern) ----
     repeat = None
     if a.n_solves > 0:
@@ -411,6 +547,25 @@ def own_arm(a):
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             cpu = {"value": None, "unit": "DOFs/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
 
+    # ---- the step through the reference-side C++ binding (per-cell std::function sampling included), rank 0, N = 1 only ----
+    binding = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            torch.cuda.synchronize()
+            binding = {}
+            for thr in (1, host_threads()):
+                r = run_binding_timing(a, thr)
+                t = r["build_s"] + r["upwards_s"] + r["solve_s"]
+                binding["sampling_threads_%d" % thr] = {"value": r["dofs"] / t, "unit": "DOFs/s", "ms_per_step": 1e3 * t, "build_ms": 1e3 * r["build_s"],
+                                                        "upwards_ms": 1e3 * r["upwards_s"], "solve_ms": 1e3 * r["solve_s"], "setup_ms": 1e3 * r["setup_s"],
+                                                        "linf_error_vs_exact": r["linf_error"]}
+            binding["what"] = ("oracle/_ref/dropin_driver --time-only: HPSAlgorithmB200 (include/EllipticForestB200.hpp) on the reference's own Mesh / "
+                               "Quadtree / FiniteVolumePatch objects; stage times from the reference's timers, i.e. including the per-cell "
+                               "std::function sampling of f (and alpha / beta / lambda) and the per-leaf Vector copies of f and u; "
+                               "sampling_threads > 1 is the binding's opt-in for thread-safe callbacks")
+        except Exception as e:
+            binding = {"error": str(e)}
+
     def cleanup():
         # torch frees pinned buffers by recording events on the streams they were used on: release every tensor
         # while the library's stream still exists, then the handles, then the process group
@@ -461,10 +616,10 @@ def own_arm(a):
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "dofs": dofs, "leaves": mesh.n_leaves, "mesh": mesh_stats, "l2": "inputs larger than L2 (%.1f GB of operators streamed per step)" % (tot["device_bytes"] / 1e9),
-                   "sharding": hps.sharding(), "tuning": a.tuning, "root_dtn": "deferred to its first reader (EFGPU_LAZY_ROOT_DTN)" if a.lazy_root_dtn else "formed by the build",
+                   "sharding": hps.sharding(), "parity": parity, "tuning": a.tuning, "root_dtn": "deferred to its first reader (EFGPU_LAZY_ROOT_DTN)" if a.lazy_root_dtn else "formed by the build",
                    "merge_plan": "general (EFGPU_NO_SYMMETRY)" if a.no_symmetry else "symmetric where the subtree is uniform with constant-coefficient leaves%s" % (
                        "" if (a.adaptive or a.problem == "varcoef") else " (every merge of this workload)")},
-        "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms,
+        "stages": {"build_ms": build_ms, "upwards_ms": up_ms, "solve_ms": so_ms, "samples": "median of %d runs per stage" % reps,
                    "build_dofs_per_s": dofs / (build_ms * 1e-3), "solve_dofs_per_s": dofs / ((up_ms + so_ms) * 1e-3),
                    "upwards_gbs": tot["upwards_bytes"] / (up_ms * 1e-3) / 1e9, "solve_gbs": tot["solve_bytes"] / (so_ms * 1e-3) / 1e9,
                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
@@ -473,6 +628,7 @@ def own_arm(a):
         "linf_error_vs_exact": err, "e2e_vs_device_max_abs_diff": err_e2e,
         "e2e": {"value": dofs * a.steps / e2e_wall_s, "unit": "DOFs/s", "h2d_bytes_per_step": int(f_host.nbytes * (7 if a.problem == "varcoef" else 1) + g_host.nbytes),
                 "d2h_bytes_per_step": int(f_host.nbytes), "ms_per_step": 1e3 * e2e_wall_s / a.steps, "timer": "host wall clock between device synchronisations"},
+        "e2e_device_sampling": e2e_devsample, "e2e_cpp_binding": binding,
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)%s" % (" on rank 0" if world > 1 else ""),
                      "achieved": gemm_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": (gemm_tf / dgemm_tf) if (gemm_tf and dgemm_tf) else None,

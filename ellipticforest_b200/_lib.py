@@ -20,7 +20,7 @@ class TreeDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "dofs", "n_leaves", "n_nodes", "build_ms", "upwards_ms", "solve_ms", "merge_flops_canonical",
-        "merge_flops_issued", "upwards_bytes", "solve_bytes", "device_bytes", "min_pivot")]
+        "merge_flops_issued", "upwards_bytes", "solve_bytes", "device_bytes", "min_pivot", "max_pivot", "pivot_ratio_min", "negative_pivots", "inverse_residual")]
 
 
 REFINE_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_double, C.c_void_p)
@@ -39,6 +39,7 @@ SIGNATURES = {
     "efgpu_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "efgpu_set_symmetric_leaves": (C.c_int, [_P, C.c_int]),
     "efgpu_is_symmetric": (C.c_int, [_P]),
+    "efgpu_set_refine_inverse": (C.c_int, [_P, C.c_int]),
     "efgpu_debug_merge_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _I, _P, _P, _I, _P, _I, _P]),
     "efgpu_build_begin": (C.c_int, [_P, C.c_uint]),
     "efgpu_build_level": (C.c_int, [_P, C.c_int, C.c_int]),

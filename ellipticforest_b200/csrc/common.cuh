@@ -78,10 +78,13 @@ void launch_btranspose(double* const* ptab, int nops, const TransOp* d_ops, cons
 
 // In-place inverse of `batch` small dense N x N matrices (N <= 128) held at
 // ptab[z*nops+op] + off with leading dimension ld; Gauss-Jordan in shared memory, no pivoting
-// (the merge matrices are SPD / diagonally dominant).  min |pivot| is folded
-// into *min_pivot (device scalar) for singularity reporting.  off2 >= 0: a second block per entry in the same launch.
+// (the merge matrices are SPD / diagonally dominant).  Pivot statistics are folded
+// into the 4-double tracker `min_pivot` ([0] min |pivot|, [1] max |pivot|, [2] smallest per-block min / max ratio,
+// [3] number of negative pivots as a 64-bit count) for singularity / conditioning reports.
+// off2 >= 0: a second block per entry in the same launch.
 void launch_invert_small(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int N, int batch,
                          double* min_pivot, cudaStream_t stream);
+void launch_pivot_tracker_reset(double* tracker, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // ---- mbarrier / bulk-copy (cp.async.bulk global -> shared) helpers shared by the streaming kernels ----

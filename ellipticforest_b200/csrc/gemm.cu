@@ -351,6 +351,33 @@ void launch_btranspose(double* const* ptab, int nops, const TransOp* d_ops, cons
 // Small in-place inverse (base case of the blocked inversion of X): one CTA per matrix,
 // Gauss-Jordan in shared memory.
 // ---------------------------------------------------------------------------------------------
+// Pivot tracker of the unpivoted base case (one per thread, every thread of a CTA sees every pivot): smallest and largest
+// |pivot| of this block and the number of negative pivots (an SPD merge matrix has none).  publish() folds them into the
+// handle's tracker: [0] global min |pivot|, [1] global max |pivot|, [2] smallest per-block ratio min / max, [3] count of
+// negative pivots (unsigned 64-bit).  Non-negative doubles order like their bit patterns.
+struct PivotTrack {
+    double mn = 1e300, mx = 0.0; unsigned neg = 0;
+    __device__ __forceinline__ void see(double piv) { const double a = fabs(piv); mn = fmin(mn, a); mx = fmax(mx, a); neg += piv < 0.0 ? 1u : 0u; }
+    __device__ __forceinline__ void publish(double* t) const {
+        unsigned long long* u = reinterpret_cast<unsigned long long*>(t);
+        atomicMin(u + 0, (unsigned long long)__double_as_longlong(mn));
+        atomicMax(u + 1, (unsigned long long)__double_as_longlong(mx));
+        atomicMin(u + 2, (unsigned long long)__double_as_longlong(mx > 0.0 ? mn / mx : 0.0));
+        if (neg) atomicAdd(u + 3, (unsigned long long)neg);
+    }
+};
+
+__global__ void pivot_tracker_reset_kernel(double* t)
+{
+    unsigned long long* u = reinterpret_cast<unsigned long long*>(t);
+    t[0] = 1e300; t[1] = 0.0; t[2] = 1e300; u[3] = 0ull; t[4] = 0.0;
+}
+void launch_pivot_tracker_reset(double* tracker, cudaStream_t s)
+{
+    pivot_tracker_reset_kernel<<<1, 1, 0, s>>>(tracker);
+    EF_CUDA(cudaGetLastError());
+}
+
 __global__ void __launch_bounds__(256)
 invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, int N,
                     double* __restrict__ min_pivot)
@@ -364,11 +391,11 @@ invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long lon
     const int tid = threadIdx.x, NT = blockDim.x;
     for (int e = tid; e < N * N; e += NT) { int r = e / N, c = e % N; A[r * LDS + c] = G[(long long)r * ld + c]; }
     __syncthreads();
-    double minp = 1e300;
+    PivotTrack pt;
     for (int k = 0; k < N; k++) {
         const double piv = A[k * LDS + k];
         const double p = 1.0 / piv;
-        minp = fmin(minp, fabs(piv));
+        pt.see(piv);
         for (int r = tid; r < N; r += NT) colk[r] = A[r * LDS + k];
         __syncthreads();
         // scale pivot row
@@ -384,10 +411,7 @@ invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long lon
         __syncthreads();
     }
     for (int e = tid; e < N * N; e += NT) { int r = e / N, c = e % N; G[(long long)r * ld + c] = A[r * LDS + c]; }
-    if (tid == 0 && min_pivot) {
-        // positive doubles order like their bit patterns
-        atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
-    }
+    if (tid == 0 && min_pivot) pt.publish(min_pivot);
 }
 
 // Register-resident variant: 256 threads as a 16 x 16 grid, thread (tr, tc) owns the elements
@@ -406,12 +430,12 @@ invert_small_kernel(double* const* __restrict__ ptab, int nops, int op, long lon
 //    constant (no dispatch chains).
 template <int TI, int KI, int K1I>
 __device__ __forceinline__ void gj_pivot(double (&a)[TI][TI], double (*sRow)[16 * TI], double (*sCol)[16 * TI], double (*sPiv)[2],
-                                         unsigned long long* bar, int kr, int tr, int tc, bool last, double& minp)
+                                         unsigned long long* bar, int kr, int tr, int tc, bool last, PivotTrack& minp)
 {
     const int b = kr & 1;                                   // N is a multiple of 16: k and kr have the same parity
     mbar_wait(bar, (unsigned)b);                            // phase k: row / column k are published, buffer b ^ 1 is free
     const double p = sPiv[b][1];
-    minp = fmin(minp, fabs(sPiv[b][0]));
+    minp.see(sPiv[b][0]);
     double rk[TI], ck[TI];
 #pragma unroll
     for (int j = 0; j < TI; j++) rk[j] = sRow[b][tc + 16 * j];   // row k, already divided by the pivot
@@ -463,7 +487,7 @@ __device__ __forceinline__ void gj_pivot(double (&a)[TI][TI], double (*sRow)[16 
 
 template <int TI, int KI>
 __device__ __forceinline__ void gj_block(double (&a)[TI][TI], double (*sRow)[16 * TI], double (*sCol)[16 * TI], double (*sPiv)[2],
-                                         unsigned long long* bar, int tr, int tc, double& minp)
+                                         unsigned long long* bar, int tr, int tc, PivotTrack& minp)
 {
     if constexpr (KI < TI) {
         for (int kr = 0; kr < 15; kr++) gj_pivot<TI, KI, KI>(a, sRow, sCol, sPiv, bar, kr, tr, tc, false, minp);
@@ -508,14 +532,13 @@ invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long 
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&bar);         // phase 0: row / column 0 are published
-    double minp = 1e300;
+    PivotTrack minp;
     gj_block<TI, 0>(a, sRow, sCol, sPiv, &bar, tr, tc, minp);
 #pragma unroll
     for (int i = 0; i < TI; i++)
 #pragma unroll
         for (int j = 0; j < TI; j++) G[(long long)(tr + 16 * i) * ld + tc + 16 * j] = a[i][j];
-    if (threadIdx.x == 0 && min_pivot)
-        atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
+    if (threadIdx.x == 0 && min_pivot) minp.publish(min_pivot);
 }
 
 void launch_invert_small(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int N, int batch,

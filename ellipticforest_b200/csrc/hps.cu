@@ -28,7 +28,7 @@ static const int h_tau_side[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
 static const int h_kk[4][2] = {{0, 2}, {1, 2}, {0, 3}, {1, 3}};
 static const int h_pos[8] = {0, 4, 2, 5, 1, 6, 3, 7};  // inverse of pi = {0,4,2,6,1,3,5,7}
 
-enum { OP_TC0 = 0, OP_XINV = 4, OP_S = 5, OP_T = 6, OP_W1 = 7, OP_W2 = 8, OP_W3 = 9, NOPS = 10 };
+enum { OP_TC0 = 0, OP_XINV = 4, OP_S = 5, OP_T = 6, OP_W1 = 7, OP_W2 = 8, OP_W3 = 9, OP_XCOPY = 10, NOPS = 11 };
 
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
@@ -66,7 +66,7 @@ struct NodeH {
 };
 
 struct Step {
-    int kind; int first, count; long long off; int N; int cls;   // kind 0: small inverse, 1: gemm, 2: block transposes; cls: profiling class
+    int kind; int first, count; long long off; int N; int cls;   // kind 0: small inverse, 1: gemm, 2: block transposes, 3: OP_T scratch E <- I + E (off: element offset, N: order), 4: Xinv <- Xinv + scratch (off); cls: profiling class
     long long off2 = -1;              // kind 0: a second, independent N x N block inverted by the same launch (-1: none)
     // row-partitioned step of a replicated tree: after the GEMM the g_rows x g_cols result is all-gathered over the ranks.
     // gk 1: the destination (op g_op, offset g_off) is contiguous (ld == g_cols): in place.  gk 2: the GEMM wrote its rows into
@@ -81,6 +81,7 @@ struct BatchH {
     std::vector<TransOp> trans;       // block transposes of the symmetric plan
     std::vector<Step> steps;          // general plan: inversion, then S, then T
     std::vector<Step> steps_sym;      // plan for symmetric merge matrices (symcand batches only)
+    std::vector<Step> steps_refine;   // one Newton-Schulz step on X^-1 (indefinite problems), run between the inversion and S
     bool symcand = false;             // structurally symmetric: square patches, no coarsening anywhere below
     bool use_sym = false;             // decided at build time (leaf operator self-adjoint, EFGPU_NO_SYMMETRY not set)
     const std::vector<Step>& active() const { return use_sym ? steps_sym : steps; }
@@ -122,6 +123,9 @@ struct efgpu_handle {
     // leaf model
     int leaf_kind = EFGPU_LEAF_CONSTANT; double lambda = 0.0;
     bool ext_sym = false;                        // external leaves declared signed-symmetric (efgpu_set_symmetric_leaves)
+    double lambda_max = 0.0;                     // variable-coefficient leaves: largest sampled lambda
+    int refine_mode = -1;                        // efgpu_set_refine_inverse: -1 automatic (lambda > 0), 0 never, 1 always
+    bool refine_inverse = false;                 // this build: one Newton-Schulz step on every X^-1 (decided in build_begin)
     // device state
     DevBuf d_leaf_build, d_leaf_src; int n_leaf_build = 0;   // constant-coefficient leaves: one DtN computation per class of identical (dx, dy)
     DevBuf d_Q, d_boxes, d_leaf_nodes, d_leafT, d_vec, d_ws, d_leaf_h, d_leaf_g, d_f, d_u, d_minpiv;
@@ -347,10 +351,12 @@ static bool clip_rows(GemmBlock& g, long long r0, long long lo, long long hi)
     return true;
 }
 
+static void plan_refine(BatchH& b);
+
 static void plan_batch_gemms(BatchH& b, int rank, int nranks)
 {
     const int n = b.n, N = 4 * n;
-    b.blocks.clear(); b.trans.clear(); b.steps.clear(); b.steps_sym.clear();
+    b.blocks.clear(); b.trans.clear(); b.steps.clear(); b.steps_sym.clear(); b.steps_refine.clear();
     if (nranks > 1 && ((4 * n) % (8 * nranks) != 0))
         throw Error{EF_ERR_BAD_SHAPE, "row partition: 4 n must be a multiple of 8 * nranks for every merge of the replicated tree"};
     const long long s_lo = (long long)rank * (4 * n) / nranks, s_hi = (long long)(rank + 1) * (4 * n) / nranks;
@@ -471,6 +477,28 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
             Step st{}; st.kind = 2; st.first = tfirst; st.count = (int)b.trans.size() - tfirst; st.cls = EFGPU_PROF_MIRROR_T; steps.push_back(st);
         }
     }
+    plan_refine(b);
+}
+
+// One Newton-Schulz step  X^-1 <- X^-1 + X^-1 (I - X X^-1)  on the result of the unpivoted block inversion (see build_begin:
+// indefinite problems only).  X is the copy kept in OP_XCOPY; the two N x N temporaries live in this merge's own DtN slot
+// OP_T (64 n^2 doubles, not yet written when the step runs): E at offset 0, X^-1 E at offset N^2.  Replicated on every rank
+// of a row partition.
+static void plan_refine(BatchH& b)
+{
+    const int N = 4 * b.n;
+    const long long NN = (long long)N * N;
+    auto gemm = [&](long long c_off, int a_op, long long a_off, int b_op, long long b_off, bool neg) {
+        GemmBlock g{};
+        g.c_op = OP_T; g.c_off = c_off; g.ldc = N; g.c0_op = -1; g.rows = N; g.cols = N; g.nterms = 1;
+        g.t[0] = GemmTerm{a_op, b_op, N, N, a_off, b_off, N, neg ? 0x80000000u : 0u};
+        Step st{}; st.kind = 1; st.first = (int)b.blocks.size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
+        b.blocks.push_back(g); b.steps_refine.push_back(st);
+    };
+    gemm(0, OP_XCOPY, 0, OP_XINV, 0, true);                                    // E = -X X^-1
+    { Step st{}; st.kind = 3; st.off = 0; st.N = N; st.cls = EFGPU_PROF_TRANSPOSE; b.steps_refine.push_back(st); }   // E += I
+    gemm(NN, OP_XINV, 0, OP_T, 0, false);                                      // D = X^-1 E
+    { Step st{}; st.kind = 4; st.off = NN; st.N = N; st.cls = EFGPU_PROF_TRANSPOSE; b.steps_refine.push_back(st); }  // X^-1 += D
 }
 
 static void compute_flop_model(efgpu_handle* H)
@@ -485,6 +513,7 @@ static void compute_flop_model(efgpu_handle* H)
             if (st.kind == 1 && !(st.cls == EFGPU_PROF_GEMM_T && b.level == 0 && (H->cur_flags & EFGPU_LAZY_ROOT_DTN)))
                 for (int k = st.first; k < st.first + st.count; k++)
                     for (int t = 0; t < b.blocks[k].nterms; t++) issued += b.count * 2.0 * b.blocks[k].rows * b.blocks[k].cols * b.blocks[k].t[t].K;
+        if (H->refine_inverse) issued += b.count * 2.0 * 2.0 * 64.0 * n3;   // two (4n)^3 products of the Newton-Schulz step
         up_bytes += b.count * 8.0 * (16.0 + 16.0) * b.n * b.n;
         so_bytes += b.count * 8.0 * 32.0 * b.n * b.n;
     }
@@ -621,7 +650,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
         H->d_f.alloc((size_t)H->n_leaves * M * M * sizeof(double));
         H->d_u.alloc((size_t)H->n_leaves * M * M * sizeof(double));
     }
-    H->d_minpiv.alloc(sizeof(double));
+    H->d_minpiv.alloc(5 * sizeof(double));   // pivot tracker (common.cuh: launch_invert_small) + [4] max |I - X X^-1| of the refinement
     double* vec = H->d_vec.as<double>();
     for (int l = 0; l < H->n_leaves; l++) H->nodes[H->leaf_nodes[l]].Tbuf.assign(1, H->d_leafT.as<double>() + H->leafT_off[l]);
     std::vector<double*> lh(H->n_leaves), lg(H->n_leaves);
@@ -654,7 +683,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             b.Hc.alloc(cnt * 16 * n * n * sizeof(double));
             if (H->lean_T) { b.T.release(); b.Tbase = H->d_Tarena[lev & 1].as<double>() + arena_off; arena_off += cnt * 64 * n * n; }
             else { b.T.alloc(cnt * 64 * n * n * sizeof(double)); b.Tbase = b.T.as<double>(); }
-            if (flags & EFGPU_KEEP_X) b.Xcopy.alloc(cnt * 16 * n * n * sizeof(double));
+            if (flags & EFGPU_KEEP_X) b.Xcopy.alloc(cnt * 16 * n * n * sizeof(double)); else b.Xcopy.release();
             ws_max = std::max(ws_max, cnt * b.ws_per_entry);
             for (size_t sl = 0; sl < cnt; sl++) H->nodes[b.parents[sl]].Tbuf.assign(1, b.Tbase + sl * 64 * n * n);
         }
@@ -699,7 +728,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             e.T = b.Tbase + sl * 64 * n * n;
             e.Xcopy = (flags & EFGPU_KEEP_X) ? b.Xcopy.as<double>() + sl * 16 * n * n : nullptr;
             e.hd = vec + P.hd_off; e.h = vec + P.hbuf[0]; e.w = vec + P.w_off; e.g = vec + P.gbuf[0];
-            ptab[sl * NOPS + OP_XINV] = e.Xinv; ptab[sl * NOPS + OP_S] = e.S; ptab[sl * NOPS + OP_T] = e.T;
+            ptab[sl * NOPS + OP_XINV] = e.Xinv; ptab[sl * NOPS + OP_S] = e.S; ptab[sl * NOPS + OP_T] = e.T; ptab[sl * NOPS + OP_XCOPY] = e.Xcopy;
             ptab[sl * NOPS + OP_W1] = H->d_ws.as<double>() + sl * b.ws_per_entry;
             ptab[sl * NOPS + OP_W2] = H->d_ws.as<double>() + sl * b.ws_per_entry + b.w2_off;
             ptab[sl * NOPS + OP_W3] = H->d_ws.as<double>() + sl * b.ws_per_entry + b.w3_off;
@@ -776,6 +805,13 @@ static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
 //   build_end              synchronise, singularity report
 static void build_begin(efgpu_handle* H, unsigned flags)
 {
+    // Indefinite problems (lambda > 0: tolerated by the reference, hstcrt.f:450-452 / FiniteVolumeSolver.cpp:270): the merge
+    // matrices lose positive definiteness and the unpivoted block inversion can lose digits against the reference's pivoted
+    // dgesv (measured on the CPU emulation of the plan: 2e-10 instead of 1e-12 next to a resonance).  Every X^-1 then gets one
+    // Newton-Schulz step, which squares the residual I - X X^-1; it needs X, so such builds keep the copy of EFGPU_KEEP_X.
+    const double lam_hi = H->external_leaves ? 0.0 : (H->leaf_kind == EFGPU_LEAF_CONSTANT ? H->lambda : H->lambda_max);
+    H->refine_inverse = H->refine_mode == 1 || (H->refine_mode < 0 && lam_hi > 0.0);
+    if (H->refine_inverse) flags |= EFGPU_KEEP_X;
     if (!H->allocated || ((flags ^ H->build_flags) & (EFGPU_KEEP_X | EFGPU_LEAN_T))) allocate_device(H, flags);
     cudaStream_t s = H->stream;
     // symmetric plan where the structure allows it and the leaf DtN maps are signed-symmetric: constant-coefficient leaves
@@ -785,8 +821,7 @@ static void build_begin(efgpu_handle* H, unsigned flags)
     for (auto& b : H->batches) b.use_sym = b.symcand && leaves_sym && !(flags & EFGPU_NO_SYMMETRY);
     H->cur_flags = flags;
     compute_flop_model(H);
-    const double big = 1e300;
-    EF_CUDA(cudaMemcpyAsync(H->d_minpiv.p, &big, sizeof(double), cudaMemcpyHostToDevice, s));
+    launch_pivot_tracker_reset(H->d_minpiv.as<double>(), s);
     EF_CUDA(cudaEventRecord(H->ev0, s));
     H->built = false; H->root_T_distributed = false; H->root_T_pending = false;
     timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, flags); });
@@ -822,9 +857,18 @@ static void build_level(efgpu_handle* H, int lev, int phase)
         auto run_transposes = [&](const Step& st) {
             timed(H, st.cls, 1, [&] { launch_btranspose(ptab, NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, b.count, s); });
         };
+        auto run_refine = [&]() {   // indefinite problems: X^-1 <- X^-1 + X^-1 (I - X X^-1), every rank of a partition alike
+            for (const Step& st : b.steps_refine)
+                timed(H, st.cls, 1, [&] {
+                    if (st.kind == 1) launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
+                    else launch_refine_ew(ptab, NOPS, st.kind, st.kind == 3 ? OP_T : OP_XINV, st.kind == 3 ? st.off : 0, OP_T, st.off, st.N, b.count,
+                                          H->d_minpiv.as<double>() + 4, s);
+                });
+        };
         for (const Step& st : b.active()) {
             if (st.cls == EFGPU_PROF_MIRROR_T) continue;   // after the gather of T, below
             const bool is_T = st.cls == EFGPU_PROF_GEMM_T;
+            if (phase == 0 && st.cls == EFGPU_PROF_GEMM_S && H->refine_inverse) run_refine();
             if (is_T != (phase == 1) || (st.kind == 1 && st.count == 0)) continue;
             if (st.kind == 2) { run_transposes(st); continue; }
             timed(H, st.cls, 1, [&] {
@@ -896,14 +940,31 @@ static void build_end(efgpu_handle* H)
 {
     cudaStream_t s = H->stream;
     EF_CUDA(cudaEventRecord(H->ev1, s));
-    double minpiv = 0;
-    EF_CUDA(cudaMemcpyAsync(&minpiv, H->d_minpiv.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    double trk[5] = {0, 0, 0, 0, 0};
+    EF_CUDA(cudaMemcpyAsync(trk, H->d_minpiv.p, sizeof(trk), cudaMemcpyDeviceToHost, s));
     EF_CUDA(cudaStreamSynchronize(s));
     collect_profile(H);
     float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1));
+    const double minpiv = trk[0];
+    unsigned long long nneg = 0; std::memcpy(&nneg, &trk[3], sizeof(nneg));
+    const bool none = trk[1] == 0.0;   // no base-case inversion ran (a handle without merges): nothing to report
     H->stats.build_ms = ms; H->stats.min_pivot = minpiv;
+    H->stats.max_pivot = trk[1]; H->stats.pivot_ratio_min = none ? 1.0 : trk[2]; H->stats.negative_pivots = (double)nneg;
+    H->stats.inverse_residual = H->refine_inverse ? trk[4] : -1.0;
     H->built = true; H->upwards_done = false;
-    if (!(minpiv > 0.0) || !std::isfinite(minpiv)) throw Error{EF_ERR_SINGULAR, "non-positive or non-finite pivot in the merge factorisation"};
+    if (!(minpiv > 0.0) || !std::isfinite(minpiv) || !std::isfinite(trk[1]))
+        throw Error{EF_ERR_SINGULAR, "zero or non-finite pivot in the merge factorisation"};
+    // The merge matrices are inverted WITHOUT pivoting (the reference: dgesv, partial pivoting).  That is safe for the SPD /
+    // diagonally dominant X of lambda <= 0; for indefinite problems (lambda > 0) a leading block can be nearly singular while
+    // X is not.  A base-case block whose pivots span more than pivot_ratio_limit (default 1e10, EFGPU_PIVOT_RATIO_LIMIT) is
+    // reported as singular instead of returning operators of unknown accuracy.
+    static const double limit = [] { const char* e = getenv("EFGPU_PIVOT_RATIO_LIMIT"); const double v = e ? atof(e) : 0.0; return v > 1.0 ? v : 1e10; }();
+    if (!none && trk[2] * limit < 1.0)
+        throw Error{EF_ERR_SINGULAR, "ill-conditioned pivot block in the unpivoted merge factorisation (min/max |pivot| = " + std::to_string(trk[2]) +
+                                     " in one base-case block, " + std::to_string(nneg) + " negative pivots): result would not meet the 1e-10 parity tolerance"};
+    // Newton-Schulz squares the residual: E = I - X X^-1 with max |E_ij| above 1e-4 leaves more than ~1e-8 * N behind
+    if (H->refine_inverse && !(trk[4] < 1e-4))
+        throw Error{EF_ERR_SINGULAR, "unpivoted inversion of an indefinite merge matrix too inaccurate to refine (max |I - X X^-1| = " + std::to_string(trk[4]) + ")"};
 }
 
 static void do_build(efgpu_handle* H, unsigned flags)
@@ -1041,6 +1102,15 @@ int efgpu_set_leaf_constant(efgpu_handle* H, double lambda)
     return EF_OK;
 }
 
+// largest sampled lambda of variable-coefficient leaves (> 0: indefinite operator, the build refines every X^-1)
+static void sampled_lambda_max(efgpu_handle* H)
+{
+    H->d_err.alloc(sizeof(double));
+    launch_max_positive(H->d_coef_in[5].as<double>(), (size_t)H->n_leaves * H->M * H->M, H->d_err.as<double>(), H->stream);
+    EF_CUDA(cudaMemcpyAsync(&H->lambda_max, H->d_err.p, sizeof(double), cudaMemcpyDeviceToHost, H->stream));
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+}
+
 int efgpu_set_leaf_variable(efgpu_handle* H, const double* alpha, const double* beta_w, const double* beta_e, const double* beta_s,
                             const double* beta_n, const double* lambda)
 {
@@ -1056,6 +1126,7 @@ int efgpu_set_leaf_variable(efgpu_handle* H, const double* alpha, const double* 
     }
     EF_CUDA(cudaStreamSynchronize(H->stream));
     H->leaf_kind = EFGPU_LEAF_VARIABLE; H->built = false;
+    sampled_lambda_max(H);
     EF_CATCH(H)
 }
 
@@ -1074,6 +1145,7 @@ int efgpu_set_leaf_variable_device(efgpu_handle* H, const double* alpha, const d
     }
     EF_CUDA(cudaStreamSynchronize(H->stream));   // the caller's arrays are borrowed for the call only
     H->leaf_kind = EFGPU_LEAF_VARIABLE; H->built = false;
+    sampled_lambda_max(H);
     EF_CATCH(H)
 }
 
@@ -1146,6 +1218,13 @@ int efgpu_set_symmetric_leaves(efgpu_handle* H, int on)
 {
     if (!H) return EF_ERR_BAD_ARG;
     H->ext_sym = on != 0; H->built = false;
+    return EF_OK;
+}
+
+int efgpu_set_refine_inverse(efgpu_handle* H, int mode)
+{
+    if (!H || mode < -1 || mode > 1) return EF_ERR_BAD_ARG;
+    H->refine_mode = mode; H->built = false;
     return EF_OK;
 }
 

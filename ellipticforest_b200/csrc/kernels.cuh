@@ -51,6 +51,9 @@ void launch_coarsen_h(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_
 void launch_uncoarsen_g(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s);
 void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s);            // hd, w, h
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s);
+// Newton-Schulz refinement of X^-1: mode 3: dst <- I + dst, max |dst| into *resid; mode 4: dst <- dst + src (N x N, contiguous)
+void launch_refine_ew(double* const* ptab, int nops, int mode, int dst_op, long long dst_off, int src_op, long long src_off, int N, int batch,
+                      double* resid, cudaStream_t s);
 int get_tuning(int key);
 void set_tuning(int key, int value);   // efgpu_set_tuning: kernel-selection knobs for measurements
 void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s);      // parity/debug: 8n x 4n, reference order
@@ -60,6 +63,8 @@ void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s); 
 void launch_leaf_points(const double* boxes, const int* leaf_nodes, int M, int which, double* x, double* y, int n_leaves, cudaStream_t s);
 void launch_error_norms(const double* u, const double* v, const double* boxes, const int* leaf_nodes, int M, int n_leaves, double area,
                         double* part, double* out, cudaStream_t s);
+
+void launch_max_positive(const double* v, size_t n, double* out, cudaStream_t s);   // *out = max(0, max v): any sampled lambda > 0?
 
 // lu.cu: root boundary system  (diag(a) + diag(b) T) g = r - b .* h  by blocked LU with partial pivoting
 size_t robin_workspace_doubles(int N);

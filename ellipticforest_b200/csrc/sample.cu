@@ -109,4 +109,20 @@ void launch_error_norms(const double* u, const double* v, const double* boxes, c
     error_final_kernel<<<1, 1024, 0, s>>>(part, n_leaves, area, out);
 }
 
+// *out (pre-set to 0) <- max(0, max_i v[i]): tells efgpu_build whether any sampled lambda is positive (indefinite operator)
+__global__ void __launch_bounds__(256) max_positive_kernel(const double* __restrict__ v, size_t n, double* __restrict__ out)
+{
+    double mx = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) mx = fmax(mx, v[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(mx));
+}
+void launch_max_positive(const double* v, size_t n, double* out, cudaStream_t s)
+{
+    EF_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
+    const size_t blocks = (n + 255) / 256;
+    max_positive_kernel<<<(unsigned)(blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks)), 256, 0, s>>>(v, n, out);
+    EF_CUDA(cudaGetLastError());
+}
+
 }  // namespace efgpu

@@ -491,6 +491,38 @@ void launch_assemble_Hc(const MergeEntry* e, int n, int count, cudaStream_t s)
     }
     EF_CUDA(cudaGetLastError());
 }
+// Element-wise steps of the Newton-Schulz refinement of X^-1 (hps.cu: plan_refine), one batch entry per blockIdx.y:
+//   mode 3:  E <- I + E   (E = -X X^-1 on entry) and max |E_ij| folded into *resid (non-negative doubles order like their bits)
+//   mode 4:  dst <- dst + src
+__global__ void __launch_bounds__(256) refine_ew_kernel(double* const* __restrict__ ptab, int nops, int mode, int dst_op, long long dst_off,
+                                                        int src_op, long long src_off, int N, double* __restrict__ resid)
+{
+    double* dst = ptab[(size_t)blockIdx.y * nops + dst_op] + dst_off;
+    const double* src = mode == 4 ? ptab[(size_t)blockIdx.y * nops + src_op] + src_off : nullptr;
+    double mx = 0.0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)N * N; idx += (long long)gridDim.x * blockDim.x) {
+        if (mode == 3) {
+            const int r = (int)(idx / N), c = (int)(idx - (long long)r * N);
+            const double v = dst[idx] + (r == c ? 1.0 : 0.0);
+            dst[idx] = v;
+            mx = fmax(mx, fabs(v));
+        } else dst[idx] += src[idx];
+    }
+    if (mode == 3 && resid) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(resid), (unsigned long long)__double_as_longlong(mx));
+    }
+}
+void launch_refine_ew(double* const* ptab, int nops, int mode, int dst_op, long long dst_off, int src_op, long long src_off, int N, int batch,
+                      double* resid, cudaStream_t s)
+{
+    for (int off = 0; off < batch; off += 65535) {
+        const int c = batch - off < 65535 ? batch - off : 65535;
+        refine_ew_kernel<<<dim3(ew_blocks((long long)N * N), c), 256, 0, s>>>(ptab + (size_t)off * nops, nops, mode, dst_op, dst_off, src_op, src_off, N, resid);
+    }
+    EF_CUDA(cudaGetLastError());
+}
 void launch_expand_H(const double* Hc, int n, double* H_dense, cudaStream_t s)
 {
     expand_H_kernel<<<ew_blocks(32LL * n * n), 256, 0, s>>>(Hc, n, H_dense);

@@ -210,6 +210,9 @@ class HPSAlgorithm:
         # EFGPU_LAZY_ROOT_DTN: the DtN map of the whole domain is formed by its first reader (Robin solve, operator(0, "T")) instead
         # of by buildStage - nothing on the Dirichlet path reads it
         self.lazy_root_dtn = False
+        # pivoting policy (efgpu_set_refine_inverse): None = automatic - indefinite operators (lambda > 0) get one Newton-Schulz
+        # step on every X^-1 after the unpivoted block inversion; True / False force it on / off
+        self.refine_inverse = None
         # FivePointStencil leaves: the reference evaluates alpha/beta/lambda inside every leaf solve; here they are sampled on
         # the host once per buildStage.  False keeps the coefficient arrays already resident in HBM (same functions).
         self.resample_coefficients = True
@@ -250,6 +253,7 @@ class HPSAlgorithm:
                 self._coefficients_set = True
         else:
             raise ValueError("unknown solver_type")
+        check(self._lib.efgpu_set_refine_inverse(self._h, -1 if self.refine_inverse is None else int(bool(self.refine_inverse))), self._h)
         check(self._lib.efgpu_build(self._h, self._flags()), self._h)
         self.isBuilt = True
 

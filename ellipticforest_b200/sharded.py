@@ -140,8 +140,9 @@ class ShardPlan:
 
 
 # ---------------------------------------------------------------------------------------------
-def _dev_tensor(ptr: int, n: int):
-    """torch view of `n` doubles of device memory owned by libefgpu.so (no copy)."""
+def _dev_tensor(ptr: int, n: int, device: int):
+    """torch view of `n` doubles of device memory owned by libefgpu.so on GPU `device` (no copy).  The device is explicit:
+    the memory belongs to the handle's GPU whatever torch's current device is."""
     import torch
 
     class _View:
@@ -149,7 +150,21 @@ def _dev_tensor(ptr: int, n: int):
 
     v = _View()
     v.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
-    return torch.as_tensor(v, device="cuda")
+    return torch.as_tensor(v, device=torch.device("cuda", int(device)))
+
+
+def global_symmetry(dist, local_flag: bool, world: int, device=None, group=None) -> bool:
+    """The symmetric merge plan of a shared upper tree is a GLOBAL decision: efgpu_is_symmetric() only looks at the subtree
+    roots one rank built, and a rank whose subtrees are uniform would otherwise run the mirrored plan on maps another rank
+    built with coarsening (not signed-symmetric) - wrong operators, or mismatched collectives.  MIN over every rank that
+    contributes leaves to the handle (the world, or `group`)."""
+    if world <= 1:
+        return bool(local_flag)
+    import torch
+    dev = "cpu" if device is None else torch.device("cuda", int(device))
+    t = torch.tensor([1 if local_flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t[0]))
 
 
 class GpuEngine:
@@ -166,6 +181,7 @@ class GpuEngine:
         d.child = self.child.ctypes.data_as(C.POINTER(C.c_int32))
         d.box = self.box.ctypes.data_as(C.POINTER(C.c_double))
         self._h = C.c_void_p()
+        self.device = int(device)
         ext = None
         if ext_sizes is not None:
             self._ext = np.ascontiguousarray(ext_sizes, dtype=np.int32)
@@ -193,13 +209,13 @@ class GpuEngine:
     def operator_view(self, node, which):
         p, r, c = C.c_void_p(), C.c_int(), C.c_int()
         check(self._lib.efgpu_operator_device(self._h, int(node), OP[which], C.byref(p), C.byref(r), C.byref(c)), self._h)
-        return _dev_tensor(p.value, r.value * c.value)
+        return _dev_tensor(p.value, r.value * c.value, self.device)
 
     def vector_view(self, node, which):
         p, n = C.c_void_p(), C.c_int()
         code = {"h0": 5}.get(which, VEC.get(which))
         check(self._lib.efgpu_vector_device(self._h, int(node), code, C.byref(p), C.byref(n)), self._h)
-        return _dev_tensor(p.value, n.value)
+        return _dev_tensor(p.value, n.value, self.device)
 
     def build(self, flags):
         check(self._lib.efgpu_build(self._h, flags), self._h)
@@ -210,13 +226,16 @@ class GpuEngine:
     def set_symmetric_leaves(self, on):
         check(self._lib.efgpu_set_symmetric_leaves(self._h, int(bool(on))), self._h)
 
+    def set_refine_inverse(self, mode):
+        check(self._lib.efgpu_set_refine_inverse(self._h, int(mode)), self._h)
+
     def set_partition(self, rank, nranks, allgather=None):
         """Row partition of a replicated tree; `allgather(tensor)` must all-gather the tensor's equal slices in place."""
         check(self._lib.efgpu_set_partition(self._h, int(rank), int(nranks)), self._h)
         if allgather is not None:
             def _cb(buf, nbytes, _user):
                 try:
-                    allgather(_dev_tensor(buf, nbytes * nranks // 8))
+                    allgather(_dev_tensor(buf, nbytes * nranks // 8, self.device))
                     return 0
                 except Exception as e:  # never unwind through the C frames
                     import traceback
@@ -431,9 +450,13 @@ class ShardedHPS:
         if solver.solver_type not in ("FISHPACK90", "FivePointStencil"):
             raise ValueError("unknown solver_type")
         self.plan = ShardPlan(mesh.level, mesh.child, mesh.box, mesh.nx, world, cut, balance=balance)
+        if self.options["cache-operators"] and len(set(int(v) for v in np.asarray(mesh.level)[mesh.leaf_nodes])) != 1:
+            # quirk q1 (HPSAlgorithm.hpp:134-139) reuses GLOBAL leaf 0's map for every leaf; a forest handle would reuse its own
+            # first leaf's, which differs as soon as leaves have different sizes
+            raise NotImplementedError("cache-operators on a sharded tree needs leaves of one size (the option is only valid on uniform meshes)")
         ids, lev, ch, box, roots = self.plan.local_table(rank)
         self.local = GpuEngine(lev, ch, box, mesh.nx, device)
-        self._stream = torch.cuda.ExternalStream(self.local.stream())
+        self._stream = torch.cuda.ExternalStream(self.local.stream(), device=torch.device("cuda", int(device)))
         self.local_if = _LocalGpu(self.local, roots, self.plan.subtrees_of(rank))
         self.top = self.top_if = None
         if rank == 0 or top_mode == "replicated":
@@ -514,8 +537,13 @@ class ShardedHPS:
     def buildStage(self):
         fl = self._flags()
         self.local.build(fl)
-        if self.top is not None:   # the subtree roots' DtN maps are signed-symmetric when the forest used the symmetric plan
-            self.top.set_symmetric_leaves(self.local.is_symmetric())
+        # the subtree roots' DtN maps are signed-symmetric when EVERY rank's forest used the symmetric plan (collective)
+        sym = global_symmetry(self.dist, self.local.is_symmetric(), self.world, self._device)
+        # ... and the upper tree refines its X^-1 (indefinite operator, lambda > 0) when ANY forest did: not (MIN of the negation)
+        refine = not global_symmetry(self.dist, self.local.stats()["inverse_residual"] < 0.0, self.world, self._device)
+        if self.top is not None:
+            self.top.set_symmetric_leaves(sym)
+            self.top.set_refine_inverse(1 if refine else 0)
         if self.top_mode != "replicated":
             with self.torch.cuda.stream(self._stream):
                 self.xchg.gather_T(self.local_if, self.top_if)
@@ -523,7 +551,7 @@ class ShardedHPS:
                 self.top.build(fl)
             return
         with self.torch.cuda.stream(self._stream):
-            self.xchg.share(self.local_if.root_T, self.top_if.leaf_T, flat=lambda first, total: _dev_tensor(first.data_ptr(), total))
+            self.xchg.share(self.local_if.root_T, self.top_if.leaf_T, flat=lambda first, total: _dev_tensor(first.data_ptr(), total, self._device))
         # levels above the cut: X^-1 products, S and T are computed in row slices and all-gathered by the library
         # through the callback above (the root's DtN map stays row-distributed)
         self.top.build(fl)
@@ -553,7 +581,7 @@ class ShardedHPS:
         if self.top is not None:
             groot = self.top.vector_view(0, "g")
             with self.torch.cuda.stream(self._stream):
-                groot.copy_(_dev_tensor(g_dev_ptr, groot.numel()))
+                groot.copy_(_dev_tensor(g_dev_ptr, groot.numel(), self._device))
             self.top.solve_from_roots(0, fl)
         with self.torch.cuda.stream(self._stream):
             if self.top_mode == "replicated":   # every rank walked the upper tree itself: its subtree roots' g are local
@@ -566,7 +594,7 @@ class ShardedHPS:
     def upwardsStageHost(self, f_host):
         t = self.torch
         if getattr(self, "_f_dev", None) is None:
-            self._f_dev = t.empty(f_host.size, dtype=t.float64, device="cuda")
+            self._f_dev = t.empty(f_host.size, dtype=t.float64, device=t.device("cuda", self._device))
         with t.cuda.stream(self._stream):
             self._f_dev.copy_(t.from_numpy(f_host), non_blocking=True)
         self.upwardsStageDevice(self._f_dev.data_ptr(), 1.0, sync=True)
@@ -574,8 +602,8 @@ class ShardedHPS:
     def solveStageHost(self, g_host, u_host):
         t = self.torch
         if getattr(self, "_u_dev", None) is None:
-            self._u_dev = t.empty(u_host.size, dtype=t.float64, device="cuda")
-            self._g_dev = t.empty(g_host.size, dtype=t.float64, device="cuda")
+            self._u_dev = t.empty(u_host.size, dtype=t.float64, device=t.device("cuda", self._device))
+            self._g_dev = t.empty(g_host.size, dtype=t.float64, device=t.device("cuda", self._device))
         with t.cuda.stream(self._stream):
             self._g_dev.copy_(t.from_numpy(g_host), non_blocking=True)
         self.solveStageDevice(self._g_dev.data_ptr(), self._u_dev.data_ptr(), sync=False)
@@ -612,7 +640,7 @@ class ShardedHPS:
 
     def total_issued_flops(self):
         """Whole-tree issued flops (sum over ranks)."""
-        t = self.torch.tensor([self.stats()["merge_flops_issued"]], dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor([self.stats()["merge_flops_issued"]], dtype=self.torch.float64, device=self.torch.device("cuda", self._device))
         if self.world > 1:
             self.dist.all_reduce(t)
         return float(t[0])
@@ -620,7 +648,7 @@ class ShardedHPS:
     def max_error(self, u_dev, u_fn):
         X, Y = self._XY
         u = u_dev.cpu().numpy().reshape(X.shape)
-        e = self.torch.tensor([float(np.max(np.abs(u - u_fn(X, Y))))], dtype=self.torch.float64, device="cuda")
+        e = self.torch.tensor([float(np.max(np.abs(u - u_fn(X, Y))))], dtype=self.torch.float64, device=self.torch.device("cuda", self._device))
         if self.world > 1:
             self.dist.all_reduce(e, op=self.dist.ReduceOp.MAX)
         return float(e[0])
@@ -724,7 +752,7 @@ class GroupedShardedHPS(ShardedHPS):
             raise ValueError("grouped sharding needs equal subtree roots (uniform upper levels)")
         ids, lev, ch, box, roots = plan.local_table(rank)
         self.local = GpuEngine(lev, ch, box, mesh.nx, device)
-        self._stream = torch.cuda.ExternalStream(self.local.stream())
+        self._stream = torch.cuda.ExternalStream(self.local.stream(), device=torch.device("cuda", int(device)))
         self.local_if = _LocalGpu(self.local, roots, plan.subtrees_of(rank))
         self.xchg = ShardedExchange(plan, rank, dist)
         self.gx = GroupedExchange(plan, rank, world, dist)
@@ -767,17 +795,21 @@ class GroupedShardedHPS(ShardedHPS):
         n = v[0].numel()
         if any(v[j].data_ptr() != v[0].data_ptr() + 8 * j * n or v[j].numel() != n for j in range(4)):
             raise RuntimeError("leaf DtN maps are not contiguous")
-        return _dev_tensor(v[0].data_ptr(), 4 * n), n
+        return _dev_tensor(v[0].data_ptr(), 4 * n, self._device), n
 
     def buildStage(self):
         t, dist, fl = self.torch, self.dist, self._flags()
         self.local.build(fl)
-        self.mid.set_symmetric_leaves(self.local.is_symmetric())
+        # symmetric plans are decided by every rank that feeds the handle: the group for `mid`, the world for `top`
+        self.mid.set_symmetric_leaves(global_symmetry(dist, self.local.is_symmetric(), self.gs, self._device, group=self.group))
+        refine = 1 if self.local.stats()["inverse_residual"] >= 0.0 else 0      # constant lambda: the same answer on every rank
+        self.mid.set_refine_inverse(refine)
+        self.top.set_refine_inverse(refine)
         with t.cuda.stream(self._stream):
             slab, n = self._slab(self.mid, "T_uncoarsened")
             self.gx.subtree_T_to_group(slab, n, self.local_if.root_T)
         self.mid.build(fl & ~LAZY_ROOT_DTN)      # its root is a level-1 node: gathered and mirrored inside the group by the library
-        self.top.set_symmetric_leaves(self.mid.is_symmetric())
+        self.top.set_symmetric_leaves(global_symmetry(dist, self.mid.is_symmetric(), self.world, self._device))
         with t.cuda.stream(self._stream):
             slab, n = self._slab(self.top, "T_uncoarsened")
             self.gx.level1_T_to_world(self.mid.operator_view(0, "T_uncoarsened"), slab)
@@ -804,7 +836,7 @@ class GroupedShardedHPS(ShardedHPS):
         t, fl = self.torch, self._flags()
         groot = self.top.vector_view(0, "g")
         with t.cuda.stream(self._stream):
-            groot.copy_(_dev_tensor(g_dev_ptr, groot.numel()))
+            groot.copy_(_dev_tensor(g_dev_ptr, groot.numel(), self._device))
         self.top.solve_from_roots(0, fl)
         with t.cuda.stream(self._stream):
             self.mid.vector_view(0, "g").copy_(self.top.vector_view(1 + self.group_id, "g"))

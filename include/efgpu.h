@@ -99,6 +99,14 @@ typedef struct {
     double upwards_bytes, solve_bytes;       /* algorithmic HBM bytes per upwards / solve call */
     double device_bytes;           /* device memory held by the handle */
     double min_pivot;              /* smallest |pivot| met while inverting the merge matrices */
+    /* conditioning report of the UNPIVOTED inversion of the merge matrices (the reference: dgesv with partial pivoting,
+       Matrix.hpp:915-953): largest |pivot|, the smallest min/max |pivot| ratio inside one base-case block (<= 128 rows), and the
+       number of negative pivots (0 for the SPD merge matrices of lambda <= 0; > 0 marks an indefinite problem).  efgpu_build
+       returns EFGPU_ERR_SINGULAR when pivot_ratio_min < 1e-10 (EFGPU_PIVOT_RATIO_LIMIT overrides the 1e10). */
+    double max_pivot, pivot_ratio_min, negative_pivots;
+    /* indefinite problems (lambda > 0, see efgpu_set_refine_inverse): max |(I - X X^-1)_ij| over every merge BEFORE the one
+       Newton-Schulz step that squares it; -1 when the build did not refine */
+    double inverse_residual;
 } efgpu_stats_t;
 
 /* ---- lifetime: replaces HPSAlgorithm ctor (HPSAlgorithm.hpp:78-82) + the Quadtree walk ---------- */
@@ -135,6 +143,13 @@ int efgpu_set_allgather(efgpu_handle* h, efgpu_allgather_fn fn, void* user);
 /* External leaves (efgpu_create_ex): declare that the DtN maps the caller writes are signed-symmetric (diag(d) T symmetric),
  * e.g. because efgpu_is_symmetric() holds for the forest handle they were built by; enables the symmetric merge plan. */
 int efgpu_set_symmetric_leaves(efgpu_handle* h, int on);
+/* Pivoting policy (reference: dgesv with partial pivoting, Matrix.hpp:915-953; here: unpivoted recursive block inversion, safe for
+ * the SPD / diagonally dominant merge matrices of lambda <= 0).  For indefinite problems - lambda > 0, which the reference
+ * tolerates (hstcrt.f:450-452, FiniteVolumeSolver.cpp:270) - every X^-1 is refined by one Newton-Schulz step
+ * X^-1 <- X^-1 + X^-1 (I - X X^-1) (two more (4n)^3 products per merge, X kept as under EFGPU_KEEP_X), which restores the accuracy
+ * of the pivoted solve.  mode -1 (default): automatic, on when lambda > 0 (constant leaves) or any sampled lambda > 0 (variable
+ * leaves); 0: never; 1: always.  Handles with external leaves cannot see lambda: the caller passes 1 when the forests refine. */
+int efgpu_set_refine_inverse(efgpu_handle* h, int mode);
 int efgpu_is_symmetric(const efgpu_handle* h);   /* after a build: 1 when every root's DtN map was built by the symmetric plan */
 int efgpu_build_begin(efgpu_handle* h, unsigned flags);
 int efgpu_build_level(efgpu_handle* h, int level, int phase);

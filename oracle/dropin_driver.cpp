@@ -3,6 +3,10 @@
 // on two identical meshes inside one process, and reports the relative max-norm differences of
 // every node's T, S, H (build), h, w (upwards), g and leaf u (solve).  Needs a GPU at run time;
 // used by tests/test_gpu_dropin.py.  Arguments as oracle/ref_driver.cpp.
+//   --time-only K : no CPU reference run; K timed passes (after one warm-up) of setup/build/upwards/solve THROUGH THE BINDING,
+//                   i.e. with the per-cell std::function sampling and the Vector copies a reference driver pays, reported
+//                   with the reference's own stage timers (HPSAlgorithm.hpp:125-126, 183-184, 348-349); --threads T sets
+//                   HPSAlgorithmB200::sampling_threads.
 #include <EllipticForestB200.hpp>
 #include <cstdio>
 #include <cstring>
@@ -45,7 +49,7 @@ int main(int argc, char** argv) {
     int min_level = 0, max_level = 2, nx = 8; bool homogeneous = false, cache = false, robin = false;
     double xl = -10, xu = 10, yl = -10, yu = 10, threshold = 1.2;
     bool use_box = false; double rb[4] = {0, 0, 0, 0};
-    int threads = 1; bool sampling_only = false;
+    int threads = 1; bool sampling_only = false; int time_only = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() { return std::string(argv[++i]); };
@@ -60,6 +64,7 @@ int main(int argc, char** argv) {
         else if (a == "--robin") robin = std::stoi(next());
         else if (a == "--threads") threads = std::stoi(next());
         else if (a == "--sampling-only") sampling_only = true;
+        else if (a == "--time-only") time_only = std::stoi(next());
         else if (a == "--refine-box") { use_box = true; for (int k = 0; k < 4; k++) rb[k] = std::stod(next()); }
         else if (a == "--domain") { xl = std::stod(next()); xu = std::stod(next()); yl = std::stod(next()); yu = std::stod(next()); }
         else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
@@ -74,7 +79,7 @@ int main(int argc, char** argv) {
     FiniteVolumePatch root_a(MPI_COMM_WORLD, grid), root_b(MPI_COMM_WORLD, grid);
     FiniteVolumeNodeFactory factory(MPI_COMM_WORLD);
     Mesh<FiniteVolumePatch> mesh_a{}, mesh_b{};
-    mesh_a.refineByFunction(refine, threshold, min_level, max_level, root_a, factory);
+    if (!time_only) mesh_a.refineByFunction(refine, threshold, min_level, max_level, root_a, factory);
     mesh_b.refineByFunction(refine, threshold, min_level, max_level, root_b, factory);
 
     FiniteVolumeSolver solver{};
@@ -107,6 +112,32 @@ int main(int argc, char** argv) {
         }
     };
     std::function<double(int, double, double, double*, double*)> bc_fn = bc;
+    if (time_only) {
+        HPSAlgorithmB200 gpu(MPI_COMM_WORLD, mesh_b, solver);
+        gpu.sampling_threads = threads;
+        double t[4] = {0, 0, 0, 0}, emax = 0; long leaves = 0;
+        try {
+            for (int pass = 0; pass <= time_only; pass++) {
+                gpu.setupStage(); gpu.buildStage(); gpu.upwardsStage(rhs);
+                if (homogeneous) gpu.solveStage(bc_patch); else gpu.solveStage(bc_fn);
+                if (pass == 0) continue;   // warm-up: CUDA context, first-touch of the host vectors
+                t[0] += app.timers["setup-stage"].time(); t[1] += app.timers["build-stage"].time();
+                t[2] += app.timers["upwards-stage"].time(); t[3] += app.timers["solve-stage"].time();
+            }
+        } catch (const std::exception& e) {
+            printf("DROPIN_TIMING {\"error\": \"%s\"}\n", e.what()); fflush(stdout); _exit(3);
+        }
+        mesh_b.quadtree.traversePreOrder([&](NodeT* n) {
+            if (!n->leaf) return 1;
+            auto& g = n->data.grid(); auto& u = n->data.vectorU();
+            for (int i = 0; i < (int)g.nx(); i++) for (int j = 0; j < (int)g.ny(); j++) emax = fmax(emax, fabs(u[j + i * g.ny()] - P.u(g(0, i), g(1, j))));
+            leaves++; return 1; });
+        for (double& v : t) v /= time_only;
+        printf("DROPIN_TIMING {\"leaves\": %ld, \"dofs\": %ld, \"passes\": %d, \"sampling_threads\": %d, \"setup_s\": %.6f, \"build_s\": %.6f, \"upwards_s\": %.6f, "
+               "\"solve_s\": %.6f, \"linf_error\": %.6e}\n", leaves, leaves * nx * nx, time_only, threads, t[0], t[1], t[2], t[3], emax);
+        fflush(stdout);
+        _exit(0);
+    }
     HPSAlgorithm<FiniteVolumeGrid, FiniteVolumeSolver, FiniteVolumePatch, double> ref(MPI_COMM_WORLD, mesh_a, solver);
     ref.setupStage(); ref.buildStage(); ref.upwardsStage(rhs);
     if (homogeneous) ref.solveStage(bc_patch); else ref.solveStage(bc_fn);

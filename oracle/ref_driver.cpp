@@ -7,6 +7,8 @@
 //              --min-level a --max-level b --nx M --domain xl xu yl yu --threshold t
 //              [--homogeneous 0|1] [--cache 0|1] [--nsolves k] [--dump file] [--ops 0|1]
 //              [--refine-box x0 x1 y0 y1]   (refine inside a box instead of |f| > threshold)
+//              [--lambda v]                 (with --problem helmholtz: constant lambda = v instead of -1)
+//              [--dump-root-only 1]         (dump only the root's T, S, h, w and every leaf's u: parity at bench scale)
 #include <EllipticForest.hpp>
 #include <Patches/FiniteVolume/FiniteVolume.hpp>
 #include <cstdio>
@@ -48,13 +50,14 @@ struct Problem {
 int main(int argc, char** argv) {
     Problem P{"poisson", 0.0};
     std::string solver_name = "fishpack", dump;
-    int min_level = 0, max_level = 2, nx = 8, nsolves = 1; bool homogeneous = false, cache = false, ops = true;
+    int min_level = 0, max_level = 2, nx = 8, nsolves = 1; bool homogeneous = false, cache = false, ops = true, root_only = false;
     double xl = -10, xu = 10, yl = -10, yu = 10, threshold = 1.2;
     bool use_box = false; double rb[4] = {0, 0, 0, 0};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() { return std::string(argv[++i]); };
         if (a == "--problem") { P.name = next(); P.lambda0 = (P.name == "helmholtz") ? -1.0 : 0.0; }
+        else if (a == "--lambda") P.lambda0 = std::stod(next());   // after --problem helmholtz: constant lambda (> 0: indefinite)
         else if (a == "--solver") solver_name = next();
         else if (a == "--min-level") min_level = std::stoi(next());
         else if (a == "--max-level") max_level = std::stoi(next());
@@ -65,6 +68,7 @@ int main(int argc, char** argv) {
         else if (a == "--nsolves") nsolves = std::stoi(next());
         else if (a == "--ops") ops = std::stoi(next());
         else if (a == "--dump") dump = next();
+        else if (a == "--dump-root-only") root_only = std::stoi(next());
         else if (a == "--refine-box") { use_box = true; for (int k = 0; k < 4; k++) rb[k] = std::stod(next()); }
         else if (a == "--domain") { xl = std::stod(next()); xu = std::stod(next()); yl = std::stod(next()); yu = std::stod(next()); }
         else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
@@ -100,6 +104,7 @@ int main(int argc, char** argv) {
         std::vector<double> pb(post.begin(), post.end()), qb(pre.begin(), pre.end());
         rec("order/post", {(long)pb.size()}, pb.data()); rec("order/pre", {(long)qb.size()}, qb.data());
         mesh.quadtree.traversePreOrder([&](NodeT* n) {
+            if (root_only && n->path != "0") return 1;
             auto& g = n->data.grid();
             double box[6] = {g.xLower(), g.xUpper(), g.yLower(), g.yUpper(), (double)g.nx(), (double)n->level};
             rec("grid0/" + n->path, {6}, box); return 1; });
@@ -109,10 +114,11 @@ int main(int argc, char** argv) {
     HPS.buildStage();
     double t_build = app.timers["build-stage"].time();
     if (dumpf) mesh.quadtree.traversePostOrder([&](NodeT* n) {
+        if (root_only && n->path != "0") return 1;
         auto& p = n->data; std::string k = "build/" + n->path + "/";
         double meta[3] = {(double)p.n_coarsens, (double)p.grid().nx(), (double)n->leaf};
         rec(k + "meta", {3}, meta);
-        if (ops) { recMat(k + "T", p.matrixT()); recMat(k + "S", p.matrixS()); recMat(k + "X", p.matrixX()); recMat(k + "H", p.matrixH()); }
+        if (ops) { recMat(k + "T", p.matrixT()); recMat(k + "S", p.matrixS()); if (!root_only) { recMat(k + "X", p.matrixX()); recMat(k + "H", p.matrixH()); } }
         return 1; });
 
     double t_up = 0, t_solve = 0;
@@ -121,6 +127,7 @@ int main(int argc, char** argv) {
         HPS.upwardsStage([&](double x, double y) { return scale * P.f(x, y); });
         t_up += app.timers["upwards-stage"].time();
         if (dumpf && s == nsolves - 1) mesh.quadtree.traversePostOrder([&](NodeT* n) {
+            if (root_only && n->path != "0") return 1;
             auto& p = n->data; std::string k = "up/" + n->path + "/";
             recVec(k + "h", p.vectorH()); recVec(k + "w", p.vectorW()); if (n->leaf) recVec(k + "f", p.vectorF());
             return 1; });
@@ -128,7 +135,8 @@ int main(int argc, char** argv) {
         t_solve += app.timers["solve-stage"].time();
         if (dumpf && s == nsolves - 1) mesh.quadtree.traversePostOrder([&](NodeT* n) {
             auto& p = n->data; std::string k = "solve/" + n->path + "/";
-            recVec(k + "g", p.vectorG()); if (n->leaf) recVec(k + "u", p.vectorU());
+            if (!root_only || n->path == "0") recVec(k + "g", p.vectorG());
+            if (n->leaf) recVec(k + "u", p.vectorU());
             return 1; });
     }
     // error vs manufactured solution on the last solve

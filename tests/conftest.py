@@ -35,6 +35,8 @@ def golden_case_args(gold):
         k = a[i]
         if k == "--problem":
             kw["problem_name"] = a[i + 1]; i += 2
+        elif k == "--lambda":
+            kw["problem_name"] = "helmholtz:%s" % a[i + 1]; i += 2
         elif k == "--solver":
             kw["solver_kind"] = a[i + 1]; i += 2
         elif k == "--min-level":
@@ -60,4 +62,5 @@ GOLDEN_CASES = [
     "adaptive_l1_3_m8_poisson",
     "adaptive_tag2_m8_helmholtz_rect",
     "adaptive_l1_3_m8_varcoef",
+    "uniform_l2_m8_helmholtz_indefinite",
 ]

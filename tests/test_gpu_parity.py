@@ -97,6 +97,41 @@ def test_uniform_against_oracle(nx, level, problem, plan):
     assert err < 3.0 * (np.pi / (nx * 2 ** level)) ** 2
 
 
+@pytest.mark.parametrize("lam", [5.0, 9.0, 20.0])
+def test_indefinite_helmholtz_against_oracle(lam):
+    """lambda > 0 (tolerated by the reference: hstcrt.f:450-452, FiniteVolumeSolver.cpp:270): the merge matrices of the upper
+    levels are indefinite (negative pivots) and, for lambda = 5 on [0,pi]^2, close to a resonance (cond X = 1.2e5 at the root).
+    The reference pivots (dgesv); this path inverts without pivoting and then refines every X^-1 by one Newton-Schulz step
+    (efgpu_set_refine_inverse, automatic for lambda > 0).  Every operator and vector against the oracle's pivoted solve."""
+    kw = dict(problem_name="helmholtz:%g" % lam, solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16,
+              min_level=3, max_level=3, threshold=1.2, refine_box=None)
+    hps = run_gpu(kw)
+    ora = O.run(**kw)
+    worst = {}
+    for i, nd in enumerate(ora.nodes):
+        for nm in (["T"] if nd.leaf else ["T", "S", "X", "H"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.operator(i, nm), getattr(nd, nm)))
+        for nm in (["h", "g", "u"] if nd.leaf else ["h", "g", "w"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.vector(i, nm), getattr(nd, nm)))
+    st = hps.stats()
+    # the same build without the refinement, for the record (the CPU emulation of the plan predicts 2e-10 on S at lambda = 5)
+    P = O.problem(kw["problem_name"])
+    s = ef.FiniteVolumeSolver()
+    s.solver_type = "FISHPACK90"
+    s.lambda_function = P["lam"]
+    raw = ef.HPSAlgorithm(_mesh_for(kw), s)
+    raw.refine_inverse = False
+    raw.buildStage()
+    raw_S = relerr(raw.operator(0, "S"), ora.nodes[0].S)
+    print("lambda %+g: %s | pivots: min %.3e max %.3e, smallest block ratio %.3e, %d negative; max|I - X X^-1| before refinement %.2e; "
+          "root S without refinement %.2e" % (lam, {k: "%.1e" % v for k, v in worst.items()}, st["min_pivot"], st["max_pivot"],
+                                               st["pivot_ratio_min"], st["negative_pivots"], st["inverse_residual"], raw_S))
+    assert st["negative_pivots"] > 0 and st["inverse_residual"] >= 0.0
+    assert raw.stats()["inverse_residual"] == -1.0
+    for nm, v in worst.items():
+        assert v < TOL, (nm, v)
+
+
 def test_adaptive_m16_against_oracle():
     kw = dict(problem_name="poisson", solver_kind="fishpack", box=(-10.0, 10.0, -10.0, 10.0), nx=16,
               min_level=0, max_level=4, threshold=1.2, refine_box=None)

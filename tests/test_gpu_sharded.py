@@ -115,7 +115,6 @@ def test_two_gpus_over_nccl(case, top_mode, tmp_path):
     assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12
 
 
-@pytest.mark.skipif(os.environ.get("EFGPU_TEST_STAGED") != "1", reason="staged: not yet run on GPUs (set EFGPU_TEST_STAGED=1)")
 @pytest.mark.parametrize("top_mode", ["replicated", "root"])
 def test_two_gpus_variable_coefficients_balanced_by_work(top_mode, tmp_path):
     import torch
@@ -134,10 +133,6 @@ def test_two_gpus_variable_coefficients_balanced_by_work(top_mode, tmp_path):
     assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-10
 
 
-STAGED = pytest.mark.skipif(os.environ.get("EFGPU_TEST_STAGED") != "1", reason="staged: not yet run on GPUs (set EFGPU_TEST_STAGED=1)")
-
-
-@STAGED
 @pytest.mark.parametrize("top_mode", ["replicated", "root"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_cut_at_level_1_on_one_gpu(case, top_mode):
@@ -149,7 +144,6 @@ def test_cut_at_level_1_on_one_gpu(case, top_mode):
     assert relerr(rootT, single.operator(0, "T").reshape(-1)) < 1e-12
 
 
-@STAGED
 @pytest.mark.parametrize("case", list(CASES))
 def test_cut_at_level_1_on_two_gpus(case, tmp_path):
     import torch
@@ -192,7 +186,6 @@ def _worker_grouped(rank, world, port, case, out_dir):
         dist.destroy_process_group()
 
 
-@STAGED
 @pytest.mark.parametrize("world", [4, 8])
 def test_grouped_level_1_merges(world, tmp_path):
     """GroupedShardedHPS: forests, level-1 merges inside rank groups (1 rank at 4 GPUs, 2 at 8), root merge over all ranks."""

@@ -1,7 +1,7 @@
-"""Staged GPU tests: switches written after the round's GPU budget was spent (all off by default).  They run with
-EFGPU_TEST_STAGED=1 - tools/gpu_round2.sh sets it - and move into the regular parity files once they have passed on a B200.
-Each compares the switched path with the default path of the same library on the same inputs, which the regular parity
-tests tie to the reference."""
+"""GPU tests of the optional switches (all off by default) and of the size-independent properties at the full size of BASELINE
+configs[1].  Each switch test compares the switched path with the default path of the same library on the same inputs, which
+the regular parity tests tie to the reference.  (Staged behind EFGPU_TEST_STAGED in round 1, when they were written after the GPU
+budget was spent; regular since round 2.)"""
 import os
 
 import numpy as np
@@ -12,8 +12,7 @@ import hps_oracle as O
 from ellipticforest_b200 import _lib
 from test_host import _mesh_for
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("EFGPU_TEST_STAGED") != "1", reason="staged: not yet run on a GPU (set EFGPU_TEST_STAGED=1)")]
+pytestmark = pytest.mark.gpu
 
 CASES = {
     "uniform_l3_m16": dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16, min_level=3, max_level=3,

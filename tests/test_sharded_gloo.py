@@ -455,3 +455,28 @@ def test_sharding_description_strings():
             text = ShardedHPS.sharding(f)
             assert "over %d GPUs" % world in text and "%" not in text, text
             assert ("balanced by " + balance in text) == (balance != "count"), text
+
+
+def _worker_symmetry(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ellipticforest_b200.sharded import global_symmetry
+        # rank 1's forest holds an internally coarsened subtree (efgpu_is_symmetric() == 0 there), rank 0's is uniform
+        mixed = global_symmetry(dist, rank == 0, world)
+        agree = global_symmetry(dist, True, world)
+        g = dist.new_group([0, 1])
+        sub = global_symmetry(dist, rank != 1, 2, group=g) if rank < 2 else True
+        np.save(os.path.join(out_dir, "sym_%d.npy" % rank), np.array([mixed, agree, sub]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_symmetric_plan_is_a_global_decision(tmp_path):
+    """one rank with a uniform forest and one with an internally coarsened subtree of the same root size must
+    agree on the upper tree's merge plan - the answer is the MIN over the ranks that feed the handle (world or sub-group)."""
+    mp.spawn(_worker_symmetry, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    got = [np.load(tmp_path / ("sym_%d.npy" % r)) for r in range(3)]
+    for r in range(3):
+        assert not got[r][0] and got[r][1]
+    assert not got[0][2] and not got[1][2] and got[2][2]
