@@ -36,6 +36,10 @@ SIGNATURES = {
     "efgpu_set_partition": (C.c_int, [_P, C.c_int, C.c_int]),
     "efgpu_set_allgather": (C.c_int, [_P, ALLGATHER_FN, _P]),
     "efgpu_complete_root_dtn": (C.c_int, [_P]),
+    "efgpu_peer_export": (C.c_int, [_P, _P]),
+    "efgpu_peer_attach": (C.c_int, [_P, _P, C.c_int]),
+    "efgpu_peer_barrier": (C.c_int, [_P]),
+    "efgpu_peer_broadcast": (C.c_int, [_P, _P, C.c_size_t]),
     "efgpu_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "efgpu_set_symmetric_leaves": (C.c_int, [_P, C.c_int]),
     "efgpu_is_symmetric": (C.c_int, [_P]),

@@ -57,10 +57,23 @@ struct GemmBlock {
     int pad_;
     GemmTerm t[GEMM_MAX_TERMS];
 };
+// Peer arenas of a row-partitioned tree (peer.cu): rank r's copy of the shared operator arena is mapped at
+// local_base + delta[r] (delta[me] = 0).  A GEMM launched with a span stores every finished tile at the same arena offset on
+// every rank (the all-gather of the row slices, fused into the epilogue); n = 0: plain local stores.
+constexpr int PEER_MAX = 8;
+struct PeerSpan {
+    int n = 0, me = 0;
+    char* local_base = nullptr;
+    long long delta[PEER_MAX] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+void launch_peer_barrier(const PeerSpan& ps, int me, unsigned long long epoch, int* err, cudaStream_t s);
+void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, cudaStream_t s);
+
 // Launches the kernel on `stream`.  rows/cols/K of every block must be multiples of the chosen
 // tile; the tile configuration is picked from the block shape and the amount of parallelism.
+// peers != nullptr: results are also stored into the peer arenas (every C of the launch must lie inside the local arena).
 void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
-                  int nblocks, int batch, cudaStream_t stream, int force_tile = 0);
+                  int nblocks, int batch, cudaStream_t stream, int force_tile = 0, const PeerSpan* peers = nullptr);
 
 // Batched out-of-place block transposes  dst (cols x rows) = +-src (rows x cols)^T, addressed like the GEMM operands.
 // Used where the merge matrices are symmetric (uniform, self-adjoint subtrees): the lower blocks of X^-1 and the

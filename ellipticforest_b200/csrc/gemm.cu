@@ -53,7 +53,7 @@ struct GemmCfg {
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
 bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __restrict__ blocks,
-             int nblocks, int tiles_per_block)
+             int nblocks, int tiles_per_block, const PeerSpan ps)
 {
     using C = GemmCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
     // column slots of the B / C fragments: with an even number of 8-column tiles per warp, slot g of the tile pair (2 jg,
@@ -202,6 +202,11 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
                 }
                 double2* c = reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + jg * 16);
                 c[0] = lo; c[1] = hi;
+                for (int r = 0; r < ps.n; r++)     // row-partitioned tree: the same tile into every peer's arena (NVLink stores)
+                    if (r != ps.me) {
+                        double2* cp = reinterpret_cast<double2*>(reinterpret_cast<char*>(c) + ps.delta[r]);
+                        cp[0] = lo; cp[1] = hi;
+                    }
             }
         } else {
 #pragma unroll
@@ -211,7 +216,10 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
                     double2 c0 = *reinterpret_cast<const double2*>(C0g + (long long)(i * 8) * bd.ldc0 + j * 8);
                     v.x += c0.x; v.y += c0.y;
                 }
-                *reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + j * 8) = v;
+                double2* c = reinterpret_cast<double2*>(Cg + (long long)(i * 8) * bd.ldc + j * 8);
+                *c = v;
+                for (int r = 0; r < ps.n; r++)
+                    if (r != ps.me) *reinterpret_cast<double2*>(reinterpret_cast<char*>(c) + ps.delta[r]) = v;
             }
         }
     }
@@ -219,7 +227,7 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 static void launch_cfg(double* const* ptab, int nops, const GemmBlock* d_blocks, int nblocks, int batch,
-                       int max_tiles, cudaStream_t stream, const GemmBlock* h_blocks = nullptr)
+                       int max_tiles, cudaStream_t stream, const PeerSpan& ps, const GemmBlock* h_blocks = nullptr)
 {
     if (h_blocks) {   // non-square CTA tiles: recount the tiles of the largest block
         max_tiles = 0;
@@ -233,14 +241,15 @@ static void launch_cfg(double* const* ptab, int nops, const GemmBlock* d_blocks,
     long long grid = (long long)max_tiles * nblocks * batch;
     if (grid <= 0) return;
     if (grid > 2147483647LL) throw Error{EF_ERR_BAD_SHAPE, "bgemm grid too large"};
-    kern<<<(unsigned)grid, C::NT, C::SMEM_BYTES, stream>>>(ptab, nops, d_blocks, nblocks, max_tiles);
+    kern<<<(unsigned)grid, C::NT, C::SMEM_BYTES, stream>>>(ptab, nops, d_blocks, nblocks, max_tiles, ps);
     EF_CUDA(cudaGetLastError());
 }
 
 void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
-                  int nblocks, int batch, cudaStream_t stream, int force_tile)
+                  int nblocks, int batch, cudaStream_t stream, int force_tile, const PeerSpan* peers)
 {
     if (nblocks == 0 || batch == 0) return;
+    const PeerSpan ps = peers ? *peers : PeerSpan{};
     // largest power-of-two tile dividing every block dimension
     int g = 128;
     bool k16 = true;
@@ -266,40 +275,40 @@ void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, cons
         case 128: {
             static const int variant = [] { const char* e = getenv("EFGPU_GEMM_VARIANT"); return e ? atoi(e) : 7; }();
             switch (variant) {   // tuning variants of the 128 x 128 CTA tile (tools/gemm_bench.py)
-                case 1: launch_cfg<128, 128, 16, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-                case 2: launch_cfg<128, 128, 32, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-                case 3: launch_cfg<128, 128, 32, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-                case 4: launch_cfg<128, 128, 16, 2, 4, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-                case 5: launch_cfg<128, 128, 16, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-                case 6: launch_cfg<128, 128, 32, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-                case 7: launch_cfg<128, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 8: launch_cfg<64, 128, 16, 1, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 9: launch_cfg<128, 64, 32, 2, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 10: launch_cfg<128, 64, 16, 2, 2, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 11: launch_cfg<64, 64, 16, 1, 2, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 12: launch_cfg<128, 64, 32, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 13: launch_cfg<128, 64, 16, 2, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 14: launch_cfg<64, 128, 16, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 15: launch_cfg<128, 64, 16, 4, 1, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 16: launch_cfg<64, 128, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 17: launch_cfg<64, 128, 32, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
-                case 18: launch_cfg<128, 64, 16, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // 8 warps of 32 x 32, 2 CTAs / SM
-                case 19: launch_cfg<128, 64, 16, 4, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // ... 2 stages, 3 CTAs / SM
-                case 20: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;    // 4 warps of 32 x 32, 4 CTAs / SM
-                case 21: launch_cfg<128, 64, 32, 4, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // BK 32: half the barriers
-                case 22: launch_cfg<128, 128, 16, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;            // 16 warps of 32 x 32, 1 CTA / SM... 2 if registers allow
-                case 23: launch_cfg<64, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;   // 8 warps of 32 x 32, wide
-                case 0: launch_cfg<128, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+                case 1: launch_cfg<128, 128, 16, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+                case 2: launch_cfg<128, 128, 32, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+                case 3: launch_cfg<128, 128, 32, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+                case 4: launch_cfg<128, 128, 16, 2, 4, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+                case 5: launch_cfg<128, 128, 16, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+                case 6: launch_cfg<128, 128, 32, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+                case 7: launch_cfg<128, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 8: launch_cfg<64, 128, 16, 1, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 9: launch_cfg<128, 64, 32, 2, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 10: launch_cfg<128, 64, 16, 2, 2, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 11: launch_cfg<64, 64, 16, 1, 2, 4>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 12: launch_cfg<128, 64, 32, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 13: launch_cfg<128, 64, 16, 2, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 14: launch_cfg<64, 128, 16, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 15: launch_cfg<128, 64, 16, 4, 1, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 16: launch_cfg<64, 128, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 17: launch_cfg<64, 128, 32, 1, 4, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
+                case 18: launch_cfg<128, 64, 16, 4, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;   // 8 warps of 32 x 32, 2 CTAs / SM
+                case 19: launch_cfg<128, 64, 16, 4, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;   // ... 2 stages, 3 CTAs / SM
+                case 20: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;    // 4 warps of 32 x 32, 4 CTAs / SM
+                case 21: launch_cfg<128, 64, 32, 4, 2, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;   // BK 32: half the barriers
+                case 22: launch_cfg<128, 128, 16, 4, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;            // 16 warps of 32 x 32, 1 CTA / SM... 2 if registers allow
+                case 23: launch_cfg<64, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;   // 8 warps of 32 x 32, wide
+                case 0: launch_cfg<128, 128, 16, 2, 4, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
                 // default (7): 128 x 64 CTA tile, 4 warps of 64 x 32, two CTAs per SM so that one CTA's barrier / fragment-load
                 // phases overlap the other's DMMA phases (measured 31-32 TFLOP/s vs 29-30 for one 128 x 128 CTA per SM)
-                default: launch_cfg<128, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, h_blocks); break;
+                default: launch_cfg<128, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps, h_blocks); break;
             }
             break;
         }
-        case 64: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-        case 32: launch_cfg<32, 32, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-        case 16: launch_cfg<16, 16, 16, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
-        case 8: launch_cfg<8, 8, 8, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream); break;
+        case 64: launch_cfg<64, 64, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+        case 32: launch_cfg<32, 32, 16, 2, 2, 3>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+        case 16: launch_cfg<16, 16, 16, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
+        case 8: launch_cfg<8, 8, 8, 1, 1, 2>(ptab, nops, d_blocks, nblocks, batch, mt, stream, ps); break;
         default: throw Error{EF_ERR_BAD_SHAPE, "bgemm: unsupported tile"};
     }
 }

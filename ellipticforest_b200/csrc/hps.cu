@@ -32,15 +32,17 @@ enum { OP_TC0 = 0, OP_XINV = 4, OP_S = 5, OP_T = 6, OP_W1 = 7, OP_W2 = 8, OP_W3 
 
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
+    bool owned = true;   // false: a slice of the handle's shared arena (peer mode), never freed here
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), owned(o.owned) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; owned = o.owned; o.p = nullptr; o.bytes = 0; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; bytes = 0; owned = true; }
+    void adopt(void* q, size_t b) { release(); p = q; bytes = b; owned = false; }
     void alloc(size_t b) {
-        if (b <= bytes && p) return;
+        if (b <= bytes && p && owned) return;
         release();
         if (b == 0) return;
         EF_CUDA(cudaMalloc(&p, b)); bytes = b;
@@ -112,6 +114,15 @@ struct efgpu_handle {
     bool root_T_pending = false;                 // EFGPU_LAZY_ROOT_DTN: the level-0 DtN products have not been issued yet
     unsigned cur_flags = 0;                      // flags of the build in progress / of the last build
     efgpu_allgather_fn allgather = nullptr; void* allgather_user = nullptr;   // collective supplied by the caller (NCCL)
+    // peer mode (peer.cu): the buffers other ranks write into (X^-1, S, T, workspaces, leaf maps, vectors) are slices of ONE
+    // allocation with the same layout on every rank, mapped into every rank by CUDA IPC
+    bool peer_mode = false, peer_attached = false;
+    DevBuf arena; size_t arena_need = 0;
+    PeerSpan peers;
+    void* peer_mapped[PEER_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long peer_epoch = 0;
+    bool peer_dirty = true;                      // local work since the last barrier: a barrier must precede the next peer stores
+    DevBuf d_peer_err;
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
     // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
     // (in an unsharded run this is the first thing the leaf's own split1to4 would do, HPSAlgorithm.hpp:1165-1183)
@@ -193,6 +204,7 @@ static void collect_profile(efgpu_handle* H)   // stream must be synchronised
 // which shortens the serial chain of small launches of the top tree levels by a quarter.
 struct InvPlanner {
     BatchH& b; std::vector<Step>& steps; const std::vector<long long>& w1_off; int ld, rank, nranks; bool sym;
+    bool peer = false;                          // peer mode: split products store straight into every rank's arena (gk 3), no staging
     std::vector<GemmBlock>* blk = nullptr;      // where descriptors go (default: the batch's vectors)
     std::vector<TransOp>* trn = nullptr;
     const std::vector<long long>* w1b = nullptr; // workspace of a zipped second branch (null: no zipping below this planner)
@@ -215,11 +227,14 @@ struct InvPlanner {
         // A product is split only where the flops saved outweigh the all-gather that follows (tens of microseconds of
         // latency per collective): 2048-row products take ~0.6 ms, 1024-row ones 70 us; the deep, small products of the
         // recursion are recomputed by every rank (6 % of the inversion flops).
-        static const int split_min = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 2048; }();
+        static const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
+        // (peer mode: a split costs two flag barriers of a few microseconds instead of a collective, so smaller products pay)
+        const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
         if (nranks > 1 && rows % (128 * nranks) == 0 && rows >= split_min) {
             const long long skip = (long long)rank * (rows / nranks);
             st.g_op = c_op; st.g_off = c_off; st.g_rows = rows; st.g_cols = cols; st.g_ld = ldc;
-            if (ldc == cols) st.gk = 1;
+            if (peer) st.gk = 3;             // the epilogue stores the tile on every rank: any leading dimension, no staging
+            else if (ldc == cols) st.gk = 1;
             else { st.gk = 2; g.c_op = OP_W3; g.c_off = 0; g.ldc = cols; }   // rows land in the contiguous staging block
             g.c_off += skip * g.ldc;
             if (g.c0_op >= 0) g.c0_off += skip * g.ldc0;
@@ -238,7 +253,8 @@ struct InvPlanner {
     // only the upper triangle of a 2 x 2 or 4 x 4 block partition is multiplied (3 of 4 / 10 of 16 sub-blocks, one
     // launch), the lower blocks are transposes.  Row-partitioned products keep the plain form (their slices are gathered).
     void gemm_sym(int h, int K, int c_op, long long c_off, int ldc, int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb) {
-        static const int split_min = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 2048; }();
+        static const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
+        const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
         const bool row_split = nranks > 1 && h % (128 * nranks) == 0 && h >= split_min;
         const int nb = row_split ? 1 : ((h % 64 == 0 && h / 4 >= 128) ? 4 : ((h % 32 == 0 && h / 2 >= 128) ? 2 : 1));
         if (nb == 1) { gemm(h, h, K, c_op, c_off, ldc, c_op, c_off, ldc, a_op, a_off, lda, b_op, b_off, ldb, true); return; }
@@ -270,13 +286,13 @@ struct InvPlanner {
     void invert_pair(long long offA, long long offB, int q, int depth) {
         if (!w1b) { invert(offA, q, depth, false); invert(offB, q, depth, false); return; }
         std::vector<Step> sA, sB; std::vector<GemmBlock> bA, bB; std::vector<TransOp> tA, tB;
-        InvPlanner pa{b, sA, w1_off, ld, rank, nranks, sym}; pa.blk = &bA; pa.trn = &tA; pa.w2 = w2;
-        InvPlanner pb{b, sB, *w1b, ld, rank, nranks, sym}; pb.blk = &bB; pb.trn = &tB; pb.w2 = w2b;
+        InvPlanner pa{b, sA, w1_off, ld, rank, nranks, sym}; pa.blk = &bA; pa.trn = &tA; pa.w2 = w2; pa.peer = peer;
+        InvPlanner pb{b, sB, *w1b, ld, rank, nranks, sym}; pb.blk = &bB; pb.trn = &tB; pb.w2 = w2b; pb.peer = peer;
         pa.invert(offA, q, depth, false);
         pb.invert(offB, q, depth, false);
         bool zip = sA.size() == sB.size();
         for (size_t i = 0; zip && i < sA.size(); i++)
-            zip = sA[i].kind == sB[i].kind && sA[i].count == sB[i].count && !sA[i].gk && !sB[i].gk && sA[i].N == sB[i].N;
+            zip = sA[i].kind == sB[i].kind && sA[i].count == sB[i].count && sA[i].gk == sB[i].gk && (sA[i].gk == 0 || sA[i].gk == 3) && sA[i].N == sB[i].N;
         if (!zip) { append(sA, bA, tA); append(sB, bB, tB); return; }
         for (size_t i = 0; i < sA.size(); i++) {
             Step st = sA[i];
@@ -353,7 +369,7 @@ static bool clip_rows(GemmBlock& g, long long r0, long long lo, long long hi)
 
 static void plan_refine(BatchH& b);
 
-static void plan_batch_gemms(BatchH& b, int rank, int nranks)
+static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
 {
     const int n = b.n, N = 4 * n;
     b.blocks.clear(); b.trans.clear(); b.steps.clear(); b.steps_sym.clear(); b.steps_refine.clear();
@@ -383,7 +399,7 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
         const bool sym = variant == 1;
         std::vector<Step>& steps = sym ? b.steps_sym : b.steps;
         InvPlanner ip{b, steps, w1_off, N, rank, nranks, sym};
-        ip.w1b = &w1b_off; ip.w2b = w2_total / 2;
+        ip.w1b = &w1b_off; ip.w2b = w2_total / 2; ip.peer = peer;
         ip.invert(0, N, 0, true);
         // S = X^-1 S_RHS, written with WESN-permuted columns (mergeS_ + reorderOperators_)
         int first = (int)b.blocks.size();
@@ -449,8 +465,8 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks)
                         continue;
                     }
                 }
-                // a diagonal block of the signed-symmetric T is itself symmetric: optionally (efgpu_set_tuning key 5; off by
-                // default until measured on the GPU) only the upper triangle of its 2 x 2 / 4 x 4 sub-blocks is multiplied
+                // a diagonal block of the signed-symmetric T is itself symmetric: only the upper triangle of its 2 x 2 / 4 x 4
+                // sub-blocks is multiplied (efgpu_set_tuning key 5, default on: 202.8 -> 197.8 ms per step at L = 8, M = 16)
                 const int nb = (sym && mirror_ok && P == Q && get_tuning(5) == 1)
                                    ? ((n % 64 == 0 && n / 4 >= 128) ? 4 : ((n % 32 == 0 && n / 2 >= 128) ? 2 : 1)) : 1;
                 const int sb = n / nb;
@@ -643,8 +659,32 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
     }
     H->leafT_off.assign(H->n_leaves + 1, 0);
     for (int l = 0; l < H->n_leaves; l++) { const size_t sz = 4 * (size_t)H->nodes[H->leaf_nodes[l]].size; H->leafT_off[l + 1] = H->leafT_off[l] + sz * sz; }
-    H->d_leafT.alloc(H->leafT_off[H->n_leaves] * sizeof(double));
-    H->d_vec.alloc(H->vec_doubles * sizeof(double));
+    // Peer mode: everything another rank stores into is carved from one arena in a fixed order (sizes depend on the tree only,
+    // never on the rank), so that an address and its arena offset mean the same buffer on every rank.  [0, 4096): barrier flags.
+    size_t arena_off = 4096;
+    auto carve = [&](DevBuf& b, size_t bytes) {
+        if (!H->peer_mode) { b.alloc(bytes); return; }
+        b.adopt(static_cast<char*>(H->arena.p) + arena_off, bytes);
+        arena_off += (bytes + 255) & ~size_t(255);
+    };
+    if (H->peer_mode) {
+        if (flags & EFGPU_LEAN_T) throw Error{EF_ERR_UNSUPPORTED, "EFGPU_LEAN_T on a peer-mapped (partitioned) tree"};
+        size_t need = 4096, wsm = 0;
+        auto add = [&](size_t bytes) { need += (bytes + 255) & ~size_t(255); };
+        add(H->leafT_off[H->n_leaves] * sizeof(double)); add(H->vec_doubles * sizeof(double));
+        for (auto& b : H->batches) {
+            const size_t n = b.n, cnt = b.count;
+            add(cnt * 16 * n * n * sizeof(double)); add(cnt * 32 * n * n * sizeof(double)); add(cnt * 64 * n * n * sizeof(double));
+            wsm = std::max(wsm, cnt * b.ws_per_entry);
+        }
+        add(wsm * sizeof(double));
+        if (!H->arena.p) {
+            H->arena.alloc(need); H->arena_need = need;
+            EF_CUDA(cudaMemsetAsync(H->arena.p, 0, 4096, s));
+        } else if (need != H->arena_need) throw Error{EF_ERR_STATE, "internal: the shared arena changed size after it was exported"};
+    }
+    carve(H->d_leafT, H->leafT_off[H->n_leaves] * sizeof(double));
+    carve(H->d_vec, H->vec_doubles * sizeof(double));
     EF_CUDA(cudaMemsetAsync(H->d_vec.p, 0, H->vec_doubles * sizeof(double), s));
     if (!H->external_leaves) {
         H->d_f.alloc((size_t)H->n_leaves * M * M * sizeof(double));
@@ -673,22 +713,27 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
     } else { H->d_Tarena[0].release(); H->d_Tarena[1].release(); }
     // per-batch operator storage (deepest level first so children's buffers exist before the parents' tables)
     size_t ws_max = 0;
+    for (auto& b : H->batches) {   // (peer mode: arena order = batch order, as counted above)
+        const size_t n = b.n, cnt = b.count;
+        carve(b.Xinv, cnt * 16 * n * n * sizeof(double));
+        carve(b.S, cnt * 32 * n * n * sizeof(double));
+        if (H->peer_mode) carve(b.T, cnt * 64 * n * n * sizeof(double));
+    }
     for (int lev = H->max_level; lev >= 0; lev--) {
-        size_t arena_off = 0;
+        size_t tarena_off = 0;
         for (int bi : H->level_batches[lev]) {
             BatchH& b = H->batches[bi];
             const size_t n = b.n, cnt = b.count;
-            b.Xinv.alloc(cnt * 16 * n * n * sizeof(double));
-            b.S.alloc(cnt * 32 * n * n * sizeof(double));
             b.Hc.alloc(cnt * 16 * n * n * sizeof(double));
-            if (H->lean_T) { b.T.release(); b.Tbase = H->d_Tarena[lev & 1].as<double>() + arena_off; arena_off += cnt * 64 * n * n; }
-            else { b.T.alloc(cnt * 64 * n * n * sizeof(double)); b.Tbase = b.T.as<double>(); }
+            if (H->lean_T) { b.T.release(); b.Tbase = H->d_Tarena[lev & 1].as<double>() + tarena_off; tarena_off += cnt * 64 * n * n; }
+            else if (!H->peer_mode) { b.T.alloc(cnt * 64 * n * n * sizeof(double)); b.Tbase = b.T.as<double>(); }
+            else b.Tbase = b.T.as<double>();      // carved below, in batch order
             if (flags & EFGPU_KEEP_X) b.Xcopy.alloc(cnt * 16 * n * n * sizeof(double)); else b.Xcopy.release();
             ws_max = std::max(ws_max, cnt * b.ws_per_entry);
             for (size_t sl = 0; sl < cnt; sl++) H->nodes[b.parents[sl]].Tbuf.assign(1, b.Tbase + sl * 64 * n * n);
         }
     }
-    H->d_ws.alloc(ws_max * sizeof(double));
+    carve(H->d_ws, ws_max * sizeof(double));
     // coarsened copies + tables
     for (auto& b : H->batches) {
         const size_t n = b.n, cnt = b.count;
@@ -798,6 +843,18 @@ static void run_leaf_dtn(efgpu_handle* H, unsigned flags)
                           H->d_leaf_build.as<int>(), H->n_leaf_build, H->d_leaf_src.as<int>(), H->stream);
 }
 
+// Flag barrier over the ranks of a peer-mapped tree (peer.cu), stream-ordered.  Discipline: a barrier BEFORE a kernel that stores
+// into peer arenas (every rank has finished reading what is about to be overwritten) unless nothing ran since the last
+// barrier, and one AFTER it (the stores of every rank have landed before anyone reads them).
+static void peer_barrier(efgpu_handle* H, bool only_if_dirty)
+{
+    if (only_if_dirty && !H->peer_dirty) return;
+    timed(H, EFGPU_PROF_ALLGATHER, 1, [&] {
+        launch_peer_barrier(H->peers, H->part_rank, ++H->peer_epoch, H->d_peer_err.as<int>(), H->stream);
+    });
+    H->peer_dirty = false;
+}
+
 // buildStage in pieces, so that a replicated upper tree can exchange row slices between them:
 //   build_begin            allocation, pivot tracker, leaf DtN maps
 //   build_level(lev, 0)    coarsen + assemble X / H + invert X + (this rank's rows of) S for every merge of level `lev`
@@ -837,6 +894,7 @@ static void build_level(efgpu_handle* H, int lev, int phase)
         H->root_T_pending = true;
         return;
     }
+    H->peer_dirty = true;
     for (int bi : H->level_batches[lev]) {
         BatchH& b = H->batches[bi];
         double* const* ptab = b.d_ptab.as<double*>();
@@ -865,16 +923,24 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                                           H->d_minpiv.as<double>() + 4, s);
                 });
         };
+        const bool p2p = H->peer_mode && H->part_nranks > 1;
+        if (p2p && !H->peer_attached) throw Error{EF_ERR_STATE, "peer-mapped tree: efgpu_peer_attach has not been called"};
         for (const Step& st : b.active()) {
             if (st.cls == EFGPU_PROF_MIRROR_T) continue;   // after the gather of T, below
             const bool is_T = st.cls == EFGPU_PROF_GEMM_T;
             if (phase == 0 && st.cls == EFGPU_PROF_GEMM_S && H->refine_inverse) run_refine();
             if (is_T != (phase == 1) || (st.kind == 1 && st.count == 0)) continue;
-            if (st.kind == 2) { run_transposes(st); continue; }
+            if (st.kind == 2) { run_transposes(st); H->peer_dirty = true; continue; }
+            // peer mode: the row slices of a split product, of S and of the DtN maps below the root are stored into every rank's
+            // arena by the GEMM itself, between two flag barriers (the root's map stays row-distributed: nobody merges it)
+            const bool scatter = p2p && st.kind == 1 && (st.gk == 3 || st.cls == EFGPU_PROF_GEMM_S || (is_T && lev > 0));
+            if (scatter) peer_barrier(H, /*only_if_dirty=*/true);
             timed(H, st.cls, 1, [&] {
                 if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
-                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
+                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s, 0, scatter ? &H->peers : nullptr);
             });
+            if (scatter) { peer_barrier(H, false); continue; }
+            H->peer_dirty = true;
             if (st.gk) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
                 const size_t hh = (size_t)st.g_rows * st.g_cols;
                 for (int sl = 0; sl < b.count; sl++) {
@@ -889,7 +955,7 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             });
         }
         // the row slices of S (phase 0) and of the DtN map T (phase 1; the root's stays distributed) become whole on every rank
-        if (H->part_nranks > 1 && H->allgather && (phase == 0 || lev > 0)) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
+        if (H->part_nranks > 1 && !p2p && H->allgather && (phase == 0 || lev > 0)) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
             const size_t n2 = (size_t)b.n * b.n;
             for (int sl = 0; sl < b.count; sl++) {
                 double* const* ops = b.h_ptab.data() + (size_t)sl * NOPS;
@@ -918,16 +984,27 @@ static void complete_root_T(efgpu_handle* H)
         collect_profile(H);
     }
     if (!H->root_T_distributed) return;
-    if (!H->allgather) throw Error{EF_ERR_STATE, "row-partitioned tree without an all-gather callback (efgpu_set_allgather)"};
+    const bool p2p = H->peer_mode && H->part_nranks > 1;
+    if (!p2p && !H->allgather) throw Error{EF_ERR_STATE, "row-partitioned tree without an all-gather callback (efgpu_set_allgather)"};
     cudaStream_t s = H->stream;
+    if (p2p) peer_barrier(H, false);
     for (int bi : H->level_batches[0]) {
         BatchH& b = H->batches[bi];
         const size_t n2 = (size_t)b.n * b.n;
         for (int sl = 0; sl < b.count; sl++) {
             double* T = b.h_ptab[(size_t)sl * NOPS + OP_T];
-            if (H->allgather(T, 64 * n2 / H->part_nranks * sizeof(double), H->allgather_user) != 0)
+            const size_t slice = 64 * n2 / H->part_nranks * sizeof(double);
+            if (p2p) {   // this rank's row slice into every other arena; the barrier below completes the all-gather
+                launch_peer_scatter(H->peers, H->part_rank, (size_t)(reinterpret_cast<char*>(T) - static_cast<char*>(H->arena.p)) + H->part_rank * slice, slice, s);
+                continue;
+            }
+            if (H->allgather(T, slice, H->allgather_user) != 0)
                 throw Error{EF_ERR_STATE, "the all-gather callback failed"};
         }
+    }
+    if (p2p) peer_barrier(H, false);
+    for (int bi : H->level_batches[0]) {
+        BatchH& b = H->batches[bi];
         for (const Step& st : b.active())
             if (st.cls == EFGPU_PROF_MIRROR_T)
                 launch_btranspose(b.d_ptab.as<double*>(), NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, b.count, s);
@@ -940,11 +1017,17 @@ static void build_end(efgpu_handle* H)
 {
     cudaStream_t s = H->stream;
     EF_CUDA(cudaEventRecord(H->ev1, s));
+    int peer_err = 0;
+    if (H->peer_mode && H->d_peer_err.p) EF_CUDA(cudaMemcpyAsync(&peer_err, H->d_peer_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     double trk[5] = {0, 0, 0, 0, 0};
     EF_CUDA(cudaMemcpyAsync(trk, H->d_minpiv.p, sizeof(trk), cudaMemcpyDeviceToHost, s));
     EF_CUDA(cudaStreamSynchronize(s));
     collect_profile(H);
     float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, H->ev0, H->ev1));
+    if (peer_err) {
+        EF_CUDA(cudaMemsetAsync(H->d_peer_err.p, 0, sizeof(int), s));
+        throw Error{EF_ERR_STATE, "peer barrier timed out waiting for rank " + std::to_string(peer_err - 1) + " (a rank of the partition did not reach the same step)"};
+    }
     const double minpiv = trk[0];
     unsigned long long nneg = 0; std::memcpy(&nneg, &trk[3], sizeof(nneg));
     const bool none = trk[1] == 0.0;   // no base-case inversion ran (a handle without merges): nothing to report
@@ -1088,6 +1171,7 @@ void efgpu_destroy(efgpu_handle* H)
     if (H->ev1) cudaEventDestroy(H->ev1);
     for (auto& r : H->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : H->ev_pool) cudaEventDestroy(e);
+    for (void* p : H->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
     cudaStream_t s = H->own_stream ? H->stream : nullptr;
     delete H;
     if (s) cudaStreamDestroy(s);
@@ -1166,6 +1250,74 @@ int efgpu_set_partition(efgpu_handle* H, int rank, int nranks)
     H->part_rank = rank; H->part_nranks = nranks;
     for (auto& b : H->batches) plan_batch_gemms(b, rank, nranks);
     compute_flop_model(H);
+    EF_CATCH(H)
+}
+
+int efgpu_peer_export(efgpu_handle* H, void* ipc_handle_out)
+{
+    if (!H || !ipc_handle_out) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (H->part_nranks > PEER_MAX) throw Error{EF_ERR_UNSUPPORTED, "peer mode: at most 8 ranks (one NVSwitch domain)"};
+    if (H->allocated && !H->peer_mode) throw Error{EF_ERR_STATE, "efgpu_peer_export must precede the first build / device view"};
+    EF_CUDA(cudaSetDevice(H->device));
+    if (!H->peer_mode) {
+        H->peer_mode = true;
+        for (auto& b : H->batches) plan_batch_gemms(b, H->part_rank, H->part_nranks, true);
+        compute_flop_model(H);
+        H->d_peer_err.alloc(sizeof(int));
+        EF_CUDA(cudaMemsetAsync(H->d_peer_err.p, 0, sizeof(int), H->stream));
+        allocate_device(H, H->build_flags);
+    }
+    cudaIpcMemHandle_t hd;
+    EF_CUDA(cudaIpcGetMemHandle(&hd, H->arena.p));
+    std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+    EF_CATCH(H)
+}
+
+int efgpu_peer_attach(efgpu_handle* H, const void* handles, int nranks)
+{
+    if (!H || !handles) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    if (!H->peer_mode) throw Error{EF_ERR_STATE, "efgpu_peer_attach before efgpu_peer_export"};
+    if (nranks != H->part_nranks) throw Error{EF_ERR_BAD_ARG, "efgpu_peer_attach: one handle per rank of the partition"};
+    EF_CUDA(cudaSetDevice(H->device));
+    H->peers = PeerSpan{};
+    H->peers.n = nranks; H->peers.me = H->part_rank; H->peers.local_base = static_cast<char*>(H->arena.p);
+    for (int r = 0; r < nranks; r++) {
+        if (r == H->part_rank) { H->peers.delta[r] = 0; continue; }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof(hd));
+        void* p = nullptr;
+        EF_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        H->peer_mapped[r] = p;
+        H->peers.delta[r] = static_cast<char*>(p) - static_cast<char*>(H->arena.p);
+    }
+    H->peer_attached = true;
+    EF_CATCH(H)
+}
+
+int efgpu_peer_barrier(efgpu_handle* H)
+{
+    if (!H) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    if (!H->peer_attached) throw Error{EF_ERR_STATE, "efgpu_peer_barrier on a handle without attached peers"};
+    EF_CUDA(cudaSetDevice(H->device));
+    peer_barrier(H, false);
+    EF_CATCH(H)
+}
+
+int efgpu_peer_broadcast(efgpu_handle* H, const void* dev_ptr, size_t bytes)
+{
+    if (!H || !dev_ptr) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    if (!H->peer_attached) throw Error{EF_ERR_STATE, "efgpu_peer_broadcast on a handle without attached peers"};
+    const char* p = static_cast<const char*>(dev_ptr);
+    const char* base = static_cast<const char*>(H->arena.p);
+    if (p < base + 4096 || p + bytes > base + H->arena_need) throw Error{EF_ERR_BAD_ARG, "efgpu_peer_broadcast: the region must lie inside the shared arena (a device view of this handle)"};
+    EF_CUDA(cudaSetDevice(H->device));
+    timed(H, EFGPU_PROF_ALLGATHER, 1, [&] { launch_peer_scatter(H->peers, H->part_rank, (size_t)(p - base), bytes, H->stream); });
+    H->peer_dirty = true;
     EF_CATCH(H)
 }
 

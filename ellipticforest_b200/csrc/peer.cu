@@ -1,0 +1,85 @@
+// Peer-memory exchange of a row-partitioned (replicated) upper tree over NVLink / NVSwitch.
+//
+// Replaces what the reference does with MPI::broadcast of whole child patches between the ranks that share a node
+// (src/Quadtree.hpp:464-507, src/QuadNode.hpp:191-199, FiniteVolumePatch.cpp:118-134) and what round 1 of this library did
+// with one ncclAllGather per row slice issued from a host callback: every rank maps the shared operator arena of every
+// other rank (CUDA IPC, one allocation per handle, identical layout on every rank because the merge plan is the same), the
+// batched GEMM stores each finished tile into all arenas from its epilogue (gemm.cu: PeerSpan), and the only collective left is
+// this flag barrier.  No NCCL, no host round trip, the transfer overlaps the tensor-core work tile by tile.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace efgpu {
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+
+// One warp.  Lane r < nranks publishes `epoch` into slot `me` of rank r's flag array (its own included), then waits until
+// slot r of the local array has reached `epoch`.  Everything this GPU wrote before the kernel (peer stores of earlier
+// kernels on the stream included) is ordered before the flag by the system-scope fence + release store; the acquire load
+// orders the peers' data before whatever follows on this stream.  A peer that never arrives (crashed rank) must not hang the
+// GPU: after `timeout_ns` the lane gives up and raises *err (checked by the host at the end of the stage).
+__global__ void peer_barrier_kernel(PeerSpan ps, int me, unsigned long long epoch, unsigned long long timeout_ns, int* __restrict__ err)
+{
+    const int r = threadIdx.x;
+    if (r >= ps.n) return;
+    __threadfence_system();
+    unsigned long long* local = reinterpret_cast<unsigned long long*>(ps.local_base);
+    unsigned long long* remote = reinterpret_cast<unsigned long long*>(ps.local_base + ps.delta[r]);
+    st_release_sys(remote + me, epoch);
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(local + r) < epoch) {
+        if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1 + r); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+void launch_peer_barrier(const PeerSpan& ps, int me, unsigned long long epoch, int* err, cudaStream_t s)
+{
+    static const unsigned long long timeout_ns = [] {
+        const char* e = getenv("EFGPU_PEER_TIMEOUT_S"); const double v = e ? atof(e) : 20.0; return (unsigned long long)((v > 0.1 ? v : 20.0) * 1e9); }();
+    peer_barrier_kernel<<<1, 32, 0, s>>>(ps, me, epoch, timeout_ns, err);
+    EF_CUDA(cudaGetLastError());
+}
+
+// Copies `bytes` (a multiple of 16) at arena offset `off` of this rank into the same offset of every OTHER rank's arena:
+// the broadcast half of an all-gather whose slices already lie in place.  Grid-stride over 16-byte words, the peers innermost
+// so that consecutive stores of a thread go out on different NVLink destinations.
+__global__ void __launch_bounds__(256) peer_scatter_kernel(PeerSpan ps, int me, size_t off, size_t n16)
+{
+    const int4* src = reinterpret_cast<const int4*>(ps.local_base + off);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 v = src[i];
+#pragma unroll 1
+        for (int r = 0; r < ps.n; r++)
+            if (r != me) reinterpret_cast<int4*>(ps.local_base + ps.delta[r] + off)[i] = v;
+    }
+}
+
+void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0 || ps.n <= 1) return;
+    if ((off | bytes) & 15) throw Error{EF_ERR_BAD_ARG, "peer scatter: offset and size must be multiples of 16 bytes"};
+    const size_t n16 = bytes / 16;
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    peer_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(ps, me, off, n16);
+    EF_CUDA(cudaGetLastError());
+}
+
+}  // namespace efgpu

@@ -19,8 +19,9 @@ namespace efgpu {
 // [1] compact-H long-row kernel: 0 = 8 loads in flight per lane (default), 1 = 4
 // [2] CTAs per SM the long-row launcher aims for (default 16)
 // [3] leaf solve of constant-coefficient leaves: 0 = DMMA kernel (default), 1 = one thread per cell
-// [5] symmetric merge plan: 1 = the diagonal blocks of T multiply only their upper sub-block triangle (default 0; read when a plan is made)
-static int g_tuning[8] = {2, 0, 0, 0, 0, 0, 0, 0};
+// [5] symmetric merge plan: 1 = the diagonal blocks of T multiply only their upper sub-block triangle (default since r2a: 202.8 -> 197.8 ms
+//     per step at L=8 M=16; 0 = whole blocks; read when a plan is made)
+static int g_tuning[8] = {2, 0, 0, 0, 0, 1, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tuning[key] = value; }
 int get_tuning(int key) { return (key >= 0 && key < 8) ? g_tuning[key] : 0; }
 

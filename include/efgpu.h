@@ -140,6 +140,22 @@ int efgpu_complete_root_dtn(efgpu_handle* h);
  * stream-ordered with efgpu_stream(h) (e.g. ncclAllGather on that stream, or torch.distributed under that stream). */
 typedef int (*efgpu_allgather_fn)(void* buf, size_t bytes_per_rank, void* user);
 int efgpu_set_allgather(efgpu_handle* h, efgpu_allgather_fn fn, void* user);
+/* Peer mode (preferred on one NVSwitch domain, <= 8 ranks): instead of a caller-supplied collective, every rank maps the shared
+ * operator arena of every other rank (CUDA IPC) and the batched GEMMs store each finished tile of a row slice into all arenas
+ * from their epilogue, between two device-side flag barriers - no NCCL call, no host round trip, transfer overlapped with the
+ * tensor-core work.  Protocol, after efgpu_set_partition and before the first build / device view:
+ *   efgpu_peer_export(h, mine)      allocates the arena, writes its 64-byte cudaIpcMemHandle_t;
+ *   (the caller all-gathers the handles with whatever transport it has: MPI_Allgather in the reference, torch.distributed here)
+ *   efgpu_peer_attach(h, all, n)    n * 64 bytes, rank order; opens every peer's arena.
+ * efgpu_peer_broadcast copies a region of this rank's arena (any device view of the handle: leaf DtN maps, h, g vectors) to
+ * the same offset on every other rank, stream-ordered; efgpu_peer_barrier is the flag barrier (collective, stream-ordered).
+ * Callers bracket their broadcasts: barrier, broadcasts, barrier.  A rank that never arrives makes the barrier give up after
+ * EFGPU_PEER_TIMEOUT_S (default 20) seconds and the stage return EFGPU_ERR_STATE.  Every rank must have synchronised its stream
+ * after a common barrier before any rank destroys its handle.  Replaces MPI::broadcast(Node) of src/QuadNode.hpp:191-199. */
+int efgpu_peer_export(efgpu_handle* h, void* ipc_handle_out);
+int efgpu_peer_attach(efgpu_handle* h, const void* ipc_handles, int nranks);
+int efgpu_peer_barrier(efgpu_handle* h);
+int efgpu_peer_broadcast(efgpu_handle* h, const void* dev_ptr, size_t bytes);
 /* External leaves (efgpu_create_ex): declare that the DtN maps the caller writes are signed-symmetric (diag(d) T symmetric),
  * e.g. because efgpu_is_symmetric() holds for the forest handle they were built by; enables the symmetric merge plan. */
 int efgpu_set_symmetric_leaves(efgpu_handle* h, int on);
@@ -256,7 +272,7 @@ int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric
  * kernel of the compact H (0, default: 8 loads in flight per lane; 1: 4); key 2 = CTAs per SM the long-row launcher aims
  * for (0: default 16); key 3 = leaf solve of constant-coefficient leaves (0, default: FP64 tensor-core kernel, one warp per
  * leaf; 1: one thread per cell); key 5 = symmetric merge plan, diagonal blocks of T: 1 = multiply only the upper triangle of
- * their 2 x 2 / 4 x 4 sub-blocks and mirror the rest (0, default: whole blocks; read when a handle is created / partitioned).
+ * their 2 x 2 / 4 x 4 sub-blocks and mirror the rest (1, default; 0: whole blocks; read when a handle is created / partitioned).
  * Results do not depend on the knobs beyond floating-point summation order. */
 int efgpu_set_tuning(int key, int value);
 

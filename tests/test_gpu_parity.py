@@ -128,8 +128,15 @@ def test_indefinite_helmholtz_against_oracle(lam):
                                                st["pivot_ratio_min"], st["negative_pivots"], st["inverse_residual"], raw_S))
     assert st["negative_pivots"] > 0 and st["inverse_residual"] >= 0.0
     assert raw.stats()["inverse_residual"] == -1.0
+    # Two backward-stable solvers of the same merge system agree to cond(X) * eps * (modest growth), not to 1e-10, once X is
+    # ill-conditioned: lambda = 5 sits next to the Dirichlet eigenvalue 5 of [0,pi]^2 (cond X = 1.2e5 at the root), lambda = 20 has
+    # cond 1.5e4 at level 1, and the children's maps already differ from the oracle's by 1e-14.  Tolerance: 1e-10 up to
+    # cond 1e3, 1e-13 * cond beyond (measured on a B200, round 2: 2.1e-9 / 2e-12 / 1.3e-10 for lambda = 5 / 9 / 20).
+    cond = max(np.linalg.cond(nd.X) for nd in ora.nodes if not nd.leaf)
+    tol = TOL * max(1.0, cond / 1e3)
+    print("  worst cond(X) %.3g -> tolerance %.1e" % (cond, tol))
     for nm, v in worst.items():
-        assert v < TOL, (nm, v)
+        assert v < tol, (nm, v, cond)
 
 
 def test_adaptive_m16_against_oracle():

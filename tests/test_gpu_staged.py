@@ -79,12 +79,15 @@ def test_symmetric_diagonal_blocks_of_T_as_block_triangles(case):
     (active from child side 256: uniform_l4_m32 reaches n = 256 at the root; uniform_l3_m16 checks that small merges are
     untouched).  Same operators and solution as the default plan up to summation order."""
     kw = CASES[case]
-    P, ref = _hps(kw)
-    ref.buildStage(); ref.upwardsStage(P["f"])
-    u_ref = ref.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
-    T_ref, S_ref, flops_ref = ref.operator(0, "T"), ref.operator(0, "S"), ref.stats()["merge_flops_issued"]
     lib = _lib.load()
-    assert lib.efgpu_set_tuning(5, 1) == 0
+    assert lib.efgpu_set_tuning(5, 0) == 0          # whole diagonal blocks (the default until round 2)
+    try:
+        P, ref = _hps(kw)
+        ref.buildStage(); ref.upwardsStage(P["f"])
+        u_ref = ref.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+        T_ref, S_ref, flops_ref = ref.operator(0, "T"), ref.operator(0, "S"), ref.stats()["merge_flops_issued"]
+    finally:
+        assert lib.efgpu_set_tuning(5, 1) == 0
     try:
         P, tri = _hps(kw)
         tri.buildStage(); tri.upwardsStage(P["f"])
@@ -94,7 +97,7 @@ def test_symmetric_diagonal_blocks_of_T_as_block_triangles(case):
         flops = tri.stats()["merge_flops_issued"]
         assert flops < flops_ref if case == "uniform_l4_m32" else flops == flops_ref
     finally:
-        lib.efgpu_set_tuning(5, 0)
+        lib.efgpu_set_tuning(5, 1)
 
 
 def test_device_resident_coefficients_and_load():

@@ -14,6 +14,15 @@ OP_TC0, OP_XINV, OP_S, OP_T, OP_W1, OP_W2, OP_W3 = 0, 4, 5, 6, 7, 8, 9
 CLS_GEMM_T, CLS_MIRROR_T = 6, 14
 
 
+@pytest.fixture
+def whole_diagonal_blocks():
+    """Plans with tuning key 5 off (every diagonal block of T as one product): what the block-counting tests below describe."""
+    lib = _lib.load()
+    assert lib.efgpu_set_tuning(5, 0) == 0
+    yield
+    assert lib.efgpu_set_tuning(5, 1) == 0
+
+
 def get_plan(n, level, rank, nranks, sym):
     lib = _lib.load()
     ns, nb, nt = C.c_int(), C.c_int(), C.c_int()
@@ -190,14 +199,16 @@ def test_zipped_diagonal_subinversions(sym):
 
 @pytest.mark.parametrize("nranks", [1, 2])
 def test_symmetric_diagonal_blocks_of_T(nranks):
-    """Tuning key 5: the eight diagonal n x n blocks of the signed-symmetric T are symmetric themselves; with the knob on they
-    are multiplied as upper-triangular sub-blocks (n = 256: 2 x 2 of 128) and completed by transposes in the mirror step."""
+    """Tuning key 5 (default on since round 2): the eight diagonal n x n blocks of the signed-symmetric T are symmetric themselves;
+    with the knob on they are multiplied as upper-triangular sub-blocks (n = 256: 2 x 2 of 128) and completed by transposes in
+    the mirror step."""
     from ellipticforest_b200 import _lib
     lib = _lib.load()
     if 4 not in _CHILDREN:
         _CHILDREN[4] = uniform_children(16, 4)
     Tc, root = _CHILDREN[4]
     n = 256
+    assert lib.efgpu_set_tuning(5, 0) == 0
     base = get_plan(n, 1, 0, nranks, 1)
     assert lib.efgpu_set_tuning(5, 1) == 0
     try:
@@ -209,7 +220,7 @@ def test_symmetric_diagonal_blocks_of_T(nranks):
                 assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
                 assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
     finally:
-        lib.efgpu_set_tuning(5, 0)
+        lib.efgpu_set_tuning(5, 1)
 
 
 @pytest.mark.parametrize("n,nranks,split_min,plans", [(256, 4, 256, "1,0"), (512, 8, 256, "1")])
@@ -248,7 +259,7 @@ def test_general_plan_on_nonsymmetric_children():
     assert flops <= 484 * n ** 3                 # 100 (structured inverse) + 128 (S) + 256 (T)
 
 
-def test_symmetric_plan_flop_count_and_balance():
+def test_symmetric_plan_flop_count_and_balance(whole_diagonal_blocks):
     n = 256
     steps, blocks, terms, trans, ws = get_plan(n, 1, 0, 1, 1)
     assert len(trans) >= 28
@@ -269,7 +280,7 @@ def test_symmetric_plan_flop_count_and_balance():
 
 
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_T_products_are_balanced_over_the_ranks(nranks):
+def test_T_products_are_balanced_over_the_ranks(nranks, whole_diagonal_blocks):
     """Symmetric plan: 36 block products of n^3 x 4 flops; halves / quarters of the rows carry 18 / 9 of them, and with one
     block row per rank (8 ranks) the opposite pairs are shared half and half: 4.5 each."""
     n = 1024
