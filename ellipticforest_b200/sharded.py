@@ -182,6 +182,7 @@ class GpuEngine:
         d.box = self.box.ctypes.data_as(C.POINTER(C.c_double))
         self._h = C.c_void_p()
         self.device = int(device)
+        self.peer = False
         ext = None
         if ext_sizes is not None:
             self._ext = np.ascontiguousarray(ext_sizes, dtype=np.int32)
@@ -243,6 +244,29 @@ class GpuEngine:
                     return 1
             self._ag_cb = _lib.ALLGATHER_FN(_cb)      # keep the trampoline alive as long as the handle
             check(self._lib.efgpu_set_allgather(self._h, self._ag_cb, None), self._h)
+
+    def peer_setup(self, dist, world, group=None):
+        """Peer mode (include/efgpu.h: efgpu_peer_export / efgpu_peer_attach): map every rank's shared operator arena into this
+        process.  The 64-byte CUDA IPC handles travel through torch.distributed (the one host-side collective of the set-up);
+        afterwards the library exchanges row slices by itself - GEMM epilogue stores into the peers' arenas and flag barriers -
+        and no collective callback is installed."""
+        import torch
+        buf = (C.c_ubyte * 64)()
+        check(self._lib.efgpu_peer_export(self._h, buf), self._h)
+        dev = torch.device("cuda", self.device)
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        raw = bytes(bytearray(allh.cpu().numpy().tobytes()))
+        check(self._lib.efgpu_peer_attach(self._h, raw, int(world)), self._h)
+        self.peer = True
+
+    def peer_barrier(self):
+        check(self._lib.efgpu_peer_barrier(self._h), self._h)
+
+    def peer_broadcast(self, t):
+        """t: a device view of this handle (inside the shared arena): its bytes go to the same place on every other rank."""
+        check(self._lib.efgpu_peer_broadcast(self._h, C.c_void_p(t.data_ptr()), t.numel() * t.element_size()), self._h)
 
     def complete_root_T(self):
         """Collective: gather the row slices of the root's DtN map and mirror the blocks of the symmetric plan."""
@@ -441,6 +465,7 @@ class ShardedHPS:
     def __init__(self, mesh, solver, device=0, rank=0, world=1, options=None, cut=2, top_mode="replicated", balance="count"):
         import torch
         self.top_mode = top_mode
+        self.p2p = False
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.mesh, self.patch_solver, self.rank, self.world, self._device = mesh, solver, rank, world, device
@@ -466,7 +491,12 @@ class ShardedHPS:
                 def _ag(t):
                     with torch.cuda.stream(self._stream):
                         self.xchg.allgather_rows(t)
-                self.top.set_partition(rank, world, _ag if world > 1 else None)     # must precede the first device view
+                # peer mode (default on one NVSwitch domain): the library exchanges row slices itself through peer-mapped arenas;
+                # EFGPU_P2P=0 keeps round 1's path (ncclAllGather through torch.distributed from a host callback)
+                self.p2p = world > 1 and world <= 8 and os.environ.get("EFGPU_P2P", "1") != "0"
+                self.top.set_partition(rank, world, _ag if (world > 1 and not self.p2p) else None)     # must precede the first device view
+                if self.p2p:
+                    self.top.peer_setup(dist, world)
             self.top_if = _TopGpu(self.top, [int(i) for i in np.nonzero(tch[:, 0] < 0)[0]])
             self._top_level = tlev
             self._top_interior = [int(i) for i in np.nonzero(tch[:, 0] >= 0)[0]]
@@ -497,6 +527,11 @@ class ShardedHPS:
         per = ("%d per GPU" % (K // self.world) if self.plan.balance == "count" else
                "%s per GPU, balanced by %s" % ("/".join(str(len(self.plan.subtrees_of(r))) for r in range(self.world)), self.plan.balance))
         if self.top_mode == "replicated":
+            if self.p2p:
+                return ("level-%d subtrees in Morton blocks over %d GPUs (%s); upper tree replicated and row-partitioned %d ways: every rank maps every "
+                        "rank's operator arena (CUDA IPC over NVLink), the merge GEMMs store their row slices of the X^-1 products, S and T into all "
+                        "arenas from the epilogue between device-side flag barriers (no NCCL on the data path), subtree-root T / h by peer stores"
+                        % (self.plan.cut, self.world, per, self.world))
             how = "all-gathered in place (one collective)" if os.environ.get("EFGPU_SHARE_ALLGATHER") == "1" else "broadcast"
             return ("level-%d subtrees in Morton blocks over %d GPUs (%s); upper tree replicated: subtree-root T %s over NCCL, "
                     "X^-1 on every rank, rows of S and T split %d ways and all-gathered" % (self.plan.cut, self.world, per, how, self.world))
@@ -551,10 +586,24 @@ class ShardedHPS:
                 self.top.build(fl)
             return
         with self.torch.cuda.stream(self._stream):
-            self.xchg.share(self.local_if.root_T, self.top_if.leaf_T, flat=lambda first, total: _dev_tensor(first.data_ptr(), total, self._device))
+            if self.p2p:
+                self._share_p2p(self.local_if.root_T, self.top_if.leaf_T)
+            else:
+                self.xchg.share(self.local_if.root_T, self.top_if.leaf_T, flat=lambda first, total: _dev_tensor(first.data_ptr(), total, self._device))
         # levels above the cut: X^-1 products, S and T are computed in row slices and all-gathered by the library
         # through the callback above (the root's DtN map stays row-distributed)
         self.top.build(fl)
+
+    def _share_p2p(self, local_view, top_view):
+        """Every rank ends up with every subtree root's operator / vector in its upper-tree leaf buffers: the owner copies its own
+        into place and stores them into the same place of every other rank's arena (NVLink), between two flag barriers (the first:
+        nobody still reads the buffers from the previous step; the second: every rank's stores have landed)."""
+        self.top.peer_barrier()
+        for k in self.plan.subtrees_of(self.rank):
+            dst = top_view(k)
+            dst.copy_(local_view(k))
+            self.top.peer_broadcast(dst)
+        self.top.peer_barrier()
 
     def gather_root_T(self):
         """Parity/debug: the root DtN map assembled from its row slices (every rank gets the whole matrix)."""
@@ -567,7 +616,9 @@ class ShardedHPS:
         self.local.upwards(f_dev_ptr, scale, fl)
         if not (fl & HOMOGENEOUS_RHS):
             with self.torch.cuda.stream(self._stream):
-                if self.top_mode == "replicated":
+                if self.top_mode == "replicated" and self.p2p:
+                    self._share_p2p(self.local_if.root_h, self.top_if.leaf_h)
+                elif self.top_mode == "replicated":
                     self.xchg.share(self.local_if.root_h, self.top_if.leaf_h)
                 else:
                     self.xchg.gather_h(self.local_if, self.top_if)

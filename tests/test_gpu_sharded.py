@@ -29,6 +29,10 @@ EXTRA_CASES = {
     "adaptive_l2_4_m8_varcoef": dict(problem_name="varcoef", solver_kind="fivepoint", box=(-10.0, 10.0, -10.0, 10.0), nx=8, min_level=2, max_level=4,
                                      threshold=1.2, refine_box=(-10.0, 0.5, -10.0, 0.5)),
 }
+# two GPUs only: large enough (root child side n = 256, X of order 1024) that, with EFGPU_SPLIT_MIN_ROWS=256, the products of the
+# block inversion are split by rows too - in peer mode their slices are stored into the other rank's arena by the GEMM epilogue
+EXTRA_CASES["uniform_l4_m16_split"] = dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16, min_level=4,
+                                           max_level=4, threshold=1.2, refine_box=None)
 ALL_CASES = dict(CASES, **EXTRA_CASES)
 
 
@@ -86,6 +90,11 @@ def _worker(rank, world, port, case, out_dir, top_mode, balance="count", cut=2):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if case.endswith("_split"):
+        os.environ["EFGPU_SPLIT_MIN_ROWS"] = "256"
+    if top_mode == "replicated-nccl":      # round 1's exchange: ncclAllGather from a host callback instead of peer-mapped arenas
+        os.environ["EFGPU_P2P"] = "0"
+        top_mode = "replicated"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -98,7 +107,7 @@ def _worker(rank, world, port, case, out_dir, top_mode, balance="count", cut=2):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("top_mode", ["replicated", "root"])
+@pytest.mark.parametrize("top_mode", ["replicated", "replicated-nccl", "root"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_two_gpus_over_nccl(case, top_mode, tmp_path):
     import torch
@@ -108,6 +117,23 @@ def test_two_gpus_over_nccl(case, top_mode, tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path), top_mode), nprocs=2, join=True)
     single = _run_single(CASES[case])
+    u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
+    for r in range(2):
+        lo, hi = np.load(tmp_path / ("range_%d.npy" % r))
+        assert relerr(np.load(tmp_path / ("u_%d.npy" % r)), u_ref[lo:hi].reshape(-1)) < 1e-12
+    assert relerr(np.load(tmp_path / "T_root.npy"), single.operator(0, "T").reshape(-1)) < 1e-12
+
+
+@pytest.mark.parametrize("top_mode", ["replicated", "replicated-nccl"])
+def test_two_gpus_row_split_inversion_products(top_mode, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = "uniform_l4_m16_split"
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path), top_mode), nprocs=2, join=True)
+    single = _run_single(ALL_CASES[case])
     u_ref = single.u_leaves.reshape(single.mesh.n_leaves, -1)
     for r in range(2):
         lo, hi = np.load(tmp_path / ("range_%d.npy" % r))

@@ -449,9 +449,9 @@ def test_sharding_description_strings():
     class Fake:
         pass
     for world, balance in ((2, "count"), (4, "count"), (8, "count"), (4, "work"), (3, "leaves")):
-        for top_mode in ("replicated", "root"):
+        for top_mode, p2p in (("replicated", True), ("replicated", False), ("root", False)):
             f = Fake()
-            f.plan, f.world, f.top_mode = ShardPlan(*_tables(nodes), 8, world, balance=balance), world, top_mode
+            f.plan, f.world, f.top_mode, f.p2p = ShardPlan(*_tables(nodes), 8, world, balance=balance), world, top_mode, p2p
             text = ShardedHPS.sharding(f)
             assert "over %d GPUs" % world in text and "%" not in text, text
             assert ("balanced by " + balance in text) == (balance != "count"), text

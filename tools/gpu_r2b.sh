@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round 2, multi-GPU call: sharded tests on the box's GPUs, then bench lines at the given rank counts, peer mode (default) and
+# round 1's NCCL-callback path (EFGPU_P2P=0), optionally a larger tree.
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_r2b.sh r2b "2" [extra bench args]'
+TAG=${1:-r2b}; NS=${2:-"2"}; EXTRA=$3
+OUT=gpurun_out; mkdir -p $OUT
+nvidia-smi -L > $OUT/smi_$TAG.txt; nvidia-smi topo -m >> $OUT/smi_$TAG.txt 2>&1
+if [ -z "$SKIP_TESTS" ]; then
+timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -rs > $OUT/pytest_sharded_$TAG.log 2>&1; echo "pytest exit $?"; tail -6 $OUT/pytest_sharded_$TAG.log
+fi
+for N in $NS; do
+  for P2P in 1 0; do
+    [ "$P2P" = "0" ] && [ -n "$SKIP_NCCL" ] && continue
+    F=$OUT/bench_${TAG}_n${N}_p2p$P2P
+    EFGPU_P2P=$P2P timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$P2P bench.py --gpus $N --steps 5 --warmup 3 $EXTRA > $F.json 2> $F.err
+    echo "bench N=$N p2p=$P2P exit $?"; tail -3 $F.err
+    [ -s $F.json ] && python -c "import json; d=json.load(open('$F.json')); print(d['ms_per_step'], d['stages'], d['config']['parity'], d['kernel_ms_per_step'])"
+  done
+done
