@@ -230,7 +230,7 @@ struct InvPlanner {
         static const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
         // (peer mode: a split costs two flag barriers of a few microseconds instead of a collective, so smaller products pay)
         const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
-        if (nranks > 1 && rows % (128 * nranks) == 0 && rows >= split_min) {
+        if (nranks > 1 && rows % ((peer ? 64 : 128) * nranks) == 0 && rows >= split_min) {   // slices of whole 128-row (peer mode: 64-row) tiles
             const long long skip = (long long)rank * (rows / nranks);
             st.g_op = c_op; st.g_off = c_off; st.g_rows = rows; st.g_cols = cols; st.g_ld = ldc;
             if (peer) st.gk = 3;             // the epilogue stores the tile on every rank: any leading dimension, no staging
@@ -255,7 +255,7 @@ struct InvPlanner {
     void gemm_sym(int h, int K, int c_op, long long c_off, int ldc, int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb) {
         static const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
         const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
-        const bool row_split = nranks > 1 && h % (128 * nranks) == 0 && h >= split_min;
+        const bool row_split = nranks > 1 && h % ((peer ? 64 : 128) * nranks) == 0 && h >= split_min;
         const int nb = row_split ? 1 : ((h % 64 == 0 && h / 4 >= 128) ? 4 : ((h % 32 == 0 && h / 2 >= 128) ? 2 : 1));
         if (nb == 1) { gemm(h, h, K, c_op, c_off, ldc, c_op, c_off, ldc, a_op, a_off, lda, b_op, b_off, ldb, true); return; }
         const int sb = h / nb;

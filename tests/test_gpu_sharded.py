@@ -87,6 +87,8 @@ def test_forest_and_upper_tree_on_one_gpu(case, top_mode):
 
 
 def _worker(rank, world, port, case, out_dir, top_mode, balance="count", cut=2):
+    import faulthandler
+    faulthandler.enable()
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))

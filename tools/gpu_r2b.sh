@@ -6,7 +6,7 @@ TAG=${1:-r2b}; NS=${2:-"2"}; EXTRA=$3
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L > $OUT/smi_$TAG.txt; nvidia-smi topo -m >> $OUT/smi_$TAG.txt 2>&1
 if [ -z "$SKIP_TESTS" ]; then
-timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -rs > $OUT/pytest_sharded_$TAG.log 2>&1; echo "pytest exit $?"; tail -6 $OUT/pytest_sharded_$TAG.log
+timeout 900 python -m pytest tests/test_gpu_sharded.py -q -rs > $OUT/pytest_sharded_$TAG.log 2>&1; echo "pytest exit $?"; tail -6 $OUT/pytest_sharded_$TAG.log
 fi
 for N in $NS; do
   for P2P in 1 0; do
@@ -14,6 +14,22 @@ for N in $NS; do
     F=$OUT/bench_${TAG}_n${N}_p2p$P2P
     EFGPU_P2P=$P2P timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$P2P bench.py --gpus $N --steps 5 --warmup 3 $EXTRA > $F.json 2> $F.err
     echo "bench N=$N p2p=$P2P exit $?"; tail -3 $F.err
-    [ -s $F.json ] && python -c "import json; d=json.load(open('$F.json')); print(d['ms_per_step'], d['stages'], d['config']['parity'], d['kernel_ms_per_step'])"
+    [ -s $F.json ] && python -c "import json; d=json.loads(open('$F.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['stages'], d['config']['parity'], d['kernel_ms_per_step'])"
   done
 done
+if [ -n "$BIG" ]; then   # a tree that does not fit one GPU (e.g. BIG="--level 9"): peer mode only
+  for N in $NS; do
+    F=$OUT/bench_${TAG}_n${N}_big
+    timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 3 --warmup 3 $BIG > $F.json 2> $F.err
+    echo "bench N=$N $BIG exit $?"; tail -3 $F.err
+    [ -s $F.json ] && python -c "import json; d=json.loads(open('$F.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['stages'], d['config']['parity'], d['kernel_ms_per_step'], d['config']['l2'])"
+  done
+fi
+if [ -n "$SPLITS" ]; then   # A/B of the row-split threshold of the inversion's products
+  for N in $NS; do for SM in $SPLITS; do
+    F=$OUT/bench_${TAG}_n${N}_split$SM
+    EFGPU_SPLIT_MIN_ROWS=$SM timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 5 --warmup 3 > $F.json 2> $F.err
+    echo "bench N=$N split_min=$SM exit $?"; tail -3 $F.err
+    [ -s $F.json ] && python -c "import json; d=json.loads(open('$F.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['kernel_ms_per_step'])"
+  done; done
+fi
