@@ -1166,7 +1166,9 @@ void efgpu_destroy(efgpu_handle* H)
 {
     if (!H) return;
     cudaSetDevice(H->device);
-    if (H->stream) cudaStreamSynchronize(H->stream);
+    // a borrowed stream (efgpu_set_stream) may already have been destroyed by its owner when handles are released in arbitrary
+    // order (garbage-collected callers): synchronise the device instead of touching it
+    if (H->stream && H->own_stream) cudaStreamSynchronize(H->stream); else cudaDeviceSynchronize();
     if (H->ev0) cudaEventDestroy(H->ev0);
     if (H->ev1) cudaEventDestroy(H->ev1);
     for (auto& r : H->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

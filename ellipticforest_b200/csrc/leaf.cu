@@ -585,13 +585,294 @@ leaf_var_solve_kernel(const double* __restrict__ coef, const double* __restrict_
     }
 }
 
+// ---- warp-level variants for M = 8 and 16 (round 2) --------------------------------------------------------------------------
+// The CTA-per-leaf kernels above pay one __syncthreads per pivot (factor) and stage 71 KB of shared memory per CTA for the DtN
+// columns (ncu, profiles/r2a_ncu_varcoef_leaf.md: FP64 pipe 38 % / 9 % busy, 4.98 + 14.4 ms on BASELINE configs[3]).  Here:
+//   leaf_var_factor_warp_kernel   one WARP per leaf, the M x M block in registers (lane = column, M / (32 / M) rows per lane),
+//                                 Gauss-Jordan by warp shuffles: no shared memory, no barrier;
+//   leaf_var_dtn_mma_kernel       one CTA per leaf, one warp per 8 columns of T; the M x M products P_i y_i of both sweeps run on
+//                                 the FP64 tensor pipe (mma.m8n8k4), the whole intermediate Z (M^2 x 8 per warp) lives in registers
+//                                 as accumulator fragments, P_i is staged once per step for all warps, y_i crosses from the
+//                                 accumulator layout to the B-operand layout through a 768-byte per-warp tile;
+//   leaf_var_solve_warp_kernel    one warp per leaf for the single right-hand side of upwards / solve (streams P twice: HBM-bound).
+// Same arithmetic as the kernels above (block elimination without pivoting), different summation order inside the M x M products.
+template <int M>
+__global__ void __launch_bounds__(256)
+leaf_var_factor_warp_kernel(const double* __restrict__ alpha, const double* __restrict__ bw, const double* __restrict__ be,
+                            const double* __restrict__ bs, const double* __restrict__ bn, const double* __restrict__ lam,
+                            const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
+                            double* __restrict__ coef, double* __restrict__ P_all, double* __restrict__ min_pivot, int n_leaves)
+{
+    constexpr int RG = 32 / M, RPL = M / RG;   // row groups per warp, rows per lane
+    const int lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (leaf >= n_leaves) return;
+    const int c = lane % M, rg = lane / M, gbase = rg * M;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    const size_t cell0 = (size_t)leaf * M * M;
+    double* cf = coef + (size_t)leaf * 4 * M * M;
+    double prev[RPL];
+#pragma unroll
+    for (int q = 0; q < RPL; q++) prev[q] = 0.0;
+    double cE_prev = 0.0;   // cE[i-1][c]
+    double minp = 1e300;
+    for (int i = 0; i < M; i++) {
+        double a[RPL];
+#pragma unroll
+        for (int q = 0; q < RPL; q++) {
+            const int r = rg * RPL + q;
+            const size_t kr = cell0 + (size_t)i * M + r;
+            const double al = alpha[kr];
+            const double cW = al * bw[kr] / (dx * dx), cE = al * be[kr] / (dx * dx), cS = al * bs[kr] / (dy * dy), cN = al * bn[kr] / (dy * dy);
+            if (c == 0) { cf[0 * M * M + i * M + r] = cW; cf[1 * M * M + i * M + r] = cE; cf[2 * M * M + i * M + r] = cS; cf[3 * M * M + i * M + r] = cN; }
+            double v = 0.0;
+            if (r == c) {
+                double d = -al * ((be[kr] + bw[kr]) / (dx * dx) + (bn[kr] + bs[kr]) / (dy * dy)) + lam[kr];
+                if (i == 0) d -= cW;
+                if (i == M - 1) d -= cE;
+                if (r == 0) d -= cS;
+                if (r == M - 1) d -= cN;
+                v = d;
+            } else if (c == r - 1) v = cS;
+            else if (c == r + 1) v = cN;
+            if (i > 0) v -= cW * prev[q] * cE_prev;
+            a[q] = v;
+        }
+        // Gauss-Jordan inverse of the block, in registers
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            const double rowk = __shfl_sync(0xffffffffu, a[k % RPL], (k / RPL) * M + c);   // a[k][c]
+            const double piv = __shfl_sync(0xffffffffu, rowk, gbase + k);                   // a[k][k]
+            const double p = 1.0 / piv;
+            minp = fmin(minp, fabs(piv));
+#pragma unroll
+            for (int q = 0; q < RPL; q++) {
+                const int r = rg * RPL + q;
+                const double f = __shfl_sync(0xffffffffu, a[q], gbase + k);               // a[r][k]
+                if (r == k) a[q] = (c == k) ? p : a[q] * p;
+                else a[q] = (c == k) ? -f * p : a[q] - f * p * rowk;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RPL; q++) {
+            P_all[((size_t)leaf * M + i) * M * M + (rg * RPL + q) * M + c] = a[q];
+            prev[q] = a[q];
+        }
+        {   // cE[i][c] for the next block row
+            const size_t kc = cell0 + (size_t)i * M + c;
+            cE_prev = alpha[kc] * be[kc] / (dx * dx);
+        }
+    }
+    if (lane == 0 && min_pivot) atomicMin(reinterpret_cast<unsigned long long*>(min_pivot), (unsigned long long)__double_as_longlong(minp));
+}
+
+template <int M>
+__global__ void __launch_bounds__(4 * M * 4)
+leaf_var_dtn_mma_kernel(const double* __restrict__ coef, const double* __restrict__ P_all, const double* __restrict__ boxes,
+                        const int* __restrict__ leaf_nodes, double* __restrict__ T_all)
+{
+    constexpr int NW = 4 * M / 8, NT = NW * 32, MT = M / 8, KS = M / 4;
+    constexpr int SP = M + 4;     // == 4 or 12 (mod 16): A-fragment reads of a half warp (4 rows x 4 k) fall into 16 distinct bank pairs
+    constexpr int SY = 12;        // y tile M x 8, row stride 12: B-fragment reads (4 k x 4 n per half warp) conflict free
+    __shared__ __align__(16) double sP[2][M * SP];
+    __shared__ __align__(16) double sY[NW][M * SY];
+    __shared__ double sC[4][M * M];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int leaf = blockIdx.x;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    const double* cfl = coef + (size_t)leaf * 4 * M * M;
+    for (int e = tid; e < 4 * M * M; e += NT) sC[e / (M * M)][e % (M * M)] = cfl[e];
+    const double* P = P_all + (size_t)leaf * M * M * M;
+    const int col0 = warp * 8, side = col0 / M, t0 = col0 % M;    // this warp's 8 columns lie on one side: t = t0 + c
+    const int fr = lane >> 2, fc = 2 * (lane & 3);                  // accumulator fragment: row fr (+ 8 mt), columns fc, fc + 1
+    double* sy = sY[warp];
+    double z[M][MT][2];
+    constexpr bool HALF = (M * M) < NT;                             // M = 8: 64 elements of P_i, 128 threads
+    const bool loader = !HALF || tid < M * M;
+    double pnext = loader ? P[tid] : 0.0;                           // P_0
+    __syncthreads();                                                // sC
+    // ---- forward sweep: y_i = rhs_i - W_i z_{i-1},  z_i = P_i y_i
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        if (loader) sP[i & 1][(tid / M) * SP + (tid % M)] = pnext;
+        if (i + 1 < M) { if (loader) pnext = P[(size_t)(i + 1) * M * M + tid]; }
+        else if (loader) pnext = P[(size_t)(M - 2) * M * M + tid];  // first block of the backward sweep
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int j = 8 * mt + fr;
+            double y[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int t = t0 + fc + e;
+                double v = 0.0;
+                if (side == 0) { if (i == 0 && j == t) v = -2.0 * sC[0][j]; }
+                else if (side == 1) { if (i == M - 1 && j == t) v = -2.0 * sC[1][(M - 1) * M + j]; }
+                else if (side == 2) { if (j == 0 && i == t) v = -2.0 * sC[2][i * M]; }
+                else { if (j == M - 1 && i == t) v = -2.0 * sC[3][i * M + M - 1]; }
+                if (i > 0) v -= sC[0][i * M + j] * z[i > 0 ? i - 1 : 0][mt][e];
+                y[e] = v;
+            }
+            *reinterpret_cast<double2*>(sy + j * SY + fc) = make_double2(y[0], y[1]);
+        }
+        __syncthreads();                                            // P_i staged (and, warp-locally, y_i)
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+                leaf_dmma(a0, a1, sP[i & 1][(8 * mt + fr) * SP + 4 * ks + (lane & 3)], sy[(4 * ks + (lane & 3)) * SY + fr]);
+            z[i][mt][0] = a0; z[i][mt][1] = a1;
+        }
+        __syncwarp();                                               // y tile free for the next step
+    }
+    // ---- backward sweep: u_i = z_i - P_i (E_i u_{i+1})   (u overwrites z)
+#pragma unroll
+    for (int ii = 0; ii < M - 1; ii++) {
+        const int i = M - 2 - ii, buf = ii & 1;                     // buffers alternate from the forward sweep's last (M-1)&1 = 1: ii = 0 -> 0
+        if (loader) sP[buf][(tid / M) * SP + (tid % M)] = pnext;
+        if (i > 0 && loader) pnext = P[(size_t)(i - 1) * M * M + tid];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int j = 8 * mt + fr;
+            const double ce = sC[1][i * M + j];
+            *reinterpret_cast<double2*>(sy + j * SY + fc) = make_double2(ce * z[i + 1][mt][0], ce * z[i + 1][mt][1]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+                leaf_dmma(a0, a1, sP[buf][(8 * mt + fr) * SP + 4 * ks + (lane & 3)], sy[(4 * ks + (lane & 3)) * SY + fr]);
+            z[i][mt][0] -= a0; z[i][mt][1] -= a1;
+        }
+        __syncwarp();
+    }
+    // ---- T[row][col] = sign(side_row) (2 / d) (u_edge - [row == col])   (FiniteVolumeSolver.cpp:332-343, :444-452)
+    double* T = T_all + (size_t)leaf * 16 * M * M;
+    const int colb = col0 + fc;
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        const int j = 8 * mt + fr;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int col = colb + e;
+            {   // W row j: u(i = 0, j);  E row j: u(i = M-1, j)
+                const int rw = j, re = M + j;
+                T[(size_t)rw * (4 * M) + col] = (2.0 / dx) * (z[0][mt][e] - (rw == col ? 1.0 : 0.0));
+                T[(size_t)re * (4 * M) + col] = -(2.0 / dx) * (z[M - 1][mt][e] - (re == col ? 1.0 : 0.0));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int col = colb + e;
+            if (fr == 0) { const int rs = 2 * M + i; T[(size_t)rs * (4 * M) + col] = (2.0 / dy) * (z[i][0][e] - (rs == col ? 1.0 : 0.0)); }          // S: j = 0
+            if (fr == 7) { const int rn = 3 * M + i; T[(size_t)rn * (4 * M) + col] = -(2.0 / dy) * (z[i][MT - 1][e] - (rn == col ? 1.0 : 0.0)); }  // N: j = M-1
+        }
+    }
+}
+
+// mode 0: u = solve(g, f); mode 1: h = mapD2N(0, f).  One warp per leaf, z in a per-warp shared tile (M^2 doubles).
+template <int M>
+__global__ void __launch_bounds__(256)
+leaf_var_solve_warp_kernel(const double* __restrict__ coef, const double* __restrict__ P_all, const double* __restrict__ boxes,
+                           const int* __restrict__ leaf_nodes, const double* __restrict__ f, double fscale, double* const* __restrict__ g_ptrs,
+                           double* __restrict__ u_out, double* const* __restrict__ h_ptrs, int mode, int n_leaves)
+{
+    constexpr int RG = 32 / M, KP = M / RG;    // lane = (row r, part of the k range)
+    __shared__ double sZ[8][M * M];
+    __shared__ double sYv[8][M];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int leaf = blockIdx.x * 8 + w;
+    if (leaf >= n_leaves) return;
+    const int r = lane % M, part = lane / M;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    const double* cW = coef + (size_t)leaf * 4 * M * M;
+    const double* cE = cW + M * M;
+    const double* cS = cE + M * M;
+    const double* cN = cS + M * M;
+    const double* P = P_all + (size_t)leaf * M * M * M;
+    const double* gl = (mode == 0 && g_ptrs) ? g_ptrs[leaf] : nullptr;
+    const double* fl = f ? f + (size_t)leaf * M * M : nullptr;
+    double* z = sZ[w];
+    double* yv = sYv[w];
+    auto matvec = [&](int i) -> double {       // row r of P_i y, complete in every lane of the row
+        const double* pr = P + (size_t)i * M * M + r * M + part * KP;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; k++) s = fma(pr[k], yv[part * KP + k], s);
+#pragma unroll
+        for (int o = M; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        return s;
+    };
+    for (int i = 0; i < M; i++) {
+        if (part == 0) {
+            const int j = r;
+            double v = fl ? fscale * fl[i * M + j] : 0.0;
+            if (gl) {
+                if (i == 0) v += -2.0 * cW[j] * gl[j];
+                if (i == M - 1) v += -2.0 * cE[(M - 1) * M + j] * gl[M + j];
+                if (j == 0) v += -2.0 * cS[i * M] * gl[2 * M + i];
+                if (j == M - 1) v += -2.0 * cN[i * M + M - 1] * gl[3 * M + i];
+            }
+            if (i > 0) v -= cW[i * M + j] * z[(i - 1) * M + j];
+            yv[j] = v;
+        }
+        __syncwarp();
+        const double s = matvec(i);
+        __syncwarp();
+        if (part == 0) z[i * M + r] = s;
+    }
+    for (int i = M - 2; i >= 0; i--) {
+        __syncwarp();
+        if (part == 0) yv[r] = cE[i * M + r] * z[(i + 1) * M + r];
+        __syncwarp();
+        const double s = matvec(i);
+        if (part == 0) z[i * M + r] -= s;
+    }
+    __syncwarp();
+    if (mode == 0) {
+        for (int e = lane; e < M * M; e += 32) u_out[(size_t)leaf * M * M + e] = z[e];
+    } else {
+        double* h = h_ptrs[leaf];
+        for (int e = lane; e < 4 * M; e += 32) {
+            const int side = e / M, t = e % M;
+            double v;
+            if (side == 0) v = (2.0 / dx) * z[0 * M + t];
+            else if (side == 1) v = -(2.0 / dx) * z[(M - 1) * M + t];
+            else if (side == 2) v = (2.0 / dy) * z[t * M + 0];
+            else v = -(2.0 / dy) * z[t * M + M - 1];
+            h[e] = v;
+        }
+    }
+}
+
 template <int M>
 static void var_factor_M(const double* const* cin, const double* boxes, const int* leaf_nodes, double* coef, double* P, double* minpiv, int n, cudaStream_t s) {
+    if constexpr (M == 8 || M == 16) {
+        if (get_tuning(6) == 0) {   // default: one warp per leaf, Gauss-Jordan by shuffles
+            leaf_var_factor_warp_kernel<M><<<(n + 7) / 8, 256, 0, s>>>(cin[0], cin[1], cin[2], cin[3], cin[4], cin[5], boxes, leaf_nodes, coef, P, minpiv, n);
+            return;
+        }
+    }
     leaf_var_factor_kernel<M><<<n, M * M, 0, s>>>(cin[0], cin[1], cin[2], cin[3], cin[4], cin[5], boxes, leaf_nodes, coef, P, minpiv);
 }
 template <int M>
 static void var_solve_M(const double* coef, const double* P, const double* boxes, const int* leaf_nodes, const double* f, double fscale,
                         double* const* g_ptrs, double* u_out, double* const* h_ptrs, double* T_all, int mode, int n_leaves, cudaStream_t s) {
+    if constexpr (M == 8 || M == 16) {
+        if (get_tuning(6) == 0) {   // default: FP64 tensor-core DtN kernel / warp-per-leaf single right-hand side
+            if (mode == 2) leaf_var_dtn_mma_kernel<M><<<n_leaves, 4 * M * 4, 0, s>>>(coef, P, boxes, leaf_nodes, T_all);
+            else leaf_var_solve_warp_kernel<M><<<(n_leaves + 7) / 8, 256, 0, s>>>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves);
+            return;
+        }
+    }
     const int C = mode == 2 ? (M >= 32 ? 16 : (4 * M < 32 ? 4 * M : 32)) : 1;
     const int smem = (M * (M + 1) + M * C + M * M * C) * (int)sizeof(double);
     auto kern = leaf_var_solve_kernel<M>;

@@ -21,6 +21,7 @@ namespace efgpu {
 // [3] leaf solve of constant-coefficient leaves: 0 = DMMA kernel (default), 1 = one thread per cell
 // [5] symmetric merge plan: 1 = the diagonal blocks of T multiply only their upper sub-block triangle (default since r2a: 202.8 -> 197.8 ms
 //     per step at L=8 M=16; 0 = whole blocks; read when a plan is made)
+// [6] variable-coefficient leaves with M = 8, 16: 0 = warp-level / tensor-core kernels (default), 1 = the CTA-per-leaf kernels of round 1
 static int g_tuning[8] = {2, 0, 0, 0, 0, 1, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tuning[key] = value; }
 int get_tuning(int key) { return (key >= 0 && key < 8) ? g_tuning[key] : 0; }
