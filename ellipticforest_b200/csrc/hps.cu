@@ -78,6 +78,7 @@ struct Step {
 
 struct BatchH {
     int level = 0, n = 0, count = 0;
+    int lane = 0;                     // stream lane of this batch inside its level (batches of one level are independent), 0 = the handle's stream
     std::vector<int> parents;
     std::vector<GemmBlock> blocks;    // all descriptors of this batch (host copy), both plans
     std::vector<TransOp> trans;       // block transposes of the symmetric plan
@@ -153,6 +154,21 @@ struct efgpu_handle {
     std::string last_error;
     efgpu_stats_t stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Batches of one tree level are independent: on adaptive trees (several child sizes per level) they run on parallel stream
+    // lanes, forked from / joined into the handle's stream at every level; and the launch sequence of a whole stage is captured
+    // into a CUDA graph the second time it is issued with the same key (flags, leaf model, layout generation), so that repeated
+    // builds / solves replay it without per-launch host cost.
+    static constexpr int MAX_LANES = 4;
+    int n_lanes = 1; bool lanes_on = false;
+    cudaStream_t lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr; unsigned long long key = ~0ull; int seen = 0;
+        double launches[EFGPU_PROF_NCLASSES] = {0};
+    };
+    GraphSlot g_build, g_up, g_solve;
+    unsigned long long graph_gen = 0;
+    bool graphs_on = true;
     // optional per-kernel-class timing (efgpu_set_profiling): event pairs around every launch group
     bool profiling = false;
     struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -190,6 +206,70 @@ static void collect_profile(efgpu_handle* H)   // stream must be synchronised
         H->ev_pool.push_back(r.a); H->ev_pool.push_back(r.b);
     }
     H->prof_recs.clear();
+}
+
+// Stream lanes of one tree level: the first use of a lane in a level makes it wait for everything issued on the handle's stream
+// so far; join() makes the handle's stream wait for every lane used.  Works the same inside a stream capture (the events become
+// graph edges).  Off (everything on the handle's stream) while profiling: the per-class event pairs are recorded there.
+struct LaneSet {
+    efgpu_handle* H; unsigned used = 0; bool forked = false;
+    explicit LaneSet(efgpu_handle* h) : H(h) {}
+    cudaStream_t get(const BatchH& b) {
+        if (!H->lanes_on || H->profiling || b.lane <= 0 || b.lane >= H->n_lanes) return H->stream;
+        if (!forked) { EF_CUDA(cudaEventRecord(H->ev_fork, H->stream)); forked = true; }
+        if (!(used & (1u << b.lane))) { EF_CUDA(cudaStreamWaitEvent(H->lane[b.lane], H->ev_fork, 0)); used |= 1u << b.lane; }
+        return H->lane[b.lane];
+    }
+    void join() {
+        for (int k = 1; k < efgpu_handle::MAX_LANES; k++)
+            if (used & (1u << k)) {
+                EF_CUDA(cudaEventRecord(H->ev_join[k], H->lane[k]));
+                EF_CUDA(cudaStreamWaitEvent(H->stream, H->ev_join[k], 0));
+            }
+        used = 0; forked = false;
+    }
+};
+
+static unsigned long long graph_key(const efgpu_handle* H, unsigned flags)
+{
+    unsigned long long k = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { k ^= v; k *= 1099511628211ull; };
+    unsigned long long lam; std::memcpy(&lam, &H->lambda, 8);
+    mix(flags); mix((unsigned long long)H->leaf_kind); mix(lam); mix(H->refine_inverse ? 1 : 0); mix(H->graph_gen);
+    mix(H->ext_sym ? 1 : 0); mix((unsigned long long)(uintptr_t)H->stream);
+    for (int t = 0; t < 8; t++) mix((unsigned long long)get_tuning(t));
+    return k;
+}
+
+// Runs `body` (launches on the handle's stream and its lanes) eagerly the first time a key is seen - one-time function
+// attributes and occupancy queries happen there -, captures it into a graph the second time, and replays the graph from then on.
+template <class F>
+static void run_graphed(efgpu_handle* H, efgpu_handle::GraphSlot& g, unsigned long long key, F&& body)
+{
+    const bool can = H->graphs_on && !H->profiling && H->part_nranks == 1 && !H->allgather && !H->peer_mode;
+    if (!can) { body(); return; }
+    if (g.exec && g.key == key) {
+        EF_CUDA(cudaGraphLaunch(g.exec, H->stream));
+        for (int c = 0; c < EFGPU_PROF_NCLASSES; c++) H->prof_launches[c] += g.launches[c];
+        return;
+    }
+    if (g.key != key) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        g.key = key; g.seen = 0;
+    }
+    if (g.seen++ == 0) { body(); return; }
+    double before[EFGPU_PROF_NCLASSES];
+    for (int c = 0; c < EFGPU_PROF_NCLASSES; c++) before[c] = H->prof_launches[c];
+    EF_CUDA(cudaStreamBeginCapture(H->stream, cudaStreamCaptureModeRelaxed));
+    cudaGraph_t graph = nullptr;
+    try { body(); }
+    catch (...) { cudaStreamEndCapture(H->stream, &graph); if (graph) cudaGraphDestroy(graph); g.key = ~0ull; throw; }
+    EF_CUDA(cudaStreamEndCapture(H->stream, &graph));
+    cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { g.exec = nullptr; g.key = ~0ull; throw Error{EF_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)}; }
+    for (int c = 0; c < EFGPU_PROF_NCLASSES; c++) { g.launches[c] = H->prof_launches[c] - before[c]; H->prof_launches[c] = before[c] + g.launches[c]; }
+    EF_CUDA(cudaGraphLaunch(g.exec, H->stream));
 }
 
 // Planner of the blocked inversion of X (in place, op OP_XINV).  Two properties of the merge matrix are used:
@@ -617,6 +697,18 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* 
         b.parents.push_back(i);
     }
     for (auto& b : H->batches) { b.count = (int)b.parents.size(); plan_batch_gemms(b, H->part_rank, H->part_nranks); }
+    // lanes: the batches of a level in order of decreasing merge work, the heaviest on the handle's own stream
+    H->n_lanes = 1;
+    for (auto& lb : H->level_batches) {
+        std::vector<int> order(lb);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+            const BatchH& x = H->batches[a]; const BatchH& y = H->batches[c];
+            return (double)x.count * x.n * x.n * x.n > (double)y.count * y.n * y.n * y.n; });
+        for (size_t i = 0; i < order.size(); i++) {
+            H->batches[order[i]].lane = (int)(i % efgpu_handle::MAX_LANES);
+            H->n_lanes = std::max(H->n_lanes, H->batches[order[i]].lane + 1);
+        }
+    }
     // vector arena offsets
     size_t off = 0;
     auto take = [&](size_t nd_) { size_t o = off; off += (nd_ + 1) & ~size_t(1); return o; };
@@ -733,7 +825,19 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             for (size_t sl = 0; sl < cnt; sl++) H->nodes[b.parents[sl]].Tbuf.assign(1, b.Tbase + sl * 64 * n * n);
         }
     }
+    // workspace: one region per lane (batches on different lanes run concurrently), sized by the largest batch of the lane
+    { const char* le = getenv("EFGPU_LANES"); H->lanes_on = !H->peer_mode && H->part_nranks == 1 && H->n_lanes > 1 && (!le || atoi(le) > 0); }
+    size_t ws_lane[efgpu_handle::MAX_LANES] = {0, 0, 0, 0}, ws_base[efgpu_handle::MAX_LANES] = {0, 0, 0, 0};
+    for (auto& b : H->batches) { const int k = H->lanes_on ? b.lane : 0; ws_lane[k] = std::max(ws_lane[k], (size_t)b.count * b.ws_per_entry); }
+    { size_t acc_ws = 0; for (int k = 0; k < efgpu_handle::MAX_LANES; k++) { ws_base[k] = acc_ws; acc_ws += (ws_lane[k] + 31) & ~size_t(31); } ws_max = acc_ws; }
     carve(H->d_ws, ws_max * sizeof(double));
+    if (H->lanes_on)
+        for (int k = 1; k < H->n_lanes; k++) {
+            if (!H->lane[k]) EF_CUDA(cudaStreamCreateWithFlags(&H->lane[k], cudaStreamNonBlocking));
+            if (!H->ev_join[k]) EF_CUDA(cudaEventCreateWithFlags(&H->ev_join[k], cudaEventDisableTiming));
+        }
+    if (!H->ev_fork) EF_CUDA(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
+    H->graph_gen++;
     // coarsened copies + tables
     for (auto& b : H->batches) {
         const size_t n = b.n, cnt = b.count;
@@ -774,9 +878,10 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             e.Xcopy = (flags & EFGPU_KEEP_X) ? b.Xcopy.as<double>() + sl * 16 * n * n : nullptr;
             e.hd = vec + P.hd_off; e.h = vec + P.hbuf[0]; e.w = vec + P.w_off; e.g = vec + P.gbuf[0];
             ptab[sl * NOPS + OP_XINV] = e.Xinv; ptab[sl * NOPS + OP_S] = e.S; ptab[sl * NOPS + OP_T] = e.T; ptab[sl * NOPS + OP_XCOPY] = e.Xcopy;
-            ptab[sl * NOPS + OP_W1] = H->d_ws.as<double>() + sl * b.ws_per_entry;
-            ptab[sl * NOPS + OP_W2] = H->d_ws.as<double>() + sl * b.ws_per_entry + b.w2_off;
-            ptab[sl * NOPS + OP_W3] = H->d_ws.as<double>() + sl * b.ws_per_entry + b.w3_off;
+            double* wsb = H->d_ws.as<double>() + ws_base[H->lanes_on ? b.lane : 0];
+            ptab[sl * NOPS + OP_W1] = wsb + sl * b.ws_per_entry;
+            ptab[sl * NOPS + OP_W2] = wsb + sl * b.ws_per_entry + b.w2_off;
+            ptab[sl * NOPS + OP_W3] = wsb + sl * b.ws_per_entry + b.w3_off;
             // this parent's own Dirichlet data arrives coarsened when it was tagged: uncoarsen before the split
             for (int t = P.ncoarsen; t >= 1; t--) {
                 const int step = P.ncoarsen - t;
@@ -878,15 +983,19 @@ static void build_begin(efgpu_handle* H, unsigned flags)
     for (auto& b : H->batches) b.use_sym = b.symcand && leaves_sym && !(flags & EFGPU_NO_SYMMETRY);
     H->cur_flags = flags;
     compute_flop_model(H);
-    launch_pivot_tracker_reset(H->d_minpiv.as<double>(), s);
     EF_CUDA(cudaEventRecord(H->ev0, s));
     H->built = false; H->root_T_distributed = false; H->root_T_pending = false;
-    timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, flags); });
+}
+
+// device work of build_begin: pivot tracker, leaf DtN maps (part of the captured build graph)
+static void build_leaves(efgpu_handle* H)
+{
+    launch_pivot_tracker_reset(H->d_minpiv.as<double>(), H->stream);
+    timed(H, EFGPU_PROF_LEAF_DTN, 1, [&] { run_leaf_dtn(H, H->cur_flags); });
 }
 
 static void build_level(efgpu_handle* H, int lev, int phase)
 {
-    cudaStream_t s = H->stream;
     if (lev < 0 || lev > H->max_level) throw Error{EF_ERR_BAD_ARG, "bad level"};
     if (lev == 0 && phase == 1 && (H->cur_flags & EFGPU_LAZY_ROOT_DTN) && !H->level_batches[0].empty()) {
         // the DtN map of the whole domain is read by nothing on the Dirichlet path (only by the root's Robin system, a parent
@@ -895,8 +1004,10 @@ static void build_level(efgpu_handle* H, int lev, int phase)
         return;
     }
     H->peer_dirty = true;
+    LaneSet lanes(H);
     for (int bi : H->level_batches[lev]) {
         BatchH& b = H->batches[bi];
+        cudaStream_t s = lanes.get(b);
         double* const* ptab = b.d_ptab.as<double*>();
         if (phase == 0) {
             for (size_t t = 0; t < b.cT.size(); t++)
@@ -967,6 +1078,7 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             else for (const Step& st : b.active()) if (st.cls == EFGPU_PROF_MIRROR_T) run_transposes(st);
         }
     }
+    lanes.join();
 }
 
 // Partitioned tree: the root's DtN map is only needed by the Robin solve and by parity readers, so its row slices stay
@@ -1053,7 +1165,12 @@ static void build_end(efgpu_handle* H)
 static void do_build(efgpu_handle* H, unsigned flags)
 {
     build_begin(H, flags);
-    for (int lev = H->max_level; lev >= 0; lev--) { build_level(H, lev, 0); build_level(H, lev, 1); }
+    run_graphed(H, H->g_build, graph_key(H, H->cur_flags), [&] {
+        build_leaves(H);
+        for (int lev = H->max_level; lev >= 0; lev--) { build_level(H, lev, 0); build_level(H, lev, 1); }
+    });
+    // host-side state a replayed graph does not set
+    if ((H->cur_flags & EFGPU_LAZY_ROOT_DTN) && !H->level_batches[0].empty()) H->root_T_pending = true;
     build_end(H);
 }
 
@@ -1071,13 +1188,19 @@ static void do_upwards(efgpu_handle* H, const double* f_dev, double fscale, unsi
                                     f_dev, fscale, nullptr, nullptr, H->d_leaf_h.as<double*>(), 1, H->n_leaves, s);
     });
     if (!(flags & EFGPU_HOMOGENEOUS_RHS))   // upwards4to1 is skipped entirely (HPSAlgorithm.hpp:532)
-        for (int lev = H->max_level; lev >= 0; lev--)
-            for (int bi : H->level_batches[lev]) {
-                BatchH& b = H->batches[bi];
-                for (size_t t = 0; t < b.cH.size(); t++)
-                    timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_coarsen_h(b.d_cH[t]->as<CoarsenOp>(), (int)b.cH[t].size(), b.cH_max[t], s); });
-                timed(H, EFGPU_PROF_UPWARDS_MATVEC, 3, [&] { launch_upwards(b.d_entries.as<MergeEntry>(), b.n, b.count, s); });
+        run_graphed(H, H->g_up, graph_key(H, 0), [&] {
+            for (int lev = H->max_level; lev >= 0; lev--) {
+                LaneSet lanes(H);
+                for (int bi : H->level_batches[lev]) {
+                    BatchH& b = H->batches[bi];
+                    cudaStream_t ls = lanes.get(b);
+                    for (size_t t = 0; t < b.cH.size(); t++)
+                        timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_coarsen_h(b.d_cH[t]->as<CoarsenOp>(), (int)b.cH[t].size(), b.cH_max[t], ls); });
+                    timed(H, EFGPU_PROF_UPWARDS_MATVEC, 3, [&] { launch_upwards(b.d_entries.as<MergeEntry>(), b.n, b.count, ls); });
+                }
+                lanes.join();
             }
+        });
     EF_CUDA(cudaEventRecord(H->ev1, s));
     H->upwards_done = true;
 }
@@ -1087,15 +1210,21 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
     // root Dirichlet data must already be in the root's g buffer
     cudaStream_t s = H->stream;
     const bool homogeneous = (flags & EFGPU_HOMOGENEOUS_RHS) != 0;
-    for (int lev = 0; lev <= H->max_level; lev++)
-        for (int bi : H->level_batches[lev]) {
-            BatchH& b = H->batches[bi];
-            for (size_t t = 0; t < b.cG.size(); t++)
-                timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(b.d_cG[t]->as<CoarsenOp>(), (int)b.cG[t].size(), b.cG_max[t], s); });
-            timed(H, EFGPU_PROF_SOLVE_MATVEC, 1, [&] { launch_solve_split(b.d_entries.as<MergeEntry>(), b.n, b.count, !homogeneous, s); });
+    run_graphed(H, H->g_solve, graph_key(H, homogeneous ? 1u : 0u), [&] {
+        for (int lev = 0; lev <= H->max_level; lev++) {
+            LaneSet lanes(H);
+            for (int bi : H->level_batches[lev]) {
+                BatchH& b = H->batches[bi];
+                cudaStream_t ls = lanes.get(b);
+                for (size_t t = 0; t < b.cG.size(); t++)
+                    timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(b.d_cG[t]->as<CoarsenOp>(), (int)b.cG[t].size(), b.cG_max[t], ls); });
+                timed(H, EFGPU_PROF_SOLVE_MATVEC, 1, [&] { launch_solve_split(b.d_entries.as<MergeEntry>(), b.n, b.count, !homogeneous, ls); });
+            }
+            lanes.join();
         }
-    for (size_t t = 0; t < H->extG.size(); t++)
-        timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(H->d_extG[t]->as<CoarsenOp>(), (int)H->extG[t].size(), H->extG_max[t], s); });
+        for (size_t t = 0; t < H->extG.size(); t++)
+            timed(H, EFGPU_PROF_COARSEN_VEC, 1, [&] { launch_uncoarsen_g(H->d_extG[t]->as<CoarsenOp>(), (int)H->extG[t].size(), H->extG_max[t], s); });
+    });
     if (!H->external_leaves) timed(H, EFGPU_PROF_LEAF_SOLVE, 1, [&] {
         if (H->leaf_kind == EFGPU_LEAF_VARIABLE)
             launch_leaf_var_solve(H->M, H->d_coef.as<double>(), H->d_P.as<double>(), H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(),
@@ -1156,6 +1285,7 @@ int efgpu_create_ex(const efgpu_tree_desc* desc, int device, const int32_t* exte
         make_plan(H, desc, external_leaf_size);
         EF_CUDA(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
         EF_CUDA(cudaEventCreate(&H->ev0)); EF_CUDA(cudaEventCreate(&H->ev1));
+        { const char* ge = getenv("EFGPU_GRAPHS"); H->graphs_on = !ge || atoi(ge) != 0; }
         *out = H;
         return EF_OK;
     } catch (const efgpu::Error& e) { g_create_error = e.msg; delete H; return e.code; }
@@ -1174,6 +1304,9 @@ void efgpu_destroy(efgpu_handle* H)
     for (auto& r : H->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : H->ev_pool) cudaEventDestroy(e);
     for (void* p : H->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
+    for (efgpu_handle::GraphSlot* g : {&H->g_build, &H->g_up, &H->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
+    for (int k = 1; k < efgpu_handle::MAX_LANES; k++) { if (H->lane[k]) cudaStreamDestroy(H->lane[k]); if (H->ev_join[k]) cudaEventDestroy(H->ev_join[k]); }
+    if (H->ev_fork) cudaEventDestroy(H->ev_fork);
     cudaStream_t s = H->own_stream ? H->stream : nullptr;
     delete H;
     if (s) cudaStreamDestroy(s);
@@ -1249,7 +1382,7 @@ int efgpu_set_partition(efgpu_handle* H, int rank, int nranks)
     if (!H || nranks < 1 || rank < 0 || rank >= nranks) return EF_ERR_BAD_ARG;
     EF_TRY(H)
     if (H->allocated) throw Error{EF_ERR_STATE, "efgpu_set_partition must precede the first build / device view"};
-    H->part_rank = rank; H->part_nranks = nranks;
+    H->part_rank = rank; H->part_nranks = nranks; H->graph_gen++;
     for (auto& b : H->batches) plan_batch_gemms(b, rank, nranks);
     compute_flop_model(H);
     EF_CATCH(H)
@@ -1399,6 +1532,7 @@ int efgpu_build_begin(efgpu_handle* H, unsigned flags)
     EF_TRY(H)
     EF_CUDA(cudaSetDevice(H->device));
     build_begin(H, flags);
+    build_leaves(H);
     EF_CATCH(H)
 }
 

@@ -802,16 +802,25 @@ leaf_var_solve_warp_kernel(const double* __restrict__ coef, const double* __rest
     const double* fl = f ? f + (size_t)leaf * M * M : nullptr;
     double* z = sZ[w];
     double* yv = sYv[w];
-    auto matvec = [&](int i) -> double {       // row r of P_i y, complete in every lane of the row
+    // this lane's slice of row r of P_i, fetched one step ahead of its use (the sweeps are a chain of 2 M dependent steps: without
+    // the prefetch every step waits for a round trip to HBM - ncu r2d: long-scoreboard stalls 138 per issue, 27 % of DRAM peak)
+    double pc[KP], pn[KP];
+    auto fetch = [&](int i, double (&dst)[KP]) {
         const double* pr = P + (size_t)i * M * M + r * M + part * KP;
+#pragma unroll
+        for (int k = 0; k < KP; k += 2) { const double2 v = *reinterpret_cast<const double2*>(pr + k); dst[k] = v.x; dst[k + 1] = v.y; }
+    };
+    auto matvec = [&](const double (&pv)[KP]) -> double {       // row r of P_i y, complete in every lane of the row
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < KP; k++) s = fma(pr[k], yv[part * KP + k], s);
+        for (int k = 0; k < KP; k++) s = fma(pv[k], yv[part * KP + k], s);
 #pragma unroll
         for (int o = M; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         return s;
     };
+    fetch(0, pc);
     for (int i = 0; i < M; i++) {
+        fetch(i + 1 < M ? i + 1 : M - 2, pn);          // after the last forward block: the first block of the backward sweep
         if (part == 0) {
             const int j = r;
             double v = fl ? fscale * fl[i * M + j] : 0.0;
@@ -825,16 +834,21 @@ leaf_var_solve_warp_kernel(const double* __restrict__ coef, const double* __rest
             yv[j] = v;
         }
         __syncwarp();
-        const double s = matvec(i);
+        const double s = matvec(pc);
         __syncwarp();
         if (part == 0) z[i * M + r] = s;
+#pragma unroll
+        for (int k = 0; k < KP; k++) pc[k] = pn[k];
     }
     for (int i = M - 2; i >= 0; i--) {
+        if (i > 0) fetch(i - 1, pn);
         __syncwarp();
         if (part == 0) yv[r] = cE[i * M + r] * z[(i + 1) * M + r];
         __syncwarp();
-        const double s = matvec(i);
+        const double s = matvec(pc);
         if (part == 0) z[i * M + r] -= s;
+#pragma unroll
+        for (int k = 0; k < KP; k++) pc[k] = pn[k];
     }
     __syncwarp();
     if (mode == 0) {
