@@ -68,6 +68,7 @@ SIGNATURES = {
     "efgpu_vector_device": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I]),
     "efgpu_solve_robin": (C.c_int, [_P, _P, _P, _P, C.c_uint, _P]),
     "efgpu_sync": (C.c_int, [_P]),
+    "efgpu_write_vtu": (C.c_int, [_P, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_P)]),
     "efgpu_stream": (_P, [_P]),
     "efgpu_set_stream": (C.c_int, [_P, _P]),
     "efgpu_node_info": (C.c_int, [_P, C.c_int, _I, _I, _I, _I]),

@@ -1829,6 +1829,25 @@ int efgpu_error_norms(efgpu_handle* H, const double* exact, double* l1, double* 
     EF_CATCH(H)
 }
 
+int efgpu_write_vtu(efgpu_handle* H, const char* path, int n_fields, const char* const* names, const double* const* fields_dev)
+{
+    if (!H || !path || n_fields < 0 || (n_fields > 0 && (!names || !fields_dev))) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    points_tables(H);
+    std::vector<const double*> f(n_fields);
+    for (int k = 0; k < n_fields; k++) {
+        if (!names[k]) throw Error{EF_ERR_BAD_ARG, "efgpu_write_vtu: null field name"};
+        f[k] = fields_dev[k];
+        if (!f[k]) {   // the handle's own solution
+            if (!H->solve_done) throw Error{EF_ERR_STATE, "efgpu_write_vtu: no solution yet (null field pointer = the last solve stage's u)"};
+            f[k] = H->d_u.as<double>();
+        }
+    }
+    EF_CUDA(cudaStreamSynchronize(H->stream));
+    write_vtu(path, H->d_boxes.as<double>(), H->d_leaf_nodes.as<int>(), H->M, H->n_leaves, n_fields, names, f.data(), H->stream);
+    EF_CATCH(H)
+}
+
 int efgpu_sync(efgpu_handle* H)
 {
     if (!H) return EF_ERR_BAD_ARG;

@@ -66,6 +66,10 @@ void launch_error_norms(const double* u, const double* v, const double* boxes, c
 
 void launch_max_positive(const double* v, size_t n, double* out, cudaStream_t s);   // *out = max(0, max v): any sampled lambda > 0?
 
+// vtk.cu: binary .vtu (raw appended data) of the leaf cells and `n_fields` cell fields (device arrays, one double per cell)
+void write_vtu(const char* path, const double* boxes, const int* leaf_nodes, int M, long long n_leaves, int n_fields,
+               const char* const* names, const double* const* fields, cudaStream_t s);
+
 // lu.cu: root boundary system  (diag(a) + diag(b) T) g = r - b .* h  by blocked LU with partial pivoting
 size_t robin_workspace_doubles(int N);
 void robin_solve(const double* T, const double* a, const double* b, const double* r, const double* h, int N, double* ws,

@@ -48,7 +48,7 @@ class SingleGpuHPS(HPSAlgorithm):
         return float(np.max(np.abs(u - u_fn(X, Y))))
 
 
-def make_hps(mesh, solver, device=0, rank=0, world=1, options=None, cut=2, grouped=False):
+def make_hps(mesh, solver, device=0, rank=0, world=1, options=None, cut=2, grouped=False, balance="count"):
     """cut: tree level whose 4^cut subtrees are dealt to the ranks (2: the 16 subtrees of SURVEY 8(e); 1: four subtrees, for 2 or 4
     ranks - the level-1 merges then run whole on their owners and only the root merge is row-partitioned)."""
     if world == 1:
@@ -57,4 +57,4 @@ def make_hps(mesh, solver, device=0, rank=0, world=1, options=None, cut=2, group
         from .sharded import GroupedShardedHPS
         return GroupedShardedHPS(mesh, solver, device=device, rank=rank, world=world, options=options)
     from .sharded import ShardedHPS
-    return ShardedHPS(mesh, solver, device=device, rank=rank, world=world, options=options, cut=cut)
+    return ShardedHPS(mesh, solver, device=device, rank=rank, world=world, options=options, cut=cut, balance=balance)

@@ -373,6 +373,14 @@ class HPSAlgorithm:
                                                  *[C.byref(v) for v in out]), self._h)
         return tuple(v.value for v in out)
 
+    def toVTK(self, filename, fields=None):
+        """Mesh + cell fields as one binary .vtu written from device buffers (src/Mesh.hpp:186-267 + src/VTK.cpp:237-300 write
+        ASCII from the host).  fields: {name: device pointer or None}; None = the solution of the last solveStage."""
+        fields = {"u": None} if fields is None else fields
+        names = (C.c_char_p * len(fields))(*[k.encode() for k in fields])
+        ptrs = (C.c_void_p * len(fields))(*[C.c_void_p(int(v)) if v else None for v in fields.values()])
+        check(self._lib.efgpu_write_vtu(self._h, str(filename).encode(), len(fields), names, ptrs), self._h)
+
     def sync(self):
         check(self._lib.efgpu_sync(self._h), self._h)
 

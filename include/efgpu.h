@@ -220,6 +220,12 @@ int efgpu_leaf_points(efgpu_handle* h, int which, double* x, double* y);   /* ho
  * resident in the handle.  Deterministic (fixed reduction order); any of l1 / l2 / linf may be NULL. */
 int efgpu_error_norms_device(efgpu_handle* h, const double* u_dev, const double* exact_dev, double* l1, double* l2, double* linf);
 int efgpu_error_norms(efgpu_handle* h, const double* exact, double* l1, double* l2, double* linf);   /* exact: host array */
+/* Mesh and cell fields as ONE binary .vtu (UnstructuredGrid, raw appended data, UInt64 headers, little endian), streamed from
+ * device buffers: replaces Mesh::setMeshFromQuadtree + UnstructuredGridVTK::toVTK (src/Mesh.hpp:186-267, src/VTK.cpp:237-300),
+ * which format every number as ASCII on the host.  Same cells, same point order (four own corners per leaf cell, leaves in
+ * traversePreOrder, cells i-slow j-fast), same corner formulas.  fields_dev[k]: one double per cell, leaf-major, cell index
+ * j + i*ny (the layout of vectorU / vectorF); NULL = the solution of the last solve stage.  SURVEY.md 8(f) rank 3. */
+int efgpu_write_vtu(efgpu_handle* h, const char* path, int n_fields, const char* const* names, const double* const* fields_dev);
 void* efgpu_stream(efgpu_handle* h);   /* the cudaStream_t all work of this handle is issued on */
 int efgpu_set_stream(efgpu_handle* h, void* stream);   /* adopt a caller-owned cudaStream_t (e.g. share one stream between two handles) */
 
