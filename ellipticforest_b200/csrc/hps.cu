@@ -616,8 +616,12 @@ static void compute_flop_model(efgpu_handle* H)
     H->stats.merge_flops_canonical = canon;
     H->stats.merge_flops_issued = issued;
     const double leaf_cells = H->external_leaves ? 0.0 : (double)H->n_leaves * M * M;
-    H->stats.upwards_bytes = up_bytes + 8.0 * leaf_cells;
-    H->stats.solve_bytes = so_bytes + 16.0 * leaf_cells;
+    // leaves: f (8 B / DOF) in, h out (upwards); f, g in, u out (solve).  Variable-coefficient leaves also stream the stored inverse
+    // diagonal blocks P_i of their block-tridiagonal factorisation twice per right-hand side (forward and backward sweep):
+    // 2 M doubles per DOF
+    const double leaf_extra = (!H->external_leaves && H->leaf_kind == EFGPU_LEAF_VARIABLE) ? 16.0 * M * leaf_cells : 0.0;
+    H->stats.upwards_bytes = up_bytes + 8.0 * leaf_cells + leaf_extra;
+    H->stats.solve_bytes = so_bytes + 16.0 * leaf_cells + leaf_extra;
     H->stats.n_leaves = H->n_leaves;
     H->stats.n_nodes = nn;
     H->stats.dofs = leaf_cells;
