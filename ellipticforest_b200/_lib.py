@@ -59,6 +59,7 @@ SIGNATURES = {
     "efgpu_error_norms_device": (C.c_int, [_P, _P, _P, _D, _D, _D]),
     "efgpu_error_norms": (C.c_int, [_P, _P, _D, _D, _D]),
     "efgpu_build": (C.c_int, [_P, C.c_uint]),
+    "efgpu_rebuild_from": (C.c_int, [_P, _P, C.c_uint, _D, _D]),
     "efgpu_upwards": (C.c_int, [_P, _P, C.c_double, C.c_uint]),
     "efgpu_upwards_device": (C.c_int, [_P, _P, C.c_double, C.c_uint, C.c_int]),
     "efgpu_solve_dirichlet": (C.c_int, [_P, _P, C.c_uint, _P]),

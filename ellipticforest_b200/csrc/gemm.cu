@@ -19,6 +19,8 @@
 
 namespace efgpu {
 
+int get_tuning(int key);   // vec.cu
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -550,6 +552,159 @@ invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long 
     if (threadIdx.x == 0 && min_pivot) minp.publish(min_pivot);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Blocked Gauss-Jordan inverse of a 128 x 128 block on the FP64 tensor pipe (round 2).
+//
+// invert_reg_kernel pays one barrier phase per pivot: 128 dependent phases of ~0.57 us, FP64 pipe 31 % busy, 73 us per matrix -
+// and at the top tree levels these base cases form a chain of N/128 sequential launches.  Here the pivots are taken eight at a
+// time.  The matrix lives in registers as 16 x 16 accumulator tiles of mma.m8n8k4 (8 warps as a 2 x 4 grid, 8 x 4 tiles each).
+// Block step kb with pivot block P = A[K,K] (K = 8 kb .. 8 kb + 7), row panel R = A[K,:], column panel C = A[:,K]:
+//     A[K,K] <- P^-1,   A[K,J] <- P^-1 R_J,   A[I,K] <- -C_I P^-1,   A[I,J] <- A[I,J] - C_I (P^-1 R_J)
+//  1. the owners publish R (8 x 128) and C (128 x 8) to shared memory (double buffered: one __syncthreads per block step);
+//  2. every warp inverts P itself (8 x 8 Gauss-Jordan on its lanes by shuffles: no second barrier);
+//  3. (P^-1 R_J)^T = R_J^T P^-T comes out of a DMMA in accumulator layout, which - with the k slots of the next DMMA pair
+//     permuted to {0,2,4,6} / {1,3,5,7} - IS the B-operand layout of the trailing update: no layout change through memory;
+//  4. trailing update: two DMMAs per tile, A operand = -C_I read as 16-byte pairs.
+// No pivoting, like the kernel it replaces (pivoting policy); different rounding (block order), same parity tests.
+__device__ __forceinline__ void inv8x8_warp(double& p0, double& p1, int r, int q, PivotTrack& pt)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int kq = k >> 1;
+        const double rk0 = __shfl_sync(0xffffffffu, p0, 4 * k + q), rk1 = __shfl_sync(0xffffffffu, p1, 4 * k + q);    // row k at my columns
+        const double mine = (k & 1) ? p1 : p0;
+        const double ck = __shfl_sync(0xffffffffu, mine, 4 * r + kq);                                                  // A[r][k]
+        const double piv = __shfl_sync(0xffffffffu, mine, 4 * k + kq);                                                 // A[k][k]
+        const double pinv = 1.0 / piv;
+        pt.see(piv);
+        if (r == k) {
+            p0 = (2 * q == k) ? pinv : rk0 * pinv;
+            p1 = (2 * q + 1 == k) ? pinv : rk1 * pinv;
+        } else {
+            const double f = ck * pinv;
+            p0 = (2 * q == k) ? -f : fma(-f, rk0, p0);
+            p1 = (2 * q + 1 == k) ? -f : fma(-f, rk1, p1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, double* __restrict__ min_pivot)
+{
+    constexpr int LR = 132;     // row panel 8 x 128, row stride == 4 (mod 16): the fragment reads (4 k' rows x 4 columns per half warp) are conflict free
+    constexpr int LC = 8;       // column panel 128 x 8, unpadded: the 16-byte pair reads of a quarter warp (2 rows x 4 pairs) cover 128 contiguous bytes
+    constexpr int LP = 10;
+    __shared__ __align__(16) double sR[2][8 * LR];
+    __shared__ __align__(16) double sC[2][128 * LC];
+    __shared__ __align__(16) double sPi[8][8 * LP];
+    const int nmat = off2 >= 0 ? 2 : 1;
+    double* G = ptab[(long long)(blockIdx.x / nmat) * nops + op] + ((blockIdx.x % nmat) ? off2 : off);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wr = w >> 2, wc = w & 3;                 // this warp: tile rows 8 wr .. 8 wr + 7, tile columns 4 wc .. 4 wc + 3
+    const int r = lane >> 2, q = lane & 3;             // accumulator fragment: row r, columns 2 q, 2 q + 1 of a tile
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double2 v = *reinterpret_cast<const double2*>(G + (long long)(8 * (8 * wr + i) + r) * ld + 8 * (4 * wc + j) + 2 * q);
+            acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+        }
+    PivotTrack pt;
+    double* spi = sPi[w];
+    // (the inner eight block steps are unrolled so that the accumulator tile picked by kb is a compile-time register index:
+    // a run-time subscript would push the whole matrix into local memory)
+    for (int kbh = 0; kbh < 2; kbh++)
+#pragma unroll
+    for (int kbl = 0; kbl < 8; kbl++) {
+        const int kb = 8 * kbh + kbl;
+        const int buf = kbl & 1;
+        double* sr = sR[buf];
+        double* sc = sC[buf];
+        // 1. publish the raw row / column panels
+        if (wr == kbh) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == kbl) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        *reinterpret_cast<double2*>(sr + r * LR + 8 * (4 * wc + j) + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+        }
+        if (wc == (kb >> 2)) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j == (kbl & 3)) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        *reinterpret_cast<double2*>(sc + (8 * (8 * wr + i) + r) * LC + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+        }
+        __syncthreads();
+        // 2. P^-1, by every warp on its own lanes
+        double p0, p1;
+        { const double2 v = *reinterpret_cast<const double2*>(sr + r * LR + 8 * kb + 2 * q); p0 = v.x; p1 = v.y; }
+        inv8x8_warp(p0, p1, r, q, pt);
+        *reinterpret_cast<double2*>(spi + r * LP + 2 * q) = make_double2(p0, p1);
+        __syncwarp();
+        // fragments of P^-1: as A operand (rows r, k' = q, q + 4) and, transposed, as B operand of step 3 (B[k'][n] = Pinv[n][k'])
+        const double pa0 = spi[r * LP + q], pa1 = spi[r * LP + q + 4];
+        // B operand of the column-kb tiles: B[k = 2 q + e][n = r] = Pinv[2 q + e][r]
+        const double pb0 = spi[(2 * q) * LP + r], pb1 = spi[(2 * q + 1) * LP + r];
+        // 3. xt[j] = (P^-1 R_j)^T in accumulator layout = B operand pair of the update; row-kb tiles get P^-1 R_j itself
+        double xt[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int tj = 4 * wc + j;
+            const double ra0 = sr[q * LR + 8 * tj + r], ra1 = sr[(q + 4) * LR + 8 * tj + r];     // A[m = r][k' = q (+4)] = R[k'][8 tj + r]
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, ra0, pa0);     // B[k' = q][n = r] = Pinv[r][q]
+            dmma884(x0, x1, ra1, pa1);
+            xt[j][0] = x0; xt[j][1] = x1;
+        }
+        // 4. trailing update and the special tile row / column
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int ti = 8 * wr + i;
+            const double2 cv = *reinterpret_cast<const double2*>(sc + (8 * ti + r) * LC + 2 * q);   // C[8 ti + r][2 q], [2 q + 1]
+            const double a0 = -cv.x, a1 = -cv.y;
+            const bool col_owner = wc == (kb >> 2);
+            if (!(wr == kbh && i == kbl)) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (!(col_owner && j == (kbl & 3))) {
+                        dmma884(acc[i][j][0], acc[i][j][1], a0, xt[j][0]);
+                        dmma884(acc[i][j][0], acc[i][j][1], a1, xt[j][1]);
+                    } else {           // A[I,K] <- -C_I P^-1
+                        double y0 = 0.0, y1 = 0.0;
+                        dmma884(y0, y1, a0, pb0);
+                        dmma884(y0, y1, a1, pb1);
+                        acc[i][j][0] = y0; acc[i][j][1] = y1;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int tj = 4 * wc + j;
+                    if (!(col_owner && j == (kbl & 3))) {    // A[K,J] <- P^-1 R_J: A operand P^-1 (rows r, k' = q, q + 4), B[k'][n = r] = R[k'][8 tj + r]
+                        double y0 = 0.0, y1 = 0.0;
+                        dmma884(y0, y1, pa0, sr[q * LR + 8 * tj + r]);
+                        dmma884(y0, y1, pa1, sr[(q + 4) * LR + 8 * tj + r]);
+                        acc[i][j][0] = y0; acc[i][j][1] = y1;
+                    } else { acc[i][j][0] = p0; acc[i][j][1] = p1; }
+                }
+            }
+        }
+        __syncwarp();      // spi is rewritten in the next step
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            *reinterpret_cast<double2*>(G + (long long)(8 * (8 * wr + i) + r) * ld + 8 * (4 * wc + j) + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
+    if (threadIdx.x == 0 && min_pivot) pt.publish(min_pivot);
+}
+
 void launch_invert_small(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int N, int batch,
                          double* min_pivot, cudaStream_t stream)
 {
@@ -560,7 +715,13 @@ void launch_invert_small(double* const* ptab, int nops, int op, long long off, l
         case 48: invert_reg_kernel<3><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
         case 64: invert_reg_kernel<4><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
         case 96: invert_reg_kernel<6><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
-        case 128: invert_reg_kernel<8><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;
+        case 128:
+            // default: blocked Gauss-Jordan on the tensor pipe; efgpu_set_tuning(7, 1): the per-pivot register kernel of round 1.
+            // Needs 16-byte aligned rows (even ld and offsets: always true for the merge matrices, whose blocks are multiples of 8)
+            if (get_tuning(7) == 0 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
+                invert_blk128_kernel<<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
+            else invert_reg_kernel<8><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
+            EF_CUDA(cudaGetLastError()); return;
         default: break;
     }
     int smem = (N * (N + 1) + N) * (int)sizeof(double);

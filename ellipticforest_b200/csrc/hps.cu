@@ -96,6 +96,12 @@ struct BatchH {
     std::vector<int> cT_max, cH_max, cG_max;
     size_t ws_per_entry = 0, w2_off = 0, w3_off = 0;   // per-entry workspace: [W1 blocks per depth | W2 | W3 staging]
     std::vector<double*> h_ptab;   // host copy of the operand table (all-gather callbacks need host-side addresses)
+    std::vector<MergeEntry> h_ent; // host copy of the merge entries
+    std::vector<std::vector<int>> cT_slot;   // parent slot of every coarsening op of cT (to restrict them to a subset of the parents)
+    // adaptive re-build (efgpu_rebuild_from): the build runs on the dirty parents only - compact copies of the tables above
+    bool sub_on = false; int sub_count = 0;
+    DevBuf sub_entries, sub_ptab;
+    std::vector<std::unique_ptr<DevBuf>> sub_cT; std::vector<int> sub_cT_n, sub_cT_max;
 };
 
 }  // namespace efgpu
@@ -853,7 +859,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             }
         b.Tcoarse.alloc(coarse_doubles * sizeof(double));
         size_t coff = 0;
-        b.cT.clear(); b.cH.clear(); b.cG.clear();
+        b.cT.clear(); b.cH.clear(); b.cG.clear(); b.cT_slot.clear();
         std::vector<MergeEntry> ent(cnt);
         std::vector<double*> ptab(cnt * NOPS, nullptr);
         for (size_t sl = 0; sl < cnt; sl++) {
@@ -867,6 +873,8 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
                     ch.Tbuf[t] = b.Tcoarse.as<double>() + coff; coff += sz * sz;
                     if ((int)b.cT.size() < t) { b.cT.resize(t); b.cH.resize(t); }
                     b.cT[t - 1].push_back(CoarsenOp{ch.Tbuf[t - 1], ch.Tbuf[t], ch.size >> (t - 1), 0});
+                    if ((int)b.cT_slot.size() < t) b.cT_slot.resize(t);
+                    b.cT_slot[t - 1].push_back((int)sl);
                     b.cH[t - 1].push_back(CoarsenOp{vec + ch.hbuf[t - 1], vec + ch.hbuf[t], ch.size >> (t - 1), 0});
                 }
                 if ((ch.size >> ch.ncoarsen) != (int)n) throw Error{EF_ERR_STATE, "internal: child size mismatch after coarsening"};
@@ -894,7 +902,7 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
             }
         }
         b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s); b.d_trans.upload(b.trans, s);
-        b.h_ptab = ptab;
+        b.h_ptab = ptab; b.h_ent = ent;
         auto up = [&](std::vector<std::vector<CoarsenOp>>& v, std::vector<std::unique_ptr<DevBuf>>& dv, std::vector<int>& mx) {
             dv.clear(); mx.clear();
             for (auto& ops : v) {
@@ -1012,14 +1020,21 @@ static void build_level(efgpu_handle* H, int lev, int phase)
     for (int bi : H->level_batches[lev]) {
         BatchH& b = H->batches[bi];
         cudaStream_t s = lanes.get(b);
-        double* const* ptab = b.d_ptab.as<double*>();
+        // adaptive re-build: only the dirty parents of the batch (compact tables), possibly none
+        if (b.sub_on && b.sub_count == 0) continue;
+        const int bcount = b.sub_on ? b.sub_count : b.count;
+        double* const* ptab = b.sub_on ? b.sub_ptab.as<double*>() : b.d_ptab.as<double*>();
         if (phase == 0) {
-            for (size_t t = 0; t < b.cT.size(); t++)
-                timed(H, EFGPU_PROF_COARSEN_T, 1, [&] { launch_coarsen_T(b.d_cT[t]->as<CoarsenOp>(), (int)b.cT[t].size(), b.cT_max[t], s); });
-            const MergeEntry* ent = b.d_entries.as<MergeEntry>();
+            if (b.sub_on) {
+                for (size_t t = 0; t < b.sub_cT.size(); t++)
+                    if (b.sub_cT_n[t]) timed(H, EFGPU_PROF_COARSEN_T, 1, [&] { launch_coarsen_T(b.sub_cT[t]->as<CoarsenOp>(), b.sub_cT_n[t], b.sub_cT_max[t], s); });
+            } else
+                for (size_t t = 0; t < b.cT.size(); t++)
+                    timed(H, EFGPU_PROF_COARSEN_T, 1, [&] { launch_coarsen_T(b.d_cT[t]->as<CoarsenOp>(), (int)b.cT[t].size(), b.cT_max[t], s); });
+            const MergeEntry* ent = b.sub_on ? b.sub_entries.as<MergeEntry>() : b.d_entries.as<MergeEntry>();
             timed(H, EFGPU_PROF_ASSEMBLE, 2, [&] {
-                launch_assemble_X(ent, b.n, b.count, s);
-                launch_assemble_Hc(ent, b.n, b.count, s);
+                launch_assemble_X(ent, b.n, bcount, s);
+                launch_assemble_Hc(ent, b.n, bcount, s);
             });
         }
         auto gather = [&](double* buf, size_t doubles_total) {
@@ -1028,13 +1043,13 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                 throw Error{EF_ERR_STATE, "the all-gather callback failed"};
         };
         auto run_transposes = [&](const Step& st) {
-            timed(H, st.cls, 1, [&] { launch_btranspose(ptab, NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, b.count, s); });
+            timed(H, st.cls, 1, [&] { launch_btranspose(ptab, NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, bcount, s); });
         };
         auto run_refine = [&]() {   // indefinite problems: X^-1 <- X^-1 + X^-1 (I - X X^-1), every rank of a partition alike
             for (const Step& st : b.steps_refine)
                 timed(H, st.cls, 1, [&] {
-                    if (st.kind == 1) launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s);
-                    else launch_refine_ew(ptab, NOPS, st.kind, st.kind == 3 ? OP_T : OP_XINV, st.kind == 3 ? st.off : 0, OP_T, st.off, st.N, b.count,
+                    if (st.kind == 1) launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s);
+                    else launch_refine_ew(ptab, NOPS, st.kind, st.kind == 3 ? OP_T : OP_XINV, st.kind == 3 ? st.off : 0, OP_T, st.off, st.N, bcount,
                                           H->d_minpiv.as<double>() + 4, s);
                 });
         };
@@ -1051,8 +1066,8 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             const bool scatter = p2p && st.kind == 1 && (st.gk == 3 || st.cls == EFGPU_PROF_GEMM_S || (is_T && lev > 0));
             if (scatter) peer_barrier(H, /*only_if_dirty=*/true);
             timed(H, st.cls, 1, [&] {
-                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, b.count, H->d_minpiv.as<double>(), s);
-                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, b.count, s, 0, scatter ? &H->peers : nullptr);
+                if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, bcount, H->d_minpiv.as<double>(), s);
+                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s, 0, scatter ? &H->peers : nullptr);
             });
             if (scatter) { peer_barrier(H, false); continue; }
             H->peer_dirty = true;
@@ -1240,6 +1255,137 @@ static void do_solve(efgpu_handle* H, const double* f_dev, double fscale, unsign
     H->solve_done = !H->external_leaves;
 }
 
+// ---- adaptive re-build -----------------------------------------------------------------------------------
+// The paper advertises re-using the factorisation when the mesh is refined or coarsened locally (paper.md:44); the reference never
+// implements it (HPSAlgorithm::isBuilt is unused, src/HPSAlgorithm.hpp:50-55: every buildStage starts from the leaves).  Here a
+// node of the new tree is CLEAN when an identical subtree (same boxes bit for bit, same structure) exists in the old, built tree:
+// its X^-1, S, H and DtN map are copied device to device, and the build runs on the other (dirty) parents only - the ancestor
+// chains of what changed.  Every kernel sees the same operands as in a build from scratch and the batched kernels compute each
+// batch entry independently of the others, so the result is bit-identical to efgpu_build on the new tree.
+struct SubtreeKey {
+    uint64_t h; uint64_t box[4];
+    bool operator<(const SubtreeKey& o) const { return std::tie(h, box[0], box[1], box[2], box[3]) < std::tie(o.h, o.box[0], o.box[1], o.box[2], o.box[3]); }
+};
+static std::vector<SubtreeKey> subtree_keys(const efgpu_handle* H)
+{
+    std::vector<SubtreeKey> k(H->n_nodes);
+    auto mix = [](uint64_t a, uint64_t b) { a ^= b + 0x9e3779b97f4a7c15ull + (a << 6) + (a >> 2); return a * 0xff51afd7ed558ccdull; };
+    for (int i = H->n_nodes - 1; i >= 0; i--) {   // children have larger ids
+        const NodeH& nd = H->nodes[i];
+        std::memcpy(k[i].box, nd.box, sizeof(k[i].box));
+        uint64_t h = mix(0x1234567ull, (uint64_t)nd.size);
+        for (int c = 0; c < 4; c++) h = mix(h, k[i].box[c]);
+        if (!nd.leaf) for (int c = 0; c < 4; c++) { h = mix(h, k[nd.child[c]].h); h = mix(h, (uint64_t)H->nodes[nd.child[c]].ncoarsen); }
+        k[i].h = h;
+    }
+    return k;
+}
+
+
+static void do_rebuild_from(efgpu_handle* H, efgpu_handle* old, unsigned flags, double* reused_nodes, double* rebuilt_merges)
+{
+    if (!old->built) throw Error{EF_ERR_STATE, "efgpu_rebuild_from: the old handle has not been built"};
+    if (old->device != H->device || old->M != H->M) throw Error{EF_ERR_BAD_ARG, "efgpu_rebuild_from: handles on different devices / patch sizes"};
+    if (H->external_leaves || old->external_leaves || H->part_nranks > 1 || old->part_nranks > 1)
+        throw Error{EF_ERR_UNSUPPORTED, "efgpu_rebuild_from: plain (unsharded) handles only"};
+    if ((flags | old->build_flags) & EFGPU_LEAN_T) throw Error{EF_ERR_UNSUPPORTED, "efgpu_rebuild_from: the DtN maps of interior nodes must be resident (no EFGPU_LEAN_T)"};
+    if (H->leaf_kind != old->leaf_kind || (H->leaf_kind == EFGPU_LEAF_CONSTANT && H->lambda != old->lambda))
+        throw Error{EF_ERR_BAD_ARG, "efgpu_rebuild_from: the leaf model changed - every operator is dirty, use efgpu_build"};
+    if ((old->cur_flags ^ flags) & (EFGPU_NO_SYMMETRY | EFGPU_CACHE_OPERATORS | EFGPU_LAZY_ROOT_DTN))
+        throw Error{EF_ERR_BAD_ARG, "efgpu_rebuild_from: build flags differ from the old build"};
+    if (flags & EFGPU_CACHE_OPERATORS) throw Error{EF_ERR_UNSUPPORTED, "efgpu_rebuild_from with cache-operators (a uniform-mesh option)"};
+    build_begin(H, flags);
+    cudaStream_t s = H->stream;
+    EF_CUDA(cudaStreamSynchronize(old->stream));
+    // clean nodes: identical subtree in the old tree, and merged by the same plan (symmetric / general) there
+    const std::vector<SubtreeKey> kn = subtree_keys(H), ko = subtree_keys(old);
+    std::map<SubtreeKey, int> where;
+    for (int i = 0; i < old->n_nodes; i++) where.emplace(ko[i], i);
+    std::vector<int> twin(H->n_nodes, -1);
+    for (int i = 0; i < H->n_nodes; i++) {
+        auto it = where.find(kn[i]);
+        if (it == where.end()) continue;
+        const NodeH& a = H->nodes[i]; const NodeH& o = old->nodes[it->second];
+        if (a.leaf != o.leaf) continue;
+        if (!a.leaf && H->batches[a.batch].use_sym != old->batches[o.batch].use_sym) continue;
+        twin[i] = it->second;
+    }
+    // leaves: every leaf map is recomputed (constant coefficients: one map per class of cell sizes; variable: the block LU is
+    // needed by the leaf solves of the new handle anyway)
+    build_leaves(H);
+    // copies
+    std::vector<CopyOp> cp;
+    double nclean = 0, ndirty = 0;
+    for (int i = 0; i < H->n_nodes; i++) {
+        const NodeH& a = H->nodes[i];
+        if (a.leaf) continue;
+        if (twin[i] < 0) { ndirty++; continue; }
+        nclean++;
+        const NodeH& o = old->nodes[twin[i]];
+        const size_t n = a.size / 2;
+        BatchH& bn = H->batches[a.batch]; BatchH& bo = old->batches[o.batch];
+        cp.push_back({bo.Xinv.as<double>() + (size_t)o.slot * 16 * n * n, bn.Xinv.as<double>() + (size_t)a.slot * 16 * n * n, 16 * n * n});
+        cp.push_back({bo.S.as<double>() + (size_t)o.slot * 32 * n * n, bn.S.as<double>() + (size_t)a.slot * 32 * n * n, 32 * n * n});
+        cp.push_back({bo.Hc.as<double>() + (size_t)o.slot * 16 * n * n, bn.Hc.as<double>() + (size_t)a.slot * 16 * n * n, 16 * n * n});
+        cp.push_back({o.Tbuf[0], a.Tbuf[0], 64 * n * n});
+        if (bn.Xcopy.p && bo.Xcopy.p) cp.push_back({bo.Xcopy.as<double>() + (size_t)o.slot * 16 * n * n, bn.Xcopy.as<double>() + (size_t)a.slot * 16 * n * n, 16 * n * n});
+        else if (bn.Xcopy.p) throw Error{EF_ERR_STATE, "efgpu_rebuild_from: X is kept (EFGPU_KEEP_X / refinement) in the new build but was not in the old one"};
+        // the coarsened copies of a clean parent's children are only read by that parent's merge, which does not run again;
+        // they are copied all the same so that the parity accessors see them (quirk q3: the child's stored T is the coarsened one)
+        for (int c = 0; c < 4; c++) {
+            const NodeH& ca = H->nodes[a.child[c]]; const NodeH& co = old->nodes[o.child[c]];
+            for (int t = 1; t <= ca.ncoarsen; t++) { const size_t sz = 4 * (size_t)(ca.size >> t); cp.push_back({co.Tbuf[t], ca.Tbuf[t], sz * sz}); }
+        }
+    }
+    DevBuf d_cp;
+    if (!cp.empty()) { d_cp.upload(cp, s); launch_copy_many(d_cp.as<CopyOp>(), (int)cp.size(), s); }
+    // dirty subsets of every batch
+    for (auto& b : H->batches) {
+        std::vector<int> slots;
+        for (int sl = 0; sl < b.count; sl++) if (twin[b.parents[sl]] < 0) slots.push_back(sl);
+        b.sub_on = true; b.sub_count = (int)slots.size();
+        if (slots.empty()) continue;
+        std::vector<MergeEntry> ent(slots.size());
+        std::vector<double*> ptab(slots.size() * NOPS);
+        const int lane = H->lanes_on ? b.lane : 0;
+        (void)lane;
+        for (size_t k = 0; k < slots.size(); k++) {
+            ent[k] = b.h_ent[slots[k]];
+            for (int o = 0; o < NOPS; o++) ptab[k * NOPS + o] = b.h_ptab[(size_t)slots[k] * NOPS + o];
+            // workspace: the compact index addresses the lane's region (its size covers the whole batch)
+            double* ws0 = b.h_ptab[OP_W1];
+            ptab[k * NOPS + OP_W1] = ws0 + k * b.ws_per_entry;
+            ptab[k * NOPS + OP_W2] = ws0 + k * b.ws_per_entry + b.w2_off;
+            ptab[k * NOPS + OP_W3] = ws0 + k * b.ws_per_entry + b.w3_off;
+        }
+        b.sub_entries.upload(ent, s); b.sub_ptab.upload(ptab, s);
+        std::vector<char> dirty(b.count, 0);
+        for (int sl : slots) dirty[sl] = 1;
+        b.sub_cT.clear(); b.sub_cT_n.clear(); b.sub_cT_max.clear();
+        for (size_t t = 0; t < b.cT.size(); t++) {
+            std::vector<CoarsenOp> ops; int mx = 0;
+            for (size_t k = 0; k < b.cT[t].size(); k++) if (dirty[b.cT_slot[t][k]]) { ops.push_back(b.cT[t][k]); mx = std::max(mx, b.cT[t][k].nfine); }
+            b.sub_cT.emplace_back(new DevBuf()); if (!ops.empty()) b.sub_cT.back()->upload(ops, s);
+            b.sub_cT_n.push_back((int)ops.size()); b.sub_cT_max.push_back(mx);
+        }
+    }
+    EF_CUDA(cudaStreamSynchronize(s));   // the host staging vectors go out of scope
+    struct Off { efgpu_handle* H; ~Off() { for (auto& b : H->batches) { b.sub_on = false; b.sub_entries.release(); b.sub_ptab.release(); b.sub_cT.clear(); } } } off{H};
+    for (int lev = H->max_level; lev >= 0; lev--) { build_level(H, lev, 0); build_level(H, lev, 1); }
+    if ((H->cur_flags & EFGPU_LAZY_ROOT_DTN) && !H->level_batches[0].empty()) H->root_T_pending = true;
+    // flops actually issued by this re-build
+    double issued = 0;
+    for (auto& b : H->batches) {
+        for (const Step& st : b.active())
+            if (st.kind == 1) for (int k = st.first; k < st.first + st.count; k++)
+                for (int t = 0; t < b.blocks[k].nterms; t++) issued += b.sub_count * 2.0 * b.blocks[k].rows * b.blocks[k].cols * b.blocks[k].t[t].K;
+    }
+    build_end(H);
+    H->stats.merge_flops_issued = issued;
+    if (reused_nodes) *reused_nodes = nclean;
+    if (rebuilt_merges) *rebuilt_merges = ndirty;
+}
+
 }  // namespace efgpu
 
 // =================================================================================================
@@ -1378,6 +1524,15 @@ int efgpu_build(efgpu_handle* H, unsigned flags)
     EF_TRY(H)
     EF_CUDA(cudaSetDevice(H->device));
     do_build(H, flags);
+    EF_CATCH(H)
+}
+
+int efgpu_rebuild_from(efgpu_handle* H, efgpu_handle* old, unsigned flags, double* reused_merges, double* rebuilt_merges)
+{
+    if (!H || !old || H == old) return EF_ERR_BAD_ARG;
+    EF_TRY(H)
+    EF_CUDA(cudaSetDevice(H->device));
+    do_rebuild_from(H, old, flags, reused_merges, rebuilt_merges);
     EF_CATCH(H)
 }
 

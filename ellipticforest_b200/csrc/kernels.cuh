@@ -51,6 +51,9 @@ void launch_coarsen_h(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_
 void launch_uncoarsen_g(const CoarsenOp* ops, int nops, int max_nfine, cudaStream_t s);
 void launch_upwards(const MergeEntry* e, int n, int count, cudaStream_t s);            // hd, w, h
 void launch_solve_split(const MergeEntry* e, int n, int count, bool add_w, cudaStream_t s);
+// batched device-to-device copies of n doubles each (adaptive re-build: operators of unchanged subtrees)
+struct CopyOp { const double* src; double* dst; size_t n; };
+void launch_copy_many(const CopyOp* ops, int nops, cudaStream_t s);
 // Newton-Schulz refinement of X^-1: mode 3: dst <- I + dst, max |dst| into *resid; mode 4: dst <- dst + src (N x N, contiguous)
 void launch_refine_ew(double* const* ptab, int nops, int mode, int dst_op, long long dst_off, int src_op, long long src_off, int N, int batch,
                       double* resid, cudaStream_t s);

@@ -21,6 +21,7 @@ namespace efgpu {
 // [3] leaf solve of constant-coefficient leaves: 0 = DMMA kernel (default), 1 = one thread per cell
 // [5] symmetric merge plan: 1 = the diagonal blocks of T multiply only their upper sub-block triangle (default since r2a: 202.8 -> 197.8 ms
 //     per step at L=8 M=16; 0 = whole blocks; read when a plan is made)
+// [7] base case of the block inversion, 128 x 128: 0 = blocked Gauss-Jordan on the tensor pipe, 1 = per-pivot register kernel (round 1)
 // [6] variable-coefficient leaves with M = 8, 16: 0 = warp-level / tensor-core kernels (default), 1 = the CTA-per-leaf kernels of round 1
 static int g_tuning[8] = {2, 0, 0, 0, 0, 1, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tuning[key] = value; }
@@ -522,6 +523,25 @@ void launch_refine_ew(double* const* ptab, int nops, int mode, int dst_op, long 
     for (int off = 0; off < batch; off += 65535) {
         const int c = batch - off < 65535 ? batch - off : 65535;
         refine_ew_kernel<<<dim3(ew_blocks((long long)N * N), c), 256, 0, s>>>(ptab + (size_t)off * nops, nops, mode, dst_op, dst_off, src_op, src_off, N, resid);
+    }
+    EF_CUDA(cudaGetLastError());
+}
+// Batched device-to-device copies (adaptive re-build: the operators of clean subtrees): blockIdx.y = copy, grid-stride over
+// 16-byte words (every operator slab is a multiple of 16 bytes and 16-byte aligned)
+__global__ void __launch_bounds__(256) copy_many_kernel(const CopyOp* __restrict__ ops)
+{
+    const CopyOp op = ops[blockIdx.y];
+    const size_t n2 = op.n / 2;
+    const double2* s2 = reinterpret_cast<const double2*>(op.src);
+    double2* d2 = reinterpret_cast<double2*>(op.dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) d2[i] = s2[i];
+    if ((op.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) op.dst[op.n - 1] = op.src[op.n - 1];
+}
+void launch_copy_many(const CopyOp* ops, int nops, cudaStream_t s)
+{
+    for (int off = 0; off < nops; off += 65535) {
+        const int c = nops - off < 65535 ? nops - off : 65535;
+        copy_many_kernel<<<dim3(64, c), 256, 0, s>>>(ops + off);
     }
     EF_CUDA(cudaGetLastError());
 }

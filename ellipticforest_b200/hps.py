@@ -257,6 +257,22 @@ class HPSAlgorithm:
         check(self._lib.efgpu_build(self._h, self._flags()), self._h)
         self.isBuilt = True
 
+    def rebuildStage(self, old: "HPSAlgorithm"):
+        """buildStage of a CHANGED mesh that re-uses `old`'s operators for every unchanged subtree (efgpu_rebuild_from): what
+        paper.md:44 describes and the reference leaves as a TODO (isBuilt, HPSAlgorithm.hpp:50-55).  Returns (merges copied,
+        merges computed); the result is bit-identical to buildStage()."""
+        s = self.patch_solver
+        if s.solver_type == "FISHPACK90":
+            check(self._lib.efgpu_set_leaf_constant(self._h, float(s.lambda_function(np.float64(0.0), np.float64(0.0)))), self._h)
+        elif self.resample_coefficients or not self._coefficients_set:
+            self._set_variable_coefficients()
+            self._coefficients_set = True
+        check(self._lib.efgpu_set_refine_inverse(self._h, -1 if self.refine_inverse is None else int(bool(self.refine_inverse))), self._h)
+        reused, rebuilt = C.c_double(), C.c_double()
+        check(self._lib.efgpu_rebuild_from(self._h, old._h, self._flags(), C.byref(reused), C.byref(rebuilt)), self._h)
+        self.isBuilt = True
+        return int(reused.value), int(rebuilt.value)
+
     def _set_variable_coefficients(self):
         """Sample alpha, beta, lambda where FiniteVolumeSolver.cpp:63-79 samples them (sample_leaf_coefficients) and hand the
         six leaf-major arrays to the library."""

@@ -189,6 +189,14 @@ int efgpu_set_leaf_variable_device(efgpu_handle* h, const double* alpha_dev, con
 /* ---- stages ------------------------------------------------------------------------------------ */
 /* buildStage (HPSAlgorithm.hpp:120-161): leaf buildD2N + every merge4to1. */
 int efgpu_build(efgpu_handle* h, unsigned flags);
+/* Adaptive re-build (the capability paper.md:44 advertises and the reference leaves unimplemented:
+ * isBuilt is never read, src/HPSAlgorithm.hpp:50-55).  `h` is a fresh handle of the CHANGED mesh (efgpu_create + leaf model), `old` a
+ * built handle of the previous mesh on the same device (it stays valid).  Nodes of the new tree whose whole subtree is unchanged
+ * (same boxes bit for bit, same structure) take their X^-1, S, H and DtN map from `old` by device-to-device copies; only the
+ * other merges - the ancestor chains of what was refined or coarsened - are computed.  Result bit-identical to efgpu_build(h).
+ * reused / rebuilt (may be NULL): number of merges copied / computed; efgpu_get_stats(h).merge_flops_issued counts the computed
+ * ones only.  Plain handles only (no partition, no external leaves, no EFGPU_LEAN_T); same leaf model and flags as the old build. */
+int efgpu_rebuild_from(efgpu_handle* h, efgpu_handle* old, unsigned flags, double* reused_merges, double* rebuilt_merges);
 /* upwardsStage (HPSAlgorithm.hpp:178-272): f_leaves = vectorF of every leaf (n_leaves*nx*ny), scaled by fscale. */
 int efgpu_upwards(efgpu_handle* h, const double* f_leaves, double fscale, unsigned flags);
 int efgpu_upwards_device(efgpu_handle* h, const double* f_leaves_dev, double fscale, unsigned flags, int sync);

@@ -22,3 +22,35 @@ def test_single_patch_tree(nx, problem):
     for nm in ("h", "g", "u"):
         assert relerr(hps.vector(0, nm), getattr(nd, nm)) < TOL, nm
     assert hps.stats()["merge_flops_issued"] == 0.0
+
+
+def test_blocked_tensor_core_base_case_against_register_kernel():
+    """efgpu_set_tuning(7, ...): the 128 x 128 base case of the block inversion as a blocked Gauss-Jordan on the FP64 tensor pipe
+    (default) against the per-pivot register kernel of round 1: same operators up to rounding, both within 1e-10 of the oracle
+    (uniform level-4 tree of 16x16 patches: base cases of 64 and 128 rows, zipped pairs at the root)."""
+    import ellipticforest_b200 as ef
+    from ellipticforest_b200 import _lib
+    from test_host import _mesh_for
+    kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16, min_level=4, max_level=4,
+              threshold=1.2, refine_box=None)
+    P = O.problem(kw["problem_name"])
+    lib = _lib.load()
+    out = {}
+    for key in (1, 0):
+        assert lib.efgpu_set_tuning(7, key) == 0
+        try:
+            s = ef.FiniteVolumeSolver()
+            s.solver_type = "FISHPACK90"
+            s.lambda_function = P["lam"]
+            hps = ef.HPSAlgorithm(_mesh_for(kw), s)
+            hps.buildStage(); hps.upwardsStage(P["f"])
+            u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+            out[key] = (u, hps.operator(0, "T"), hps.operator(0, "S"), hps.operator(0, "Xinv"), hps.stats())
+        finally:
+            lib.efgpu_set_tuning(7, 0)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    for k in range(4):
+        assert rel(out[0][k], out[1][k]) < 1e-11, k
+    assert abs(out[0][4]["min_pivot"] / out[1][4]["min_pivot"] - 1.0) < 1e-6       # the same pivots, in blocks of eight
+    ora = O.run(**kw)
+    assert rel(out[0][1], ora.nodes[0].T) < 1e-10 and rel(out[0][2], ora.nodes[0].S) < 1e-10
