@@ -54,7 +54,13 @@ struct GemmBlock {
     long long c_off, c0_off;
     int rows, cols;
     int nterms;
-    int pad_;
+    // optional second destination: the (signed) TRANSPOSE of the result block, stored by the same epilogue - element (r, c) of the
+    // block also goes to ptab[ct_op1 - 1] + ct_off + c * ldct + r.  0 = none.  Replaces the separate block-transpose launches of
+    // the symmetric plans (lower blocks of X^-1, mirrored blocks of the DtN map).
+    int ct_op1;
+    int ldct;
+    unsigned ct_neg;          // 0 or 0x80000000
+    long long ct_off;
     GemmTerm t[GEMM_MAX_TERMS];
 };
 // Peer arenas of a row-partitioned tree (peer.cu): rank r's copy of the shared operator arena is mapped at

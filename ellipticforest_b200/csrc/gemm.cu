@@ -188,6 +188,15 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
     // tile; paired: the four adjacent columns 4 (lane%4) .. + 3 of every 16-column group (slots 0/1 of its two tiles interleaved)
     const int col0 = tn * BN + wn0 + (PAIRED_N ? 4 : 2) * (lane & 3);
     double* Cg = ops[bd.c_op] + bd.c_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc + col0;
+    // second destination: the signed transpose of the block (lanes lane/4 = 0..7 of a fragment write 8 consecutive doubles)
+    double* Ctg = bd.ct_op1 ? ops[bd.ct_op1 - 1] + bd.ct_off + (long long)col0 * bd.ldct + (tm * BM + wm0 + (lane >> 2)) : nullptr;
+    const unsigned ctn = bd.ct_neg;
+    auto store_t = [&](double* p, double v) {
+        v = flip_sign(v, ctn);
+        *p = v;
+        for (int r = 0; r < ps.n; r++)
+            if (r != ps.me) *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + ps.delta[r]) = v;
+    };
     const double* C0g = nullptr;
     if (bd.c0_op >= 0) C0g = ops[bd.c0_op] + bd.c0_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc0 + col0;
 #pragma unroll
@@ -209,6 +218,10 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
                         double2* cp = reinterpret_cast<double2*>(reinterpret_cast<char*>(c) + ps.delta[r]);
                         cp[0] = lo; cp[1] = hi;
                     }
+                if (Ctg) {
+                    double* t = Ctg + (long long)(jg * 16) * bd.ldct + i * 8;
+                    store_t(t, lo.x); store_t(t + bd.ldct, lo.y); store_t(t + 2LL * bd.ldct, hi.x); store_t(t + 3LL * bd.ldct, hi.y);
+                }
             }
         } else {
 #pragma unroll
@@ -222,6 +235,10 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
                 *c = v;
                 for (int r = 0; r < ps.n; r++)
                     if (r != ps.me) *reinterpret_cast<double2*>(reinterpret_cast<char*>(c) + ps.delta[r]) = v;
+                if (Ctg) {
+                    double* t = Ctg + (long long)(j * 8) * bd.ldct + i * 8;
+                    store_t(t, v.x); store_t(t + bd.ldct, v.y);
+                }
             }
         }
     }

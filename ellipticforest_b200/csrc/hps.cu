@@ -303,17 +303,20 @@ struct InvPlanner {
         steps.push_back(st);
     }
     // C (rows x cols) = [C0] +- A (rows x K) B (K x cols); split by rows over the ranks when each slice keeps full 128-row tiles
+    // ct_op >= 0: the result's transpose is stored as well (cols x rows block at ct_off, leading dimension ldct)
     void gemm(int rows, int cols, int K, int c_op, long long c_off, int ldc, int c0_op, long long c0_off, int ldc0,
-              int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb, bool neg) {
+              int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb, bool neg,
+              int ct_op = -1, long long ct_off = 0, int ldct = 0) {
         GemmBlock g{};
         g.c_op = c_op; g.c_off = c_off; g.ldc = ldc; g.c0_op = c0_op; g.c0_off = c0_off; g.ldc0 = ldc0;
         g.rows = rows; g.cols = cols; g.nterms = 1;
+        if (ct_op >= 0) { g.ct_op1 = ct_op + 1; g.ct_off = ct_off; g.ldct = ldct; }
         g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, K, neg ? 0x80000000u : 0u};
         Step st{}; st.kind = 1; st.first = (int)B_().size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
         // A product is split only where the flops saved outweigh the all-gather that follows (tens of microseconds of
         // latency per collective): 2048-row products take ~0.6 ms, 1024-row ones 70 us; the deep, small products of the
         // recursion are recomputed by every rank (6 % of the inversion flops).
-        static const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
+        const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();   // read per plan
         // (peer mode: a split costs two flag barriers of a few microseconds instead of a collective, so smaller products pay)
         const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
         if (nranks > 1 && rows % ((peer ? 64 : 128) * nranks) == 0 && rows >= split_min) {   // slices of whole 128-row (peer mode: 64-row) tiles
@@ -325,11 +328,15 @@ struct InvPlanner {
             g.c_off += skip * g.ldc;
             if (g.c0_op >= 0) g.c0_off += skip * g.ldc0;
             g.t[0].a_off += skip * lda;
+            g.ct_off += skip;      // rows [skip, skip + rows / nranks) of the result = those columns of its transpose
             g.rows = rows / nranks;
         }
         steps.push_back(st);
         B_().push_back(g);
     }
+    // whether transposes can ride on the producing GEMM's epilogue: not when row slices are exchanged by a caller-supplied
+    // all-gather (round 1's path), which only knows the primary destination
+    bool fused_transposes() const { return nranks == 1 || peer; }
     void transpose(int rows, int cols, int s_op, long long s_off, int lds, int d_op, long long d_off, int ldd) {
         Step st{}; st.kind = 2; st.first = (int)T_().size(); st.count = 1; st.cls = EFGPU_PROF_TRANSPOSE;
         T_().push_back(TransOp{s_op, d_op, lds, ldd, s_off, d_off, rows, cols, 0u, 0});
@@ -339,7 +346,7 @@ struct InvPlanner {
     // only the upper triangle of a 2 x 2 or 4 x 4 block partition is multiplied (3 of 4 / 10 of 16 sub-blocks, one
     // launch), the lower blocks are transposes.  Row-partitioned products keep the plain form (their slices are gathered).
     void gemm_sym(int h, int K, int c_op, long long c_off, int ldc, int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb) {
-        static const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
+        const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
         const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
         const bool row_split = nranks > 1 && h % ((peer ? 64 : 128) * nranks) == 0 && h >= split_min;
         const int nb = row_split ? 1 : ((h % 64 == 0 && h / 4 >= 128) ? 4 : ((h % 32 == 0 && h / 2 >= 128) ? 2 : 1));
@@ -354,11 +361,15 @@ struct InvPlanner {
                 g.c_op = c_op; g.c_off = cij; g.ldc = ldc; g.c0_op = c_op; g.c0_off = cij; g.ldc0 = ldc;
                 g.rows = sb; g.cols = sb; g.nterms = 1;
                 g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off + (long long)I * sb * lda, b_off + (long long)J * sb, K, 0x80000000u};
+                if (J > I) {   // the mirrored block: by the same epilogue, or (caller-supplied all-gather) by a transpose step
+                    const long long cji = c_off + (long long)J * sb * ldc + (long long)I * sb;
+                    if (fused_transposes()) { g.ct_op1 = c_op + 1; g.ct_off = cji; g.ldct = ldc; }
+                    else { T_().push_back(TransOp{c_op, c_op, ldc, ldc, cij, cji, sb, sb, 0u, 0}); tr.count++; }
+                }
                 B_().push_back(g); st.count++;
-                if (J > I) { T_().push_back(TransOp{c_op, c_op, ldc, ldc, cij, c_off + (long long)J * sb * ldc + (long long)I * sb, sb, sb, 0u, 0}); tr.count++; }
             }
         steps.push_back(st);
-        steps.push_back(tr);
+        if (tr.count) steps.push_back(tr);
     }
     // appends the steps of a sub-plan (descriptor indices rebased)
     void append(const std::vector<Step>& ss, const std::vector<GemmBlock>& bb, const std::vector<TransOp>& tt) {
@@ -417,6 +428,13 @@ struct InvPlanner {
             } else gemm(h, h, h, OP_W1, W1, h, -1, 0, 0, OP_XINV, A, ld, OP_XINV, B, ld, false);
             gemm_sym(h, h, OP_XINV, D, ld, OP_XINV, C, ld, OP_W1, W1, h);                                 // D <- D - C W1   (Schur complement, symmetric)
             invert(D, h, depth + 1, false);                                                               // D <- S^-1
+            if (fused_transposes()) {
+                // B <- -W1 S^-1 and, from the same epilogue, C <- B^T.  The update of the leading block needs no W1^T either:
+                // B W1^T is symmetric (= -W1 S^-1 W1^T), hence equal to its transpose W1 B^T = W1 C.
+                gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true, OP_XINV, C, ld);
+                gemm_sym(h, h, OP_XINV, A, ld, OP_W1, W1, h, OP_XINV, C, ld);                              // A <- A^-1 - W1 C (symmetric)
+                return;
+            }
             gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true);                  // B <- -W1 S^-1
             transpose(h, h, OP_XINV, B, ld, OP_XINV, C, ld);                                              // C <- B^T
             transpose(h, h, OP_W1, W1, h, OP_W2, w2, h);                                                   // W2 = W1^T  (= C A^-1)
@@ -546,8 +564,11 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                     // carry 5 products and 1, 3, 4, 6 carry 4, so halves and quarters of the rows - 2 and 4 ranks - get 18 and 9 each)
                     if (!(dl < 4 || (dl == 4 && ((P < 4) != ((P & 1) != 0))))) {
                         const unsigned neg = ((P ^ Q) & 2) ? 0x80000000u : 0u;   // W, W, E, E, S, S, N, N: d = -1 where bit 1 is clear
-                        b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
-                                                  (long long)(P * n) * (8 * n) + Q * n, n, n, neg, 0});
+                        // unpartitioned: written by the epilogue of the product that computes (Q, P) (below); partitioned: a
+                        // transpose step after the row slices have been gathered
+                        if (nranks > 1)
+                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
+                                                      (long long)(P * n) * (8 * n) + Q * n, n, n, neg, 0});
                         continue;
                     }
                 }
@@ -568,8 +589,18 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                             g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n + I * sb) * N + h_iface[c][k] * n,
                                               (long long)(k * n) * (8 * n) + Q * n + J * sb, n, 0u};
                         }
+                        // mirrored partner written by the same epilogue (unpartitioned trees): the signed transpose block (Q, P) of an
+                        // off-diagonal block of the symmetric plan, the lower sub-block of a diagonal block's triangle
+                        if (sym && mirror_ok && nranks == 1) {
+                            if (P != Q) {
+                                g.ct_op1 = OP_T + 1; g.ct_off = (long long)(Q * n) * (8 * n) + P * n; g.ldct = 8 * n;
+                                g.ct_neg = ((P ^ Q) & 2) ? 0x80000000u : 0u;
+                            } else if (J > I) {
+                                g.ct_op1 = OP_T + 1; g.ct_off = (long long)(P * n + J * sb) * (8 * n) + Q * n + I * sb; g.ldct = 8 * n;
+                            }
+                        }
                         if (clip_rows(g, (long long)P * n + I * sb, t_lo, t_hi)) b.blocks.push_back(g);
-                        if (J > I)
+                        if (J > I && nranks > 1)
                             b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(P * n + I * sb) * (8 * n) + Q * n + J * sb,
                                                       (long long)(P * n + J * sb) * (8 * n) + Q * n + I * sb, sb, sb, 0u, 0});
                     }
@@ -1625,10 +1656,16 @@ int efgpu_set_allgather(efgpu_handle* H, efgpu_allgather_fn fn, void* user)
 int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric, int64_t* steps, int* n_steps,
                            int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws)
 {
+    return efgpu_debug_merge_plan_ex(n, level, rank, nranks, symmetric, 0, steps, n_steps, blocks, terms, n_blocks, trans, n_trans, ws);
+}
+
+int efgpu_debug_merge_plan_ex(int n, int level, int rank, int nranks, int symmetric, int peer, int64_t* steps, int* n_steps,
+                              int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws)
+{
     if (n < 8 || n % 8 || nranks < 1 || rank < 0 || rank >= nranks || !n_steps || !n_blocks || !n_trans) return EF_ERR_BAD_ARG;
     try {
         BatchH b; b.n = n; b.level = level; b.count = 1; b.symcand = symmetric != 0;
-        plan_batch_gemms(b, rank, nranks);
+        plan_batch_gemms(b, rank, nranks, peer != 0);
         const std::vector<Step>& st = symmetric ? b.steps_sym : b.steps;
         *n_steps = (int)st.size(); *n_blocks = (int)b.blocks.size(); *n_trans = (int)b.trans.size();
         if (ws) { ws[0] = (int64_t)b.w2_off; ws[1] = (int64_t)(b.w3_off - b.w2_off); ws[2] = (int64_t)(b.ws_per_entry - b.w3_off); }
@@ -1640,6 +1677,7 @@ int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric
         if (blocks && terms) for (size_t i = 0; i < b.blocks.size(); i++) {
             int64_t* r = blocks + 16 * i; const GemmBlock& g = b.blocks[i];
             r[0] = g.c_op; r[1] = g.c0_op; r[2] = g.ldc; r[3] = g.ldc0; r[4] = g.c_off; r[5] = g.c0_off; r[6] = g.rows; r[7] = g.cols; r[8] = g.nterms;
+            r[9] = g.ct_op1; r[10] = g.ldct; r[11] = g.ct_off; r[12] = g.ct_neg ? 1 : 0;
             for (int t = 0; t < 2; t++) {
                 int64_t* q = terms + 16 * i + 8 * t; const GemmTerm& m = g.t[t];
                 q[0] = m.a_op; q[1] = m.b_op; q[2] = m.lda; q[3] = m.ldb; q[4] = m.a_off; q[5] = m.b_off; q[6] = m.K; q[7] = m.neg ? 1 : 0;

@@ -273,13 +273,19 @@ void efgpu_mesh_destroy(efgpu_mesh* m);
  * Serialises the step list the build would run for a merge with child side n on tree level `level`, as seen by rank
  * `rank` of `nranks` (row partition), general (symmetric = 0) or symmetric plan.  Every record is 16 int64:
  *   steps : kind, first, count, off, N, cls, gk, g_op, g_rows, g_cols, g_ld, g_off
- *   blocks: c_op, c0_op, ldc, ldc0, c_off, c0_off, rows, cols, nterms   then per term (2 records of 8 int64 follow
+ *   blocks: c_op, c0_op, ldc, ldc0, c_off, c0_off, rows, cols, nterms, ct_op + 1 (0: none), ldct, ct_off, ct_neg (the result's signed
+ *           transpose is stored there as well)   then per term (2 records of 8 int64 follow
  *           in `terms`): a_op, b_op, lda, ldb, a_off, b_off, K, neg
  *   trans : src_op, dst_op, lds, ldd, src_off, dst_off, rows, cols, neg
  * ws[3] receives the per-entry workspace sizes (doubles) of W1, W2 and W3.  Returns the counts through n_*; arrays may
  * be NULL to query the counts only. */
 int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric, int64_t* steps, int* n_steps,
                            int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws);
+
+/* the same for the plan of a peer-mapped tree (peer != 0: split products of the inversion have gk = 3 and keep their destination;
+ * their row slices, those of S and of the DtN maps below the root are stored into every rank's arena by the producing GEMM) */
+int efgpu_debug_merge_plan_ex(int n, int level, int rank, int nranks, int symmetric, int peer, int64_t* steps, int* n_steps,
+                              int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws);
 
 /* Process-wide kernel-selection knobs for measurements (A/B runs of the bandwidth-bound kernels): key 0 = matvec kernels
  * for rows of <= 256 doubles (2, default: row-batch kernels; 0: one row per warp, as for longer rows); key 1 = long-row

@@ -11,7 +11,7 @@ from ellipticforest_b200 import _lib
 import hps_oracle as O
 
 OP_TC0, OP_XINV, OP_S, OP_T, OP_W1, OP_W2, OP_W3 = 0, 4, 5, 6, 7, 8, 9
-CLS_GEMM_T, CLS_MIRROR_T = 6, 14
+CLS_GEMM_S, CLS_GEMM_T, CLS_MIRROR_T = 5, 6, 14
 
 
 @pytest.fixture
@@ -23,18 +23,18 @@ def whole_diagonal_blocks():
     assert lib.efgpu_set_tuning(5, 1) == 0
 
 
-def get_plan(n, level, rank, nranks, sym):
+def get_plan(n, level, rank, nranks, sym, peer=0):
     lib = _lib.load()
     ns, nb, nt = C.c_int(), C.c_int(), C.c_int()
     ws = np.zeros(3, dtype=np.int64)
     args = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-    assert lib.efgpu_debug_merge_plan(n, level, rank, nranks, sym, None, C.byref(ns), None, None, C.byref(nb), None, C.byref(nt), args(ws)) == 0
+    assert lib.efgpu_debug_merge_plan_ex(n, level, rank, nranks, sym, peer, None, C.byref(ns), None, None, C.byref(nb), None, C.byref(nt), args(ws)) == 0
     steps = np.zeros((ns.value, 16), dtype=np.int64)
     blocks = np.zeros((nb.value, 16), dtype=np.int64)
     terms = np.zeros((nb.value, 2, 8), dtype=np.int64)
     trans = np.zeros((max(nt.value, 1), 16), dtype=np.int64)
-    assert lib.efgpu_debug_merge_plan(n, level, rank, nranks, sym, args(steps), C.byref(ns), args(blocks), args(terms), C.byref(nb),
-                                      args(trans), C.byref(nt), args(ws)) == 0
+    assert lib.efgpu_debug_merge_plan_ex(n, level, rank, nranks, sym, peer, args(steps), C.byref(ns), args(blocks), args(terms), C.byref(nb),
+                                         args(trans), C.byref(nt), args(ws)) == 0
     return steps, blocks, terms, trans[:nt.value], ws
 
 
@@ -52,7 +52,8 @@ class RankState:
         for k, op in enumerate((OP_W1, OP_W2, OP_W3)):
             self.ops[op] = np.full(int(ws[k]) + 1, np.nan)
 
-    def gemm(self, blk, trm):
+    def gemm(self, blk, trm, targets=None):
+        """targets: the states that receive the result (peer mode: the epilogue stores into every rank's arena); default: this one"""
         c_op, c0_op, ldc, ldc0, c_off, c0_off, rows, cols, nterms = (int(v) for v in blk[:9])
         acc = np.zeros((rows, cols))
         if c0_op >= 0:
@@ -61,9 +62,13 @@ class RankState:
             a_op, b_op, lda, ldb, a_off, b_off, K, neg = (int(v) for v in trm[t])
             p = view(self.ops[a_op], a_off, lda, rows, K) @ view(self.ops[b_op], b_off, ldb, K, cols)
             acc += -p if neg else p
-        view(self.ops[c_op], c_off, ldc, rows, cols)[...] = acc
+        ct_op1, ldct, ct_off, ct_neg = (int(v) for v in blk[9:13])
+        for st in (targets if targets is not None else [self]):
+            view(st.ops[c_op], c_off, ldc, rows, cols)[...] = acc
+            if ct_op1:               # second destination: the signed transpose of the block, from the same epilogue
+                view(st.ops[ct_op1 - 1], ct_off, ldct, cols, rows)[...] = (-acc if ct_neg else acc).T
 
-    def run_step(self, st, blocks, terms, trans, n):
+    def run_step(self, st, blocks, terms, trans, n, targets=None):
         kind, first, count, off, N = (int(v) for v in st[:5])
         if kind == 0:
             for o in [off] + ([int(st[12])] if int(st[12]) >= 0 else []):    # a launch may invert two independent blocks
@@ -72,7 +77,7 @@ class RankState:
         elif kind == 1:
             results = []   # one launch: every block reads the state before the launch
             for k in range(first, first + count):
-                self.gemm(blocks[k], terms[k])
+                self.gemm(blocks[k], terms[k], targets)
         else:
             for k in range(first, first + count):
                 s_op, d_op, lds, ldd, s_off, d_off, rows, cols, neg = (int(v) for v in trans[k][:9])
@@ -88,17 +93,28 @@ def allgather(states, op, off, doubles):
         s.ops[op][off: off + doubles] = full
 
 
-def emulate(n, level, nranks, sym, Tc, X):
-    plans = [get_plan(n, level, r, nranks, sym) for r in range(nranks)]
+def emulate(n, level, nranks, sym, Tc, X, peer=0):
+    """peer = 1: the plan of a peer-mapped tree - the GEMMs of split products (gk 3), of S and of the DtN maps below the root
+    store their results (and transposed second destinations) into EVERY rank's state, nothing is gathered afterwards."""
+    plans = [get_plan(n, level, r, nranks, sym, peer) for r in range(nranks)]
     states = [RankState(n, Tc, X, plans[r][4]) for r in range(nranks)]
     nsteps = len(plans[0][0])
     assert all(len(p[0]) == nsteps for p in plans)
 
     def run(i):
+        st = plans[0][0][i]
+        scatter = peer and nranks > 1 and int(st[0]) == 1 and (int(st[6]) == 3 or int(st[5]) == CLS_GEMM_S or (int(st[5]) == CLS_GEMM_T and level > 0))
+        if scatter:      # all ranks read the state before the launch (flag barrier), then store into every arena
+            frozen = [RankState.__new__(RankState) for _ in range(nranks)]
+            for r in range(nranks):
+                frozen[r].ops = {k: v.copy() for k, v in states[r].ops.items()}
+            for r in range(nranks):
+                steps, blocks, terms, trans, _ = plans[r]
+                frozen[r].run_step(steps[i], blocks, terms, trans, n, targets=states)
+            return
         for r in range(nranks):
             steps, blocks, terms, trans, _ = plans[r]
             states[r].run_step(steps[i], blocks, terms, trans, n)
-        st = plans[0][0][i]
         gk, g_op, g_rows, g_cols, g_ld, g_off = (int(v) for v in st[6:12])
         if gk == 1:
             allgather(states, g_op, g_off, g_rows * g_cols)
@@ -111,12 +127,12 @@ def emulate(n, level, nranks, sym, Tc, X):
     for i in range(nsteps):          # phase 0: everything but T
         if cls[i] not in (CLS_GEMM_T, CLS_MIRROR_T):
             run(i)
-    if nranks > 1:
+    if nranks > 1 and not peer:
         allgather(states, OP_S, 0, 32 * n * n)
     for i in range(nsteps):          # phase 1
         if cls[i] == CLS_GEMM_T:
             run(i)
-    if nranks > 1:   # level 0: efgpu_complete_root_dtn (the root's map is gathered and mirrored only on demand)
+    if nranks > 1 and (not peer or level == 0):   # level 0: efgpu_complete_root_dtn (the root's map is gathered and mirrored only on demand)
         allgather(states, OP_T, 0, 64 * n * n)
     for i in range(nsteps):
         if cls[i] == CLS_MIRROR_T:
@@ -213,7 +229,13 @@ def test_symmetric_diagonal_blocks_of_T(nranks):
     assert lib.efgpu_set_tuning(5, 1) == 0
     try:
         split = get_plan(n, 1, 0, nranks, 1)
-        assert len(split[3]) == len(base[3]) + 8             # one mirrored sub-block per diagonal block
+        # one mirrored sub-block per diagonal block: a transpose step on a partitioned tree, a second (transposed) destination
+        # of the producing block otherwise
+        fused = lambda plan: int(np.sum(plan[1][:, 9] != 0))
+        if nranks > 1:
+            assert len(split[3]) == len(base[3]) + 8
+        else:
+            assert len(split[3]) == len(base[3]) == 0 and fused(split) == fused(base) + 8
         for level in ((0, 1) if nranks > 1 else (0,)):
             states, flops = emulate(n, level, nranks, 1, Tc, root.X)
             for s in states:
@@ -262,16 +284,19 @@ def test_general_plan_on_nonsymmetric_children():
 def test_symmetric_plan_flop_count_and_balance(whole_diagonal_blocks):
     n = 256
     steps, blocks, terms, trans, ws = get_plan(n, 1, 0, 1, 1)
-    assert len(trans) >= 28
-    mirror = [t for t in trans if int(t[0]) == OP_T]
-    assert len(mirror) == 28
-    # every off-diagonal block of T is either computed or mirrored, never both
+    assert len(trans) == 0          # unpartitioned: no transpose launches at all, the mirrored blocks ride on the epilogues
+    # every off-diagonal block of T is either computed or mirrored (second, transposed destination of its partner), never both
     tsteps = [st for st in steps if int(st[5]) == CLS_GEMM_T]
-    computed = set()
+    computed, mirrored = set(), set()
     for st in tsteps:
         for k in range(int(st[1]), int(st[1]) + int(st[2])):
             off = int(blocks[k][4]); computed.add((off // (8 * n) // n, off % (8 * n) // n))
-    mirrored = {(int(t[5]) // (8 * n) // n, int(t[5]) % (8 * n) // n) for t in mirror}
+            if int(blocks[k][9]):
+                assert int(blocks[k][9]) - 1 == OP_T
+                toff = int(blocks[k][11]); mirrored.add((toff // (8 * n) // n, toff % (8 * n) // n))
+    assert len(mirrored) == 28
+    steps2, blocks2, terms2, trans2, ws2 = get_plan(n, 1, 0, 2, 1)      # a partitioned tree keeps the 28 transposes
+    assert len([t for t in trans2 if int(t[0]) == OP_T]) == 28
     assert len(computed) == 36 and not (computed & mirrored) and len(computed | mirrored) == 64
     for (p, q) in mirrored:
         assert (q, p) in computed
@@ -294,3 +319,24 @@ def test_T_products_are_balanced_over_the_ranks(nranks, whole_diagonal_blocks):
                     f += sum(2 * int(blocks[k][6]) * int(blocks[k][7]) * int(terms[k][t][6]) for t in range(int(blocks[k][8])))
         per_rank.append(f / n ** 3)
     assert per_rank == [144.0 / nranks] * nranks, per_rank
+
+
+@pytest.mark.parametrize("nranks,n", [(2, 256), (4, 256), (8, 512)])
+@pytest.mark.parametrize("level", [0, 1])
+def test_peer_plan_reproduces_oracle_merge(nranks, n, level, monkeypatch):
+    """The plan of a peer-mapped tree (efgpu_peer_export): products of the inversion split down to 64-row slices per rank (here
+    forced with EFGPU_SPLIT_MIN_ROWS), stored into every rank's arena together with their fused transposes; 8 ranks: one block
+    row of T per rank with the opposite pairs shared half and half.  Every rank must end with the oracle's X^-1, S and T."""
+    depth = {256: 4, 512: 5}[n]
+    if depth not in _CHILDREN:
+        _CHILDREN[depth] = uniform_children(16, depth)
+    Tc, root = _CHILDREN[depth]
+    monkeypatch.setenv("EFGPU_SPLIT_MIN_ROWS", "256")        # read whenever a plan is made
+    states, flops = emulate(n, level, nranks, 1, Tc, root.X, peer=1)
+    split_steps = sum(1 for st in get_plan(n, level, 0, nranks, 1, 1)[0] if int(st[6]) == 3)
+    for s in states:
+        assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(root.X)) < 1e-11
+        assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
+        assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
+    assert split_steps > 0
+    print("peer plan n=%d ranks=%d level=%d: %d split products" % (n, nranks, level, split_steps))
