@@ -598,7 +598,7 @@ def own_arm(a):
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = {"bytes": tr["traffic_bytes_per_launch"], "algorithmic_bytes": tr["algorithmic_bytes_per_launch"],
-                   "launch": tr["launch"], "source": tr["source"]}
+                   "launch": tr["launch"], "source": tr["source"], "captured_at_commit": tr.get("commit")}
         traffic_bytes = tr["traffic_bytes_per_launch"]
     except Exception:
         pass

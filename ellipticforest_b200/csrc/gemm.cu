@@ -583,28 +583,35 @@ invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long 
 //     permuted to {0,2,4,6} / {1,3,5,7} - IS the B-operand layout of the trailing update: no layout change through memory;
 //  4. trailing update: two DMMAs per tile, A operand = -C_I read as 16-byte pairs.
 // No pivoting, like the kernel it replaces (pivoting policy); different rounding (block order), same parity tests.
+__device__ __forceinline__ void inv8x8_pivot(int k, double& p0, double& p1, int r, int q, PivotTrack& pt)
+{
+    const int kq = k >> 1;
+    const double rk0 = __shfl_sync(0xffffffffu, p0, 4 * k + q), rk1 = __shfl_sync(0xffffffffu, p1, 4 * k + q);    // row k at my columns
+    const double mine = (k & 1) ? p1 : p0;
+    const double ck = __shfl_sync(0xffffffffu, mine, 4 * r + kq);                                                  // A[r][k]
+    const double piv = __shfl_sync(0xffffffffu, mine, 4 * k + kq);                                                 // A[k][k]
+    const double pinv = 1.0 / piv;
+    pt.see(piv);
+    if (r == k) {
+        p0 = (2 * q == k) ? pinv : rk0 * pinv;
+        p1 = (2 * q + 1 == k) ? pinv : rk1 * pinv;
+    } else {
+        const double f = ck * pinv;
+        p0 = (2 * q == k) ? -f : fma(-f, rk0, p0);
+        p1 = (2 * q + 1 == k) ? -f : fma(-f, rk1, p1);
+    }
+}
 __device__ __forceinline__ void inv8x8_warp(double& p0, double& p1, int r, int q, PivotTrack& pt)
 {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int kq = k >> 1;
-        const double rk0 = __shfl_sync(0xffffffffu, p0, 4 * k + q), rk1 = __shfl_sync(0xffffffffu, p1, 4 * k + q);    // row k at my columns
-        const double mine = (k & 1) ? p1 : p0;
-        const double ck = __shfl_sync(0xffffffffu, mine, 4 * r + kq);                                                  // A[r][k]
-        const double piv = __shfl_sync(0xffffffffu, mine, 4 * k + kq);                                                 // A[k][k]
-        const double pinv = 1.0 / piv;
-        pt.see(piv);
-        if (r == k) {
-            p0 = (2 * q == k) ? pinv : rk0 * pinv;
-            p1 = (2 * q + 1 == k) ? pinv : rk1 * pinv;
-        } else {
-            const double f = ck * pinv;
-            p0 = (2 * q == k) ? -f : fma(-f, rk0, p0);
-            p1 = (2 * q + 1 == k) ? -f : fma(-f, rk1, p1);
-        }
-    }
+    for (int k = 0; k < 8; k++) inv8x8_pivot(k, p0, p1, r, q, pt);
 }
 
+// LA (look-ahead, default): the inverse of the NEXT pivot block is taken off the critical path.  The owner of tile (kb+1, kb+1)
+// publishes it with the panels of step kb; every warp forms its updated value itself (four DMMAs) and interleaves the eight
+// pivots of its 8 x 8 inverse with the eight tile rows of the trailing update, so that the dependent shuffle / reciprocal chain
+// runs in the shadow of the tensor-pipe work and step kb+1 starts with P^-1 already in registers.
+template <bool LA>
 __global__ void __launch_bounds__(256, 1)
 invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, double* __restrict__ min_pivot)
 {
@@ -614,6 +621,7 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
     __shared__ __align__(16) double sR[2][8 * LR];
     __shared__ __align__(16) double sC[2][128 * LC];
     __shared__ __align__(16) double sPi[8][8 * LP];
+    __shared__ __align__(16) double sD[2][8 * LP];      // LA: the next pivot block before this step's update
     const int nmat = off2 >= 0 ? 2 : 1;
     double* G = ptab[(long long)(blockIdx.x / nmat) * nops + op] + ((blockIdx.x % nmat) ? off2 : off);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -629,6 +637,7 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
         }
     PivotTrack pt;
     double* spi = sPi[w];
+    double p0 = 0.0, p1 = 0.0;         // P^-1 of the current block step (LA: computed during the previous step)
     // (the inner eight block steps are unrolled so that the accumulator tile picked by kb is a compile-time register index:
     // a run-time subscript would push the whole matrix into local memory)
     for (int kbh = 0; kbh < 2; kbh++)
@@ -657,11 +666,23 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
                         *reinterpret_cast<double2*>(sc + (8 * (8 * wr + i) + r) * LC + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
                 }
         }
+        if (LA && kb < 15) {     // the owner of tile (kb+1, kb+1) publishes it
+            const int t = kb + 1;
+            if (wr == (t >> 3) && wc == (t >> 2)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (i == ((kbl + 1) & 7) && j == ((kbl + 1) & 3))
+                            *reinterpret_cast<double2*>(sD[buf] + r * LP + 2 * q) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        }
         __syncthreads();
-        // 2. P^-1, by every warp on its own lanes
-        double p0, p1;
-        { const double2 v = *reinterpret_cast<const double2*>(sr + r * LR + 8 * kb + 2 * q); p0 = v.x; p1 = v.y; }
-        inv8x8_warp(p0, p1, r, q, pt);
+        // 2. P^-1, by every warp on its own lanes (LA: only at the first step, afterwards it is already there)
+        if (!LA || kb == 0) {
+            const double2 v = *reinterpret_cast<const double2*>(sr + r * LR + 8 * kb + 2 * q); p0 = v.x; p1 = v.y;
+            inv8x8_warp(p0, p1, r, q, pt);
+        }
         *reinterpret_cast<double2*>(spi + r * LP + 2 * q) = make_double2(p0, p1);
         __syncwarp();
         // fragments of P^-1: as A operand (rows r, k' = q, q + 4) and, transposed, as B operand of step 3 (B[k'][n] = Pinv[n][k'])
@@ -679,9 +700,25 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
             dmma884(x0, x1, ra1, pa1);
             xt[j][0] = x0; xt[j][1] = x1;
         }
-        // 4. trailing update and the special tile row / column
+        // LA: the next pivot block after this step's update, P' = D - C_t (P^-1 R_t), t = kb + 1
+        double pn0 = 0.0, pn1 = 0.0;
+        const bool la = LA && kb < 15;
+        if (la) {
+            const int t = kb + 1;
+            const double ra0 = sr[q * LR + 8 * t + r], ra1 = sr[(q + 4) * LR + 8 * t + r];
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, ra0, pa0);
+            dmma884(x0, x1, ra1, pa1);
+            const double2 cv = *reinterpret_cast<const double2*>(sc + (8 * t + r) * LC + 2 * q);
+            const double2 dv = *reinterpret_cast<const double2*>(sD[buf] + r * LP + 2 * q);
+            pn0 = dv.x; pn1 = dv.y;
+            dmma884(pn0, pn1, -cv.x, x0);
+            dmma884(pn0, pn1, -cv.y, x1);
+        }
+        // 4. trailing update and the special tile row / column (LA: one pivot of the next inverse per tile row)
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+            if (la) inv8x8_pivot(i, pn0, pn1, r, q, pt);
             const int ti = 8 * wr + i;
             const double2 cv = *reinterpret_cast<const double2*>(sc + (8 * ti + r) * LC + 2 * q);   // C[8 ti + r][2 q], [2 q + 1]
             const double a0 = -cv.x, a1 = -cv.y;
@@ -712,6 +749,7 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
                 }
             }
         }
+        if (la) { p0 = pn0; p1 = pn1; }
         __syncwarp();      // spi is rewritten in the next step
     }
 #pragma unroll
@@ -735,8 +773,11 @@ void launch_invert_small(double* const* ptab, int nops, int op, long long off, l
         case 128:
             // default: blocked Gauss-Jordan on the tensor pipe; efgpu_set_tuning(7, 1): the per-pivot register kernel of round 1.
             // Needs 16-byte aligned rows (even ld and offsets: always true for the merge matrices, whose blocks are multiples of 8)
+            // (7, 2): the blocked kernel without the look-ahead of the next pivot block
             if (get_tuning(7) == 0 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
-                invert_blk128_kernel<<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
+                invert_blk128_kernel<true><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
+            else if (get_tuning(7) == 2 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
+                invert_blk128_kernel<false><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
             else invert_reg_kernel<8><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
             EF_CUDA(cudaGetLastError()); return;
         default: break;
