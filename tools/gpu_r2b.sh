@@ -33,3 +33,15 @@ if [ -n "$SPLITS" ]; then   # A/B of the row-split threshold of the inversion's 
     [ -s $F.json ] && python -c "import json; d=json.loads(open('$F.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['kernel_ms_per_step'])"
   done; done
 fi
+if [ -n "$ADAPT" ]; then   # sharded adaptive / variable-coefficient workloads (BASELINE configs[0], configs[3])
+  for N in $NS; do
+    F=$OUT/bench_${TAG}_n${N}_c0
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 5 --warmup 3 --adaptive 2 7 > $F.json 2> $F.err
+    echo "bench N=$N adaptive 2-7 exit $?"; tail -3 $F.err
+    [ -s $F.json ] && python -c "import json; d=json.loads(open('$F.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['linf_error_vs_exact'], d['stages'], d['config']['sharding'][:120])"
+    F=$OUT/bench_${TAG}_n${N}_c3
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus $N --steps 5 --warmup 3 --adaptive 4 9 --threshold 1.6 --problem varcoef > $F.json 2> $F.err
+    echo "bench N=$N adaptive 4-9 varcoef exit $?"; tail -3 $F.err
+    [ -s $F.json ] && python -c "import json; d=json.loads(open('$F.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['linf_error_vs_exact'], d['stages'], d['kernel_ms_per_step'])"
+  done
+fi
