@@ -321,8 +321,7 @@ def test_T_products_are_balanced_over_the_ranks(nranks, whole_diagonal_blocks):
     assert per_rank == [144.0 / nranks] * nranks, per_rank
 
 
-@pytest.mark.parametrize("nranks,n", [(2, 256), (4, 256), (8, 512)])
-@pytest.mark.parametrize("level", [0, 1])
+@pytest.mark.parametrize("nranks,n,level", [(2, 256, 0), (4, 256, 1), (8, 256, 0), (8, 256, 1)])
 def test_peer_plan_reproduces_oracle_merge(nranks, n, level, monkeypatch):
     """The plan of a peer-mapped tree (efgpu_peer_export): products of the inversion split down to 64-row slices per rank (here
     forced with EFGPU_SPLIT_MIN_ROWS), stored into every rank's arena together with their fused transposes; 8 ranks: one block
