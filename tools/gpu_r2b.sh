@@ -6,7 +6,7 @@ TAG=${1:-r2b}; NS=${2:-"2"}; EXTRA=$3
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L > $OUT/smi_$TAG.txt; nvidia-smi topo -m >> $OUT/smi_$TAG.txt 2>&1
 if [ -z "$SKIP_TESTS" ]; then
-timeout 900 python -m pytest tests/test_gpu_sharded.py -q -rs > $OUT/pytest_sharded_$TAG.log 2>&1; echo "pytest exit $?"; tail -6 $OUT/pytest_sharded_$TAG.log
+timeout 900 python -m pytest tests/test_gpu_sharded.py -q -rs ${TESTK:+-k "$TESTK"} > $OUT/pytest_sharded_$TAG.log 2>&1; echo "pytest exit $?"; tail -6 $OUT/pytest_sharded_$TAG.log
 fi
 for N in $NS; do
   for P2P in 1 0; do
