@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <exception>
 #include <map>
 #include <mutex>
@@ -54,6 +55,10 @@ public:
     // clock.  > 1: the leaves are sampled in contiguous blocks on this many host threads - only for callbacks that are
     // thread-safe, hence opt-in.  The values and where they are stored do not depend on it.
     int sampling_threads = 1;
+    // Host threads for the binding's own per-leaf copies that call no user code and no MPI (u into every leaf's vectorU): at
+    // 1e7 cells these loops over the reference's containers cost more than the stages on the device (bench.py:
+    // e2e_cpp_binding).  The values written do not depend on it.
+    int copy_threads = 8;
 
     HPSAlgorithmB200(MPI::Communicator comm, Mesh<PatchT>& mesh, FiniteVolumeSolver& solver, int device = 0)
         : Base(comm, mesh, solver), device(device) {}
@@ -93,7 +98,7 @@ public:
         }
         check_(efgpu_build(h_, flags_()), "efgpu_build");
         // mergePatch_ (:1004-1009) and coarsen_ (:736): merged grids and n_coarsens are visible to callers
-        for (size_t i = nodes_.size(); i-- > 0;) {
+        for (size_t i = nodes_.size(); i-- > 0;) {     // (serial: the grid constructor queries the MPI communicator)
             int size = 0, nco = 0, leaf = 0, li = 0;
             efgpu_node_info(h_, (int)i, &size, &nco, &leaf, &li);
             PatchT& p = nodes_[i]->data;
@@ -129,7 +134,7 @@ public:
         for_leaves_([&](size_t l) {
             PatchT& patch = nodes_[leaves_[l]]->data;
             FiniteVolumeGrid& grid = patch.grid();
-            patch.vectorF() = Vector<double>(cells);
+            if ((size_t)patch.vectorF().size() != cells) patch.vectorF() = Vector<double>(cells);
             for (int i = 0; i < nx_; i++) {
                 const double x = grid(0, i);
                 for (int j = 0; j < nx_; j++) {
@@ -265,9 +270,12 @@ private:
 
     // body(l) for every leaf l, serially or in contiguous blocks on `sampling_threads` host threads
     template <class F>
-    void for_leaves_(F&& body) {
-        const size_t n = leaves_.size();
-        const size_t nt = std::min<size_t>((size_t)std::max(1, sampling_threads), n);
+    void for_leaves_(F&& body) { parallel_for_(leaves_.size(), sampling_threads, body); }
+
+    // body(i) for i in [0, n), serially or in contiguous blocks on `threads` host threads
+    template <class F>
+    void parallel_for_(size_t n, int threads, F&& body) {
+        const size_t nt = std::min<size_t>((size_t)std::max(1, threads), n);
         if (nt <= 1) { for (size_t l = 0; l < n; l++) body(l); return; }
         std::vector<std::thread> pool;
         std::exception_ptr err;
@@ -315,11 +323,11 @@ private:
 
     void scatter_solution_() {
         const size_t cells = (size_t)nx_ * nx_;
-        for (size_t l = 0; l < leaves_.size(); l++) {
+        parallel_for_(leaves_.size(), copy_threads, [&](size_t l) {
             Vector<double>& u = nodes_[leaves_[l]]->data.vectorU();
-            u = Vector<double>(cells);
-            for (size_t c = 0; c < cells; c++) u[c] = u_[l * cells + c];
-        }
+            if ((size_t)u.size() != cells) u = Vector<double>(cells);     // repeated solves: the leaf's vector is reused
+            std::memcpy(u.dataPointer(), &u_[l * cells], cells * sizeof(double));
+        });
         if (!copy_back_operators) return;
         for (size_t i = 0; i < nodes_.size(); i++) fetch_vector_((int)i, EFGPU_VEC_G, nodes_[i]->data.vectorG());
     }

@@ -117,11 +117,13 @@ int main(int argc, char** argv) {
         gpu.sampling_threads = threads;
         double t[4] = {0, 0, 0, 0}, emax = 0; long leaves = 0;
         try {
+            gpu.setupStage();          // once, as the reference's drivers do (examples/elliptic-single/main.cpp:190)
+            t[0] = app.timers["setup-stage"].time() * time_only;
             for (int pass = 0; pass <= time_only; pass++) {
-                gpu.setupStage(); gpu.buildStage(); gpu.upwardsStage(rhs);
+                gpu.buildStage(); gpu.upwardsStage(rhs);
                 if (homogeneous) gpu.solveStage(bc_patch); else gpu.solveStage(bc_fn);
                 if (pass == 0) continue;   // warm-up: CUDA context, first-touch of the host vectors
-                t[0] += app.timers["setup-stage"].time(); t[1] += app.timers["build-stage"].time();
+                t[1] += app.timers["build-stage"].time();
                 t[2] += app.timers["upwards-stage"].time(); t[3] += app.timers["solve-stage"].time();
             }
         } catch (const std::exception& e) {
