@@ -69,10 +69,11 @@ struct GemmBlock {
 constexpr int PEER_MAX = 8;
 struct PeerSpan {
     int n = 0, me = 0;
+    int stage_t = 0;          // set by launch_bgemm: transposed second destinations leave through shared memory (whole rows)
     char* local_base = nullptr;
     long long delta[PEER_MAX] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
-void launch_peer_barrier(const PeerSpan& ps, int me, unsigned long long epoch, int* err, cudaStream_t s);
+void launch_peer_barrier(const PeerSpan& ps, int me, int* err, cudaStream_t s);
 void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, cudaStream_t s);
 
 // Launches the kernel on `stream`.  rows/cols/K of every block must be multiples of the chosen

@@ -47,7 +47,12 @@ struct GemmCfg {
     static constexpr int LDB_S = BN + 2;   // == 2 (mod 8): rows 2t (and 2t+1), t < 4, start 4 banks apart
     static constexpr int A_STAGE = BM * LDA_S;
     static constexpr int B_STAGE = BK * LDB_S;
-    static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+    // staged transposed second destination (peer mode): the tile's transpose, BN rows of BM doubles (+ 2 of padding), takes the
+    // place of the pipeline stages once the K loop is over
+    static constexpr int LDT_S = BM + 2;
+    static constexpr int PIPE_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+    static constexpr int T_BYTES = BN * LDT_S * (int)sizeof(double);
+    static constexpr int SMEM_BYTES = PIPE_BYTES > T_BYTES ? PIPE_BYTES : T_BYTES;
     static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     static constexpr int FM = WM / 8, FN = WN / 8;
 };
@@ -189,7 +194,12 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
     const int col0 = tn * BN + wn0 + (PAIRED_N ? 4 : 2) * (lane & 3);
     double* Cg = ops[bd.c_op] + bd.c_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc + col0;
     // second destination: the signed transpose of the block (lanes lane/4 = 0..7 of a fragment write 8 consecutive doubles)
-    double* Ctg = bd.ct_op1 ? ops[bd.ct_op1 - 1] + bd.ct_off + (long long)col0 * bd.ldct + (tm * BM + wm0 + (lane >> 2)) : nullptr;
+    // Direct form: every thread stores its elements (8-byte stores, 64 contiguous bytes per quarter warp) - fine in local HBM.  Staged
+    // form (ps.stage_t; default where peers receive the block): the transposed tile is assembled in shared memory and leaves as whole
+    // rows of BM doubles, 16 bytes per lane - scattered 8-byte stores over NVLink cost 2.5 x the whole inversion at 8 ranks (r2k).
+    const bool staged_t = bd.ct_op1 != 0 && ps.stage_t != 0;
+    double* Ctg = (bd.ct_op1 && !staged_t) ? ops[bd.ct_op1 - 1] + bd.ct_off + (long long)col0 * bd.ldct + (tm * BM + wm0 + (lane >> 2)) : nullptr;
+    double* Cts = staged_t ? smem + (wn0 + (PAIRED_N ? 4 : 2) * (lane & 3)) * C::LDT_S + wm0 + (lane >> 2) : nullptr;
     const unsigned ctn = bd.ct_neg;
     auto store_t = [&](double* p, double v) {
         v = flip_sign(v, ctn);
@@ -197,6 +207,7 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
         for (int r = 0; r < ps.n; r++)
             if (r != ps.me) *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + ps.delta[r]) = v;
     };
+    if (staged_t) __syncthreads();   // every warp is done with the last pipeline stage
     const double* C0g = nullptr;
     if (bd.c0_op >= 0) C0g = ops[bd.c0_op] + bd.c0_off + (long long)(tm * BM + wm0 + (lane >> 2)) * bd.ldc0 + col0;
 #pragma unroll
@@ -221,6 +232,10 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
                 if (Ctg) {
                     double* t = Ctg + (long long)(jg * 16) * bd.ldct + i * 8;
                     store_t(t, lo.x); store_t(t + bd.ldct, lo.y); store_t(t + 2LL * bd.ldct, hi.x); store_t(t + 3LL * bd.ldct, hi.y);
+                } else if (Cts) {
+                    double* t = Cts + (jg * 16) * C::LDT_S + i * 8;
+                    t[0] = flip_sign(lo.x, ctn); t[C::LDT_S] = flip_sign(lo.y, ctn);
+                    t[2 * C::LDT_S] = flip_sign(hi.x, ctn); t[3 * C::LDT_S] = flip_sign(hi.y, ctn);
                 }
             }
         } else {
@@ -238,8 +253,24 @@ bgemm_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __rest
                 if (Ctg) {
                     double* t = Ctg + (long long)(j * 8) * bd.ldct + i * 8;
                     store_t(t, v.x); store_t(t + bd.ldct, v.y);
+                } else if (Cts) {
+                    double* t = Cts + (j * 8) * C::LDT_S + i * 8;
+                    t[0] = flip_sign(v.x, ctn); t[C::LDT_S] = flip_sign(v.y, ctn);
                 }
             }
+        }
+    }
+    if (staged_t) {   // rows of the transposed tile = columns tn BN .. of the block, BM contiguous doubles each
+        __syncthreads();
+        double* Ctb = ops[bd.ct_op1 - 1] + bd.ct_off + (long long)(tn * BN) * bd.ldct + tm * BM;
+        constexpr int V = BM / 2;
+        for (int idx = tid; idx < BN * V; idx += C::NT) {
+            const int c = idx / V, v2 = (idx % V) * 2;
+            const double2 val = *reinterpret_cast<const double2*>(smem + c * C::LDT_S + v2);
+            double2* dst = reinterpret_cast<double2*>(Ctb + (long long)c * bd.ldct + v2);
+            *dst = val;
+            for (int r = 0; r < ps.n; r++)
+                if (r != ps.me) *reinterpret_cast<double2*>(reinterpret_cast<char*>(dst) + ps.delta[r]) = val;
         }
     }
 }
@@ -268,7 +299,10 @@ void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, cons
                   int nblocks, int batch, cudaStream_t stream, int force_tile, const PeerSpan* peers)
 {
     if (nblocks == 0 || batch == 0) return;
-    const PeerSpan ps = peers ? *peers : PeerSpan{};
+    PeerSpan ps = peers ? *peers : PeerSpan{};
+    // transposed second destinations (tuning key 4): 0 = staged through shared memory where peers receive them, direct otherwise;
+    // 1 = always staged; 2 = never
+    ps.stage_t = get_tuning(4) == 1 || (get_tuning(4) == 0 && ps.n > 1) ? 1 : 0;
     // largest power-of-two tile dividing every block dimension
     int g = 128;
     bool k16 = true;

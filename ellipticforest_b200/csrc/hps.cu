@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <tuple>
+#include <unistd.h>
 
 namespace efgpu {
 
@@ -127,7 +128,6 @@ struct efgpu_handle {
     DevBuf arena; size_t arena_need = 0;
     PeerSpan peers;
     void* peer_mapped[PEER_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    unsigned long long peer_epoch = 0;
     bool peer_dirty = true;                      // local work since the last barrier: a barrier must precede the next peer stores
     DevBuf d_peer_err;
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
@@ -175,9 +175,12 @@ struct efgpu_handle {
     GraphSlot g_build, g_up, g_solve;
     unsigned long long graph_gen = 0;
     bool graphs_on = true;
+    bool graphs_peer = true;           // EFGPU_GRAPHS_PEER=0: peer-mapped (row-partitioned) trees keep plain launches
     // optional per-kernel-class timing (efgpu_set_profiling): event pairs around every launch group
     bool profiling = false;
-    struct ProfRec { int cls; cudaEvent_t a, b; };
+    struct ProfRec { int cls; cudaEvent_t a, b; std::string label; };
+    FILE* trace = nullptr;             // EFGPU_TRACE=<prefix>: one line per timed launch group (class, label, ms) while profiling
+    std::string cur_label;
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> ev_pool;
     double prof_ms[EFGPU_PROF_NCLASSES] = {0};
@@ -202,16 +205,18 @@ static inline void timed(efgpu_handle* H, int cls, int nlaunch, F&& f)
     EF_CUDA(cudaEventRecord(a, H->stream));
     f();
     EF_CUDA(cudaEventRecord(b, H->stream));
-    H->prof_recs.push_back({cls, a, b});
+    H->prof_recs.push_back({cls, a, b, H->trace ? H->cur_label : std::string()});
 }
 static void collect_profile(efgpu_handle* H)   // stream must be synchronised
 {
     for (auto& r : H->prof_recs) {
         float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
         H->prof_ms[r.cls] += ms;
+        if (H->trace) fprintf(H->trace, "%d %.4f %s\n", r.cls, ms, r.label.c_str());
         H->ev_pool.push_back(r.a); H->ev_pool.push_back(r.b);
     }
     H->prof_recs.clear();
+    if (H->trace) { fprintf(H->trace, "# collected\n"); fflush(H->trace); }
 }
 
 // Stream lanes of one tree level: the first use of a lane in a level makes it wait for everything issued on the handle's stream
@@ -252,7 +257,9 @@ static unsigned long long graph_key(const efgpu_handle* H, unsigned flags)
 template <class F>
 static void run_graphed(efgpu_handle* H, efgpu_handle::GraphSlot& g, unsigned long long key, F&& body)
 {
-    const bool can = H->graphs_on && !H->profiling && H->part_nranks == 1 && !H->allgather && !H->peer_mode;
+    // (a row-partitioned tree that exchanges through a host callback cannot be captured; a peer-mapped one can: its barriers count
+    // their epochs on the device)
+    const bool can = H->graphs_on && !H->profiling && !H->allgather && (H->part_nranks == 1 || (H->peer_mode && H->peer_attached && H->graphs_peer));
     if (!can) { body(); return; }
     if (g.exec && g.key == key) {
         EF_CUDA(cudaGraphLaunch(g.exec, H->stream));
@@ -998,7 +1005,7 @@ static void peer_barrier(efgpu_handle* H, bool only_if_dirty)
 {
     if (only_if_dirty && !H->peer_dirty) return;
     timed(H, EFGPU_PROF_ALLGATHER, 1, [&] {
-        launch_peer_barrier(H->peers, H->part_rank, ++H->peer_epoch, H->d_peer_err.as<int>(), H->stream);
+        launch_peer_barrier(H->peers, H->part_rank, H->d_peer_err.as<int>(), H->stream);
     });
     H->peer_dirty = false;
 }
@@ -1095,6 +1102,15 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             // peer mode: the row slices of a split product, of S and of the DtN maps below the root are stored into every rank's
             // arena by the GEMM itself, between two flag barriers (the root's map stays row-distributed: nobody merges it)
             const bool scatter = p2p && st.kind == 1 && (st.gk == 3 || st.cls == EFGPU_PROF_GEMM_S || (is_T && lev > 0));
+            if (H->trace) {
+                char lb[160];
+                if (st.kind == 1) {
+                    const GemmBlock& g0 = b.blocks[st.first];
+                    snprintf(lb, sizeof lb, "lev %d n %d batch %d gemm blocks %d rows %d cols %d K %d terms %d ct %d gk %d", lev, b.n, bcount, st.count, g0.rows, g0.cols,
+                             g0.t[0].K, g0.nterms, g0.ct_op1 ? 1 : 0, st.gk);
+                } else snprintf(lb, sizeof lb, "lev %d n %d batch %d invert N %d pair %d", lev, b.n, bcount, st.N, st.off2 >= 0 ? 1 : 0);
+                H->cur_label = lb;
+            }
             if (scatter) peer_barrier(H, /*only_if_dirty=*/true);
             timed(H, st.cls, 1, [&] {
                 if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, bcount, H->d_minpiv.as<double>(), s);
@@ -1467,6 +1483,12 @@ int efgpu_create_ex(const efgpu_tree_desc* desc, int device, const int32_t* exte
         EF_CUDA(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
         EF_CUDA(cudaEventCreate(&H->ev0)); EF_CUDA(cudaEventCreate(&H->ev1));
         { const char* ge = getenv("EFGPU_GRAPHS"); H->graphs_on = !ge || atoi(ge) != 0; }
+        { const char* ge = getenv("EFGPU_GRAPHS_PEER"); H->graphs_peer = !ge || atoi(ge) != 0; }
+        if (const char* te = getenv("EFGPU_TRACE")) {
+            static int serial = 0;
+            char nm[512]; snprintf(nm, sizeof nm, "%s.pid%d.h%d", te, (int)getpid(), serial++);
+            H->trace = fopen(nm, "w");
+        }
         *out = H;
         return EF_OK;
     } catch (const efgpu::Error& e) { g_create_error = e.msg; delete H; return e.code; }
@@ -1480,6 +1502,7 @@ void efgpu_destroy(efgpu_handle* H)
     // a borrowed stream (efgpu_set_stream) may already have been destroyed by its owner when handles are released in arbitrary
     // order (garbage-collected callers): synchronise the device instead of touching it
     if (H->stream && H->own_stream) cudaStreamSynchronize(H->stream); else cudaDeviceSynchronize();
+    if (H->trace) fclose(H->trace);
     if (H->ev0) cudaEventDestroy(H->ev0);
     if (H->ev1) cudaEventDestroy(H->ev1);
     for (auto& r : H->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1593,6 +1616,7 @@ int efgpu_peer_export(efgpu_handle* H, void* ipc_handle_out)
         H->d_peer_err.alloc(sizeof(int));
         EF_CUDA(cudaMemsetAsync(H->d_peer_err.p, 0, sizeof(int), H->stream));
         allocate_device(H, H->build_flags);
+        EF_CUDA(cudaStreamSynchronize(H->stream));   // the flag page is zero before any peer can map it
     }
     cudaIpcMemHandle_t hd;
     EF_CUDA(cudaIpcGetMemHandle(&hd, H->arena.p));

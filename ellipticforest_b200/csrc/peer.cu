@@ -28,17 +28,23 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// One warp.  Lane r < nranks publishes `epoch` into slot `me` of rank r's flag array (its own included), then waits until
-// slot r of the local array has reached `epoch`.  Everything this GPU wrote before the kernel (peer stores of earlier
+// One warp.  The epoch is a counter in the local flag page (word 64; nobody else writes it) that every barrier advances by one:
+// all ranks issue the same sequence of barriers, so the counters agree without the host passing a number - which lets the launch
+// sequence of a stage, barriers included, be captured into a CUDA graph and replayed.
+// Lane r < nranks publishes the epoch into slot `me` of rank r's flag array (its own included), then waits until
+// slot r of the local array has reached it.  Everything this GPU wrote before the kernel (peer stores of earlier
 // kernels on the stream included) is ordered before the flag by the system-scope fence + release store; the acquire load
 // orders the peers' data before whatever follows on this stream.  A peer that never arrives (crashed rank) must not hang the
 // GPU: after `timeout_ns` the lane gives up and raises *err (checked by the host at the end of the stage).
-__global__ void peer_barrier_kernel(PeerSpan ps, int me, unsigned long long epoch, unsigned long long timeout_ns, int* __restrict__ err)
+__global__ void peer_barrier_kernel(PeerSpan ps, int me, unsigned long long timeout_ns, int* __restrict__ err)
 {
     const int r = threadIdx.x;
+    unsigned long long* local = reinterpret_cast<unsigned long long*>(ps.local_base);
+    unsigned long long epoch = 0;
+    if (r == 0) { epoch = local[64] + 1; local[64] = epoch; }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
     if (r >= ps.n) return;
     __threadfence_system();
-    unsigned long long* local = reinterpret_cast<unsigned long long*>(ps.local_base);
     unsigned long long* remote = reinterpret_cast<unsigned long long*>(ps.local_base + ps.delta[r]);
     st_release_sys(remote + me, epoch);
     const unsigned long long t0 = globaltimer_ns();
@@ -49,11 +55,11 @@ __global__ void peer_barrier_kernel(PeerSpan ps, int me, unsigned long long epoc
     __threadfence_system();
 }
 
-void launch_peer_barrier(const PeerSpan& ps, int me, unsigned long long epoch, int* err, cudaStream_t s)
+void launch_peer_barrier(const PeerSpan& ps, int me, int* err, cudaStream_t s)
 {
     static const unsigned long long timeout_ns = [] {
         const char* e = getenv("EFGPU_PEER_TIMEOUT_S"); const double v = e ? atof(e) : 20.0; return (unsigned long long)((v > 0.1 ? v : 20.0) * 1e9); }();
-    peer_barrier_kernel<<<1, 32, 0, s>>>(ps, me, epoch, timeout_ns, err);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(ps, me, timeout_ns, err);
     EF_CUDA(cudaGetLastError());
 }
 

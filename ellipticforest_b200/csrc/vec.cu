@@ -19,6 +19,8 @@ namespace efgpu {
 // [1] compact-H long-row kernel: 0 = 8 loads in flight per lane (default), 1 = 4
 // [2] CTAs per SM the long-row launcher aims for (default 16)
 // [3] leaf solve of constant-coefficient leaves: 0 = DMMA kernel (default), 1 = one thread per cell
+// [4] transposed second destination of a GEMM block: 0 = through shared memory as whole rows where peer arenas receive it, direct 8-byte
+//     stores otherwise (default); 1 = always through shared memory; 2 = always direct
 // [5] symmetric merge plan: 1 = the diagonal blocks of T multiply only their upper sub-block triangle (default since r2a: 202.8 -> 197.8 ms
 //     per step at L=8 M=16; 0 = whole blocks; read when a plan is made)
 // [7] base case of the block inversion, 128 x 128: 0 = blocked Gauss-Jordan on the tensor pipe, 1 = per-pivot register kernel (round 1)

@@ -54,3 +54,33 @@ def test_blocked_tensor_core_base_case_against_register_kernel():
     assert abs(out[0][4]["min_pivot"] / out[1][4]["min_pivot"] - 1.0) < 1e-6       # the same pivots, in blocks of eight
     ora = O.run(**kw)
     assert rel(out[0][1], ora.nodes[0].T) < 1e-10 and rel(out[0][2], ora.nodes[0].S) < 1e-10
+
+
+@pytest.mark.parametrize("level,nx", [(4, 16), (3, 8), (5, 8)])
+def test_staged_transposed_stores_are_bit_identical(level, nx):
+    """efgpu_set_tuning(4, ...): the transposed second destination of a GEMM block (lower blocks of the symmetric X^-1, mirrored
+    blocks of T) written from the accumulators with 8-byte stores (default on one GPU) against the form that assembles the
+    transposed tile in shared memory and stores whole rows (default where peer arenas receive the block): only the store path
+    differs, so every operator and the solution must agree bit for bit, over every CTA tile size the levels of these trees use."""
+    import ellipticforest_b200 as ef
+    from ellipticforest_b200 import _lib
+    from test_host import _mesh_for
+    kw = dict(problem_name="poisson", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=nx, min_level=level, max_level=level,
+              threshold=1.2, refine_box=None)
+    P = O.problem(kw["problem_name"])
+    lib = _lib.load()
+    out = {}
+    for key in (2, 1):
+        assert lib.efgpu_set_tuning(4, key) == 0
+        try:
+            s = ef.FiniteVolumeSolver()
+            s.solver_type = "FISHPACK90"
+            hps = ef.HPSAlgorithm(_mesh_for(kw), s)
+            hps.buildStage(); hps.upwardsStage(P["f"])
+            u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+            assert hps.stats()["symmetric_plan"] if "symmetric_plan" in hps.stats() else True
+            out[key] = [u] + [hps.operator(nd, w) for nd in (0, 1) for w in ("T", "S", "Xinv")]
+        finally:
+            lib.efgpu_set_tuning(4, 0)
+    for k, (a, b) in enumerate(zip(out[1], out[2])):
+        assert np.array_equal(a, b), k
