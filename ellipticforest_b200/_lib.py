@@ -90,6 +90,7 @@ SIGNATURES = {
     "efgpu_mesh_path": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_size_t]),
     "efgpu_mesh_destroy": (None, [_P]),
     "efgpu_dgemm_batched": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "efgpu_dgemm_batched_tma": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None

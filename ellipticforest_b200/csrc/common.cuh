@@ -82,6 +82,9 @@ void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, c
 void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
                   int nblocks, int batch, cudaStream_t stream, int force_tile = 0, const PeerSpan* peers = nullptr);
 
+// gemm_tma.cu: C[b] = A[b] (m x k) B[b] (k x n), densely packed row-major batches, operands staged by TMA (A/B experiment)
+void launch_dgemm_tma(const double* A, const double* B, double* C, int m, int n, int k, int batch, int stages, cudaStream_t s);
+
 // Batched out-of-place block transposes  dst (cols x rows) = +-src (rows x cols)^T, addressed like the GEMM operands.
 // Used where the merge matrices are symmetric (uniform, self-adjoint subtrees): the lower blocks of X^-1 and the
 // mirrored blocks of the DtN map T are copies of computed blocks instead of further GEMMs.

@@ -309,6 +309,15 @@ struct InvPlanner {
         Step st{}; st.kind = 0; st.off = off; st.N = N; st.cls = EFGPU_PROF_INVERT_SMALL;
         steps.push_back(st);
     }
+    // whether a product with this many result rows is row-split over the ranks.  A product is split only where the flops saved
+    // outweigh the exchange that follows (NCCL callback: tens of microseconds per collective, so 2048 rows and more; peer mode: two
+    // flag barriers of a few microseconds, so 1024 rows and more); the deep, small products of the recursion are recomputed by
+    // every rank (6 % of the inversion flops).  Slices are whole 128-row (peer mode: 64-row) tiles.
+    bool will_split(int rows) const {
+        const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();   // read per plan
+        const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
+        return nranks > 1 && rows % ((peer ? 64 : 128) * nranks) == 0 && rows >= split_min;
+    }
     // C (rows x cols) = [C0] +- A (rows x K) B (K x cols); split by rows over the ranks when each slice keeps full 128-row tiles
     // ct_op >= 0: the result's transpose is stored as well (cols x rows block at ct_off, leading dimension ldct)
     void gemm(int rows, int cols, int K, int c_op, long long c_off, int ldc, int c0_op, long long c0_off, int ldc0,
@@ -320,13 +329,7 @@ struct InvPlanner {
         if (ct_op >= 0) { g.ct_op1 = ct_op + 1; g.ct_off = ct_off; g.ldct = ldct; }
         g.t[0] = GemmTerm{a_op, b_op, lda, ldb, a_off, b_off, K, neg ? 0x80000000u : 0u};
         Step st{}; st.kind = 1; st.first = (int)B_().size(); st.count = 1; st.cls = EFGPU_PROF_GEMM_XINV;
-        // A product is split only where the flops saved outweigh the all-gather that follows (tens of microseconds of
-        // latency per collective): 2048-row products take ~0.6 ms, 1024-row ones 70 us; the deep, small products of the
-        // recursion are recomputed by every rank (6 % of the inversion flops).
-        const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();   // read per plan
-        // (peer mode: a split costs two flag barriers of a few microseconds instead of a collective, so smaller products pay)
-        const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
-        if (nranks > 1 && rows % ((peer ? 64 : 128) * nranks) == 0 && rows >= split_min) {   // slices of whole 128-row (peer mode: 64-row) tiles
+        if (will_split(rows)) {
             const long long skip = (long long)rank * (rows / nranks);
             st.g_op = c_op; st.g_off = c_off; st.g_rows = rows; st.g_cols = cols; st.g_ld = ldc;
             if (peer) st.gk = 3;             // the epilogue stores the tile on every rank: any leading dimension, no staging
@@ -353,9 +356,7 @@ struct InvPlanner {
     // only the upper triangle of a 2 x 2 or 4 x 4 block partition is multiplied (3 of 4 / 10 of 16 sub-blocks, one
     // launch), the lower blocks are transposes.  Row-partitioned products keep the plain form (their slices are gathered).
     void gemm_sym(int h, int K, int c_op, long long c_off, int ldc, int a_op, long long a_off, int lda, int b_op, long long b_off, int ldb) {
-        const int split_min_env = [] { const char* e = getenv("EFGPU_SPLIT_MIN_ROWS"); return e ? atoi(e) : 0; }();
-        const int split_min = split_min_env > 0 ? split_min_env : (peer ? 1024 : 2048);
-        const bool row_split = nranks > 1 && h % ((peer ? 64 : 128) * nranks) == 0 && h >= split_min;
+        const bool row_split = will_split(h);
         const int nb = row_split ? 1 : ((h % 64 == 0 && h / 4 >= 128) ? 4 : ((h % 32 == 0 && h / 2 >= 128) ? 2 : 1));
         if (nb == 1) { gemm(h, h, K, c_op, c_off, ldc, c_op, c_off, ldc, a_op, a_off, lda, b_op, b_off, ldb, true); return; }
         const int sb = h / nb;
@@ -438,7 +439,14 @@ struct InvPlanner {
             if (fused_transposes()) {
                 // B <- -W1 S^-1 and, from the same epilogue, C <- B^T.  The update of the leading block needs no W1^T either:
                 // B W1^T is symmetric (= -W1 S^-1 W1^T), hence equal to its transpose W1 B^T = W1 C.
-                gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true, OP_XINV, C, ld);
+                // Row-split products of a peer-mapped tree keep the transpose out of the epilogue: a rank's slice of B is a COLUMN
+                // slab of C, and storing those into seven peer arenas ran at 75-160 GB/s (r2m trace: 2.46 ms against 0.89 ms for
+                // the same product without it); every rank transposes the gathered B locally instead (50 us at the root).
+                if (peer && will_split(h)) {
+                    gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true);
+                    transpose(h, h, OP_XINV, B, ld, OP_XINV, C, ld);
+                } else
+                    gemm(h, h, h, OP_XINV, B, ld, -1, 0, 0, OP_W1, W1, h, OP_XINV, D, ld, true, OP_XINV, C, ld);
                 gemm_sym(h, h, OP_XINV, A, ld, OP_W1, W1, h, OP_XINV, C, ld);                              // A <- A^-1 - W1 C (symmetric)
                 return;
             }
@@ -2242,6 +2250,23 @@ int efgpu_dgemm_batched(const double* A, const double* B, double* C, int m, int 
         launch_bgemm(dp.as<double*>(), 3, db.as<GemmBlock>(), gb.data(), 1, batch, s, tile);
         EF_CUDA(cudaEventRecord(e0, s));
         for (int it = 0; it < iters; it++) launch_bgemm(dp.as<double*>(), 3, db.as<GemmBlock>(), gb.data(), 1, batch, s, tile);
+        EF_CUDA(cudaEventRecord(e1, s));
+        EF_CUDA(cudaStreamSynchronize(s));
+        float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return EF_OK;
+    } catch (const efgpu::Error& e) { g_create_error = e.msg; return e.code; }
+}
+
+int efgpu_dgemm_batched_tma(const double* A, const double* B, double* C, int m, int n, int k, int batch, int stages, int iters, float* ms_out)
+{
+    try {
+        cudaStream_t s = nullptr;
+        cudaEvent_t e0, e1; EF_CUDA(cudaEventCreate(&e0)); EF_CUDA(cudaEventCreate(&e1));
+        launch_dgemm_tma(A, B, C, m, n, k, batch, stages, s);
+        EF_CUDA(cudaEventRecord(e0, s));
+        for (int it = 0; it < iters; it++) launch_dgemm_tma(A, B, C, m, n, k, batch, stages, s);
         EF_CUDA(cudaEventRecord(e1, s));
         EF_CUDA(cudaStreamSynchronize(s));
         float ms = 0; EF_CUDA(cudaEventElapsedTime(&ms, e0, e1));

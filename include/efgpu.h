@@ -299,6 +299,11 @@ int efgpu_set_tuning(int key, int value);
 /* ---- stand-alone access to the GEMM kernel for unit tests and roofline measurements ------------ */
 int efgpu_dgemm_batched(const double* A_dev, const double* B_dev, double* C_dev, int m, int n, int k, int batch,
                         int tile, int iters, float* ms_per_iter);
+/* The same product with TMA-staged operands (cp.async.bulk.tensor.2d + mbarrier ring, producer warp, 128-byte swizzle; `stages` = 3,
+ * 4 or 6): the A/B experiment behind DESIGN.md section 4's choice of operand path.  m % 128 == n % 64 == k % 16 == 0.  Bit-identical
+ * to efgpu_dgemm_batched (same k order). */
+int efgpu_dgemm_batched_tma(const double* A_dev, const double* B_dev, double* C_dev, int m, int n, int k, int batch,
+                            int stages, int iters, float* ms_per_iter);
 
 #ifdef __cplusplus
 }

@@ -347,3 +347,26 @@ def test_dgemm_kernel_against_numpy():
         assert rc == 0
         ref = A @ B
         assert relerr(dC.cpu().numpy(), ref) < 1e-13, (m, n, k, batch, tile)
+
+
+@pytest.mark.parametrize("variant", [4, 6, 3, 64])
+def test_tma_staged_gemm_is_bit_identical_to_the_ldgsts_kernel(variant):
+    """efgpu_dgemm_batched_tma (csrc/gemm_tma.cu: operands staged by cp.async.bulk.tensor.2d into 128-byte-swizzled shared memory, mbarrier
+    ring) against efgpu_dgemm_batched (cp.async into padded shared memory): the same DMMA sequence in the same k order, so the products
+    agree bit for bit; both within rounding of numpy.  Shapes cover one tile, several k-tiles beyond the ring depth, and batches."""
+    import ctypes as C
+    import torch
+    from ellipticforest_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for (m, n, k, batch) in [(128, 128, 16, 1), (128, 128, 160, 3), (256, 384, 512, 2), (512, 128, 48, 5)]:
+        A = torch.randn(batch, m, k, dtype=torch.float64, device="cuda", generator=g)
+        B = torch.randn(batch, k, n, dtype=torch.float64, device="cuda", generator=g)
+        C0 = torch.zeros(batch, m, n, dtype=torch.float64, device="cuda")
+        C1 = torch.full((batch, m, n), float("nan"), dtype=torch.float64, device="cuda")
+        assert lib.efgpu_dgemm_batched(A.data_ptr(), B.data_ptr(), C0.data_ptr(), m, n, k, batch, 128, 0, None) == 0
+        assert lib.efgpu_dgemm_batched_tma(A.data_ptr(), B.data_ptr(), C1.data_ptr(), m, n, k, batch, variant, 0, None) == 0, lib.efgpu_last_error(None)
+        torch.cuda.synchronize()
+        assert torch.equal(C0, C1), (m, n, k, batch)
+        ref = (A.cpu().numpy() @ B.cpu().numpy())
+        assert np.max(np.abs(C1.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-13

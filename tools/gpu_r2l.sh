@@ -26,6 +26,6 @@ run() {   # name, env..., -- bench args
 }
 BARGS=""
 run graphs EFGPU_TRACE=$OUT/trace_${TAG}_n${N}
-run plain EFGPU_GRAPHS_PEER=0
+[ -z "$SKIP_PLAIN" ] && run plain EFGPU_GRAPHS_PEER=0
 if [ -n "$BIG" ]; then BARGS="$BIG"; run big EFGPU_X=0; fi
 ls $OUT | grep trace_${TAG} | head -40
