@@ -76,11 +76,27 @@ struct PeerSpan {
 void launch_peer_barrier(const PeerSpan& ps, int me, int* err, cudaStream_t s);
 void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, cudaStream_t s);
 
+// TMA-staged operands (gemm_tma.cu): a view is one matrix an operand block lies in - (operand slot, origin inside the slot, leading
+// dimension); every (batch entry, view) has a tensor map for its use as A operand (128 x 16 boxes) and as B operand (16 x 16 boxes);
+// a block's terms name their views and the coordinates of their (0, 0) element.
+constexpr int TMA_MAP_BYTES = 128;
+struct TmaTerm { int a_view, b_view, a_row, a_col, b_row, b_col; };
+struct TmaBlock { TmaTerm t[GEMM_MAX_TERMS]; };
+struct TmaArgs {
+    const TmaBlock* d_tblocks = nullptr;   // parallel to the GemmBlock array of the launch
+    const void* mapsA = nullptr;           // CUtensorMap[batch][nviews]
+    const void* mapsB = nullptr;
+    int nviews = 0;
+};
+void encode_operand_maps(const double* base, unsigned long long ld, void* mapA_out, void* mapB_out);
+void launch_bgemm_tma(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks, int nblocks, int batch,
+                      cudaStream_t stream, const PeerSpan& ps, const TmaArgs& tma);
+
 // Launches the kernel on `stream`.  rows/cols/K of every block must be multiples of the chosen
 // tile; the tile configuration is picked from the block shape and the amount of parallelism.
 // peers != nullptr: results are also stored into the peer arenas (every C of the launch must lie inside the local arena).
 void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
-                  int nblocks, int batch, cudaStream_t stream, int force_tile = 0, const PeerSpan* peers = nullptr);
+                  int nblocks, int batch, cudaStream_t stream, int force_tile = 0, const PeerSpan* peers = nullptr, const TmaArgs* tma = nullptr);
 
 // gemm_tma.cu: C[b] = A[b] (m x k) B[b] (k x n), densely packed row-major batches, operands staged by TMA (A/B experiment)
 void launch_dgemm_tma(const double* A, const double* B, double* C, int m, int n, int k, int batch, int stages, cudaStream_t s);

@@ -17,6 +17,7 @@
 // Same k order and slot assignment as bgemm_kernel, so the results are bit-identical (tests/test_gpu_parity.py).
 #include "common.cuh"
 #include <cuda.h>
+#include <cstring>
 
 namespace efgpu {
 
@@ -159,6 +160,193 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
 }
 
+// ---- the descriptor-driven form: bgemm_kernel's semantics (two-term blocks, additive C0, signed transposed second destination,
+// stores into peer arenas) on TMA-staged operands.  Operands are addressed through per-(batch entry, view) tensor maps - a view is
+// (operand slot, origin inside the slot, leading dimension), a few dozen per batch - and block-relative coordinates (TmaBlock).
+// 128 x 64 CTA tile, four warps of 64 x 32, four stages, two CTAs per SM.
+__device__ __forceinline__ double flip_sign_t(double x, unsigned neg) {
+    return __hiloint2double(__double2hiint(x) ^ (int)neg, __double2loint(x));
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(128, 2)
+bgemm_tma_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __restrict__ blocks, const TmaBlock* __restrict__ tblocks,
+                 const CUtensorMap* __restrict__ mapsA, const CUtensorMap* __restrict__ mapsB, int nviews,
+                 int nblocks, int tiles_per_block, const PeerSpan ps)
+{
+    using Cfg = TmaCfg<64, STAGES>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK;
+    constexpr int LDT_S = BM + 2;
+    static_assert(STAGES * Cfg::STAGE_BYTES >= BN * LDT_S * 8, "the transposed tile reuses the pipeline stages");
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES];
+    const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+    const long long bid = blockIdx.x;
+    const int tile = (int)(bid % tiles_per_block);
+    const int blk = (int)((bid / tiles_per_block) % nblocks);
+    const long long z = bid / ((long long)tiles_per_block * nblocks);
+    const GemmBlock& bd = blocks[blk];
+    const TmaBlock& tb = tblocks[blk];
+    const int tiles_n = bd.cols / BN;
+    const int tm = tile / tiles_n, tn = tile % tiles_n;
+    if (tm >= bd.rows / BM) return;
+    double* const* ops = ptab + z * nops;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], Cfg::CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nterms = bd.nterms;
+    const int nk0 = bd.t[0].K / BK;
+    const int nk = nk0 + (nterms > 1 ? bd.t[1].K / BK : 0);
+    const int t1 = nterms > 1 ? 1 : 0;
+    const unsigned neg0 = bd.t[0].neg, neg1 = bd.t[t1].neg;
+
+    // producer state (thread 0 only uses it)
+    const CUtensorMap* mA0 = mapsA + z * nviews + tb.t[0].a_view;
+    const CUtensorMap* mB0 = mapsB + z * nviews + tb.t[0].b_view;
+    const CUtensorMap* mA1 = mapsA + z * nviews + tb.t[t1].a_view;
+    const CUtensorMap* mB1 = mapsB + z * nviews + tb.t[t1].b_view;
+    const int ar0 = tb.t[0].a_row + tm * BM, ac0 = tb.t[0].a_col, br0 = tb.t[0].b_row, bc0 = tb.t[0].b_col + tn * BN;
+    const int ar1 = tb.t[t1].a_row + tm * BM, ac1 = tb.t[t1].a_col, br1 = tb.t[t1].b_row, bc1 = tb.t[t1].b_col + tn * BN;
+    auto issue = [&](int kl) {
+        const int s = kl % STAGES;
+        const unsigned st = base + s * Cfg::STAGE_BYTES;
+        const bool second = kl >= nk0;
+        const int kt = second ? kl - nk0 : kl;
+        const CUtensorMap* mA = second ? mA1 : mA0;
+        const CUtensorMap* mB = second ? mB1 : mB0;
+        const int ar = second ? ar1 : ar0, ac = (second ? ac1 : ac0) + kt * BK;
+        const int br = (second ? br1 : br0) + kt * BK, bc = second ? bc1 : bc0;
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        tma_load_2d(st, mA, ac, ar, &full_bar[s]);
+#pragma unroll
+        for (int j = 0; j < BN / 16; j++) tma_load_2d(st + Cfg::A_BYTES + j * Cfg::B_BOX, mB, bc + 16 * j, br, &full_bar[s]);
+    };
+    if (tid == 0)
+        for (int kl = 0; kl < Cfg::DIST && kl < nk; kl++) issue(kl);
+
+    const int wm0 = (warp >> 1) * 64, wn0 = (warp & 1) * 32;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int FM = 8, FN = 4;
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int rl = wm0 + 8 * (g >> 1) + 4 * (g & 1);       // this lane's tile row for m-tile 0; m-tile i adds 32 (i >> 2) + (i & 3)
+    const unsigned a_lane = (unsigned)rl * 128u;
+    unsigned a_x[8];
+#pragma unroll
+    for (int x = 0; x < 8; x++) a_x[x] = a_lane + ((unsigned)((t ^ (4 * (g & 1))) ^ x) << 4);
+    const unsigned b_lane0 = (unsigned)(Cfg::A_BYTES + (wn0 / 16) * Cfg::B_BOX + (2 * t) * 128 + ((g ^ (2 * t)) << 4));
+    const unsigned b_lane1 = (unsigned)(Cfg::A_BYTES + (wn0 / 16) * Cfg::B_BOX + (2 * t + 1) * 128 + ((g ^ (2 * t + 1)) << 4));
+
+    const bool flip_mid = nterms > 1 && neg0 != neg1;
+    for (int kt = 0; kt < nk; kt++) {
+        const int s = kt % STAGES;
+        if (tid == 0 && kt + Cfg::DIST < nk) {
+            if (kt >= 2) mbar_wait(&empty_bar[(kt - 2) % STAGES], ((kt - 2) / STAGES) & 1);
+            issue(kt + Cfg::DIST);
+        }
+        __syncwarp();
+        mbar_wait(&full_bar[s], (kt / STAGES) & 1);
+        if (flip_mid && kt == nk0) {
+#pragma unroll
+            for (int i = 0; i < FM; i++)
+#pragma unroll
+                for (int j = 0; j < FN; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
+        }
+        const unsigned st = base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int kp = 0; kp < BK / 8; kp++) {
+            double2 a[FM];
+            double b0[FN], b1[FN];
+#pragma unroll
+            for (int i = 0; i < FM; i++)
+                a[i] = lds128(st + a_x[(4 * kp) ^ (i & 3)] + (32 * (i >> 2) + (i & 3)) * 128);
+#pragma unroll
+            for (int jg = 0; jg < FN / 2; jg++) {
+                const double2 v0 = lds128(st + b_lane0 + jg * Cfg::B_BOX + kp * 8 * 128);
+                const double2 v1 = lds128(st + b_lane1 + jg * Cfg::B_BOX + kp * 8 * 128);
+                b0[2 * jg] = v0.x; b0[2 * jg + 1] = v0.y; b1[2 * jg] = v1.x; b1[2 * jg + 1] = v1.y;
+            }
+#pragma unroll
+            for (int i = 0; i < FM; i++)
+#pragma unroll
+                for (int j = 0; j < FN; j++) dmma884_t(acc[i][j][0], acc[i][j][1], a[i].x, b0[j]);
+#pragma unroll
+            for (int i = 0; i < FM; i++)
+#pragma unroll
+                for (int j = 0; j < FN; j++) dmma884_t(acc[i][j][0], acc[i][j][1], a[i].y, b1[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    if (neg1) {
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+            for (int j = 0; j < FN; j++) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
+    }
+
+    // epilogue: C = acc (+ C0) at the permuted tile rows, four adjacent columns per lane and 16-column group; the transposed second
+    // destination always leaves through shared memory as whole rows (the pipeline stages are free: every issued tile was consumed)
+    const int col0 = tn * BN + wn0 + 4 * t;
+    double* Cg = ops[bd.c_op] + bd.c_off + (long long)(tm * BM + rl) * bd.ldc + col0;
+    const double* C0g = bd.c0_op >= 0 ? ops[bd.c0_op] + bd.c0_off + (long long)(tm * BM + rl) * bd.ldc0 + col0 : nullptr;
+    const bool staged_t = bd.ct_op1 != 0;
+    const unsigned ctn = bd.ct_neg;
+    double* smem_d = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
+    double* Cts = smem_d + (wn0 + 4 * t) * LDT_S + rl;
+    if (staged_t) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < FM; i++) {
+        const int ro = 32 * (i >> 2) + (i & 3);
+#pragma unroll
+        for (int jg = 0; jg < FN / 2; jg++) {
+            double2 lo = make_double2(acc[i][2 * jg][0], acc[i][2 * jg + 1][0]);
+            double2 hi = make_double2(acc[i][2 * jg][1], acc[i][2 * jg + 1][1]);
+            if (C0g) {
+                const double2* c0 = reinterpret_cast<const double2*>(C0g + (long long)ro * bd.ldc0 + jg * 16);
+                const double2 c0l = c0[0], c0h = c0[1];
+                lo.x += c0l.x; lo.y += c0l.y; hi.x += c0h.x; hi.y += c0h.y;
+            }
+            double2* c = reinterpret_cast<double2*>(Cg + (long long)ro * bd.ldc + jg * 16);
+            c[0] = lo; c[1] = hi;
+            for (int r = 0; r < ps.n; r++)
+                if (r != ps.me) {
+                    double2* cp = reinterpret_cast<double2*>(reinterpret_cast<char*>(c) + ps.delta[r]);
+                    cp[0] = lo; cp[1] = hi;
+                }
+            if (staged_t) {
+                double* tt = Cts + (jg * 16) * LDT_S + ro;
+                tt[0] = flip_sign_t(lo.x, ctn); tt[LDT_S] = flip_sign_t(lo.y, ctn);
+                tt[2 * LDT_S] = flip_sign_t(hi.x, ctn); tt[3 * LDT_S] = flip_sign_t(hi.y, ctn);
+            }
+        }
+    }
+    if (staged_t) {
+        __syncthreads();
+        double* Ctb = ops[bd.ct_op1 - 1] + bd.ct_off + (long long)(tn * BN) * bd.ldct + tm * BM;
+        constexpr int V = BM / 2;
+        for (int idx = tid; idx < BN * V; idx += 128) {
+            const int c = idx / V, v2 = (idx % V) * 2;
+            const double2 val = *reinterpret_cast<const double2*>(smem_d + c * LDT_S + v2);
+            double2* dst = reinterpret_cast<double2*>(Ctb + (long long)c * bd.ldct + v2);
+            *dst = val;
+            for (int r = 0; r < ps.n; r++)
+                if (r != ps.me) *reinterpret_cast<double2*>(reinterpret_cast<char*>(dst) + ps.delta[r]) = val;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -186,6 +374,32 @@ static CUtensorMap make_map(const double* ptr, unsigned long long rows, unsigned
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error{EF_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
     return mp;
+}
+
+// tensor maps of one operand view (base pointer of the matrix, leading dimension): boxes of 128 x 16 (A operand) and 16 x 16 (B operand)
+void encode_operand_maps(const double* base, unsigned long long ld, void* mapA_out, void* mapB_out)
+{
+    static_assert(sizeof(CUtensorMap) == TMA_MAP_BYTES, "tensor map size");
+    const unsigned long long rows = 1ull << 30;   // views are windows into larger buffers: the row bound is never the limit
+    const CUtensorMap a = make_map(base, rows, ld, ld, 128), b = make_map(base, rows, ld, ld, 16);
+    std::memcpy(mapA_out, &a, sizeof(a)); std::memcpy(mapB_out, &b, sizeof(b));
+}
+
+void launch_bgemm_tma(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks, int nblocks, int batch,
+                      cudaStream_t stream, const PeerSpan& ps, const TmaArgs& tma)
+{
+    using Cfg = TmaCfg<64, 4>;
+    auto kern = bgemm_tma_kernel<4>;
+    static unsigned long long prepared = 0;
+    if (first_use_on_device(prepared)) EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int max_tiles = 0;
+    for (int b = 0; b < nblocks; b++) { const int v = (h_blocks[b].rows / Cfg::BM) * (h_blocks[b].cols / Cfg::BN); if (v > max_tiles) max_tiles = v; }
+    const long long grid = (long long)max_tiles * nblocks * batch;
+    if (grid <= 0) return;
+    if (grid > 2147483647LL) throw Error{EF_ERR_BAD_SHAPE, "bgemm grid too large"};
+    kern<<<(unsigned)grid, 128, Cfg::SMEM_BYTES, stream>>>(ptab, nops, d_blocks, tma.d_tblocks, static_cast<const CUtensorMap*>(tma.mapsA),
+                                                           static_cast<const CUtensorMap*>(tma.mapsB), tma.nviews, nblocks, max_tiles, ps);
+    EF_CUDA(cudaGetLastError());
 }
 
 template <int BN_, int STAGES>

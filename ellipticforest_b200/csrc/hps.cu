@@ -75,6 +75,7 @@ struct Step {
     // gk 1: the destination (op g_op, offset g_off) is contiguous (ld == g_cols): in place.  gk 2: the GEMM wrote its rows into
     // the staging block OP_W3 (ld = g_cols); after the all-gather the block is copied to op g_op, offset g_off, leading dimension g_ld.
     int gk = 0, g_op = 0, g_rows = 0, g_cols = 0, g_ld = 0; long long g_off = 0;
+    bool tma = false;                 // kind 1: every block of the step has tensor-map views (plan_tma): operands can be staged by TMA
 };
 
 struct BatchH {
@@ -90,6 +91,12 @@ struct BatchH {
     bool use_sym = false;             // decided at build time (leaf operator self-adjoint, EFGPU_NO_SYMMETRY not set)
     const std::vector<Step>& active() const { return use_sym ? steps_sym : steps; }
     DevBuf d_blocks, d_trans, d_entries, d_ptab;
+    // TMA operand staging (gemm_tma.cu): the matrices the operand blocks of the 128-row products lie in, per-block coordinates, and
+    // one pair of tensor maps per (parent, view), encoded when the buffers are allocated
+    struct TmaView { int op; long long origin; int ld; };
+    std::vector<TmaView> views;
+    std::vector<TmaBlock> tblocks;
+    DevBuf d_tblocks, d_mapsA, d_mapsB;
     DevBuf Xinv, S, Hc, T, Xcopy, Tcoarse;
     double* Tbase = nullptr;          // this batch's DtN slab: its own buffer T, or a slice of the handle's transient arena (EFGPU_LEAN_T)
     std::vector<std::vector<CoarsenOp>> cT, cH, cG;  // per step
@@ -248,7 +255,7 @@ static unsigned long long graph_key(const efgpu_handle* H, unsigned flags)
     unsigned long long lam; std::memcpy(&lam, &H->lambda, 8);
     mix(flags); mix((unsigned long long)H->leaf_kind); mix(lam); mix(H->refine_inverse ? 1 : 0); mix(H->graph_gen);
     mix(H->ext_sym ? 1 : 0); mix((unsigned long long)(uintptr_t)H->stream);
-    for (int t = 0; t < 8; t++) mix((unsigned long long)get_tuning(t));
+    for (int t = 0; t < 16; t++) mix((unsigned long long)get_tuning(t));
     return k;
 }
 
@@ -488,6 +495,50 @@ static bool clip_rows(GemmBlock& g, long long r0, long long lo, long long hi)
 
 static void plan_refine(BatchH& b);
 
+// Tensor-map views of the operand blocks (TMA staging of the 128 x 64 CTA tiles).  A block qualifies when its shape is made of whole
+// tiles (rows % 128, cols % 64, K % 16) and each operand block lies inside one row-major matrix: every operand slot is one matrix
+// starting at the slot's base (its offsets decompose as row * ld + col without wrapping) except OP_W1, whose slots per recursion depth
+// start at `w1_starts`.  Steps whose blocks all qualify are marked; everything else keeps the cp.async kernel.
+static void plan_tma(BatchH& b, const std::vector<long long>& w1_starts)
+{
+    b.views.clear();
+    TmaBlock none{};
+    for (auto& t : none.t) t.a_view = t.b_view = -1;
+    b.tblocks.assign(b.blocks.size(), none);
+    auto view_of = [&](int op, long long off, int ld, int width, int& row, int& col) -> int {
+        long long origin = 0;
+        if (op == OP_W1) for (long long st : w1_starts) if (st <= off && st > origin) origin = st;
+        const long long rel = off - origin;
+        if (ld < 16 || (ld & 1) || (origin & 1) || rel / ld >= (1ll << 30)) return -1;
+        row = (int)(rel / ld); col = (int)(rel % ld);
+        if (col + width > ld) return -1;
+        for (size_t v = 0; v < b.views.size(); v++)
+            if (b.views[v].op == op && b.views[v].origin == origin && b.views[v].ld == ld) return (int)v;
+        b.views.push_back(BatchH::TmaView{op, origin, ld});
+        return (int)b.views.size() - 1;
+    };
+    for (size_t k = 0; k < b.blocks.size(); k++) {
+        const GemmBlock& g = b.blocks[k];
+        bool ok = g.rows > 0 && g.rows % 128 == 0 && g.cols % 64 == 0;
+        for (int t = 0; t < g.nterms; t++) ok = ok && g.t[t].K > 0 && g.t[t].K % 16 == 0;
+        if (!ok) continue;
+        TmaBlock tb = none;
+        for (int t = 0; t < g.nterms && ok; t++) {
+            tb.t[t].a_view = view_of(g.t[t].a_op, g.t[t].a_off, g.t[t].lda, g.t[t].K, tb.t[t].a_row, tb.t[t].a_col);
+            tb.t[t].b_view = view_of(g.t[t].b_op, g.t[t].b_off, g.t[t].ldb, g.cols, tb.t[t].b_row, tb.t[t].b_col);
+            ok = tb.t[t].a_view >= 0 && tb.t[t].b_view >= 0;
+        }
+        if (!ok) continue;
+        if (g.nterms == 1) tb.t[1] = tb.t[0];
+        b.tblocks[k] = tb;
+    }
+    for (std::vector<Step>* ss : {&b.steps, &b.steps_sym, &b.steps_refine})
+        for (Step& st : *ss) {
+            st.tma = st.kind == 1 && st.count > 0;
+            for (int k = st.first; st.tma && k < st.first + st.count; k++) st.tma = b.tblocks[k].t[0].a_view >= 0;
+        }
+}
+
 static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
 {
     const int n = b.n, N = 4 * n;
@@ -626,6 +677,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
         }
     }
     plan_refine(b);
+    std::vector<long long> w1_starts(w1_off);
+    w1_starts.insert(w1_starts.end(), w1b_off.begin(), w1b_off.end());
+    plan_tma(b, w1_starts);
 }
 
 // One Newton-Schulz step  X^-1 <- X^-1 + X^-1 (I - X X^-1)  on the result of the unpivoted block inversion (see build_begin:
@@ -949,6 +1003,21 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
         }
         b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s); b.d_trans.upload(b.trans, s);
         b.h_ptab = ptab; b.h_ent = ent;
+        if (!b.views.empty()) {   // tensor maps of every (parent, view): base = the slot's pointer + the view's origin
+            const size_t nv = b.views.size();
+            std::vector<unsigned char> ma(cnt * nv * TMA_MAP_BYTES, 0), mb(cnt * nv * TMA_MAP_BYTES, 0);
+            for (size_t sl = 0; sl < cnt; sl++)
+                for (size_t v = 0; v < nv; v++) {
+                    const double* basep = ptab[sl * NOPS + b.views[v].op];
+                    if (!basep) continue;   // a slot this build does not have (the copy of X): its steps do not run either
+                    encode_operand_maps(basep + b.views[v].origin, (unsigned long long)b.views[v].ld, ma.data() + (sl * nv + v) * TMA_MAP_BYTES,
+                                        mb.data() + (sl * nv + v) * TMA_MAP_BYTES);
+                }
+            b.d_mapsA.alloc(ma.size()); b.d_mapsB.alloc(mb.size());
+            EF_CUDA(cudaMemcpy(b.d_mapsA.p, ma.data(), ma.size(), cudaMemcpyHostToDevice));
+            EF_CUDA(cudaMemcpy(b.d_mapsB.p, mb.data(), mb.size(), cudaMemcpyHostToDevice));
+            b.d_tblocks.upload(b.tblocks, s);
+        }
         auto up = [&](std::vector<std::vector<CoarsenOp>>& v, std::vector<std::unique_ptr<DevBuf>>& dv, std::vector<int>& mx) {
             dv.clear(); mx.clear();
             for (auto& ops : v) {
@@ -1091,10 +1160,17 @@ static void build_level(efgpu_handle* H, int lev, int phase)
         auto run_transposes = [&](const Step& st) {
             timed(H, st.cls, 1, [&] { launch_btranspose(ptab, NOPS, b.d_trans.as<TransOp>() + st.first, b.trans.data() + st.first, st.count, bcount, s); });
         };
+        // TMA operand staging where the step's blocks all have views (not on the compact sub-batches of an adaptive re-build: the
+        // tensor maps are indexed by parent slot)
+        auto tma_args = [&](const Step& st, TmaArgs& ta) -> const TmaArgs* {
+            if (!st.tma || b.sub_on || !b.d_mapsA.p || !b.d_tblocks.p) return nullptr;
+            ta.d_tblocks = b.d_tblocks.as<TmaBlock>() + st.first; ta.mapsA = b.d_mapsA.p; ta.mapsB = b.d_mapsB.p; ta.nviews = (int)b.views.size();
+            return &ta;
+        };
         auto run_refine = [&]() {   // indefinite problems: X^-1 <- X^-1 + X^-1 (I - X X^-1), every rank of a partition alike
             for (const Step& st : b.steps_refine)
                 timed(H, st.cls, 1, [&] {
-                    if (st.kind == 1) launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s);
+                    if (st.kind == 1) { TmaArgs ta; launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s, 0, nullptr, tma_args(st, ta)); }
                     else launch_refine_ew(ptab, NOPS, st.kind, st.kind == 3 ? OP_T : OP_XINV, st.kind == 3 ? st.off : 0, OP_T, st.off, st.N, bcount,
                                           H->d_minpiv.as<double>() + 4, s);
                 });
@@ -1122,7 +1198,7 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             if (scatter) peer_barrier(H, /*only_if_dirty=*/true);
             timed(H, st.cls, 1, [&] {
                 if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, bcount, H->d_minpiv.as<double>(), s);
-                else launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s, 0, scatter ? &H->peers : nullptr);
+                else { TmaArgs ta; launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s, 0, scatter ? &H->peers : nullptr, tma_args(st, ta)); }
             });
             if (scatter) { peer_barrier(H, false); continue; }
             H->peer_dirty = true;

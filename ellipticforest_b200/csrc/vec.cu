@@ -25,9 +25,11 @@ namespace efgpu {
 //     per step at L=8 M=16; 0 = whole blocks; read when a plan is made)
 // [7] base case of the block inversion, 128 x 128: 0 = blocked Gauss-Jordan on the tensor pipe, 1 = per-pivot register kernel (round 1)
 // [6] variable-coefficient leaves with M = 8, 16: 0 = warp-level / tensor-core kernels (default), 1 = the CTA-per-leaf kernels of round 1
-static int g_tuning[8] = {2, 0, 0, 0, 0, 1, 0, 0};
-void set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tuning[key] = value; }
-int get_tuning(int key) { return (key >= 0 && key < 8) ? g_tuning[key] : 0; }
+// [8] operand staging of the 128-row GEMM tiles: 1 = TMA (cp.async.bulk.tensor.2d, swizzled shared memory, mbarrier ring; default),
+//     0 = cp.async (LDGSTS) into padded shared memory; read at every launch
+static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+void set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tuning[key] = value; }
+int get_tuning(int key) { return (key >= 0 && key < 16) ? g_tuning[key] : 0; }
 
 // side of child c that faces interior interface k (-1: not adjacent)
 __constant__ int c_iface[4][4] = {{3, -1, 1, -1}, {-1, 3, 0, -1}, {2, -1, -1, 1}, {-1, 2, -1, 0}};

@@ -84,3 +84,33 @@ def test_staged_transposed_stores_are_bit_identical(level, nx):
             lib.efgpu_set_tuning(4, 0)
     for k, (a, b) in enumerate(zip(out[1], out[2])):
         assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("level,nx,problem", [(6, 16, "poisson"), (5, 32, "helmholtz")])
+def test_tma_operand_staging_is_bit_identical(level, nx, problem):
+    """efgpu_set_tuning(8, ...): the 128-row tiles of the merge products with operands staged by TMA (cp.async.bulk.tensor.2d through
+    per-(parent, view) tensor maps, swizzled shared memory, mbarrier ring; default) against the cp.async kernel: the same DMMA sequence
+    in the same k order, so every operator and the solution agree bit for bit.  Trees whose upper levels are large enough for the
+    128 x 64 tiles to be chosen (root child side 512: S, T, the split recursion of X^-1, transposed second destinations)."""
+    import ellipticforest_b200 as ef
+    from ellipticforest_b200 import _lib
+    from test_host import _mesh_for
+    kw = dict(problem_name=problem, solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=nx, min_level=level, max_level=level,
+              threshold=1.2, refine_box=None)
+    P = O.problem(kw["problem_name"])
+    lib = _lib.load()
+    out = {}
+    for key in (0, 1):
+        assert lib.efgpu_set_tuning(8, key) == 0
+        try:
+            s = ef.FiniteVolumeSolver()
+            s.solver_type = "FISHPACK90"
+            s.lambda_function = P["lam"]
+            hps = ef.HPSAlgorithm(_mesh_for(kw), s)
+            hps.buildStage(); hps.upwardsStage(P["f"])
+            u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+            out[key] = [u] + [hps.operator(nd, w) for nd in (0, 1) for w in ("T", "S", "Xinv")]
+        finally:
+            lib.efgpu_set_tuning(8, 1)
+    for k, (a, b) in enumerate(zip(out[1], out[0])):
+        assert np.array_equal(a, b), k
