@@ -1801,7 +1801,7 @@ int efgpu_debug_merge_plan_ex(int n, int level, int rank, int nranks, int symmet
 
 int efgpu_set_tuning(int key, int value)
 {
-    if (key < 0 || key >= 8) return EF_ERR_BAD_ARG;
+    if (key < 0 || key >= 16) return EF_ERR_BAD_ARG;
     efgpu::set_tuning(key, value);
     return EF_OK;
 }
