@@ -295,6 +295,44 @@ static void launch_cfg(double* const* ptab, int nops, const GemmBlock* d_blocks,
     EF_CUDA(cudaGetLastError());
 }
 
+// Blocks that are not made of 8 x 8 tensor-core tiles (4 x 4 blocks, K = 4: the first merge level above 4 x 4 leaf patches, which the
+// reference's convergence driver uses, examples/elliptic-multiple/main.cpp:444): one thread per result element, plain FMAs.  Same
+// descriptor semantics as bgemm_kernel (two terms, additive C0, signed transposed second destination, peer arenas).
+__global__ void __launch_bounds__(256)
+bgemm_scalar_kernel(double* const* __restrict__ ptab, int nops, const GemmBlock* __restrict__ blocks, int nblocks, int elems_per_block,
+                    long long total, const PeerSpan ps)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % elems_per_block);
+        const int blk = (int)((idx / elems_per_block) % nblocks);
+        const long long z = idx / ((long long)elems_per_block * nblocks);
+        const GemmBlock& bd = blocks[blk];
+        if (e >= bd.rows * bd.cols) continue;
+        const int r = e / bd.cols, c = e % bd.cols;
+        double* const* ops = ptab + z * nops;
+        double acc = 0.0;
+        for (int t = 0; t < bd.nterms; t++) {
+            const double* A = ops[bd.t[t].a_op] + bd.t[t].a_off + (long long)r * bd.t[t].lda;
+            const double* B = ops[bd.t[t].b_op] + bd.t[t].b_off + c;
+            double sum = 0.0;
+            for (int k = 0; k < bd.t[t].K; k++) sum = fma(A[k], B[(long long)k * bd.t[t].ldb], sum);
+            acc += bd.t[t].neg ? -sum : sum;
+        }
+        if (bd.c0_op >= 0) acc += ops[bd.c0_op][bd.c0_off + (long long)r * bd.ldc0 + c];
+        double* cp = ops[bd.c_op] + bd.c_off + (long long)r * bd.ldc + c;
+        *cp = acc;
+        for (int q = 0; q < ps.n; q++)
+            if (q != ps.me) *reinterpret_cast<double*>(reinterpret_cast<char*>(cp) + ps.delta[q]) = acc;
+        if (bd.ct_op1) {
+            double* tp = ops[bd.ct_op1 - 1] + bd.ct_off + (long long)c * bd.ldct + r;
+            const double v = flip_sign(acc, bd.ct_neg);
+            *tp = v;
+            for (int q = 0; q < ps.n; q++)
+                if (q != ps.me) *reinterpret_cast<double*>(reinterpret_cast<char*>(tp) + ps.delta[q]) = v;
+        }
+    }
+}
+
 void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, const GemmBlock* h_blocks,
                   int nblocks, int batch, cudaStream_t stream, int force_tile, const PeerSpan* peers, const TmaArgs* tma)
 {
@@ -305,16 +343,25 @@ void launch_bgemm(double* const* ptab, int nops, const GemmBlock* d_blocks, cons
     ps.stage_t = get_tuning(4) == 1 || (get_tuning(4) == 0 && ps.n > 1) ? 1 : 0;
     // largest power-of-two tile dividing every block dimension
     int g = 128;
-    bool k16 = true;
+    bool k16 = true, k8 = true;
     for (int b = 0; b < nblocks; b++) {
         const GemmBlock& bd = h_blocks[b];
         while (g > 1 && (bd.rows % g || bd.cols % g)) g >>= 1;
         for (int t = 0; t < bd.nterms; t++) {
             if (bd.t[t].K % 16) k16 = false;
-            if (bd.t[t].K % 8) throw Error{EF_ERR_BAD_SHAPE, "bgemm: K must be a multiple of 8"};
+            if (bd.t[t].K % 8) k8 = false;
         }
     }
-    if (g < 8) throw Error{EF_ERR_BAD_SHAPE, "bgemm: block dimensions must be multiples of 8"};
+    if (g < 8 || !k8) {   // not made of tensor-core tiles: scalar kernel
+        int epb = 0;
+        for (int b = 0; b < nblocks; b++) epb = epb > h_blocks[b].rows * h_blocks[b].cols ? epb : h_blocks[b].rows * h_blocks[b].cols;
+        const long long total = (long long)epb * nblocks * batch;
+        if (total <= 0) return;
+        const long long want = (total + 255) / 256;
+        bgemm_scalar_kernel<<<(unsigned)(want < 148 * 32 ? want : 148 * 32), 256, 0, stream>>>(ptab, nops, d_blocks, nblocks, epb, total, ps);
+        EF_CUDA(cudaGetLastError());
+        return;
+    }
     if (!k16 && g > 8) g = 8;
     auto tiles_for = [&](int t) { int m = 0; for (int b = 0; b < nblocks; b++) { int v = (h_blocks[b].rows / t) * (h_blocks[b].cols / t); if (v > m) m = v; } return m; };
     int tile = g;

@@ -737,7 +737,7 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* 
 {
     const int nn = d->n_nodes, M = d->nx;
     if (nn <= 0 || !d->level || !d->child || !d->box) throw Error{EF_ERR_BAD_ARG, "empty tree description"};
-    if (M < 8 || M % 8) throw Error{EF_ERR_BAD_SHAPE, "nx must be a multiple of 8 (8, 16, 24, 32)"};
+    if (M != 4 && (M < 8 || M % 8)) throw Error{EF_ERR_BAD_SHAPE, "nx must be 4 or a multiple of 8 (4, 8, 16, 24, 32, 64)"};
     H->external_leaves = ext_leaf_size != nullptr;
     H->M = M; H->n_nodes = nn;
     H->nodes.resize(nn);

@@ -168,6 +168,130 @@ leaf_solve_const_kernel(const double* __restrict__ Q, const double* __restrict__
 }
 
 
+// Patches too large for one thread per cell (M = 64: the reference's plots carry a 64 x 64 series; hstcrt accepts any M > 2,
+// extern/fishpack90/src/hstcrt.f:336-339): the same two kernels with NT threads looping over the M^2 cells and the tiles in
+// dynamic shared memory.  Same arithmetic, same summation order per element.
+template <int M, int NT>
+__global__ void __launch_bounds__(NT)
+leaf_dtn_const_loop_kernel(const double* __restrict__ Q, const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
+                           double lambda, double* __restrict__ T_all, const int* __restrict__ build_list, int n_build)
+{
+    extern __shared__ __align__(16) double sml[];
+    constexpr int LD = M + 1;
+    double* sQ = sml; double* sDinv = sQ + M * LD; double* sZ = sDinv + M * LD; double* sP = sZ + M * LD; double* sMu = sP + M * LD;
+    if ((int)blockIdx.x >= n_build) return;
+    const int leaf = build_list ? build_list[blockIdx.x] : blockIdx.x;
+    const int tid = threadIdx.x;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    for (int e = tid; e < M * M; e += NT) sQ[(e / M) * LD + e % M] = Q[e];
+    for (int e = tid; e < M; e += NT) sMu[e] = 2.0 * cospi((double)(e + 1) / M) - 2.0;
+    __syncthreads();
+    for (int e = tid; e < M * M; e += NT) sDinv[(e / M) * LD + e % M] = 1.0 / (sMu[e / M] / (dx * dx) + sMu[e % M] / (dy * dy) + lambda);
+    __syncthreads();
+    double* T = T_all + (size_t)leaf * (16 * M * M);
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+            const bool ax = a < 2, bx = b < 2;
+            const int ea = (a & 1) ? M - 1 : 0, eb = (b & 1) ? M - 1 : 0;
+            for (int e = tid; e < M * M; e += NT) {
+                const int r = e / M, c = e % M;
+                double z = 0.0;
+                if (ax && bx) { if (r == c) for (int k = 0; k < M; k++) z += sQ[ea * LD + k] * sQ[eb * LD + k] * sDinv[k * LD + r]; }
+                else if (!ax && !bx) { if (r == c) for (int l = 0; l < M; l++) z += sQ[ea * LD + l] * sQ[eb * LD + l] * sDinv[r * LD + l]; }
+                else if (ax && !bx) z = sQ[ea * LD + c] * sQ[eb * LD + r] * sDinv[c * LD + r];
+                else z = sQ[ea * LD + c] * sQ[eb * LD + r] * sDinv[r * LD + c];
+                sZ[r * LD + c] = z;
+            }
+            __syncthreads();
+            for (int e = tid; e < M * M; e += NT) {
+                const int r = e / M, c = e % M;
+                double p = 0.0;
+#pragma unroll 8
+                for (int m = 0; m < M; m++) p += sQ[r * LD + m] * sZ[m * LD + c];
+                sP[r * LD + c] = p;
+            }
+            __syncthreads();
+            const double da = ax ? dx : dy, db = bx ? dx : dy;
+            for (int e = tid; e < M * M; e += NT) {
+                const int r = e / M, c = e % M;
+                double g = 0.0;
+#pragma unroll 8
+                for (int m = 0; m < M; m++) g += sP[r * LD + m] * sQ[c * LD + m];
+                const double v = -(2.0 / (db * db)) * g - ((a == b && r == c) ? 1.0 : 0.0);
+                T[(size_t)(a * M + r) * (4 * M) + b * M + c] = side_sign(a) * (2.0 / da) * v;
+            }
+            __syncthreads();
+        }
+}
+
+template <int M, int NT>
+__global__ void __launch_bounds__(NT)
+leaf_solve_const_loop_kernel(const double* __restrict__ Q, const double* __restrict__ boxes, const int* __restrict__ leaf_nodes,
+                             double lambda, const double* __restrict__ f, double fscale, double* const* __restrict__ g_ptrs,
+                             double* __restrict__ u_out, double* const* __restrict__ h_ptrs, int mode, int n_leaves)
+{
+    extern __shared__ __align__(16) double sml[];
+    constexpr int LD = M + 1;
+    double* sQ = sml; double* sA = sQ + M * LD; double* sB = sA + M * LD; double* sMu = sB + M * LD; double* sG = sMu + M;
+    const int leaf = blockIdx.x, tid = threadIdx.x;
+    if (leaf >= n_leaves) return;
+    const double* box = boxes + 4 * (size_t)leaf_nodes[leaf];
+    const double dx = (box[1] - box[0]) / M, dy = (box[3] - box[2]) / M;
+    for (int e = tid; e < M * M; e += NT) sQ[(e / M) * LD + e % M] = Q[e];
+    for (int e = tid; e < M; e += NT) sMu[e] = 2.0 * cospi((double)(e + 1) / M) - 2.0;
+    for (int e = tid; e < 4 * M; e += NT) sG[e] = g_ptrs ? g_ptrs[leaf][e] : 0.0;
+    __syncthreads();
+    for (int e = tid; e < M * M; e += NT) {
+        const int i = e / M, j = e % M;
+        double rhs = f ? fscale * f[(size_t)leaf * M * M + e] : 0.0;
+        if (i == 0) rhs -= 2.0 / (dx * dx) * sG[j];
+        if (i == M - 1) rhs -= 2.0 / (dx * dx) * sG[M + j];
+        if (j == 0) rhs -= 2.0 / (dy * dy) * sG[2 * M + i];
+        if (j == M - 1) rhs -= 2.0 / (dy * dy) * sG[3 * M + i];
+        sA[i * LD + j] = rhs;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * M; e += NT) {
+        const int i = e / M, j = e % M;
+        double t = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < M; m++) t += sQ[m * LD + i] * sA[m * LD + j];
+        sB[i * LD + j] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * M; e += NT) {
+        const int i = e / M, j = e % M;
+        double t = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < M; m++) t += sB[i * LD + m] * sQ[m * LD + j];
+        sA[i * LD + j] = t / (sMu[i] / (dx * dx) + sMu[j] / (dy * dy) + lambda);
+    }
+    __syncthreads();
+    for (int e = tid; e < M * M; e += NT) {
+        const int i = e / M, j = e % M;
+        double t = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < M; m++) t += sQ[i * LD + m] * sA[m * LD + j];
+        sB[i * LD + j] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * M; e += NT) {
+        const int i = e / M, j = e % M;
+        double t = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < M; m++) t += sB[i * LD + m] * sQ[j * LD + m];
+        if (mode == 0) u_out[(size_t)leaf * M * M + e] = t;
+        else {
+            double* h = h_ptrs[leaf];
+            if (i == 0) h[j] = (2.0 / dx) * (t - sG[j]);
+            if (i == M - 1) h[M + j] = -(2.0 / dx) * (t - sG[M + j]);
+            if (j == 0) h[2 * M + i] = (2.0 / dy) * (t - sG[2 * M + i]);
+            if (j == M - 1) h[3 * M + i] = -(2.0 / dy) * (t - sG[3 * M + i]);
+        }
+    }
+}
+
 // FP64 tensor-core variant of the leaf solve, M = 8, 16, 24, 32: ONE WARP PER LEAF, the four M x M products of the
 // fast diagonalisation issued as DMMA m8n8k4 (same instruction as csrc/gemm.cu).  The whole M x M result of a product
 // lives in the warp's accumulator registers, so one padded shared-memory tile per warp is enough: read fragments,
@@ -901,11 +1025,12 @@ void launch_leaf_var_factor(int M, const double* const* coef_in, const double* b
 {
     if (n_leaves == 0) return;
     switch (M) {
+        case 4: var_factor_M<4>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
         case 8: var_factor_M<8>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
         case 16: var_factor_M<16>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
         case 24: var_factor_M<24>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
         case 32: var_factor_M<32>(coef_in, boxes, leaf_nodes, coef, P, min_pivot, n_leaves, s); break;
-        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 4, 8, 16, 24, 32 or (constant coefficients) 64 cells per side"};
     }
     EF_CUDA(cudaGetLastError());
 }
@@ -915,11 +1040,12 @@ void launch_leaf_var_solve(int M, const double* coef, const double* P, const dou
 {
     if (n_leaves == 0) return;
     switch (M) {
+        case 4: var_solve_M<4>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
         case 8: var_solve_M<8>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
         case 16: var_solve_M<16>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
         case 24: var_solve_M<24>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
         case 32: var_solve_M<32>(coef, P, boxes, leaf_nodes, f, fscale, g_ptrs, u_out, h_ptrs, T_all, mode, n_leaves, s); break;
-        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 4, 8, 16, 24, 32 or (constant coefficients) 64 cells per side"};
     }
     EF_CUDA(cudaGetLastError());
 }
@@ -933,12 +1059,26 @@ void launch_broadcast_leaf_T(double* T_all, int M, int n_leaves, cudaStream_t s)
 
 template <int M>
 static void dtn_const_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, double* T_all, const int* build_list, int n_build, cudaStream_t s) {
-    leaf_dtn_const_kernel<M><<<n_build, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build);
+    if constexpr (M * M <= 1024) leaf_dtn_const_kernel<M><<<n_build, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build);
+    else {
+        constexpr int smem = (4 * M * (M + 1) + M) * (int)sizeof(double);
+        auto kern = leaf_dtn_const_loop_kernel<M, 1024>;
+        static unsigned long long prepared = 0;
+        if (first_use_on_device(prepared)) EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<n_build, 1024, smem, s>>>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build);
+    }
 }
 template <int M>
 static void solve_const_M(const double* Q, const double* boxes, const int* leaf_nodes, double lambda, const double* f, double fscale,
                           double* const* g_ptrs, double* u_out, double* const* h_ptrs, int mode, int n_leaves, cudaStream_t s) {
-    leaf_solve_const_kernel<M><<<n_leaves, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves);
+    if constexpr (M * M <= 1024) leaf_solve_const_kernel<M><<<n_leaves, M * M, 0, s>>>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves);
+    else {
+        constexpr int smem = (3 * M * (M + 1) + 5 * M) * (int)sizeof(double);
+        auto kern = leaf_solve_const_loop_kernel<M, 1024>;
+        static unsigned long long prepared = 0;
+        if (first_use_on_device(prepared)) EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<n_leaves, 1024, smem, s>>>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves);
+    }
 }
 
 void launch_leaf_dtn_const(int M, const double* Q, const double* boxes, const int* leaf_nodes, double lambda,
@@ -949,11 +1089,13 @@ void launch_leaf_dtn_const(int M, const double* Q, const double* boxes, const in
     if (cache_operators) { build_list = nullptr; n_build = 1; }   // quirk q1: the first leaf's T for every leaf
     else if (!build_list) n_build = n_leaves;
     switch (M) {
+        case 4: dtn_const_M<4>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
+        case 64: dtn_const_M<64>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
         case 8: dtn_const_M<8>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
         case 16: dtn_const_M<16>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
         case 24: dtn_const_M<24>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
         case 32: dtn_const_M<32>(Q, boxes, leaf_nodes, lambda, T_all, build_list, n_build, s); break;
-        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 4, 8, 16, 24, 32 or (constant coefficients) 64 cells per side"};
     }
     EF_CUDA(cudaGetLastError());
     if (cache_operators && n_leaves > 1) {
@@ -972,23 +1114,25 @@ void launch_leaf_solve_const(int M, const double* Q, const double* boxes, const 
 {
     if (n_leaves == 0) return;
     // default: FP64 tensor-core kernel, one warp per leaf (its bulk copies need f on a 16-byte boundary)
-    if (get_tuning(3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+    if (get_tuning(3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && M != 4 && M != 64) {   // (4: no 8 x 8 tiles; 64: the result does not fit a warp's registers)
         switch (M) {
             case 8: solve_const_mma_M<8>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
             case 16: solve_const_mma_M<16>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
             case 24: solve_const_mma_M<24>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
             case 32: solve_const_mma_M<32>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
-            default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+            default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 4, 8, 16, 24, 32 or (constant coefficients) 64 cells per side"};
         }
         EF_CUDA(cudaGetLastError());
         return;
     }
     switch (M) {   // one thread per cell: any alignment of f (a caller-owned device pointer in efgpu_upwards_device)
+        case 4: solve_const_M<4>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
+        case 64: solve_const_M<64>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
         case 8: solve_const_M<8>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
         case 16: solve_const_M<16>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
         case 24: solve_const_M<24>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
         case 32: solve_const_M<32>(Q, boxes, leaf_nodes, lambda, f, fscale, g_ptrs, u_out, h_ptrs, mode, n_leaves, s); break;
-        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 8, 16, 24 or 32 cells per side"};
+        default: throw Error{EF_ERR_UNSUPPORTED, "leaf patches must be 4, 8, 16, 24, 32 or (constant coefficients) 64 cells per side"};
     }
     EF_CUDA(cudaGetLastError());
 }

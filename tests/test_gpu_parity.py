@@ -370,3 +370,27 @@ def test_tma_staged_gemm_is_bit_identical_to_the_ldgsts_kernel(variant):
         assert torch.equal(C0, C1), (m, n, k, batch)
         ref = (A.cpu().numpy() @ B.cpu().numpy())
         assert np.max(np.abs(C1.cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-13
+
+
+@pytest.mark.parametrize("nx,lo,hi,problem,solver", [(4, 3, 3, "poisson", "fishpack"), (4, 1, 5, "helmholtz", "fishpack"), (4, 2, 4, "varcoef", "fivepoint"),
+                                                     (64, 1, 1, "helmholtz", "fishpack")])
+def test_patch_sizes_4_and_64_against_oracle(nx, lo, hi, problem, solver):
+    """The reference's convergence driver runs 4 x 4 ... 32 x 32 patches (examples/elliptic-multiple/main.cpp:444) and its plots carry a
+    64 x 64 series; hstcrt accepts any M > 2 (hstcrt.f:336-339).  4 x 4: the first merge level has 4 x 4 blocks (K = 4: scalar product
+    kernel, 16 x 16 base case) and the leaves one thread per cell; 64 x 64 (constant coefficients): looping leaf kernels, 256 x 256 leaf
+    maps.  Uniform and adaptive (coarsening 8 -> 4) trees, every operator and vector against the oracle."""
+    box = (0.0, np.pi, 0.0, np.pi) if lo == hi else (-10.0, 10.0, -10.0, 10.0)
+    kw = dict(problem_name=problem, solver_kind=solver, box=box, nx=nx, min_level=lo, max_level=hi, threshold=1.2, refine_box=None)
+    hps = run_gpu(kw)
+    ora = O.run(**kw)
+    assert len(ora.nodes) == hps.mesh.n_nodes
+    worst = {}
+    for i, nd in enumerate(ora.nodes):
+        assert hps.mesh.path(i) == nd.path
+        for nm in (["T"] if nd.leaf else ["T", "S", "X", "H"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.operator(i, nm), getattr(nd, nm)))
+        for nm in (["h", "g", "u"] if nd.leaf else ["h", "g", "w"]):
+            worst[nm] = max(worst.get(nm, 0.0), relerr(hps.vector(i, nm), getattr(nd, nm)))
+    print(nx, lo, hi, problem, {k: "%.1e" % v for k, v in worst.items()})
+    for nm, v in worst.items():
+        assert v < TOL, (nm, v)
