@@ -764,7 +764,7 @@ static void make_plan(efgpu_handle* H, const efgpu_tree_desc* d, const int32_t* 
         NodeH& nd = H->nodes[i];
         if (nd.leaf) {
             nd.size = ext_leaf_size ? ext_leaf_size[nd.leaf_idx] : M;
-            if (nd.size < 8 || nd.size % 8) throw Error{EF_ERR_BAD_SHAPE, "external leaf sizes must be multiples of 8"};
+            if (nd.size != 4 && (nd.size < 8 || nd.size % 8)) throw Error{EF_ERR_BAD_SHAPE, "external leaf sizes must be 4 or multiples of 8"};
             continue;
         }
         int mn = 1 << 30;
