@@ -637,7 +637,7 @@ def own_arm(a):
                 "d2h_bytes_per_step": int(f_host.nbytes), "ms_per_step": 1e3 * e2e_wall_s / a.steps, "timer": "host wall clock between device synchronisations"},
         "e2e_device_sampling": e2e_devsample, "e2e_cpp_binding": binding,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T)%s" % (" on rank 0" if world > 1 else ""),
+        "roofline": {"bound": "tensor", "kernel": "bgemm_tma_kernel / bgemm_kernel (FP64 DMMA batched GEMM of the merges: X^-1 blocks, S, T; 128-row tiles on TMA-staged operands, smaller tiles on cp.async)%s" % (" on rank 0" if world > 1 else ""),
                      "achieved": gemm_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": (gemm_tf / dgemm_tf) if (gemm_tf and dgemm_tf) else None,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure; NVIDIA nominal FP64 tensor 37-40 TFLOP/s)",
                      "flops": "issued to the tensor pipe (symmetric plan: ~327 n^3 per merge, general plan 484 n^3; the reference's dgesv+dgemm count is 810.67 n^3)",
