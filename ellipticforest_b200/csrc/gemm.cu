@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include <type_traits>
 
 namespace efgpu {
@@ -847,10 +848,166 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
     if (threadIdx.x == 0 && min_pivot) pt.publish(min_pivot);
 }
 
+// ---- cluster-cooperative base case: one N x N block (N = 256: eight CTAs, N = 128: four) inverted by a thread-block cluster ------------
+// The serial chain of the top tree levels (a handful of merges, X of order 4096 and 8192) is a sequence of 128-row base cases (48 us
+// each on ONE SM, bounded by that SM's tensor pipe: 1900 cycles of trailing update per block of eight pivots) glued by small products
+// that are pure launch latency.  Here a whole 256 x 256 block (two base cases + four products + their launches: 136 us) is one kernel:
+// CTA c of the cluster keeps the column slab [32 c, 32 c + 32) in shared memory; per block of eight pivots the slab's owner inverts the
+// 8 x 8 pivot block, pushes it and its 256 x 8 column panel into every CTA's shared memory (distributed shared memory, one cluster
+// barrier per step, double-buffered), and every CTA applies the rank-8 update to its own 32 columns with DMMA.  Blocked Gauss-Jordan
+// without pivoting, the same scalar pivots as the other base cases.
+template <int N, int CL>
+struct ClusterInvCfg {
+    static constexpr int W = N / CL;                   // columns per CTA
+    static constexpr int LDW = 40, LDC = 12, LDR = 36; // slab / column panel / row panel leading dimensions (bank-conflict-free fragment reads)
+    static constexpr int DOUBLES = N * LDW + 2 * N * LDC + 2 * 64 + 8 * LDR + 64 + 4 * 8;
+    static constexpr int SMEM_BYTES = DOUBLES * 8;
+};
+
+template <int N, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
+invert_cluster_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, double* __restrict__ min_pivot)
+{
+    namespace cg = cooperative_groups;
+    using Cfg = ClusterInvCfg<N, CL>;
+    constexpr int W = Cfg::W, LDW = Cfg::LDW, LDC = Cfg::LDC, LDR = Cfg::LDR;
+    static_assert(W == 32, "one CTA owns 32 columns");
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double smc[];
+    double* slab = smc;                        // N x LDW: this CTA's 32 columns
+    double* cpan = slab + N * LDW;             // 2 x (N x LDC): column panel of the current pivot block, pushed by its owner
+    double* pinv = cpan + 2 * N * LDC;         // 2 x 64: inverse of the pivot block, pushed by its owner
+    double* rbuf = pinv + 2 * 64;              // 8 x LDR: P^-1 A[kb, own columns]
+    double* p8 = rbuf + 8 * LDR;               // 8 x 8 scratch of the pivot-block inversion
+    double* stat = p8 + 64;                    // CL x 4 pivot statistics (gathered in CTA 0)
+    const int cr = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nmat = off2 >= 0 ? 2 : 1;
+    const int mat = blockIdx.x / CL;
+    double* G = ptab[(long long)(mat / nmat) * nops + op] + ((mat % nmat) ? off2 : off) + cr * W;
+
+    for (int e = tid; e < N * (W / 2); e += 256) {
+        const int r = e / (W / 2), c2 = (e % (W / 2)) * 2;
+        *reinterpret_cast<double2*>(slab + r * LDW + c2) = *reinterpret_cast<const double2*>(G + (long long)r * ld + c2);
+    }
+    __syncthreads();
+    cluster.sync();   // every CTA of the cluster is resident before anybody writes into its shared memory
+
+    PivotTrack pt;
+    bool owned_any = false;
+    const int g = lane >> 2, t = lane & 3;
+    for (int kb = 0; kb < N / 8; kb++) {
+        const int ow = (kb * 8) / W, lc = kb * 8 - ow * W, buf = kb & 1;
+        if (cr == ow) {
+            owned_any = true;
+            // 1a. invert the 8 x 8 pivot block (warp 0: lane = row * 4 + column pair), scalar Gauss-Jordan through the p8 scratch
+            if (warp == 0) {
+                const int i = lane >> 2, j0 = (lane & 3) * 2;
+                double a0 = slab[(kb * 8 + i) * LDW + lc + j0], a1 = slab[(kb * 8 + i) * LDW + lc + j0 + 1];
+                p8[i * 8 + j0] = a0; p8[i * 8 + j0 + 1] = a1;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double piv = p8[k * 8 + k];
+                    const double rk0 = p8[k * 8 + j0], rk1 = p8[k * 8 + j0 + 1], ck = p8[i * 8 + k];
+                    const double p = 1.0 / piv;
+                    if (lane == 0) pt.see(piv);
+                    if (i == k) { a0 = (j0 == k) ? p : a0 * p; a1 = (j0 + 1 == k) ? p : a1 * p; }
+                    else {
+                        a0 = (j0 == k) ? -ck * p : a0 - ck * (rk0 * p);
+                        a1 = (j0 + 1 == k) ? -ck * p : a1 - ck * (rk1 * p);
+                    }
+                    __syncwarp();
+                    p8[i * 8 + j0] = a0; p8[i * 8 + j0 + 1] = a1;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // 1b. push the column panel (rows of the other blocks: A[i, kb]) and P^-1 into every CTA of the cluster
+            for (int e = tid; e < N * 4; e += 256) {
+                const int r = e >> 2, j2 = (e & 3) * 2;
+                const double2 v = *reinterpret_cast<const double2*>(slab + r * LDW + lc + j2);
+#pragma unroll
+                for (int d = 0; d < CL; d++)
+                    *reinterpret_cast<double2*>(cluster.map_shared_rank(cpan, d) + buf * N * LDC + r * LDC + j2) = v;
+            }
+            if (tid < 64) {
+                const double v = p8[tid];
+#pragma unroll
+                for (int d = 0; d < CL; d++) cluster.map_shared_rank(pinv, d)[buf * 64 + tid] = v;
+            }
+        }
+        cluster.sync();
+        const double* cp = cpan + buf * N * LDC;
+        const double* pi = pinv + buf * 64;
+        // 2a. row panel of the own columns: R = P^-1 A[kb, own]; in the owner's pivot columns P^-1 itself (new A[kb, kb] = P^-1, and
+        //     new A[i, kb] = -A[i, kb] P^-1 comes out of the same update with a zero accumulator)
+        {
+            const int i = tid >> 5, c = tid & 31;
+            double r = 0.0;
+            if (cr == ow && c >= lc && c < lc + 8) r = pi[i * 8 + (c - lc)];
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) r = fma(pi[i * 8 + k], slab[(kb * 8 + k) * LDW + c], r);
+            }
+            rbuf[i * LDR + c] = r;
+        }
+        __syncthreads();
+        // 2b. rank-8 update of every other row block: A[rt, own] <- A[rt, own] - A[rt, kb] R   (DMMA m8n8k4, two k-steps)
+        const int pct = (cr == ow) ? lc / 8 : -1;
+        for (int rt = warp; rt < N / 8; rt += 8) {
+            if (rt == kb) continue;
+            const double a0 = -cp[(rt * 8 + g) * LDC + t], a1 = -cp[(rt * 8 + g) * LDC + t + 4];
+#pragma unroll
+            for (int ct = 0; ct < W / 8; ct++) {
+                double2* cptr = reinterpret_cast<double2*>(slab + (rt * 8 + g) * LDW + ct * 8 + 2 * t);
+                double2 acc = (ct == pct) ? make_double2(0.0, 0.0) : *cptr;
+                dmma884(acc.x, acc.y, a0, rbuf[t * LDR + ct * 8 + g]);
+                dmma884(acc.x, acc.y, a1, rbuf[(t + 4) * LDR + ct * 8 + g]);
+                *cptr = acc;
+            }
+        }
+        // row block kb itself becomes R (nobody reads rows kb of the slab in 2b)
+        { const int i = tid >> 5, c = tid & 31; slab[(kb * 8 + i) * LDW + c] = rbuf[i * LDR + c]; }
+        __syncthreads();
+    }
+
+    // pivot statistics of the whole block: gathered in CTA 0, published once
+    if (tid == 0) {
+        double* st0 = cluster.map_shared_rank(stat, 0) + cr * 4;
+        st0[0] = owned_any ? pt.mn : 1e300; st0[1] = owned_any ? pt.mx : 0.0; st0[2] = (double)pt.neg;
+    }
+    for (int e = tid; e < N * (W / 2); e += 256) {
+        const int r = e / (W / 2), c2 = (e % (W / 2)) * 2;
+        *reinterpret_cast<double2*>(G + (long long)r * ld + c2) = *reinterpret_cast<const double2*>(slab + r * LDW + c2);
+    }
+    cluster.sync();   // (also: no CTA leaves while another may still write into its shared memory)
+    if (cr == 0 && tid == 0 && min_pivot) {
+        PivotTrack all;
+        for (int d = 0; d < CL; d++) { all.mn = fmin(all.mn, stat[d * 4]); all.mx = fmax(all.mx, stat[d * 4 + 1]); all.neg += (unsigned)stat[d * 4 + 2]; }
+        all.publish(min_pivot);
+    }
+}
+
+template <int N, int CL>
+static void launch_invert_cluster(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int batch, double* min_pivot, cudaStream_t stream)
+{
+    using Cfg = ClusterInvCfg<N, CL>;
+    auto kern = invert_cluster_kernel<N, CL>;
+    static unsigned long long prepared = 0;
+    if (first_use_on_device(prepared)) EF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<batch * CL, 256, Cfg::SMEM_BYTES, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
+    EF_CUDA(cudaGetLastError());
+}
+
 void launch_invert_small(double* const* ptab, int nops, int op, long long off, long long off2, int ld, int N, int batch,
                          double* min_pivot, cudaStream_t stream)
 {
     batch *= off2 >= 0 ? 2 : 1;   // CTAs: two blocks per entry
+    if (N == 256 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0)) {   // planned only where few blocks are inverted at a time (top tree levels)
+        launch_invert_cluster<256, 8>(ptab, nops, op, off, off2, ld, batch, min_pivot, stream);
+        return;
+    }
     if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "invert_small: N > 128"};
     switch (N) {
         case 32: invert_reg_kernel<2><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot); EF_CUDA(cudaGetLastError()); return;

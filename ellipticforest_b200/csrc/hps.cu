@@ -424,8 +424,13 @@ struct InvPlanner {
     // inverts the N x N block at `off`; depth = log2(size of X / N) selects the W1 slot; `diag2`: the leading and the
     // trailing half are themselves block diagonal with blocks of N/4 (only the top level of X)
     void invert(long long off, int N, int depth, bool diag2) {
-        const bool can_split = N > 128 && (N / 2) % 16 == 0;   // base case: one CTA, register-resident Gauss-Jordan (N <= 128)
+        // base case: one CTA, register-resident Gauss-Jordan (N <= 128) - or, where only a few blocks are inverted at a time (the
+        // serial chain of the top tree levels: batches of at most four merges), a whole 256 x 256 block by a cluster of eight CTAs
+        // (invert_cluster_kernel; tuning key 9, read when the plan is made)
+        const bool cluster256 = N == 256 && b.count <= 4 && get_tuning(9) == 1;
+        const bool can_split = N > 128 && (N / 2) % 16 == 0 && !cluster256;
         if (!can_split) {
+            if (cluster256) { small(off, N); return; }
             if (N > 128) throw Error{EF_ERR_BAD_SHAPE, "merge matrix cannot be blocked (patch size must be 8*2^k, 16*2^k, 24*2^k ...)"};
             small(off, N);
             return;

@@ -114,3 +114,40 @@ def test_tma_operand_staging_is_bit_identical(level, nx, problem):
             lib.efgpu_set_tuning(8, 1)
     for k, (a, b) in enumerate(zip(out[1], out[0])):
         assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("level,nx,problem", [(4, 16, "helmholtz"), (3, 32, "poisson"), (5, 8, "helmholtz:9")])
+def test_cluster_base_case_against_the_128_row_recursion(level, nx, problem):
+    """efgpu_set_tuning(9, ...): in batches of at most four merges (the serial chain of the top tree levels) a whole 256 x 256 block of
+    the block inversion is one kernel - eight CTAs of a thread-block cluster, column slabs in distributed shared memory, DMMA rank-8
+    updates (default) - against the recursion down to 128 x 128 base cases: same operators up to rounding, same pivots, both within
+    1e-10 of the oracle.  Trees whose root X has order 512 (two 256-blocks per half, zipped pairs) and whose level 1 has order 256."""
+    import ellipticforest_b200 as ef
+    from ellipticforest_b200 import _lib
+    from test_host import _mesh_for
+    kw = dict(problem_name=problem, solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=nx, min_level=level, max_level=level,
+              threshold=1.2, refine_box=None)
+    P = O.problem(kw["problem_name"])
+    lib = _lib.load()
+    out = {}
+    for key in (0, 1):
+        assert lib.efgpu_set_tuning(9, key) == 0
+        try:
+            s = ef.FiniteVolumeSolver()
+            s.solver_type = "FISHPACK90"
+            s.lambda_function = P["lam"]
+            hps = ef.HPSAlgorithm(_mesh_for(kw), s)
+            hps.buildStage(); hps.upwardsStage(P["f"])
+            u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+            out[key] = ([u] + [hps.operator(nd, w) for nd in (0, 1) for w in ("T", "S", "Xinv")], hps.stats())
+        finally:
+            lib.efgpu_set_tuning(9, 1)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    tol = 1e-11 if ":" not in problem else 1e-9      # indefinite operator: conditioning, see test_indefinite_helmholtz_against_oracle
+    for k, (a, b) in enumerate(zip(out[1][0], out[0][0])):
+        assert rel(a, b) < tol, (k, rel(a, b))
+    assert abs(out[1][1]["min_pivot"] / out[0][1]["min_pivot"] - 1.0) < 1e-6
+    assert out[1][1]["negative_pivots"] == out[0][1]["negative_pivots"]
+    if ":" not in problem:
+        ora = O.run(**kw)
+        assert rel(out[1][0][1], ora.nodes[0].T) < 1e-10 and rel(out[1][0][2], ora.nodes[0].S) < 1e-10
