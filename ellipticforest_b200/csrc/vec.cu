@@ -27,9 +27,11 @@ namespace efgpu {
 // [6] variable-coefficient leaves with M = 8, 16: 0 = warp-level / tensor-core kernels (default), 1 = the CTA-per-leaf kernels of round 1
 // [8] operand staging of the 128-row GEMM tiles: 1 = TMA (cp.async.bulk.tensor.2d, swizzled shared memory, mbarrier ring; default),
 //     0 = cp.async (LDGSTS) into padded shared memory; read at every launch
-// [9] base case of the block inversion in batches of at most four merges: 1 = 256 x 256 blocks by a cluster of eight CTAs (default),
-//     0 = recursion down to 128 x 128 everywhere; read when a plan is made
-static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0};
+// [9] base case of the block inversion in batches of at most four merges: 1 = 256 x 256 blocks by a cluster of eight CTAs, 0 = recursion
+//     down to 128 x 128 everywhere (default: measured r2t, 190 us per 256-block against 136 us - the owner's serial section, eight
+//     dependent reciprocals per pivot block plus the push, leaves the other seven CTAs in the cluster barrier 61 % of the time);
+//     read when a plan is made
+static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tuning[key] = value; }
 int get_tuning(int key) { return (key >= 0 && key < 16) ? g_tuning[key] : 0; }
 

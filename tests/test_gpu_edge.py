@@ -120,7 +120,7 @@ def test_tma_operand_staging_is_bit_identical(level, nx, problem):
 def test_cluster_base_case_against_the_128_row_recursion(level, nx, problem):
     """efgpu_set_tuning(9, ...): in batches of at most four merges (the serial chain of the top tree levels) a whole 256 x 256 block of
     the block inversion is one kernel - eight CTAs of a thread-block cluster, column slabs in distributed shared memory, DMMA rank-8
-    updates (default) - against the recursion down to 128 x 128 base cases: same operators up to rounding, same pivots, both within
+    updates - against the recursion down to 128 x 128 base cases: same operators up to rounding, same pivots, both within
     1e-10 of the oracle.  Trees whose root X has order 512 (two 256-blocks per half, zipped pairs) and whose level 1 has order 256."""
     import ellipticforest_b200 as ef
     from ellipticforest_b200 import _lib
@@ -141,7 +141,7 @@ def test_cluster_base_case_against_the_128_row_recursion(level, nx, problem):
             u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
             out[key] = ([u] + [hps.operator(nd, w) for nd in (0, 1) for w in ("T", "S", "Xinv")], hps.stats())
         finally:
-            lib.efgpu_set_tuning(9, 1)
+            lib.efgpu_set_tuning(9, 0)
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     tol = 1e-11 if ":" not in problem else 1e-9      # indefinite operator: conditioning, see test_indefinite_helmholtz_against_oracle
     for k, (a, b) in enumerate(zip(out[1][0], out[0][0])):

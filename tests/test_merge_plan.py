@@ -200,7 +200,7 @@ def test_plan_reproduces_oracle_merge_uniform(sym, nranks, depth):
 def test_zipped_diagonal_subinversions(sym, cluster):
     """n = 256: X is 1024 x 1024, the two 256 x 256 diagonal blocks of its leading block recurse (products inside), and
     their step lists are zipped into launches that carry both blocks (second branch on its own workspace slots).  With tuning
-    key 9 (default on) a batch of at most four merges stops the recursion at 256 x 256 blocks (cluster-cooperative base case):
+    key 9 (off by default) a batch of at most four merges stops the recursion at 256 x 256 blocks (cluster-cooperative base case):
     the pair is then ONE paired base-case launch and the Schur complement two more 256-blocks."""
     if 4 not in _CHILDREN:
         _CHILDREN[4] = uniform_children(16, 4)
@@ -218,7 +218,7 @@ def test_zipped_diagonal_subinversions(sym, cluster):
             assert any(int(st[0]) == 1 and int(st[2]) == 2 and int(st[5]) == 4 for st in steps)  # paired products of the inversion
         states, flops = emulate(n, 0, 1, sym, Tc, root.X)
     finally:
-        assert lib.efgpu_set_tuning(9, 1) == 0
+        assert lib.efgpu_set_tuning(9, 0) == 0
     s = states[0]
     assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(root.X)) < 1e-11
     assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
