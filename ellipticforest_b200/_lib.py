@@ -46,6 +46,7 @@ SIGNATURES = {
     "efgpu_set_refine_inverse": (C.c_int, [_P, C.c_int]),
     "efgpu_debug_merge_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _I, _P, _P, _I, _P, _I, _P]),
     "efgpu_debug_merge_plan_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _I, _P, _P, _I, _P, _I, _P]),
+    "efgpu_debug_tma_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _I, _P, _P]),
     "efgpu_build_begin": (C.c_int, [_P, C.c_uint]),
     "efgpu_build_level": (C.c_int, [_P, C.c_int, C.c_int]),
     "efgpu_build_end": (C.c_int, [_P]),

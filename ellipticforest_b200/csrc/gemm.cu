@@ -671,6 +671,18 @@ invert_reg_kernel(double* const* __restrict__ ptab, int nops, int op, long long 
 //     permuted to {0,2,4,6} / {1,3,5,7} - IS the B-operand layout of the trailing update: no layout change through memory;
 //  4. trailing update: two DMMAs per tile, A operand = -C_I read as 16-byte pairs.
 // No pivoting, like the kernel it replaces (pivoting policy); different rounding (block order), same parity tests.
+// Reciprocal of a pivot off the IEEE division sequence: hardware seed (20 bits) + two Newton steps = four dependent DFMAs instead of
+// MUFU + ~7 DFMAs + the slow-path check, on the critical path of every one of the 128 sequential pivots of a base case.  Relative
+// error ~1 ulp (not correctly rounded); pivots are never subnormal or near overflow (the tracker rejects such blocks).
+__device__ __forceinline__ double fast_rcp(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0); r = fma(r, e, r);
+    e = fma(-a, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+template <bool FR = false>
 __device__ __forceinline__ void inv8x8_pivot(int k, double& p0, double& p1, int r, int q, PivotTrack& pt)
 {
     const int kq = k >> 1;
@@ -678,7 +690,7 @@ __device__ __forceinline__ void inv8x8_pivot(int k, double& p0, double& p1, int 
     const double mine = (k & 1) ? p1 : p0;
     const double ck = __shfl_sync(0xffffffffu, mine, 4 * r + kq);                                                  // A[r][k]
     const double piv = __shfl_sync(0xffffffffu, mine, 4 * k + kq);                                                 // A[k][k]
-    const double pinv = 1.0 / piv;
+    const double pinv = FR ? fast_rcp(piv) : 1.0 / piv;
     pt.see(piv);
     if (r == k) {
         p0 = (2 * q == k) ? pinv : rk0 * pinv;
@@ -689,17 +701,18 @@ __device__ __forceinline__ void inv8x8_pivot(int k, double& p0, double& p1, int 
         p1 = (2 * q + 1 == k) ? -f : fma(-f, rk1, p1);
     }
 }
+template <bool FR = false>
 __device__ __forceinline__ void inv8x8_warp(double& p0, double& p1, int r, int q, PivotTrack& pt)
 {
 #pragma unroll
-    for (int k = 0; k < 8; k++) inv8x8_pivot(k, p0, p1, r, q, pt);
+    for (int k = 0; k < 8; k++) inv8x8_pivot<FR>(k, p0, p1, r, q, pt);
 }
 
 // LA (look-ahead, efgpu_set_tuning(7, 2)): the inverse of the NEXT pivot block is taken off the critical path.  The owner of tile (kb+1, kb+1)
 // publishes it with the panels of step kb; every warp forms its updated value itself (four DMMAs) and interleaves the eight
 // pivots of its 8 x 8 inverse with the eight tile rows of the trailing update, so that the dependent shuffle / reciprocal chain
 // runs in the shadow of the tensor-pipe work and step kb+1 starts with P^-1 already in registers.
-template <bool LA>
+template <bool LA, bool FR = false>
 __global__ void __launch_bounds__(256, 1)
 invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long long off, long long off2, int ld, double* __restrict__ min_pivot)
 {
@@ -769,7 +782,7 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
         // 2. P^-1, by every warp on its own lanes (LA: only at the first step, afterwards it is already there)
         if (!LA || kb == 0) {
             const double2 v = *reinterpret_cast<const double2*>(sr + r * LR + 8 * kb + 2 * q); p0 = v.x; p1 = v.y;
-            inv8x8_warp(p0, p1, r, q, pt);
+            inv8x8_warp<FR>(p0, p1, r, q, pt);
         }
         *reinterpret_cast<double2*>(spi + r * LP + 2 * q) = make_double2(p0, p1);
         __syncwarp();
@@ -806,7 +819,7 @@ invert_blk128_kernel(double* const* __restrict__ ptab, int nops, int op, long lo
         // 4. trailing update and the special tile row / column (LA: one pivot of the next inverse per tile row)
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            if (la) inv8x8_pivot(i, pn0, pn1, r, q, pt);
+            if (la) inv8x8_pivot<FR>(i, pn0, pn1, r, q, pt);
             const int ti = 8 * wr + i;
             const double2 cv = *reinterpret_cast<const double2*>(sc + (8 * ti + r) * LC + 2 * q);   // C[8 ti + r][2 q], [2 q + 1]
             const double a0 = -cv.x, a1 = -cv.y;
@@ -1019,7 +1032,10 @@ void launch_invert_small(double* const* ptab, int nops, int op, long long off, l
             // Needs 16-byte aligned rows (even ld and offsets: always true for the merge matrices, whose blocks are multiples of 8)
             // (7, 2): the blocked kernel with a look-ahead of the next pivot block - measured (r2i): 8.62 against 8.12 ms of base
             // cases per step, the redundant work and register pressure cost more than the shortened chain gains; kept as a knob
-            if (get_tuning(7) == 0 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
+            // tuning key 10 = 1: pivot reciprocals by hardware seed + two Newton steps instead of the IEEE division
+            if (get_tuning(7) == 0 && get_tuning(10) == 1 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
+                invert_blk128_kernel<false, true><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
+            else if (get_tuning(7) == 0 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
                 invert_blk128_kernel<false><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);
             else if (get_tuning(7) == 2 && ld % 2 == 0 && off % 2 == 0 && (off2 < 0 || off2 % 2 == 0))
                 invert_blk128_kernel<true><<<batch, 256, 0, stream>>>(ptab, nops, op, off, off2, ld, min_pivot);

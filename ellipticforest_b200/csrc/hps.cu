@@ -1804,6 +1804,26 @@ int efgpu_debug_merge_plan_ex(int n, int level, int rank, int nranks, int symmet
     } catch (const efgpu::Error& e) { g_create_error = e.msg; return e.code; }
 }
 
+int efgpu_debug_tma_plan(int n, int level, int rank, int nranks, int symmetric, int peer, int64_t* views, int* n_views,
+                         int64_t* tblocks, int64_t* step_tma)
+{
+    if (n < 8 || n % 8 || nranks < 1 || rank < 0 || rank >= nranks || !n_views) return EF_ERR_BAD_ARG;
+    try {
+        BatchH b; b.n = n; b.level = level; b.count = 1; b.symcand = symmetric != 0;
+        plan_batch_gemms(b, rank, nranks, peer != 0);
+        const std::vector<Step>& st = symmetric ? b.steps_sym : b.steps;
+        *n_views = (int)b.views.size();
+        if (views) for (size_t v = 0; v < b.views.size(); v++) { views[3 * v] = b.views[v].op; views[3 * v + 1] = b.views[v].origin; views[3 * v + 2] = b.views[v].ld; }
+        if (tblocks) for (size_t k = 0; k < b.tblocks.size(); k++)
+            for (int t = 0; t < 2; t++) {
+                int64_t* q = tblocks + 12 * k + 6 * t; const TmaTerm& m = b.tblocks[k].t[t];
+                q[0] = m.a_view; q[1] = m.b_view; q[2] = m.a_row; q[3] = m.a_col; q[4] = m.b_row; q[5] = m.b_col;
+            }
+        if (step_tma) for (size_t i = 0; i < st.size(); i++) step_tma[i] = st[i].tma ? 1 : 0;
+        return EF_OK;
+    } catch (const efgpu::Error& e) { g_create_error = e.msg; return e.code; }
+}
+
 int efgpu_set_tuning(int key, int value)
 {
     if (key < 0 || key >= 16) return EF_ERR_BAD_ARG;

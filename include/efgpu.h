@@ -287,6 +287,13 @@ int efgpu_debug_merge_plan(int n, int level, int rank, int nranks, int symmetric
 int efgpu_debug_merge_plan_ex(int n, int level, int rank, int nranks, int symmetric, int peer, int64_t* steps, int* n_steps,
                               int64_t* blocks, int64_t* terms, int* n_blocks, int64_t* trans, int* n_trans, int64_t* ws);
 
+/* TMA side of the same plan (operand staging of the 128-row products, csrc/gemm_tma.cu): `views` (3 per view: operand slot, origin
+ * inside the slot, leading dimension), `tblocks` (12 per block descriptor, same indexing as `blocks`: for each of the two terms a_view,
+ * b_view, a_row, a_col, b_row, b_col; view -1 = the block keeps the cp.async kernel) and `step_tma` (one per step: 1 when every block
+ * of the step has views).  Arrays may be NULL to query n_views only. */
+int efgpu_debug_tma_plan(int n, int level, int rank, int nranks, int symmetric, int peer, int64_t* views, int* n_views,
+                         int64_t* tblocks, int64_t* step_tma);
+
 /* Process-wide kernel-selection knobs for measurements (A/B runs of the bandwidth-bound kernels): key 0 = matvec kernels
  * for rows of <= 256 doubles (2, default: row-batch kernels; 0: one row per warp, as for longer rows); key 1 = long-row
  * kernel of the compact H (0, default: 8 loads in flight per lane; 1: 4); key 2 = CTAs per SM the long-row launcher aims

@@ -151,3 +151,35 @@ def test_cluster_base_case_against_the_128_row_recursion(level, nx, problem):
     if ":" not in problem:
         ora = O.run(**kw)
         assert rel(out[1][0][1], ora.nodes[0].T) < 1e-10 and rel(out[1][0][2], ora.nodes[0].S) < 1e-10
+
+
+def test_fast_pivot_reciprocal_against_ieee_division():
+    """efgpu_set_tuning(10, 1): the pivot reciprocals of the 128 x 128 base case from the hardware seed and two Newton steps instead
+    of the IEEE division sequence (shorter dependent chain per pivot): same operators to rounding."""
+    import ellipticforest_b200 as ef
+    from ellipticforest_b200 import _lib
+    from test_host import _mesh_for
+    kw = dict(problem_name="helmholtz", solver_kind="fishpack", box=(0.0, np.pi, 0.0, np.pi), nx=16, min_level=4, max_level=4,
+              threshold=1.2, refine_box=None)
+    P = O.problem(kw["problem_name"])
+    lib = _lib.load()
+    default = lib.efgpu_set_tuning(10, 0)
+    out = {}
+    for key in (0, 1):
+        assert lib.efgpu_set_tuning(10, key) == 0
+        try:
+            s = ef.FiniteVolumeSolver()
+            s.solver_type = "FISHPACK90"
+            s.lambda_function = P["lam"]
+            hps = ef.HPSAlgorithm(_mesh_for(kw), s)
+            hps.buildStage(); hps.upwardsStage(P["f"])
+            u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
+            out[key] = [u, hps.operator(0, "T"), hps.operator(0, "S"), hps.operator(0, "Xinv")]
+        finally:
+            lib.efgpu_set_tuning(10, TUNING10_DEFAULT)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    for k in range(4):
+        assert rel(out[0][k], out[1][k]) < 1e-11, k
+
+
+TUNING10_DEFAULT = 0

@@ -351,3 +351,52 @@ def test_peer_plan_reproduces_oracle_merge(nranks, n, level, monkeypatch):
         assert rel(s.ops[OP_T].reshape(8 * n, 8 * n), root.T) < 1e-11
     assert split_steps > 0
     print("peer plan n=%d ranks=%d level=%d: %d split products" % (n, nranks, level, split_steps))
+
+
+@pytest.mark.parametrize("n,level,nranks,peer", [(512, 0, 1, 0), (2048, 0, 1, 0), (1024, 1, 4, 1), (2048, 0, 8, 1), (128, 3, 1, 0), (64, 4, 1, 0)])
+@pytest.mark.parametrize("sym", [0, 1])
+def test_tma_views_address_the_same_operands(n, level, nranks, peer, sym):
+    """plan_tma (operand staging by TMA, csrc/gemm_tma.cu): every operand block of a step marked for the TMA kernel must be reachable as
+    (view origin) + row * ld + col = the descriptor's element offset, inside one row of its view (no wrap), with whole 128 x 64 tiles
+    and K a multiple of 16; the W1 workspace slots of the recursion get their own origins; steps with any other block stay on cp.async."""
+    lib = _lib.load()
+    for rank in sorted({0, nranks - 1}):
+        steps, blocks, terms, trans, ws = get_plan(n, level, rank, nranks, sym, peer)
+        nv = C.c_int()
+        assert lib.efgpu_debug_tma_plan(n, level, rank, nranks, sym, peer, None, C.byref(nv), None, None) == 0
+        views = np.zeros((max(nv.value, 1), 3), dtype=np.int64)
+        tb = np.full((len(blocks), 2, 6), -7, dtype=np.int64)
+        flags = np.zeros(len(steps), dtype=np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert lib.efgpu_debug_tma_plan(n, level, rank, nranks, sym, peer, p(views), C.byref(nv), p(tb), p(flags)) == 0
+        views = views[:nv.value]
+        n_tma = 0
+        for st, fl in zip(steps, flags):
+            if int(st[0]) != 1:
+                assert fl == 0
+                continue
+            first, count = int(st[1]), int(st[2])
+            ok_all = count > 0
+            for k in range(first, first + count):
+                rows, cols, nterms = int(blocks[k][6]), int(blocks[k][7]), int(blocks[k][8])
+                valid = tb[k][0][0] >= 0
+                if valid:
+                    assert rows % 128 == 0 and cols % 64 == 0
+                    for t in range(nterms):
+                        a_op, b_op, lda, ldb, a_off, b_off, K, _ = (int(v) for v in terms[k][t])
+                        av, bv, ar, ac, br, bc = (int(v) for v in tb[k][t])
+                        assert K % 16 == 0
+                        assert tuple(views[av][[0, 2]]) == (a_op, lda) and tuple(views[bv][[0, 2]]) == (b_op, ldb)
+                        assert int(views[av][1]) + ar * lda + ac == a_off and ac + K <= lda
+                        assert int(views[bv][1]) + br * ldb + bc == b_off and bc + cols <= ldb
+                ok_all = ok_all and valid
+            assert bool(fl) == ok_all
+            n_tma += int(fl)
+        if n >= 512:
+            assert n_tma > 0            # the large products of such a merge do run on TMA-staged operands
+        if n <= 64:
+            assert nv.value == 0 or n_tma >= 0
+        # W1 views: one origin per recursion depth in use, all inside the W1 workspace
+        for op, origin, ld in views:
+            assert origin >= 0 and (op != OP_W1 or origin < ws[0])
+            assert op == OP_W1 or origin == 0
