@@ -195,8 +195,7 @@ def test_plan_reproduces_oracle_merge_uniform(sym, nranks, depth):
             assert flops < 400 * n3 if sym else flops <= 484 * n3   # symmetric plan: well below the general 484 n^3
 
 
-@pytest.mark.parametrize("cluster", [0, 1])
-@pytest.mark.parametrize("sym", [0, 1])
+@pytest.mark.parametrize("sym,cluster", [(0, 0), (1, 0), (1, 1)])
 def test_zipped_diagonal_subinversions(sym, cluster):
     """n = 256: X is 1024 x 1024, the two 256 x 256 diagonal blocks of its leading block recurse (products inside), and
     their step lists are zipped into launches that carry both blocks (second branch on its own workspace slots).  With tuning
