@@ -299,15 +299,23 @@ int efgpu_debug_tma_plan(int n, int level, int rank, int nranks, int symmetric, 
  * kernel of the compact H (0, default: 8 loads in flight per lane; 1: 4); key 2 = CTAs per SM the long-row launcher aims
  * for (0: default 16); key 3 = leaf solve of constant-coefficient leaves (0, default: FP64 tensor-core kernel, one warp per
  * leaf; 1: one thread per cell); key 5 = symmetric merge plan, diagonal blocks of T: 1 = multiply only the upper triangle of
- * their 2 x 2 / 4 x 4 sub-blocks and mirror the rest (1, default; 0: whole blocks; read when a handle is created / partitioned).
+ * their 2 x 2 / 4 x 4 sub-blocks and mirror the rest (1, default; 0: whole blocks; read when a handle is created / partitioned);
+ * key 4 = transposed second destination of a GEMM block (0, default: through shared memory as whole rows where peer arenas receive
+ * it, direct stores otherwise; 1: always through shared memory; 2: always direct); key 6 = variable-coefficient leaves of 8 / 16
+ * cells (0, default: warp-level / tensor-core kernels; 1: CTA-per-leaf kernels); key 7 = 128 x 128 base case of the block inversion
+ * (0, default: blocked Gauss-Jordan on the tensor pipe; 1: per-pivot register kernel; 2: blocked with look-ahead); key 8 = operand
+ * staging of the 128-row GEMM tiles (1, default: TMA; 0: cp.async); key 9 = 256 x 256 base case by a thread-block cluster in batches
+ * of at most four merges (0, default: off; read when a plan is made); key 10 = pivot reciprocals of the base case by hardware seed +
+ * Newton steps (0, default: IEEE division).  Keys 0 .. 15 are accepted.
  * Results do not depend on the knobs beyond floating-point summation order. */
 int efgpu_set_tuning(int key, int value);
 
 /* ---- stand-alone access to the GEMM kernel for unit tests and roofline measurements ------------ */
 int efgpu_dgemm_batched(const double* A_dev, const double* B_dev, double* C_dev, int m, int n, int k, int batch,
                         int tile, int iters, float* ms_per_iter);
-/* The same product with TMA-staged operands (cp.async.bulk.tensor.2d + mbarrier ring, producer warp, 128-byte swizzle; `stages` = 3,
- * 4 or 6): the A/B experiment behind DESIGN.md section 4's choice of operand path.  m % 128 == n % 64 == k % 16 == 0.  Bit-identical
+/* The same product with TMA-staged operands (cp.async.bulk.tensor.2d + mbarrier ring, 128-byte swizzle; `stages` = 3, 4 or 6: 128 x 128 CTA
+ * tile, that many stages; 64: 128 x 64 CTA tile, four stages, two CTAs per SM): the A/B experiment behind DESIGN.md section 4's choice of
+ * operand path.  m % 128 == n % 128 == k % 16 == 0.  Bit-identical
  * to efgpu_dgemm_batched (same k order). */
 int efgpu_dgemm_batched_tma(const double* A_dev, const double* B_dev, double* C_dev, int m, int n, int k, int batch,
                             int stages, int iters, float* ms_per_iter);
