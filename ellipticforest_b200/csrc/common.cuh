@@ -75,6 +75,7 @@ struct PeerSpan {
 };
 void launch_peer_barrier(const PeerSpan& ps, int me, int* err, cudaStream_t s);
 void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, cudaStream_t s);
+void launch_peer_scatter2d(const PeerSpan& ps, int me, size_t off, size_t rows, size_t row_bytes, size_t pitch, cudaStream_t s);
 
 // TMA-staged operands (gemm_tma.cu): a view is one matrix an operand block lies in - (operand slot, origin inside the slot, leading
 // dimension); every (batch entry, view) has a tensor map for its use as A operand (128 x 16 boxes) and as B operand (16 x 16 boxes);

@@ -88,6 +88,7 @@ struct BatchH {
     std::vector<Step> steps_sym;      // plan for symmetric merge matrices (symcand batches only)
     std::vector<Step> steps_refine;   // one Newton-Schulz step on X^-1 (indefinite problems), run between the inversion and S
     bool symcand = false;             // structurally symmetric: square patches, no coarsening anywhere below
+    bool colsplit = false;            // peer-mapped partition of S / T by block columns instead of rows (plan_batch_gemms)
     bool use_sym = false;             // decided at build time (leaf operator self-adjoint, EFGPU_NO_SYMMETRY not set)
     const std::vector<Step>& active() const { return use_sym ? steps_sym : steps; }
     DevBuf d_blocks, d_trans, d_entries, d_ptab;
@@ -136,6 +137,7 @@ struct efgpu_handle {
     PeerSpan peers;
     void* peer_mapped[PEER_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool peer_dirty = true;                      // local work since the last barrier: a barrier must precede the next peer stores
+    bool peer_pending = false;                   // column-partitioned S was stored into the peers and no barrier has completed it yet
     DevBuf d_peer_err;
     std::vector<size_t> leafT_off;               // element offset of each leaf's T inside d_leafT
     // external leaves tagged by their parent receive coarsened Dirichlet data: uncoarsen it at the end of the solve
@@ -570,6 +572,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
     // partitions with at most one block row of T per rank (8 ranks and more): the four opposite pairs are shared half and half,
     // 4.5 instead of 5 : 4 block products per row (halves of >= 128 rows / columns: full GEMM tiles)
     const bool split_opposite = nranks >= 8 && n % 256 == 0;
+    // peer-mapped trees whose rank count divides the eight WESN block columns: S and T are partitioned by COLUMNS (see below)
+    const bool colsplit = peer && nranks > 1 && 8 % nranks == 0 && get_tuning(11) == 1;
+    b.colsplit = colsplit;
     for (int variant = 0; variant < (b.symcand ? 2 : 1); variant++) {
         const bool sym = variant == 1;
         std::vector<Step>& steps = sym ? b.steps_sym : b.steps;
@@ -589,7 +594,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                     g.t[t] = GemmTerm{OP_XINV, OP_TC0 + c, N, N, (long long)(k * n) * N + k2 * n,
                                       (long long)(h_iface[c][k2] * n) * N + side * n, n, h_sgn[c][k2] < 0 ? 0x80000000u : 0u};
                 }
-                if (clip_rows(g, (long long)k * n, s_lo, s_hi)) b.blocks.push_back(g);
+                if (colsplit) {   // column partition: the blocks of this rank's WESN positions, all four block rows
+                    if ((long long)h_pos[q] * n >= t_lo && (long long)h_pos[q] * n < t_hi) b.blocks.push_back(g);
+                } else if (clip_rows(g, (long long)k * n, s_lo, s_hi)) b.blocks.push_back(g);
             }
         { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_S; steps.push_back(st); }
         // T = T_LHS + H S, rows and columns in WESN order (mergeT_ + reorderOperators_).  Symmetric plan: with the sign
@@ -597,12 +604,48 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
         // diag(d) T is symmetric, so of every off-diagonal pair of n x n blocks only one is computed - chosen on a circulant
         // pattern so that each block row carries 4 or 5 products and every half / quarter of the rows the same number (row
         // partitions over 2 and 4 ranks are balanced exactly, over 8 ranks to 5 : 4) - and the other is its signed transpose.
+        // Column partition (peer-mapped trees): the same selection with rows and columns exchanged - the owner of position O
+        // computes block (X, O) where the row partition computes (O, X) - so that every product reads S only in the columns its
+        // own rank computed: S needs no exchange before T.
         first = (int)b.blocks.size();
         const int tfirst = (int)b.trans.size();
+        // block of T at WESN block row h_pos[rowq], block column h_pos[colq], sub-range rows r0 .. r0 + nr, columns c0 .. c0 + nc
+        auto make_T = [&](int rowq, int colq, int r0, int c0, int nr_, int nc_) {
+            const int c = rowq >> 1, side_r = h_tau_side[c][rowq & 1];
+            const int c2 = colq >> 1, side_c = h_tau_side[c2][colq & 1];
+            const int PR = h_pos[rowq], PC = h_pos[colq];
+            GemmBlock g{};
+            g.c_op = OP_T; g.c_off = (long long)(PR * n + r0) * (8 * n) + PC * n + c0; g.ldc = 8 * n;
+            if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n + r0) * N + side_c * n + c0; g.ldc0 = N; }
+            else g.c0_op = -1;
+            g.rows = nr_; g.cols = nc_; g.nterms = 2;
+            for (int t = 0; t < 2; t++) {
+                const int k = h_kk[c][t];
+                g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n + r0) * N + h_iface[c][k] * n,
+                                  (long long)(k * n) * (8 * n) + PC * n + c0, n, 0u};
+            }
+            return g;
+        };
+        // the block computed by the owner `qo` against `qx`: at (qo, qx) in a row partition, transposed at (qx, qo) in a column partition
+        auto emit_T = [&](int qo, int qx, int r0, int c0, int nr_, int nc_) {
+            if (colsplit) {
+                GemmBlock g = make_T(qx, qo, c0, r0, nc_, nr_);
+                if ((long long)h_pos[qo] * n >= t_lo && (long long)h_pos[qo] * n < t_hi) b.blocks.push_back(g);
+                return g;
+            }
+            GemmBlock g = make_T(qo, qx, r0, c0, nr_, nc_);
+            if (clip_rows(g, (long long)h_pos[qo] * n + r0, t_lo, t_hi)) b.blocks.push_back(g);
+            return g;
+        };
+        // mirror step: the rows x cols block at (position SP, offset sr0; position SQ, offset sc0) goes, transposed (and signed), to
+        // (SQ, sc0; SP, sr0); a column partition exchanges the roles of source and destination coordinates
+        auto add_mirror = [&](int SP, int sr0, int SQ, int sc0, int rows, int cols, unsigned neg) {
+            if (colsplit) { std::swap(SP, SQ); std::swap(sr0, sc0); std::swap(rows, cols); }
+            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(SP * n + sr0) * (8 * n) + SQ * n + sc0,
+                                      (long long)(SQ * n + sc0) * (8 * n) + SP * n + sr0, rows, cols, neg, 0});
+        };
         for (int qr = 0; qr < 8; qr++)
             for (int qc = 0; qc < 8; qc++) {
-                const int c = qr >> 1, side_r = h_tau_side[c][qr & 1];
-                const int c2 = qc >> 1, side_c = h_tau_side[c2][qc & 1];
                 const int P = h_pos[qr], Q = h_pos[qc];
                 if (sym && mirror_ok && P != Q) {
                     const int dl = (Q - P) & 7;
@@ -612,23 +655,9 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                         // the transpose of what the partner computed (no sign: both sides lie on the same kind of axis)
                         const int hn = n / 2;
                         const int r0 = 0, c0 = P < 4 ? 0 : hn, nr_ = P < 4 ? hn : n, nc_ = P < 4 ? n : hn;
-                        GemmBlock g{};
-                        g.c_op = OP_T; g.c_off = (long long)(P * n + r0) * (8 * n) + Q * n + c0; g.ldc = 8 * n;
-                        if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n + r0) * N + side_c * n + c0; g.ldc0 = N; }
-                        else g.c0_op = -1;
-                        g.rows = nr_; g.cols = nc_; g.nterms = 2;
-                        for (int t = 0; t < 2; t++) {
-                            const int k = h_kk[c][t];
-                            g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n + r0) * N + h_iface[c][k] * n,
-                                              (long long)(k * n) * (8 * n) + Q * n + c0, n, 0u};
-                        }
-                        if (clip_rows(g, (long long)P * n + r0, t_lo, t_hi)) b.blocks.push_back(g);
-                        if (P < 4)   // lower half of (P, Q) <- transpose of the right half of (Q, P)
-                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n + hn,
-                                                      (long long)(P * n + hn) * (8 * n) + Q * n, n, hn, 0u, 0});
-                        else         // left half of (P, Q) <- transpose of the upper half of (Q, P)
-                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
-                                                      (long long)(P * n) * (8 * n) + Q * n, hn, n, 0u, 0});
+                        emit_T(qr, qc, r0, c0, nr_, nc_);
+                        if (P < 4) add_mirror(Q, 0, P, hn, n, hn, 0u);     // lower half of (P, Q) <- transpose of the right half of (Q, P)
+                        else add_mirror(Q, 0, P, 0, hn, n, 0u);           // left half of (P, Q) <- transpose of the upper half of (Q, P)
                         continue;
                     }
                     // (of the opposite pair P, P + 4 the even one of rows 0..3 / the odd one of rows 4..7 computes: block rows 0, 2, 5, 7
@@ -636,10 +665,8 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                     if (!(dl < 4 || (dl == 4 && ((P < 4) != ((P & 1) != 0))))) {
                         const unsigned neg = ((P ^ Q) & 2) ? 0x80000000u : 0u;   // W, W, E, E, S, S, N, N: d = -1 where bit 1 is clear
                         // unpartitioned: written by the epilogue of the product that computes (Q, P) (below); partitioned: a
-                        // transpose step after the row slices have been gathered
-                        if (nranks > 1)
-                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(Q * n) * (8 * n) + P * n,
-                                                      (long long)(P * n) * (8 * n) + Q * n, n, n, neg, 0});
+                        // transpose step after the slices have been gathered
+                        if (nranks > 1) add_mirror(Q, 0, P, 0, n, n, neg);
                         continue;
                     }
                 }
@@ -650,19 +677,15 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                 const int sb = n / nb;
                 for (int I = 0; I < nb; I++)
                     for (int J = I; J < nb; J++) {
-                        GemmBlock g{};
-                        g.c_op = OP_T; g.c_off = (long long)(P * n + I * sb) * (8 * n) + Q * n + J * sb; g.ldc = 8 * n;
-                        if (c == c2) { g.c0_op = OP_TC0 + c; g.c0_off = (long long)(side_r * n + I * sb) * N + side_c * n + J * sb; g.ldc0 = N; }
-                        else g.c0_op = -1;
-                        g.rows = sb; g.cols = sb; g.nterms = 2;
-                        for (int t = 0; t < 2; t++) {
-                            const int k = h_kk[c][t];
-                            g.t[t] = GemmTerm{OP_TC0 + c, OP_S, N, 8 * n, (long long)(side_r * n + I * sb) * N + h_iface[c][k] * n,
-                                              (long long)(k * n) * (8 * n) + Q * n + J * sb, n, 0u};
+                        if (nranks > 1) {
+                            emit_T(qr, qc, I * sb, J * sb, sb, sb);
+                            if (J > I) add_mirror(P, I * sb, Q, J * sb, sb, sb, 0u);
+                            continue;
                         }
+                        GemmBlock g = make_T(qr, qc, I * sb, J * sb, sb, sb);
                         // mirrored partner written by the same epilogue (unpartitioned trees): the signed transpose block (Q, P) of an
                         // off-diagonal block of the symmetric plan, the lower sub-block of a diagonal block's triangle
-                        if (sym && mirror_ok && nranks == 1) {
+                        if (sym && mirror_ok) {
                             if (P != Q) {
                                 g.ct_op1 = OP_T + 1; g.ct_off = (long long)(Q * n) * (8 * n) + P * n; g.ldct = 8 * n;
                                 g.ct_neg = ((P ^ Q) & 2) ? 0x80000000u : 0u;
@@ -670,10 +693,7 @@ static void plan_batch_gemms(BatchH& b, int rank, int nranks, bool peer = false)
                                 g.ct_op1 = OP_T + 1; g.ct_off = (long long)(P * n + J * sb) * (8 * n) + Q * n + I * sb; g.ldct = 8 * n;
                             }
                         }
-                        if (clip_rows(g, (long long)P * n + I * sb, t_lo, t_hi)) b.blocks.push_back(g);
-                        if (J > I && nranks > 1)
-                            b.trans.push_back(TransOp{OP_T, OP_T, 8 * n, 8 * n, (long long)(P * n + I * sb) * (8 * n) + Q * n + J * sb,
-                                                      (long long)(P * n + J * sb) * (8 * n) + Q * n + I * sb, sb, sb, 0u, 0});
+                        b.blocks.push_back(g);
                     }
             }
         { Step st{}; st.kind = 1; st.first = first; st.count = (int)b.blocks.size() - first; st.cls = EFGPU_PROF_GEMM_T; steps.push_back(st); }
@@ -1133,6 +1153,7 @@ static void build_level(efgpu_handle* H, int lev, int phase)
         // the DtN map of the whole domain is read by nothing on the Dirichlet path (only by the root's Robin system, a parent
         // that does not exist, and parity readers): its products are issued by complete_root_T when somebody asks for it
         H->root_T_pending = true;
+        if (H->peer_pending) { peer_barrier(H, false); H->peer_pending = false; }
         return;
     }
     H->peer_dirty = true;
@@ -1191,6 +1212,9 @@ static void build_level(efgpu_handle* H, int lev, int phase)
             // peer mode: the row slices of a split product, of S and of the DtN maps below the root are stored into every rank's
             // arena by the GEMM itself, between two flag barriers (the root's map stays row-distributed: nobody merges it)
             const bool scatter = p2p && st.kind == 1 && (st.gk == 3 || st.cls == EFGPU_PROF_GEMM_S || (is_T && lev > 0));
+            // column-partitioned S / T: the T products read S only in this rank's own columns, so the stores of S into the peers
+            // need no barrier of their own - the one after T (or, at the root, the one issued below) completes both
+            const bool defer = scatter && b.colsplit && st.cls == EFGPU_PROF_GEMM_S;
             if (H->trace) {
                 char lb[160];
                 if (st.kind == 1) {
@@ -1205,8 +1229,10 @@ static void build_level(efgpu_handle* H, int lev, int phase)
                 if (st.kind == 0) launch_invert_small(ptab, NOPS, OP_XINV, st.off, st.off2, 4 * b.n, st.N, bcount, H->d_minpiv.as<double>(), s);
                 else { TmaArgs ta; launch_bgemm(ptab, NOPS, b.d_blocks.as<GemmBlock>() + st.first, b.blocks.data() + st.first, st.count, bcount, s, 0, scatter ? &H->peers : nullptr, tma_args(st, ta)); }
             });
-            if (scatter) { peer_barrier(H, false); continue; }
+            if (defer) { H->peer_pending = true; continue; }
+            if (scatter) { peer_barrier(H, false); H->peer_pending = false; continue; }
             H->peer_dirty = true;
+            if (is_T && H->peer_pending) { peer_barrier(H, false); H->peer_pending = false; }   // root: T stays distributed, S is completed here
             if (st.gk) timed(H, EFGPU_PROF_ALLGATHER, 0, [&] {
                 const size_t hh = (size_t)st.g_rows * st.g_cols;
                 for (int sl = 0; sl < b.count; sl++) {
@@ -1261,6 +1287,12 @@ static void complete_root_T(efgpu_handle* H)
         for (int sl = 0; sl < b.count; sl++) {
             double* T = b.h_ptab[(size_t)sl * NOPS + OP_T];
             const size_t slice = 64 * n2 / H->part_nranks * sizeof(double);
+            if (p2p && b.colsplit) {   // this rank's block columns (all 8 n rows) into every other arena
+                const size_t row_bytes = 8 * (size_t)b.n / H->part_nranks * sizeof(double);
+                launch_peer_scatter2d(H->peers, H->part_rank, (size_t)(reinterpret_cast<char*>(T) - static_cast<char*>(H->arena.p)) + H->part_rank * row_bytes,
+                                      8 * (size_t)b.n, row_bytes, 8 * (size_t)b.n * sizeof(double), s);
+                continue;
+            }
             if (p2p) {   // this rank's row slice into every other arena; the barrier below completes the all-gather
                 launch_peer_scatter(H->peers, H->part_rank, (size_t)(reinterpret_cast<char*>(T) - static_cast<char*>(H->arena.p)) + H->part_rank * slice, slice, s);
                 continue;
@@ -1785,7 +1817,7 @@ int efgpu_debug_merge_plan_ex(int n, int level, int rank, int nranks, int symmet
         if (steps) for (size_t i = 0; i < st.size(); i++) {
             int64_t* r = steps + 16 * i; const Step& x = st[i];
             r[0] = x.kind; r[1] = x.first; r[2] = x.count; r[3] = x.off; r[4] = x.N; r[5] = x.cls; r[6] = x.gk; r[7] = x.g_op;
-            r[8] = x.g_rows; r[9] = x.g_cols; r[10] = x.g_ld; r[11] = x.g_off; r[12] = x.off2;
+            r[8] = x.g_rows; r[9] = x.g_cols; r[10] = x.g_ld; r[11] = x.g_off; r[12] = x.off2; r[13] = b.colsplit ? 1 : 0;
         }
         if (blocks && terms) for (size_t i = 0; i < b.blocks.size(); i++) {
             int64_t* r = blocks + 16 * i; const GemmBlock& g = b.blocks[i];

@@ -88,4 +88,30 @@ void launch_peer_scatter(const PeerSpan& ps, int me, size_t off, size_t bytes, c
     EF_CUDA(cudaGetLastError());
 }
 
+// The same for a window of `rows` row segments of `row_bytes` bytes (a multiple of 16) every `pitch` bytes: the block columns of a
+// column-partitioned DtN map.
+__global__ void __launch_bounds__(256) peer_scatter2d_kernel(PeerSpan ps, int me, size_t off, size_t rows, size_t row16, size_t pitch)
+{
+    const size_t n16 = rows * row16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / row16, c = i - r * row16;
+        const size_t byte = off + r * pitch + c * 16;
+        const int4 v = *reinterpret_cast<const int4*>(ps.local_base + byte);
+#pragma unroll 1
+        for (int q = 0; q < ps.n; q++)
+            if (q != me) *reinterpret_cast<int4*>(ps.local_base + ps.delta[q] + byte) = v;
+    }
+}
+
+void launch_peer_scatter2d(const PeerSpan& ps, int me, size_t off, size_t rows, size_t row_bytes, size_t pitch, cudaStream_t s)
+{
+    if (rows == 0 || row_bytes == 0 || ps.n <= 1) return;
+    if ((off | row_bytes | pitch) & 15) throw Error{EF_ERR_BAD_ARG, "peer scatter: offsets and sizes must be multiples of 16 bytes"};
+    const size_t n16 = rows * (row_bytes / 16);
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    peer_scatter2d_kernel<<<(unsigned)blocks, 256, 0, s>>>(ps, me, off, rows, row_bytes / 16, pitch);
+    EF_CUDA(cudaGetLastError());
+}
+
 }  // namespace efgpu

@@ -31,7 +31,10 @@ namespace efgpu {
 //     down to 128 x 128 everywhere (default: measured r2t, 190 us per 256-block against 136 us - the owner's serial section, eight
 //     dependent reciprocals per pivot block plus the push, leaves the other seven CTAs in the cluster barrier 61 % of the time);
 //     read when a plan is made
-static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+// [10] pivot reciprocals of the 128 x 128 base case: 1 = hardware seed + two Newton steps, 0 = IEEE division (default; measured r2v: no change)
+// [11] peer-mapped partitions over 2 / 4 / 8 ranks: 1 = S and T split by block COLUMNS, so that T needs no exchange of S (default), 0 = by rows;
+//      read when a plan is made
+static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tuning[key] = value; }
 int get_tuning(int key) { return (key >= 0 && key < 16) ? g_tuning[key] : 0; }
 

@@ -101,9 +101,15 @@ def emulate(n, level, nranks, sym, Tc, X, peer=0):
     nsteps = len(plans[0][0])
     assert all(len(p[0]) == nsteps for p in plans)
 
+    colsplit = bool(int(plans[0][0][0][13]))     # peer-mapped trees over 2 / 4 / 8 ranks: S and T partitioned by block columns
+
     def run(i):
         st = plans[0][0][i]
         scatter = peer and nranks > 1 and int(st[0]) == 1 and (int(st[6]) == 3 or int(st[5]) == CLS_GEMM_S or (int(st[5]) == CLS_GEMM_T and level > 0))
+        if scatter and colsplit and int(st[5]) == CLS_GEMM_S:
+            # column partition: no barrier between S and T - every rank sees only its OWN columns of S (the rest of its S is still
+            # NaN here) until the barrier after T; a T block that read another rank's columns would turn into NaN
+            scatter = False
         if scatter:      # all ranks read the state before the launch (flag barrier), then store into every arena
             frozen = [RankState.__new__(RankState) for _ in range(nranks)]
             for r in range(nranks):
@@ -132,7 +138,17 @@ def emulate(n, level, nranks, sym, Tc, X, peer=0):
     for i in range(nsteps):          # phase 1
         if cls[i] == CLS_GEMM_T:
             run(i)
-    if nranks > 1 and (not peer or level == 0):   # level 0: efgpu_complete_root_dtn (the root's map is gathered and mirrored only on demand)
+    if nranks > 1 and peer and colsplit:          # the barrier after T completes S: every rank's block columns are everywhere now
+        w = 8 * n // nranks
+        full = np.concatenate([view(states[r].ops[OP_S], r * w, 8 * n, 4 * n, w) for r in range(nranks)], axis=1)
+        for s in states:
+            s.ops[OP_S][:] = full.reshape(-1)
+    if nranks > 1 and peer and level == 0 and colsplit:   # efgpu_complete_root_dtn of a column partition: every rank's block columns to everybody
+        w = 8 * n // nranks
+        full = np.concatenate([view(states[r].ops[OP_T], r * w, 8 * n, 8 * n, w) for r in range(nranks)], axis=1)
+        for s in states:
+            s.ops[OP_T][:] = full.reshape(-1)
+    elif nranks > 1 and (not peer or level == 0):   # level 0: efgpu_complete_root_dtn (the root's map is gathered and mirrored only on demand)
         allgather(states, OP_T, 0, 64 * n * n)
     for i in range(nsteps):
         if cls[i] == CLS_MIRROR_T:
@@ -332,8 +348,8 @@ def test_T_products_are_balanced_over_the_ranks(nranks, whole_diagonal_blocks):
     assert per_rank == [144.0 / nranks] * nranks, per_rank
 
 
-@pytest.mark.parametrize("nranks,n,level", [(2, 256, 0), (4, 256, 1), (8, 256, 0), (8, 256, 1)])
-def test_peer_plan_reproduces_oracle_merge(nranks, n, level, monkeypatch):
+@pytest.mark.parametrize("nranks,n,level,sym", [(2, 256, 0, 1), (4, 256, 1, 1), (8, 256, 0, 1), (8, 256, 1, 1), (2, 256, 1, 0), (8, 256, 0, 0)])
+def test_peer_plan_reproduces_oracle_merge(nranks, n, level, sym, monkeypatch):
     """The plan of a peer-mapped tree (efgpu_peer_export): products of the inversion split down to 64-row slices per rank (here
     forced with EFGPU_SPLIT_MIN_ROWS), stored into every rank's arena together with their fused transposes; 8 ranks: one block
     row of T per rank with the opposite pairs shared half and half.  Every rank must end with the oracle's X^-1, S and T."""
@@ -342,8 +358,8 @@ def test_peer_plan_reproduces_oracle_merge(nranks, n, level, monkeypatch):
         _CHILDREN[depth] = uniform_children(16, depth)
     Tc, root = _CHILDREN[depth]
     monkeypatch.setenv("EFGPU_SPLIT_MIN_ROWS", "256")        # read whenever a plan is made
-    states, flops = emulate(n, level, nranks, 1, Tc, root.X, peer=1)
-    split_steps = sum(1 for st in get_plan(n, level, 0, nranks, 1, 1)[0] if int(st[6]) == 3)
+    states, flops = emulate(n, level, nranks, sym, Tc, root.X, peer=1)
+    split_steps = sum(1 for st in get_plan(n, level, 0, nranks, sym, 1)[0] if int(st[6]) == 3)
     for s in states:
         assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(root.X)) < 1e-11
         assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11

@@ -27,5 +27,6 @@ run() {   # name, env..., -- bench args
 BARGS=""
 run graphs EFGPU_TRACE=$OUT/trace_${TAG}_n${N}
 [ -z "$SKIP_PLAIN" ] && run plain EFGPU_GRAPHS_PEER=0
+if [ -n "$ROWSPLIT" ]; then BARGS="--tuning 11=0"; run rowsplit EFGPU_X=0; BARGS=""; fi
 if [ -n "$BIG" ]; then BARGS="$BIG"; run big EFGPU_X=0; fi
 ls $OUT | grep trace_${TAG} | head -40
