@@ -32,9 +32,10 @@ namespace efgpu {
 //     dependent reciprocals per pivot block plus the push, leaves the other seven CTAs in the cluster barrier 61 % of the time);
 //     read when a plan is made
 // [10] pivot reciprocals of the 128 x 128 base case: 1 = hardware seed + two Newton steps, 0 = IEEE division (default; measured r2v: no change)
-// [11] peer-mapped partitions over 2 / 4 / 8 ranks: 1 = S and T split by block COLUMNS, so that T needs no exchange of S (default), 0 = by rows;
-//      read when a plan is made
-static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0};
+// [11] peer-mapped partitions over 2 / 4 / 8 ranks: 1 = S and T split by block COLUMNS, so that T needs no exchange of S, 0 = by rows
+//      (default: measured r2w / r2x, 103.0 vs 102.2 ms at 2 GPUs and 43.6 vs 41.6 ms at 8 - the barrier saved does not pay for the
+//      slower column-wise products, whose stores of S and T then drain together); read when a plan is made
+static int g_tuning[16] = {2, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
 void set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tuning[key] = value; }
 int get_tuning(int key) { return (key >= 0 && key < 16) ? g_tuning[key] : 0; }
 

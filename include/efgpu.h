@@ -306,7 +306,8 @@ int efgpu_debug_tma_plan(int n, int level, int rank, int nranks, int symmetric, 
  * (0, default: blocked Gauss-Jordan on the tensor pipe; 1: per-pivot register kernel; 2: blocked with look-ahead); key 8 = operand
  * staging of the 128-row GEMM tiles (1, default: TMA; 0: cp.async); key 9 = 256 x 256 base case by a thread-block cluster in batches
  * of at most four merges (0, default: off; read when a plan is made); key 10 = pivot reciprocals of the base case by hardware seed +
- * Newton steps (0, default: IEEE division).  Keys 0 .. 15 are accepted.
+ * Newton steps (0, default: IEEE division); key 11 = peer-mapped partitions over 2 / 4 / 8 ranks split S and T by block columns
+ * instead of rows (0, default: rows; read when a plan is made).  Keys 0 .. 15 are accepted.
  * Results do not depend on the knobs beyond floating-point summation order. */
 int efgpu_set_tuning(int key, int value);
 

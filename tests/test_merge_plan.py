@@ -348,8 +348,9 @@ def test_T_products_are_balanced_over_the_ranks(nranks, whole_diagonal_blocks):
     assert per_rank == [144.0 / nranks] * nranks, per_rank
 
 
-@pytest.mark.parametrize("nranks,n,level,sym", [(2, 256, 0, 1), (4, 256, 1, 1), (8, 256, 0, 1), (8, 256, 1, 1), (2, 256, 1, 0), (8, 256, 0, 0)])
-def test_peer_plan_reproduces_oracle_merge(nranks, n, level, sym, monkeypatch):
+@pytest.mark.parametrize("nranks,n,level,sym,cols", [(2, 256, 0, 1, 0), (4, 256, 1, 1, 0), (8, 256, 0, 1, 0), (8, 256, 1, 1, 0),
+                                                     (2, 256, 1, 0, 1), (8, 256, 0, 0, 1), (4, 256, 0, 1, 1), (8, 256, 1, 1, 1)])
+def test_peer_plan_reproduces_oracle_merge(nranks, n, level, sym, cols, monkeypatch):
     """The plan of a peer-mapped tree (efgpu_peer_export): products of the inversion split down to 64-row slices per rank (here
     forced with EFGPU_SPLIT_MIN_ROWS), stored into every rank's arena together with their fused transposes; 8 ranks: one block
     row of T per rank with the opposite pairs shared half and half.  Every rank must end with the oracle's X^-1, S and T."""
@@ -358,8 +359,15 @@ def test_peer_plan_reproduces_oracle_merge(nranks, n, level, sym, monkeypatch):
         _CHILDREN[depth] = uniform_children(16, depth)
     Tc, root = _CHILDREN[depth]
     monkeypatch.setenv("EFGPU_SPLIT_MIN_ROWS", "256")        # read whenever a plan is made
-    states, flops = emulate(n, level, nranks, sym, Tc, root.X, peer=1)
-    split_steps = sum(1 for st in get_plan(n, level, 0, nranks, sym, 1)[0] if int(st[6]) == 3)
+    lib = _lib.load()
+    assert lib.efgpu_set_tuning(11, cols) == 0              # cols = 1: S and T partitioned by block columns (off by default)
+    try:
+        states, flops = emulate(n, level, nranks, sym, Tc, root.X, peer=1)
+        plan0 = get_plan(n, level, 0, nranks, sym, 1)[0]
+    finally:
+        assert lib.efgpu_set_tuning(11, 0) == 0
+    assert int(plan0[0][13]) == cols
+    split_steps = sum(1 for st in plan0 if int(st[6]) == 3)
     for s in states:
         assert rel(view(s.ops[OP_XINV], 0, 4 * n, 4 * n, 4 * n), np.linalg.inv(root.X)) < 1e-11
         assert rel(s.ops[OP_S].reshape(4 * n, 8 * n), root.S) < 1e-11
