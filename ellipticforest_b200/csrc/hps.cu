@@ -1028,20 +1028,30 @@ static void allocate_device(efgpu_handle* H, unsigned flags)
         }
         b.d_entries.upload(ent, s); b.d_ptab.upload(ptab, s); b.d_blocks.upload(b.blocks, s); b.d_trans.upload(b.trans, s);
         b.h_ptab = ptab; b.h_ent = ent;
+        b.d_mapsA.release(); b.d_mapsB.release();
         if (!b.views.empty()) {   // tensor maps of every (parent, view): base = the slot's pointer + the view's origin
             const size_t nv = b.views.size();
             std::vector<unsigned char> ma(cnt * nv * TMA_MAP_BYTES, 0), mb(cnt * nv * TMA_MAP_BYTES, 0);
-            for (size_t sl = 0; sl < cnt; sl++)
-                for (size_t v = 0; v < nv; v++) {
-                    const double* basep = ptab[sl * NOPS + b.views[v].op];
-                    if (!basep) continue;   // a slot this build does not have (the copy of X): its steps do not run either
-                    encode_operand_maps(basep + b.views[v].origin, (unsigned long long)b.views[v].ld, ma.data() + (sl * nv + v) * TMA_MAP_BYTES,
-                                        mb.data() + (sl * nv + v) * TMA_MAP_BYTES);
-                }
-            b.d_mapsA.alloc(ma.size()); b.d_mapsB.alloc(mb.size());
-            EF_CUDA(cudaMemcpy(b.d_mapsA.p, ma.data(), ma.size(), cudaMemcpyHostToDevice));
-            EF_CUDA(cudaMemcpy(b.d_mapsB.p, mb.data(), mb.size(), cudaMemcpyHostToDevice));
-            b.d_tblocks.upload(b.tblocks, s);
+            bool encoded = true;
+            try {
+                for (size_t sl = 0; sl < cnt; sl++)
+                    for (size_t v = 0; v < nv; v++) {
+                        const double* basep = ptab[sl * NOPS + b.views[v].op];
+                        if (!basep) continue;   // a slot this build does not have (the copy of X): its steps do not run either
+                        encode_operand_maps(basep + b.views[v].origin, (unsigned long long)b.views[v].ld, ma.data() + (sl * nv + v) * TMA_MAP_BYTES,
+                                            mb.data() + (sl * nv + v) * TMA_MAP_BYTES);
+                    }
+            } catch (const Error& e) {   // a driver without cuTensorMapEncodeTiled: the same products on the cp.async kernels, said once
+                encoded = false;
+                static bool told = false;
+                if (!told) { told = true; fprintf(stderr, "efgpu: TMA operand staging unavailable (%s): merge products use the cp.async kernels\n", e.msg.c_str()); }
+            }
+            if (encoded) {
+                b.d_mapsA.alloc(ma.size()); b.d_mapsB.alloc(mb.size());
+                EF_CUDA(cudaMemcpy(b.d_mapsA.p, ma.data(), ma.size(), cudaMemcpyHostToDevice));
+                EF_CUDA(cudaMemcpy(b.d_mapsB.p, mb.data(), mb.size(), cudaMemcpyHostToDevice));
+                b.d_tblocks.upload(b.tblocks, s);
+            }
         }
         auto up = [&](std::vector<std::vector<CoarsenOp>>& v, std::vector<std::unique_ptr<DevBuf>>& dv, std::vector<int>& mx) {
             dv.clear(); mx.clear();
