@@ -163,7 +163,6 @@ def test_fast_pivot_reciprocal_against_ieee_division():
               threshold=1.2, refine_box=None)
     P = O.problem(kw["problem_name"])
     lib = _lib.load()
-    default = lib.efgpu_set_tuning(10, 0)
     out = {}
     for key in (0, 1):
         assert lib.efgpu_set_tuning(10, key) == 0
@@ -176,10 +175,8 @@ def test_fast_pivot_reciprocal_against_ieee_division():
             u = hps.solveStage(lambda side, x, y: (P["u"](x, y), 1.0, 0.0)).copy()
             out[key] = [u, hps.operator(0, "T"), hps.operator(0, "S"), hps.operator(0, "Xinv")]
         finally:
-            lib.efgpu_set_tuning(10, TUNING10_DEFAULT)
+            lib.efgpu_set_tuning(10, 0)      # the default
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     for k in range(4):
         assert rel(out[0][k], out[1][k]) < 1e-11, k
 
-
-TUNING10_DEFAULT = 0
