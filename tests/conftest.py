@@ -63,4 +63,7 @@ GOLDEN_CASES = [
     "adaptive_tag2_m8_helmholtz_rect",
     "adaptive_l1_3_m8_varcoef",
     "uniform_l2_m8_helmholtz_indefinite",
+    "adaptive_l1_4_m4_helmholtz",
+    "adaptive_l1_3_m4_varcoef",
+    "single_patch_m64_poisson",
 ]

@@ -25,6 +25,10 @@ CASES = {
     "adaptive_tag2_m8_helmholtz_rect": ["--problem", "helmholtz", "--solver", "fishpack", "--min-level", "1", "--max-level", "4", "--nx", "8", "--domain", "0", "2", "0", "1", "--refine-box", "1.0", "2.0", "0.5", "1.0"],
     # indefinite operator (lambda = +5 > first Dirichlet eigenvalue 2 of [0,pi]^2; hstcrt IERROR = 6, tolerated): the root merge matrix has negative eigenvalues
     "uniform_l2_m8_helmholtz_indefinite": ["--problem", "helmholtz", "--lambda", "5.0", "--solver", "fishpack", "--min-level", "2", "--max-level", "2", "--nx", "8", "--domain", "0", PI, "0", PI],
+    # patch sizes of the reference's convergence driver / plots outside 8 ... 32 (examples/elliptic-multiple/main.cpp:444)
+    "adaptive_l1_4_m4_helmholtz": ["--problem", "helmholtz", "--solver", "fishpack", "--min-level", "1", "--max-level", "4", "--nx", "4", "--domain", "-10", "10", "-10", "10", "--refine-box", "-10", "0.5", "-10", "0.5"],
+    "adaptive_l1_3_m4_varcoef": ["--problem", "varcoef", "--solver", "fivepoint", "--min-level", "1", "--max-level", "3", "--nx", "4", "--domain", "-10", "10", "-10", "10", "--refine-box", "2", "10", "-3", "10"],
+    "single_patch_m64_poisson": ["--problem", "poisson", "--solver", "fishpack", "--min-level", "0", "--max-level", "0", "--nx", "64", "--domain", "0", PI, "0", PI],
     "adaptive_l1_3_m8_varcoef": ["--problem", "varcoef", "--solver", "fivepoint", "--min-level", "1", "--max-level", "3", "--nx", "8", "--domain", "-10", "10", "-10", "10", "--refine-box", "2", "10", "-3", "10"],
 }
 
